@@ -1,0 +1,203 @@
+/*
+ * llp_b200.h — C-ABI of the B200-native LLP hot path (libllp_b200.so).
+ *
+ * The reference (snap-research/linkless-link-prediction) is pure Python with NO FFI /
+ * plugin layer of its own: its hot-path arithmetic lives in the CUDA
+ * kernels of third-party wheels reached through Python call sites.  Each entry point below
+ * therefore cites the reference CALL SITE (file:line under /root/reference) whose
+ * third-party kernel it replaces.  INTEGRATION.md shows the ctypes binding a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory unless named host_*.
+ *   - the caller owns all memory including workspaces (sizes via *_workspace_bytes);
+ *     kernels never allocate or free.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - stateless and re-entrant; one process per GPU.
+ *   - return 0 on success, >0 = cudaError_t, <0 = LLP_E_* below.  There is NO CPU
+ *     fallback: a non-sm_100 device yields LLP_E_DEVICE.
+ *   - row-major matrices with explicit leading dimensions (ld*, in elements).
+ */
+#ifndef LLP_B200_H_
+#define LLP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define LLP_F32 0
+#define LLP_BF16 1
+
+#define LLP_E_BADARG (-1)    /* null pointer / negative size / unknown enum            */
+#define LLP_E_ALIGN (-2)     /* pointer or leading dimension not aligned as documented */
+#define LLP_E_WORKSPACE (-3) /* workspace too small                                    */
+#define LLP_E_DEVICE (-4)    /* current device is not sm_100                           */
+#define LLP_E_SHAPE (-5)     /* shape not supported by the selected backend            */
+
+#define LLP_GEMM_AUTO 0    /* bf16 -> tcgen05, f32 -> SIMT fp32                         */
+#define LLP_GEMM_SIMT 1    /* CUDA-core FFMA, fp32 accumulate (the fp32-parity path)    */
+#define LLP_GEMM_TCGEN05 2 /* tcgen05.mma + TMA + TMEM (bf16 operands, fp32 accumulate) */
+
+int llp_version(void);
+const char* llp_error_string(int code);
+/* 1 if the CURRENT device is compute capability 10.x, 0 if not, <0/>0 on error. */
+int llp_device_supported(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t llp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Graph structure.  Replaces: PyG MessagePassing.__collect__/aggregate over a dense [2,E]
+ * edge_index (models.py:113,118 -> SAGEConv.propagate; train_teacher_gnn.py:317,331) and
+ * torch_sparse's CSR conversion (sageconv_updated.py:86-89).
+ * Messages flow key-side <- value-side: pass (edge_val=src, edge_key=dst) for the forward
+ * CSR (rows = destinations) and swap them for the transpose.  Stable in the original edge
+ * order, so results are bit-reproducible.  int32 indices: N, E < 2^31.
+ * ------------------------------------------------------------------------------------- */
+size_t llp_csr_build_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int llp_csr_build(const int64_t* edge_val, const int64_t* edge_key, int64_t num_edges, int64_t num_nodes,
+                  int32_t* rowptr /*[N+1]*/, int32_t* col /*[E]*/, int32_t* perm /*[E] or NULL*/,
+                  float* inv_deg /*[N] 1/max(deg,1) or NULL*/, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Edge-balanced work plan for llp_spmm: chunk c owns rows [first_row[c], first_row[c+1]). */
+int64_t llp_spmm_num_chunks(int64_t num_edges);
+int llp_spmm_plan(const int32_t* rowptr, int64_t num_nodes, int64_t num_edges,
+                  int32_t* chunk_first_row /*[num_chunks+1]*/, void* stream);
+size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
+
+/* CSR gather-reduce SpMM: out[r,:] = (mean ? 1/max(deg r,1) : 1) * sum_{e in row r} scale[col e] * x[col e,:]
+ * Replaces torch_scatter.scatter(reduce='mean') + index_select (SAGEConv.propagate, models.py:113) and
+ * its autograd transpose (index_add_).  dtype in {LLP_F32, LLP_BF16}; fp32 accumulation in CSR order.
+ * x/out rows must be 4-byte aligned at least; 16-byte aligned rows (ld*elt % 16 == 0) take the
+ * 128-bit path.  src_scale may be NULL. */
+int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
+             int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
+             const float* src_scale, int mean, void* out, int64_t ldo, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense layers.  Replaces cuBLAS SGEMM behind F.linear (sageconv_updated.py:71,76; PyG
+ * SAGEConv lin_l/lin_r; models.py:48,143,146) plus the relu/dropout/bias ATen kernels
+ * (models.py:116-117,144-145).
+ * ------------------------------------------------------------------------------------- */
+typedef struct llp_gemm_nt_args {
+  int dtype;     /* operand dtype of A*, B* (LLP_F32 | LLP_BF16)                              */
+  int out_dtype; /* dtype of D and addend                                                     */
+  int backend;   /* LLP_GEMM_*                                                                */
+  int relu;      /* apply max(.,0) after bias/addend                                          */
+  int64_t M, N, K1, K2;
+  const void* A1; int64_t lda1; /* [M,K1]                                                     */
+  const void* B1; int64_t ldb1; /* [N,K1]   D = A1 * B1^T                                     */
+  const void* A2; int64_t lda2; /* [M,K2] or NULL                                             */
+  const void* B2; int64_t ldb2; /* [N,K2]     + A2 * B2^T                                     */
+  const float* bias;            /* [N] or NULL                                                */
+  const void* addend; int64_t ldadd; /* [M,N] out_dtype or NULL: + addend                     */
+  const void* gate; int64_t ldgate;  /* [M,N] out_dtype or NULL: D = gate>0 ? D*gate_scale : 0
+                                        (backward of relu+dropout from the saved output)      */
+  float gate_scale;
+  float dropout_p;              /* 0 = off; keep-prob 1-p, survivors scaled by 1/(1-p)        */
+  uint64_t seed, offset;        /* Philox4x32-10 stream for the dropout mask                  */
+  void* D; int64_t ldd;         /* [M,N]                                                      */
+} llp_gemm_nt_args;
+int llp_gemm_nt(const llp_gemm_nt_args* host_args, void* stream);
+
+/* Weight gradient: D[N1,N2] (fp32) = A[M,N1]^T * B[M,N2], reduction over the M rows, split
+ * across CTAs with a deterministic fixed-order reduce (autograd of F.linear). */
+size_t llp_gemm_tn_workspace_bytes(int64_t M, int64_t N1, int64_t N2);
+int llp_gemm_tn(int dtype, int backend, int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda,
+                const void* B, int64_t ldb, float* D, int64_t ldd, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* Column sums (bias gradient): out[n] (+)= sum_m A[m,n].  Deterministic. */
+size_t llp_colsum_workspace_bytes(int64_t N);
+int llp_colsum(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, float* out, int accumulate,
+               void* workspace, void* stream);
+/* dst[c,r] = (dst dtype) src[r,c]; also plain cast when transpose == 0. */
+int llp_cast2d(int src_dtype, int dst_dtype, const void* src, int64_t lds, int64_t rows, int64_t cols,
+               void* dst, int64_t ldd, int transpose, void* stream);
+/* y = gate>0 ? g*scale : 0  (relu/dropout backward from the saved forward output). */
+int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ldgate, int64_t M, int64_t N,
+             float scale, void* y, int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Edge scoring.  Replaces the two advanced-index gathers + mul feeding LinkPredictor
+ * (train_teacher_gnn.py:58,97,103,109,115; main.py:186,214; models.py:140) and their
+ * autograd (index_put_ with atomics).
+ * ------------------------------------------------------------------------------------- */
+/* z[m,:] = h[u[m],:] * h[v[m],:] */
+int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t feat, const int64_t* u, const int64_t* v,
+                      int64_t num_edges, void* z, int64_t ldz, void* stream);
+/* gh[u[m],:] += dz[m,:]*h[v[m],:]; gh[v[m],:] += dz[m,:]*h[u[m],:]   (gh fp32 [N,feat], pre-zeroed) */
+int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t feat, const int64_t* u,
+                          const int64_t* v, int64_t num_edges, const void* dz, int64_t lddz, float* gh,
+                          int64_t ldgh, void* stream);
+/* Final predictor layer with one output: logit[m] = y[m,:].w + b ; p = sigmoid(logit).
+ * (models.py:146,150 with out_channels == 1.) */
+int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w, const float* b,
+                   float* prob, void* stream);
+/* backward of llp_score_head: dlogit = dprob*p*(1-p); gy[m,:] = dlogit[m]*w ; gw (+)= sum_m dlogit*y ; gb (+)= sum dlogit */
+int llp_score_head_bwd(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w,
+                       const float* prob, const float* dprob, void* gy, int64_t ldgy, float* gw, float* gb,
+                       void* workspace, size_t workspace_bytes, void* stream);
+size_t llp_score_head_bwd_workspace_bytes(int64_t M, int64_t H);
+
+/* ---------------------------------------------------------------------------------------
+ * Losses.  BCE: nn.BCELoss (train_teacher_gnn.py:33,59; main.py:162,215).  LLP_D: kl_loss
+ * (main.py:27-31,188).  LLP_R: the rank block (main.py:190-203).  Each writes the scalar
+ * loss (deterministic reduction) and the gradient w.r.t. its student input for
+ * upstream-gradient 1.
+ * ------------------------------------------------------------------------------------- */
+size_t llp_loss_workspace_bytes(int64_t rows);
+/* labels: first n_pos entries are 1, the rest 0 (train_teacher_gnn.py:57). */
+int llp_bce(const float* prob, int64_t n, int64_t n_pos, float* loss, float* dprob, void* workspace,
+            void* stream);
+int llp_kd_d(const float* s, const float* t, int64_t rows, int64_t K, float T, float* loss, float* ds,
+             void* workspace, void* stream);
+int llp_kd_r(const float* s, const float* t, int64_t rows, int64_t K, float margin, float* loss, float* ds,
+             void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Hits@K.  Replaces ogb Evaluator._eval_hits = torch.topk on CPU tensors + compare + sum
+ * (train_teacher_gnn.py:120-145,226-249).  llp_topk_desc returns the kmax largest negative
+ * scores in descending order (padded with -inf when n < kmax) — the per-rank candidate list
+ * of the multi-GPU exchange; llp_count_greater counts positives strictly above each threshold.
+ * ------------------------------------------------------------------------------------- */
+size_t llp_topk_workspace_bytes(int64_t n, int64_t kmax);
+int llp_topk_desc(const float* scores, int64_t n, int64_t kmax, float* out /*[kmax]*/, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int llp_count_greater(const float* pos, int64_t n_pos, const float* thresholds, int64_t n_thr,
+                      int64_t* counts /*[n_thr]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Context sampling.  Replaces torch_cluster.random_walk(coalesced=False) uniform kernel
+ * (main.py:37,43,45).  rand is the [B,L] fp32 torch.rand tensor; out is [B,L+1] int64.
+ * ------------------------------------------------------------------------------------- */
+int llp_random_walk(const int64_t* rowptr, const int64_t* col, const int64_t* start, const float* rand,
+                    int64_t num_walks, int64_t walk_length, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Optimiser tail.  Replaces clip_grad_norm_ x2 + torch.optim.Adam foreach kernels
+ * (train_teacher_gnn.py:63-67; main.py:226-230) on flat fp32 buffers.  Groups are
+ * contiguous ranges [group_begin[g], group_begin[g+1]) clipped separately to max_norm.
+ * ------------------------------------------------------------------------------------- */
+size_t llp_clip_adam_workspace_bytes(int num_groups);
+int llp_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  const int64_t* host_group_begin, int num_groups, float max_norm, float grad_scale, float lr,
+                  float beta1, float beta2, float eps, int64_t step, void* bf16_copy /*[n] or NULL*/,
+                  float* group_norms /*[num_groups] out*/, void* workspace, void* stream);
+
+/* Deterministic sum of n floats (double accumulate): out[0] = scale * sum(in). */
+int llp_sum(const float* in, int64_t n, float scale, float* out, void* workspace /* >= 8 KiB */, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLP_B200_H_ */

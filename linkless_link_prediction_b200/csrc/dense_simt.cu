@@ -1,0 +1,281 @@
+// CUDA-core dense kernels: the fp32-parity GEMM backend (true fp32 FFMA, as the reference's
+// cuBLAS SGEMM with allow_tf32=False — SURVEY.md K4/H2), plus the small dense helpers
+// (column sums, cast/transposes, relu-dropout gate).  The tensor-core path is gemm_tcgen05.cu.
+#include "common.cuh"
+
+namespace llp {
+
+constexpr int kTM = 64, kTN = 64, kTK = 16, kSimtThreads = 256;
+
+struct StridedOperand {
+  const void* p;
+  int64_t s_outer;  // stride of the M (or N) index
+  int64_t s_k;      // stride of the reduction index
+  int64_t K;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_tile(const StridedOperand& op, int64_t outer0, int64_t outer_lim, int64_t k0,
+                                          int64_t k_lim, float (*tile)[kTM + 1]) {
+  const T* p = reinterpret_cast<const T*>(op.p);
+  const bool k_contig = op.s_k == 1;
+#pragma unroll
+  for (int i = 0; i < (kTM * kTK) / kSimtThreads; ++i) {
+    int idx = threadIdx.x + i * kSimtThreads;
+    int k = k_contig ? (idx % kTK) : (idx / kTM);
+    int o = k_contig ? (idx / kTK) : (idx % kTM);
+    int64_t go = outer0 + o, gk = k0 + k;
+    float v = 0.0f;
+    if (go < outer_lim && gk < k_lim) v = to_f32(p[go * op.s_outer + gk * op.s_k]);
+    tile[k][o] = v;
+  }
+}
+
+// C[m,n] = sum over operand pairs of sum_k A(m,k) * B(n,k); blockIdx.z selects a K-split.
+template <typename T, typename TO, bool kPartial>
+__global__ void __launch_bounds__(kSimtThreads)
+gemm_simt_kernel(int64_t M, int64_t N, StridedOperand a1, StridedOperand b1, StridedOperand a2, StridedOperand b2,
+                 int64_t k_per_split, EpilogueParams ep, TO* __restrict__ D, int64_t ldd, float* __restrict__ partial) {
+  __shared__ float As[kTK][kTM + 1];
+  __shared__ float Bs[kTK][kTN + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int64_t m0 = (int64_t)blockIdx.y * kTM, n0 = (int64_t)blockIdx.x * kTN;
+  float acc[4][4] = {};
+  for (int pair = 0; pair < 2; ++pair) {
+    const StridedOperand& a = pair == 0 ? a1 : a2;
+    const StridedOperand& b = pair == 0 ? b1 : b2;
+    if (a.p == nullptr) continue;
+    int64_t kb = kPartial ? (int64_t)blockIdx.z * k_per_split : 0;
+    int64_t ke = kPartial ? min(a.K, kb + k_per_split) : a.K;
+    for (int64_t k0 = kb; k0 < ke; k0 += kTK) {
+      load_tile<T>(a, m0, M, k0, ke, As);
+      load_tile<T>(b, n0, N, k0, ke, Bs);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kTK; ++k) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      if constexpr (kPartial) {
+        partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+      } else {
+        D[m * ldd + n] = from_f32<TO>(epilogue_apply<TO>(acc[i][j], m, n, ep));
+      }
+    }
+  }
+}
+
+// D[i] (+)= sum_z partial[z][i]   (fixed order => deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t rows, int64_t cols,
+                                     float* __restrict__ D, int64_t ldd, int accumulate) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float acc = 0.0f;
+  for (int z = 0; z < splits; ++z) acc += partial[(int64_t)z * rows * cols + i];
+  int64_t r = i / cols, c = i % cols;
+  D[r * ldd + c] = accumulate ? D[r * ldd + c] + acc : acc;
+}
+
+template <typename T, typename TO>
+static int gemm_nt_simt_typed(const llp_gemm_nt_args& a, cudaStream_t stream) {
+  StridedOperand a1{a.A1, a.lda1, 1, a.K1}, b1{a.B1, a.ldb1, 1, a.K1};
+  StridedOperand a2{a.A2, a.lda2, 1, a.K2}, b2{a.B2, a.ldb2, 1, a.K2};
+  if (a.A2 == nullptr || a.K2 == 0) a2.p = b2.p = nullptr;
+  EpilogueParams ep{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset};
+  dim3 grid((unsigned)ceil_div(a.N, kTN), (unsigned)ceil_div(a.M, kTM), 1);
+  gemm_simt_kernel<T, TO, false><<<grid, kSimtThreads, 0, stream>>>(a.M, a.N, a1, b1, a2, b2, 0, ep,
+                                                                  reinterpret_cast<TO*>(a.D), a.ldd, nullptr);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_nt_simt(const llp_gemm_nt_args& a, cudaStream_t stream) {
+  if (a.dtype == LLP_F32 && a.out_dtype == LLP_F32) return gemm_nt_simt_typed<float, float>(a, stream);
+  if (a.dtype == LLP_BF16 && a.out_dtype == LLP_BF16) return gemm_nt_simt_typed<__nv_bfloat16, __nv_bfloat16>(a, stream);
+  if (a.dtype == LLP_BF16 && a.out_dtype == LLP_F32) return gemm_nt_simt_typed<__nv_bfloat16, float>(a, stream);
+  if (a.dtype == LLP_F32 && a.out_dtype == LLP_BF16) return gemm_nt_simt_typed<float, __nv_bfloat16>(a, stream);
+  return LLP_E_BADARG;
+}
+
+int tn_splits(int64_t M, int64_t N1, int64_t N2) {
+  int64_t tiles = ceil_div(N1, kTM) * ceil_div(N2, kTN);
+  int64_t want = ceil_div((int64_t)kNumSMs * 4, tiles);
+  int64_t max_by_k = ceil_div(M, 256);
+  int64_t s = want < max_by_k ? want : max_by_k;
+  return (int)(s < 1 ? 1 : s);
+}
+
+template <typename T>
+static int gemm_tn_simt_typed(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, const void* B, int64_t ldb,
+                              float* D, int64_t ldd, int accumulate, float* ws, cudaStream_t stream) {
+  int splits = tn_splits(M, N1, N2);
+  int64_t k_per = ceil_div(ceil_div(M, splits), kTK) * kTK;
+  splits = (int)ceil_div(M, k_per);
+  StridedOperand a1{A, 1, lda, M}, b1{B, 1, ldb, M}, none{nullptr, 0, 0, 0};
+  EpilogueParams ep{};
+  dim3 grid((unsigned)ceil_div(N2, kTN), (unsigned)ceil_div(N1, kTM), (unsigned)splits);
+  gemm_simt_kernel<T, float, true><<<grid, kSimtThreads, 0, stream>>>(N1, N2, a1, b1, none, none, k_per, ep, nullptr, 0, ws);
+  LLP_LAUNCH_OK();
+  int64_t n = N1 * N2;
+  splitk_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ws, splits, N1, N2, D, ldd, accumulate);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_tn_simt(int dtype, int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, const void* B, int64_t ldb,
+                 float* D, int64_t ldd, int accumulate, float* ws, cudaStream_t stream) {
+  if (dtype == LLP_F32) return gemm_tn_simt_typed<float>(M, N1, N2, A, lda, B, ldb, D, ldd, accumulate, ws, stream);
+  if (dtype == LLP_BF16) return gemm_tn_simt_typed<__nv_bfloat16>(M, N1, N2, A, lda, B, ldb, D, ldd, accumulate, ws, stream);
+  return LLP_E_BADARG;
+}
+
+int splitk_reduce(const float* partial, int splits, int64_t rows, int64_t cols, float* D, int64_t ldd, int accumulate,
+                  cudaStream_t stream) {
+  int64_t n = rows * cols;
+  splitk_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(partial, splits, rows, cols, D, ldd, accumulate);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+// ---- column sums -------------------------------------------------------------------------------
+// grid (N/32 strips, S row-splits): 8 warps stride over the split's rows; partials are combined in
+// fixed order by a second tiny kernel => deterministic.
+constexpr int kColsumSplits = 64;
+
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ A, int64_t lda, int64_t M, int64_t N, int64_t rows_per_split,
+                                      float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int64_t n = (int64_t)blockIdx.x * 32 + lane;
+  int64_t mb = (int64_t)blockIdx.y * rows_per_split, me = min(M, mb + rows_per_split);
+  float acc = 0.0f;
+  if (n < N)
+    for (int64_t m = mb + w; m < me; m += 8) acc += to_f32(A[m * lda + n]);
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    partial[(int64_t)blockIdx.y * N + n] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int splits, int64_t N, float* __restrict__ out,
+                                    int accumulate) {
+  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.0f;
+  for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+// ---- cast / transpose ----------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void cast2d_kernel(const TS* __restrict__ src, int64_t lds, int64_t rows, int64_t cols, TD* __restrict__ dst,
+                              int64_t ldd, int transpose) {
+  __shared__ float tile[32][33];
+  int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? to_f32(src[r * lds + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    if (transpose) {
+      int64_t c = c0 + i, r = r0 + threadIdx.x;  // dst[c, r]
+      if (r < rows && c < cols) dst[c * ldd + r] = from_f32<TD>(tile[threadIdx.x][i]);
+    } else {
+      int64_t r = r0 + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) dst[r * ldd + c] = from_f32<TD>(tile[i][threadIdx.x]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void gate_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ gate, int64_t ldgate, int64_t M,
+                            int64_t N, float scale, T* __restrict__ y, int64_t ldy) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  int64_t m = i / N, n = i % N;
+  float v = to_f32(gate[m * ldgate + n]) > 0.0f ? to_f32(g[m * ldg + n]) * scale : 0.0f;
+  y[m * ldy + n] = from_f32<T>(v);
+}
+
+}  // namespace llp
+
+using namespace llp;
+
+extern "C" size_t llp_colsum_workspace_bytes(int64_t N) { return (size_t)kColsumSplits * (size_t)(N > 0 ? N : 1) * sizeof(float); }
+
+extern "C" int llp_colsum(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, float* out, int accumulate,
+                          void* workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(A && out && workspace && M >= 0 && N > 0 && lda >= N);
+  if (int rc = check_device()) return rc;
+  int splits = (int)imin64(kColsumSplits, imax64(1, ceil_div(M, 256)));
+  int64_t rows_per_split = ceil_div(imax64(M, 1), splits);
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)splits);
+  float* partial = reinterpret_cast<float*>(workspace);
+  if (dtype == LLP_F32) colsum_partial_kernel<float><<<grid, 256, 0, stream>>>((const float*)A, lda, M, N, rows_per_split, partial);
+  else if (dtype == LLP_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)A, lda, M, N, rows_per_split, partial);
+  else return LLP_E_BADARG;
+  LLP_LAUNCH_OK();
+  colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(partial, splits, N, out, accumulate);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int llp_cast2d(int src_dtype, int dst_dtype, const void* src, int64_t lds, int64_t rows, int64_t cols,
+                          void* dst, int64_t ldd, int transpose, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(src && dst && rows >= 0 && cols >= 0);
+  if (int rc = check_device()) return rc;
+  if (rows == 0 || cols == 0) return 0;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+#define LLP_CAST_CASE(SD, DD, TS, TD)                                                                             \
+  if (src_dtype == SD && dst_dtype == DD) {                                                                       \
+    cast2d_kernel<TS, TD><<<grid, block, 0, stream>>>((const TS*)src, lds, rows, cols, (TD*)dst, ldd, transpose); \
+    LLP_LAUNCH_OK();                                                                                              \
+    return 0;                                                                                                     \
+  }
+  LLP_CAST_CASE(LLP_F32, LLP_F32, float, float)
+  LLP_CAST_CASE(LLP_F32, LLP_BF16, float, __nv_bfloat16)
+  LLP_CAST_CASE(LLP_BF16, LLP_F32, __nv_bfloat16, float)
+  LLP_CAST_CASE(LLP_BF16, LLP_BF16, __nv_bfloat16, __nv_bfloat16)
+#undef LLP_CAST_CASE
+  return LLP_E_BADARG;
+}
+
+extern "C" int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ldgate, int64_t M, int64_t N,
+                        float scale, void* y, int64_t ldy, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(g && gate && y && M >= 0 && N >= 0);
+  if (int rc = check_device()) return rc;
+  if (M * N == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(M * N, 256);
+  if (dtype == LLP_F32) gate_kernel<float><<<blocks, 256, 0, stream>>>((const float*)g, ldg, (const float*)gate, ldgate, M, N, scale, (float*)y, ldy);
+  else if (dtype == LLP_BF16) gate_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)g, ldg, (const __nv_bfloat16*)gate, ldgate, M, N, scale, (__nv_bfloat16*)y, ldy);
+  else return LLP_E_BADARG;
+  LLP_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,235 @@
+// Edge scoring kernels: gather-Hadamard z = h[u]*h[v] (train_teacher_gnn.py:58,97; main.py:186,214;
+// models.py:140), its scatter backward, and the 1-output predictor head + sigmoid (models.py:146,150).
+#include "common.cuh"
+
+namespace llp {
+
+// one warp per edge; 16-byte vectors when rows are 16-byte aligned
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256)
+edge_hadamard_kernel(const T* __restrict__ h, int64_t ldh, int64_t F, const int64_t* __restrict__ u,
+                     const int64_t* __restrict__ v, int64_t M, T* __restrict__ z, int64_t ldz) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const T* hu = h + u[m] * ldh;
+  const T* hv = h + v[m] * ldh;
+  T* zr = z + m * ldz;
+  if constexpr (kVec) {
+    constexpr int VE = Vec16<T>::n;
+    for (int64_t c = lane * VE; c < F; c += 32 * VE) {
+      float a[VE], b[VE];
+      unpack16(ldg_v4(hu + c), a, T());
+      unpack16(ldg_v4(hv + c), b, T());
+#pragma unroll
+      for (int i = 0; i < VE; ++i) a[i] *= b[i];
+      stg_v4(zr + c, pack16(a, T()));
+    }
+  } else {
+    for (int64_t c = lane; c < F; c += 32) zr[c] = from_f32<T>(to_f32(hu[c]) * to_f32(hv[c]));
+  }
+}
+
+// gh[u] += dz*h[v]; gh[v] += dz*h[u]  — fp32 vector reductions into L2 (red.global.add.v4.f32)
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256)
+edge_hadamard_bwd_kernel(const T* __restrict__ h, int64_t ldh, int64_t F, const int64_t* __restrict__ u,
+                         const int64_t* __restrict__ v, int64_t M, const T* __restrict__ dz, int64_t lddz,
+                         float* __restrict__ gh, int64_t ldgh) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  int64_t um = u[m], vm = v[m];
+  const T* hu = h + um * ldh;
+  const T* hv = h + vm * ldh;
+  const T* dr = dz + m * lddz;
+  float* gu = gh + um * ldgh;
+  float* gv = gh + vm * ldgh;
+  if constexpr (kVec) {
+    constexpr int VE = Vec16<T>::n;
+    for (int64_t c = lane * VE; c < F; c += 32 * VE) {
+      float a[VE], b[VE], d[VE];
+      unpack16(ldg_v4(hu + c), a, T());
+      unpack16(ldg_v4(hv + c), b, T());
+      unpack16(ldg_v4(dr + c), d, T());
+#pragma unroll
+      for (int i = 0; i < VE; i += 4) {
+        atomicAdd(reinterpret_cast<float4*>(gu + c + i), make_float4(d[i] * b[i], d[i + 1] * b[i + 1], d[i + 2] * b[i + 2], d[i + 3] * b[i + 3]));
+        atomicAdd(reinterpret_cast<float4*>(gv + c + i), make_float4(d[i] * a[i], d[i + 1] * a[i + 1], d[i + 2] * a[i + 2], d[i + 3] * a[i + 3]));
+      }
+    }
+  } else {
+    for (int64_t c = lane; c < F; c += 32) {
+      float d = to_f32(dr[c]);
+      atomicAdd(gu + c, d * to_f32(hv[c]));
+      atomicAdd(gv + c, d * to_f32(hu[c]));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+score_head_kernel(const T* __restrict__ y, int64_t ldy, int64_t M, int64_t H, const float* __restrict__ w,
+                  const float* __restrict__ b, float* __restrict__ prob) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const T* yr = y + m * ldy;
+  float acc = 0.0f;
+  for (int64_t c = lane; c < H; c += 32) acc = fmaf(to_f32(yr[c]), __ldg(w + c), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float logit = acc + (b != nullptr ? b[0] : 0.0f);
+    prob[m] = 1.0f / (1.0f + expf(-logit));
+  }
+}
+
+// dlogit = dprob*p*(1-p); gy[m,:] = dlogit*w
+template <typename T>
+__global__ void __launch_bounds__(256)
+score_head_bwd_kernel(int64_t M, int64_t H, const float* __restrict__ w, const float* __restrict__ prob,
+                      const float* __restrict__ dprob, T* __restrict__ gy, int64_t ldgy, float* __restrict__ dlogit) {
+  int lane = threadIdx.x & 31;
+  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  float p = prob[m];
+  float dl = dprob[m] * p * (1.0f - p);
+  if (lane == 0) dlogit[m] = dl;
+  if (gy != nullptr)
+    for (int64_t c = lane; c < H; c += 32) gy[m * ldgy + c] = from_f32<T>(dl * __ldg(w + c));
+}
+
+// partial[s][c] = sum_{m in split s} dlogit[m]*y[m,c]
+constexpr int kHeadSplits = 64;
+template <typename T>
+__global__ void score_head_gw_kernel(const T* __restrict__ y, int64_t ldy, int64_t M, int64_t H,
+                                     const float* __restrict__ dlogit, int64_t rows_per_split, float* __restrict__ partial) {
+  __shared__ float red[8][33];
+  int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  int64_t mb = (int64_t)blockIdx.y * rows_per_split, me = min(M, mb + rows_per_split);
+  float acc = 0.0f;
+  if (c < H)
+    for (int64_t m = mb + wv; m < me; m += 8) acc = fmaf(dlogit[m], to_f32(y[m * ldy + c]), acc);
+  red[wv][lane] = acc;
+  __syncthreads();
+  if (wv == 0 && c < H) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    partial[(int64_t)blockIdx.y * H + c] = s;
+  }
+}
+
+__global__ void head_final_kernel(const float* __restrict__ partial, int splits, int64_t H, float* __restrict__ gw) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float s = 0.0f;
+  for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * H + c];
+  gw[c] = s;
+}
+
+template <typename T>
+static bool rows_vec_ok(const void* p, int64_t ld, int64_t F) {
+  return aligned(p, 16) && (ld * sizeof(T)) % 16 == 0 && F % Vec16<T>::n == 0;
+}
+
+template <typename T>
+static int hadamard_launch(const void* h, int64_t ldh, int64_t F, const int64_t* u, const int64_t* v, int64_t M, void* z,
+                           int64_t ldz, cudaStream_t stream) {
+  unsigned blocks = (unsigned)ceil_div(M * 32, 256);
+  if (rows_vec_ok<T>(h, ldh, F) && rows_vec_ok<T>(z, ldz, F))
+    edge_hadamard_kernel<T, true><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (T*)z, ldz);
+  else
+    edge_hadamard_kernel<T, false><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (T*)z, ldz);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T>
+static int hadamard_bwd_launch(const void* h, int64_t ldh, int64_t F, const int64_t* u, const int64_t* v, int64_t M,
+                               const void* dz, int64_t lddz, float* gh, int64_t ldgh, cudaStream_t stream) {
+  unsigned blocks = (unsigned)ceil_div(M * 32, 256);
+  bool vec = rows_vec_ok<T>(h, ldh, F) && rows_vec_ok<T>(dz, lddz, F) && aligned(gh, 16) && (ldgh % 4) == 0;
+  if (vec)
+    edge_hadamard_bwd_kernel<T, true><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (const T*)dz, lddz, gh, ldgh);
+  else
+    edge_hadamard_bwd_kernel<T, false><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (const T*)dz, lddz, gh, ldgh);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace llp
+
+using namespace llp;
+
+extern "C" int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t F, const int64_t* u, const int64_t* v,
+                                 int64_t M, void* z, int64_t ldz, void* stream_) {
+  LLP_CHECK_ARG(h && u && v && z && F > 0 && M >= 0 && ldh >= F && ldz >= F);
+  if (int rc = check_device()) return rc;
+  if (M == 0) return 0;
+  if (dtype == LLP_F32) return hadamard_launch<float>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
+  if (dtype == LLP_BF16) return hadamard_launch<__nv_bfloat16>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
+  return LLP_E_BADARG;
+}
+
+extern "C" int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t F, const int64_t* u,
+                                     const int64_t* v, int64_t M, const void* dz, int64_t lddz, float* gh, int64_t ldgh,
+                                     void* stream_) {
+  LLP_CHECK_ARG(h && u && v && dz && gh && F > 0 && M >= 0 && ldh >= F && lddz >= F && ldgh >= F);
+  if (int rc = check_device()) return rc;
+  if (M == 0) return 0;
+  if (dtype == LLP_F32) return hadamard_bwd_launch<float>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
+  if (dtype == LLP_BF16) return hadamard_bwd_launch<__nv_bfloat16>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
+  return LLP_E_BADARG;
+}
+
+extern "C" int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w, const float* b,
+                              float* prob, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(y && w && prob && M >= 0 && H > 0 && ldy >= H);
+  if (int rc = check_device()) return rc;
+  if (M == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(M * 32, 256);
+  if (dtype == LLP_F32) score_head_kernel<float><<<blocks, 256, 0, stream>>>((const float*)y, ldy, M, H, w, b, prob);
+  else if (dtype == LLP_BF16) score_head_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)y, ldy, M, H, w, b, prob);
+  else return LLP_E_BADARG;
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" size_t llp_score_head_bwd_workspace_bytes(int64_t M, int64_t H) {
+  return 8192 + ((size_t)(M > 0 ? M : 1) + (size_t)kHeadSplits * (size_t)(H > 0 ? H : 1)) * sizeof(float);
+}
+
+extern "C" int llp_score_head_bwd(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w,
+                                  const float* prob, const float* dprob, void* gy, int64_t ldgy, float* gw, float* gb,
+                                  void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(y && w && prob && dprob && workspace && M > 0 && H > 0 && ldy >= H);
+  if (workspace_bytes < llp_score_head_bwd_workspace_bytes(M, H)) return LLP_E_WORKSPACE;
+  if (int rc = check_device()) return rc;
+  float* dlogit = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 8192);
+  float* partial = dlogit + M;
+  unsigned blocks = (unsigned)ceil_div(M * 32, 256);
+  int splits = (int)imin64(kHeadSplits, imax64(1, ceil_div(M, 256)));
+  int64_t rows_per_split = ceil_div(M, splits);
+  dim3 grid((unsigned)ceil_div(H, 32), (unsigned)splits);
+  if (dtype == LLP_F32) {
+    score_head_bwd_kernel<float><<<blocks, 256, 0, stream>>>(M, H, w, prob, dprob, (float*)gy, ldgy, dlogit);
+    LLP_LAUNCH_OK();
+    if (gw) { score_head_gw_kernel<float><<<grid, 256, 0, stream>>>((const float*)y, ldy, M, H, dlogit, rows_per_split, partial); LLP_LAUNCH_OK(); }
+  } else if (dtype == LLP_BF16) {
+    score_head_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(M, H, w, prob, dprob, (__nv_bfloat16*)gy, ldgy, dlogit);
+    LLP_LAUNCH_OK();
+    if (gw) { score_head_gw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)y, ldy, M, H, dlogit, rows_per_split, partial); LLP_LAUNCH_OK(); }
+  } else {
+    return LLP_E_BADARG;
+  }
+  if (gw) {
+    head_final_kernel<<<(unsigned)ceil_div(H, 256), 256, 0, stream>>>(partial, splits, H, gw);
+    LLP_LAUNCH_OK();
+  }
+  if (gb) return sum_f32(dlogit, M, 1.0f, gb, workspace, stream);
+  return 0;
+}

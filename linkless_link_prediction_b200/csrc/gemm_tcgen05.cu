@@ -1,0 +1,435 @@
+// tcgen05 GEMMs for sm_100a: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM, issued by one thread) -> tcgen05.ld epilogue.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (one TMEM lane quadrant each).  Two accumulator stages in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+//   NT  : D[M,N]   = epi(A1[M,K1]*B1[N,K1]^T + A2[M,K2]*B2[N,K2]^T)      (both operands K-major)
+//         replaces F.linear / lin_l+lin_r (models.py:48,143; PyG SAGEConv; sageconv_updated.py:71,76)
+//   TN  : D[N1,N2] = A[M,N1]^T * B[M,N2]  split over M                    (both operands MN-major)
+//         the weight gradient of the same layers; fp32 partials + fixed-order reduce.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace llp {
+
+int splitk_reduce(const float* partial, int splits, int64_t rows, int64_t cols, float* D, int64_t ldd, int accumulate,
+                  cudaStream_t stream);
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kAccStages = 2;
+constexpr int kSlabBytes = BLOCK_K * 128;  // 64 rows x 128 B: one TMA box of the MN-major layout
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- descriptors -------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor: c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), a/b major bits 15/16, N>>3 at 17, M>>4 at 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct Config {
+  static constexpr int kABytes = BLOCK_M * 128;
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct Maps {
+  CUtensorMap a1, b1, a2, b2;
+};
+
+struct TcParams {
+  int64_t M, N;          // output tile space: rows (M) x cols (N)
+  int64_t K1, K2;        // reduction lengths of the two operand pairs (K2 = 0 when unused)
+  int splits;            // TN only: number of K-splits
+  int64_t k_per_split;   // TN only: reduction rows per split (multiple of BLOCK_K)
+  EpilogueParams ep;
+  void* D; int64_t ldd;
+  float* partial;        // TN: [splits][M][N] fp32
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool kTN, typename TO>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
+  using Cfg = Config<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                          // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;          // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;      // [kAccStages]
+  uint64_t* tmem_empty = tmem_full + kAccStages;      // [kAccStages]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t num_tiles = m_tiles * n_tiles * p.splits;
+  const int kb1 = kTN ? 0 : (int)((p.K1 + BLOCK_K - 1) / BLOCK_K);
+  const int kb2 = kTN ? 0 : (int)((p.K2 + BLOCK_K - 1) / BLOCK_K);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), Cfg::kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t split = tile / (m_tiles * n_tiles);
+      const int64_t mn = tile % (m_tiles * n_tiles);
+      const int m0 = (int)(mn / n_tiles) * BLOCK_M, n0 = (int)(mn % n_tiles) * BLOCK_N;
+      int num_kb; int64_t k_begin = 0;
+      if constexpr (kTN) {
+        k_begin = split * p.k_per_split;
+        int64_t k_end = k_begin + p.k_per_split < p.K1 ? k_begin + p.k_per_split : p.K1;
+        num_kb = (int)((k_end - k_begin + BLOCK_K - 1) / BLOCK_K);
+      } else {
+        num_kb = kb1 + kb2;
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(bar, Cfg::kStageBytes);
+        const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes), sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+        if constexpr (kTN) {
+          // MN-major: boxes of {64 columns, 64 reduction rows}; one box per 64-column slab
+          const int k0 = (int)(k_begin + (int64_t)kb * BLOCK_K);
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d(sa + j * kSlabBytes, &maps.a1, m0 + j * 64, k0, bar);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(sb + j * kSlabBytes, &maps.b1, n0 + j * 64, k0, bar);
+        } else {
+          const bool second = kb >= kb1;
+          const int k0 = (second ? kb - kb1 : kb) * BLOCK_K;
+          tma_load_2d(sa, second ? &maps.a2 : &maps.a1, k0, m0, bar);
+          tma_load_2d(sb, second ? &maps.b2 : &maps.b1, k0, n0, bar);
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, kTN);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int num_kb;
+      if constexpr (kTN) {
+        const int64_t split = tile / (m_tiles * n_tiles);
+        int64_t k_begin = split * p.k_per_split;
+        int64_t k_end = k_begin + p.k_per_split < p.K1 ? k_begin + p.k_per_split : p.K1;
+        num_kb = (int)((k_end - k_begin + BLOCK_K - 1) / BLOCK_K);
+      } else {
+        num_kb = kb1 + kb2;
+      }
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes), sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          uint64_t adesc, bdesc;
+          if constexpr (kTN) {
+            // MN-major, SW128: LBO = distance between 64-element MN slabs, SBO = 8 reduction rows (1024 B);
+            // one UMMA_K step = 16 reduction rows = 2048 B
+            adesc = make_smem_desc(sa + k * (UMMA_K * 128), kSlabBytes, 1024);
+            bdesc = make_smem_desc(sb + k * (UMMA_K * 128), kSlabBytes, 1024);
+          } else {
+            // K-major, SW128: rows of 128 B, SBO = 8 rows (1024 B); one UMMA_K step = 32 B inside the swizzle row
+            adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            bdesc = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+          }
+          umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs retire
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&tmem_full[acc]));      // accumulator ready for the epilogue
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t split = tile / (m_tiles * n_tiles);
+      const int64_t mn = tile % (m_tiles * n_tiles);
+      const int64_t m0 = (mn / n_tiles) * BLOCK_M, n0 = (mn % n_tiles) * BLOCK_N;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int64_t m = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        if (m < p.M) {
+          if constexpr (kTN) {
+            float* dst = p.partial + ((int64_t)split * p.M + m) * p.N + n0 + c0;
+            const bool vec = (p.N % 4 == 0) && (n0 + c0 + 32 <= p.N);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < p.N) dst[j] = __uint_as_float(r[j]);
+            }
+          } else {
+            TO* dst = reinterpret_cast<TO*>(p.D) + m * p.ldd + n0 + c0;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              f[j] = (n0 + c0 + j < p.N) ? epilogue_apply<TO>(__uint_as_float(r[j]), m, n0 + c0 + j, p.ep) : 0.0f;
+            const bool vec = (n0 + c0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            if (vec) {
+              constexpr int VE = Vec16<TO>::n;
+#pragma unroll
+              for (int j = 0; j < 32; j += VE) {
+                float g[VE];
+#pragma unroll
+                for (int i = 0; i < VE; ++i) g[i] = f[j + i];
+                stg_v4(dst + j, pack16(g, TO()));
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < p.N) dst[j] = from_f32<TO>(f[j]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld; box = {box_cols (inner), box_rows}
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return LLP_E_DEVICE;
+  if (!aligned(base, 16) || (ld * 2) % 16 != 0) return LLP_E_ALIGN;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : LLP_E_BADARG;
+}
+
+template <int BLOCK_N, bool kTN, typename TO>
+static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
+  using Cfg = Config<BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, kTN, TO>;
+  static bool configured = false;
+  if (!configured) {
+    LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  int64_t m_tiles = ceil_div(p.M, BLOCK_M), n_tiles = ceil_div(p.N, BLOCK_N);
+  int64_t tiles = m_tiles * n_tiles * p.splits;
+  unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(maps, p);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+static int pick_block_n(int64_t N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+}  // namespace tc
+
+int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
+  using namespace tc;
+  if (a.dtype != LLP_BF16) return LLP_E_SHAPE;
+  const bool dual = a.A2 != nullptr && a.K2 > 0;
+  const int bn = pick_block_n(a.N);
+  Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (int rc = make_map(&maps.a1, a.A1, a.M, a.K1, a.lda1, BLOCK_K, BLOCK_M)) return rc;
+  if (int rc = make_map(&maps.b1, a.B1, a.N, a.K1, a.ldb1, BLOCK_K, bn)) return rc;
+  if (dual) {
+    if (int rc = make_map(&maps.a2, a.A2, a.M, a.K2, a.lda2, BLOCK_K, BLOCK_M)) return rc;
+    if (int rc = make_map(&maps.b2, a.B2, a.N, a.K2, a.ldb2, BLOCK_K, bn)) return rc;
+  }
+  TcParams p{};
+  p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
+  p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset};
+  p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
+#define LLP_TC_NT(BN)                                                                                          \
+  if (bn == BN) {                                                                                              \
+    if (a.out_dtype == LLP_BF16) return launch<BN, false, __nv_bfloat16>(maps, p, stream);                     \
+    if (a.out_dtype == LLP_F32) return launch<BN, false, float>(maps, p, stream);                              \
+    return LLP_E_BADARG;                                                                                       \
+  }
+  LLP_TC_NT(256)
+  LLP_TC_NT(128)
+  LLP_TC_NT(64)
+#undef LLP_TC_NT
+  return LLP_E_SHAPE;
+}
+
+// split count so that (tiles x splits) fills the SMs; every split gets a multiple of BLOCK_K rows
+void tn_split_plan(int64_t M, int64_t N1, int64_t N2, int* splits, int64_t* k_per_split) {
+  using namespace tc;
+  int bn = pick_block_n(N2);
+  int64_t tiles = ceil_div(N1, BLOCK_M) * ceil_div(N2, bn);
+  int64_t want = ceil_div((int64_t)kNumSMs, tiles);
+  int64_t kblocks = ceil_div(M, BLOCK_K);
+  int64_t s = want < kblocks ? want : kblocks;
+  if (s < 1) s = 1;
+  int64_t per = ceil_div(kblocks, s) * BLOCK_K;
+  *k_per_split = per;
+  *splits = (int)ceil_div(M, per);
+}
+
+int gemm_tn_tcgen05(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, const void* B, int64_t ldb, float* D,
+                    int64_t ldd, int accumulate, float* ws, cudaStream_t stream) {
+  using namespace tc;
+  const int bn = pick_block_n(N2);
+  Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (int rc = make_map(&maps.a1, A, M, N1, lda, 64, BLOCK_K)) return rc;
+  if (int rc = make_map(&maps.b1, B, M, N2, ldb, 64, BLOCK_K)) return rc;
+  TcParams p{};
+  p.M = N1; p.N = N2; p.K1 = M; p.K2 = 0;
+  tn_split_plan(M, N1, N2, &p.splits, &p.k_per_split);
+  p.ep = EpilogueParams{};
+  p.D = nullptr; p.ldd = 0; p.partial = ws;
+  int rc;
+  if (bn == 256) rc = launch<256, true, float>(maps, p, stream);
+  else if (bn == 128) rc = launch<128, true, float>(maps, p, stream);
+  else rc = launch<64, true, float>(maps, p, stream);
+  if (rc) return rc;
+  return splitk_reduce(ws, p.splits, N1, N2, D, ldd, accumulate, stream);
+}
+
+}  // namespace llp

@@ -1,0 +1,332 @@
+"""Student (LLP relational distillation) training — the reference's ``src/main.py`` surface over the B200 kernels.
+
+* ``cosine_loss`` / ``kl_loss``  — src/main.py:24-31
+* ``neighbor_samplers``          — :33-50
+* ``train_minibatch``            — :52-144
+* ``train``                      — :147-236
+* ``main``                       — :238-513 (flags :240-269); unlike the reference, importing this module does
+  NOT run ``main()`` (the reference calls it at import, :515).
+"""
+from __future__ import annotations
+
+import argparse
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .loader import shuffled_batches
+from .logger import Logger, ProductionLogger
+from .models import MLP, LinkPredictor
+from .optim import FusedAdam
+from .shims import Evaluator, negative_sampling, random_walk, seed_everything
+from . import shims
+from .train_teacher_gnn import _dist, _shard, optimizer_tail, test_production, test_transductive
+
+
+def cosine_loss(s, t):
+    """KD_RM baseline (weight 0 by default; left to torch — out of the north-star scope)."""
+    return 1 - F.cosine_similarity(s.float(), t.detach().float(), dim=-1).mean()
+
+
+def kl_loss(s, t, T):
+    """LLP_D: fused softmax/KL kernel (value == F.kl_div(log_softmax(s/T), softmax(t/T), 'sum') * T^2 / B)."""
+    return ops.kl_loss(s, t, T)
+
+
+def neighbor_samplers(row, col, sample, x, step, ps_method, ns_rate, hops):
+    """Context nodes of each anchor: ``step`` uniform walks of ``hops`` ('nb') or one walk of ``step*hops`` ('rw')
+    plus ``step*hops*ns_rate`` uniformly random nodes drawn with the CPU generator (main.py:47)."""
+    batch = sample
+    if ps_method == 'rw':
+        pos_batch = random_walk(row, col, batch, walk_length=step * hops, coalesced=False)
+    elif ps_method == 'nb':
+        pos_batch = None
+        for _ in range(step):
+            w = random_walk(row, col, batch, walk_length=hops, coalesced=False)
+            pos_batch = w if pos_batch is None else torch.cat((pos_batch, w[:, 1:]), 1)
+    neg_batch = torch.randint(0, x.size(0), (batch.numel(), step * hops * ns_rate), dtype=torch.long)
+    return pos_batch.to(batch.device), neg_batch.to(batch.device)
+
+
+def _kd_losses(predictor, teacher_predictor, h, t_h, samples, args):
+    """LLP_D and LLP_R for the anchors in ``samples[:,0]`` against the contexts ``samples[:,1:]`` (main.py:183-203).
+    ``predictor(h[a].repeat(K), h[ctx])`` becomes one fused edge-scoring call over the (anchor, context) pairs."""
+    K = samples.size(1) - 1
+    anchor = samples[:, :1].expand(-1, K).contiguous()
+    ctx = samples[:, 1:].contiguous()
+    s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
+    with torch.no_grad():
+        # the teacher predictor is never put in eval() by the reference: dropout stays active
+        t_r = teacher_predictor.score(t_h, anchor, ctx).reshape(samples.size(0), K)
+    llp_d = kl_loss(s_r, t_r, 1)
+    llp_r = ops.rank_loss(s_r, t_r, args.margin)
+    return llp_d, llp_r
+
+
+def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device):
+    if args.transductive == "transductive":
+        pos_train_edge = split_edge['train']['edge'].to(data.x.device)
+        row, col = data.adj_t
+    else:
+        pos_train_edge = data.edge_index.t()
+        row, col = data.edge_index
+    edge_index = torch.stack([col, row], dim=0)
+    dev = data.x.device
+    rank, world = _dist()
+
+    model.train()
+    predictor.train()
+
+    total_loss = torch.zeros((), dtype=torch.float32, device=dev)
+    total_examples = 0
+    node_loader = shuffled_batches(data.x.size(0), args.node_batch_size * world)
+    for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size * world):
+        optimizer.zero_grad()
+        node_perm = next(node_loader).to(dev)
+        h = model(data.x)
+        edge = pos_train_edge[link_perm.to(dev)].t()
+
+        llp_d_loss = llp_r_loss = None
+        if args.LLP_R or args.LLP_D:
+            pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, data.x, args.rw_step, args.ps_method,
+                                                       args.ns_rate, args.hops)
+            samples = torch.cat((pos_sample, neg_sample), 1)
+            a_lo, a_hi = _shard(samples.size(0), rank, world)
+            llp_d_loss, llp_r_loss = _kd_losses(predictor, teacher_predictor, h, t_h, samples[a_lo:a_hi], args)
+            if world > 1:  # both are means over anchors: weight the shard by its share
+                w = (a_hi - a_lo) * world / float(samples.size(0))
+                llp_d_loss, llp_r_loss = llp_d_loss * w, llp_r_loss * w
+
+        if args.datasets != "collab":
+            neg_edge = negative_sampling(edge_index, num_nodes=data.x.size(0), num_neg_samples=link_perm.size(0),
+                                         method='dense')
+        else:
+            neg_edge = torch.randint(0, data.x.size()[0], [edge.size(0), edge.size(1)], dtype=torch.long, device=dev)
+
+        n_global = edge.size(1)
+        lo, hi = _shard(n_global, rank, world)
+        nlo, nhi = _shard(neg_edge.size(1), rank, world)
+        edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
+        train_edges = torch.cat((edge, neg_edge), dim=-1)
+        out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+        label_loss = ops.bce_loss(out, edge.size(1))
+        if world > 1:
+            label_loss = label_loss * (train_edges.size(1) * world / float(2 * n_global))
+
+        loss = args.True_label * label_loss
+        if args.KD_RM:  # baselines, weight 0 by default; the reference evaluates them regardless
+            loss = loss + args.KD_RM * cosine_loss(h[node_perm], t_h[node_perm])
+        if args.KD_LM:
+            with torch.no_grad():
+                t_out = teacher_predictor.score(t_h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+            loss = loss + args.KD_LM * F.mse_loss(out, t_out)
+        if args.LLP_D or args.LLP_R:
+            loss = loss + args.LLP_D * llp_d_loss + args.LLP_R * llp_r_loss
+
+        loss.backward()
+        optimizer_tail(model, predictor, optimizer)
+
+        total_loss += loss.detach() * n_global
+        total_examples += n_global
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(total_loss)
+        total_loss /= world
+    return total_loss.item() / total_examples
+
+
+def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device):
+    """Feature-minibatch variant (main.py:52-144): only the rows a step touches are encoded.  On a 180 GB B200 the
+    features stay resident in HBM (the reference keeps them on the host and copies rows every step, :95-96;
+    SURVEY.md N4), so the per-step gather is a device gather."""
+    if args.transductive == "transductive":
+        pos_train_edge = split_edge['train']['edge'].to(device)
+        row, col = data.adj_t
+    else:
+        pos_train_edge = data.edge_index.t().to(device)
+        row, col = data.edge_index
+    row, col = row.to(device), col.to(device)
+    edge_index = torch.stack([col, row], dim=0)
+    x = data.x.to(device)
+    if not (args.LLP_D or args.LLP_R):
+        raise NameError("name 'loss' is not defined")  # what the reference raises for this flag combination (:129-132)
+
+    model.train()
+    predictor.train()
+    total_loss = torch.zeros((), dtype=torch.float32, device=device)
+    total_examples = 0
+    node_loader = shuffled_batches(x.size(0), args.node_batch_size)
+    for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size):
+        optimizer.zero_grad()
+        node_perm = next(node_loader).to(device)
+        edge = pos_train_edge[link_perm.to(device)].t()
+        if args.datasets != "collab":
+            neg_edge = negative_sampling(edge_index, num_nodes=x.size(0), num_neg_samples=link_perm.size(0),
+                                         method='dense')
+        else:
+            neg_edge = torch.randint(0, x.size()[0], [edge.size(0), edge.size(1)], dtype=torch.long).to(device)
+        train_edges = torch.cat((edge, neg_edge), dim=-1)
+        src, dst = train_edges[0], train_edges[1]
+
+        pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, x, args.rw_step, args.ps_method, args.ns_rate,
+                                                   args.hops)
+        samples = torch.cat((pos_sample, neg_sample), 1)
+        this_target = torch.cat((samples.reshape(-1), src, dst), 0)
+        h = model(x[this_target])  # rows of the touched nodes only
+        n_s = samples.numel()
+        # positions inside h of every sample / edge endpoint
+        local = torch.arange(n_s, device=device).reshape(samples.shape)
+        K = samples.size(1) - 1
+        anchor = local[:, :1].expand(-1, K).contiguous()
+        ctx = local[:, 1:].contiguous()
+        s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
+        with torch.no_grad():
+            t_r = teacher_predictor.score(t_h.to(device), samples[:, :1].expand(-1, K).contiguous(),
+                                          samples[:, 1:].contiguous()).reshape(samples.size(0), K)
+        llp_d_loss = kl_loss(s_r, t_r, 1)
+        llp_r_loss = ops.rank_loss(s_r, t_r, args.margin)
+
+        src_pos = torch.arange(n_s, n_s + src.numel(), device=device)
+        dst_pos = src_pos + src.numel()
+        out = predictor.score(h, src_pos, dst_pos).reshape(-1)
+        label_loss = ops.bce_loss(out, edge.size(1))
+        loss = args.True_label * label_loss + args.LLP_D * llp_d_loss + args.LLP_R * llp_r_loss
+        loss.backward()
+        optimizer_tail(model, predictor, optimizer)
+        total_loss += loss.detach() * edge.size(1)
+        total_examples += edge.size(1)
+    return total_loss.item() / total_examples
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='OGBL-DDI (GNN)')
+    parser.add_argument('--device', type=int, default=0)
+    parser.add_argument('--log_steps', type=int, default=1)
+    parser.add_argument('--encoder', type=str, default='sage')
+    parser.add_argument('--num_layers', type=int, default=2)
+    parser.add_argument('--hidden_channels', type=int, default=256)
+    parser.add_argument('--dropout', type=float, default=0.5)
+    parser.add_argument('--link_batch_size', type=int, default=64 * 1024)
+    parser.add_argument('--node_batch_size', type=int, default=64 * 1024)
+    parser.add_argument('--lr', type=float, default=0.005)
+    parser.add_argument('--epochs', type=int, default=20000)
+    parser.add_argument('--eval_steps', type=int, default=5)
+    parser.add_argument('--runs', type=int, default=10)
+    parser.add_argument('--dataset_dir', type=str, default='../data')
+    parser.add_argument('--datasets', type=str, default='collab')
+    parser.add_argument('--predictor', type=str, default='mlp', choices=['inner', 'mlp'])
+    parser.add_argument('--patience', type=int, default=100, help='number of patience steps for early stopping')
+    parser.add_argument('--metric', type=str, default='Hits@20', choices=['auc', 'hits@20', 'hits@50'],
+                        help='main evaluation metric')
+    parser.add_argument('--use_valedges_as_input', action='store_true')
+    parser.add_argument('--True_label', default=0.1, type=float, help="true_label loss")
+    parser.add_argument('--KD_RM', default=0, type=float, help="Representation-based matching KD")
+    parser.add_argument('--KD_LM', default=0, type=float, help="logit-based matching KD")
+    parser.add_argument('--LLP_D', default=1, type=float, help="distribution-based matching kd")
+    parser.add_argument('--LLP_R', default=1, type=float, help="rank-based matching kd")
+    parser.add_argument('--margin', default=0.1, type=float, help="margin for rank-based kd")
+    parser.add_argument('--rw_step', type=int, default=3, help="nearby nodes sampled times")
+    parser.add_argument('--ns_rate', type=int, default=1, help="randomly sampled rate over # nearby nodes")
+    parser.add_argument('--hops', type=int, default=2, help="random_walk step for each sampling time")
+    parser.add_argument('--ps_method', type=str, default='nb', help="positive sampling is rw or nb")
+    parser.add_argument('--transductive', type=str, default='transductive', choices=['transductive', 'production'])
+    parser.add_argument('--minibatch', action='store_true')
+    parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'])
+    parser.add_argument('--synthetic_scale', type=float, default=1.0)
+    return parser
+
+
+def main(argv=None):
+    import os
+    from .data import synthetic_dataset
+    args = build_parser().parse_args(argv)
+    print(args)
+    ops.set_compute_dtype(args.precision)
+    os.makedirs("../results", exist_ok=True)
+    Logger_file = "../results/" + args.datasets + "_KD_" + args.transductive + ".txt"
+    with open(Logger_file, "a") as file:
+        file.write(str(args) + "\n")
+        if args.KD_RM != 0:
+            file.write("Logit-matching\n")
+        elif args.KD_LM != 0:
+            file.write("Representation-matching\n")
+        elif args.LLP_D != 0 or args.LLP_R != 0:
+            file.write("LLP (Relational Distillation)\n")
+    if not torch.cuda.is_available():
+        raise RuntimeError("this implementation has no CPU path: an sm_100 (B200) GPU is required")
+    device = torch.device(f'cuda:{args.device}')
+    torch.cuda.set_device(device)
+    if args.transductive != "transductive":
+        raise NotImplementedError("production split generation is a 'next' row (SURVEY.md N3)")
+
+    data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=args.synthetic_scale)
+    input_size = data.x.size(1)
+    args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
+    data = data.to(device)
+    args.node_batch_size = int(data.x.size()[0] / (split_edge['train']['edge'].size()[0] / args.link_batch_size))
+
+    model = MLP(args.num_layers, input_size, args.hidden_channels, args.hidden_channels, args.dropout).to(device)
+    predictor = LinkPredictor(args.predictor, args.hidden_channels, args.hidden_channels, 1, args.num_layers,
+                              args.dropout).to(device)
+    tag = args.datasets + "-" + args.encoder + "_" + args.transductive + ".pkl"
+    pretrained_model = torch.load("../saved-models/" + tag, map_location=device)
+    teacher_predictor = LinkPredictor(args.predictor, 256, 256, 1, 2, args.dropout)
+    teacher_predictor.load_state_dict(pretrained_model['predictor'], strict=True)
+    teacher_predictor.to(device)
+    t_h = torch.load("../saved-features/" + tag, map_location=device)['features']
+    for para in teacher_predictor.parameters():
+        para.requires_grad = False
+
+    evaluator = Evaluator(name='ogbl-ddi')
+    keys = ['Hits@10', 'Hits@50', 'Hits@100', 'AUC'] if args.datasets == "collab" else \
+        ['Hits@10', 'Hits@20', 'Hits@30', 'Hits@50', 'AUC']
+    loggers = {k: Logger(args.runs, args) for k in keys}
+
+    for run in range(args.runs):
+        seed_everything(run + 1)
+        model.reset_parameters()
+        predictor.reset_parameters()
+        optimizer = FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=args.lr)
+        cnt_wait, best_val = 0, 0.0
+        for epoch in range(1, 1 + args.epochs):
+            step_fn = train_minibatch if args.minibatch else train
+            loss = step_fn(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device)
+            results, h = test_transductive(model, predictor, data, split_edge, evaluator, args.link_batch_size, 'mlp',
+                                           args.datasets, args)
+            if results[args.metric][0] >= best_val:
+                best_val, cnt_wait = results[args.metric][0], 0
+            else:
+                cnt_wait += 1
+            for key, result in results.items():
+                loggers[key].add_result(run, result)
+            if epoch % args.log_steps == 0:
+                for key, result in results.items():
+                    valid_hits, test_hits = result
+                    print(key)
+                    print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, '
+                          f'Valid: {100 * valid_hits:.2f}%, Test: {100 * test_hits:.2f}%')
+                print('---')
+            if cnt_wait >= args.patience:
+                break
+        for key in loggers.keys():
+            print(key)
+            loggers[key].print_statistics(run)
+
+    with open(Logger_file, "a") as file:
+        file.write('All runs:\n')
+        for key in loggers.keys():
+            print(key)
+            loggers[key].print_statistics()
+            file.write(f'{key}:\n')
+            best_results = []
+            for r in loggers[key].results:
+                r = 100 * torch.tensor(r)
+                best_results.append((r[:, 0].max().item(), r[r[:, 0].argmax(), 1].item()))
+            r = torch.tensor(best_results)[:, 1]
+            file.write(f'Test: {r.mean():.4f} ± {r.std():.4f}\n')
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""Model library with the reference's class / constructor / forward / state-dict surface
+(``src/models.py``): ``MLP`` (:6-54), ``SAGE`` (:82-119), ``LinkPredictor`` (:121-150).
+``GCN`` (:56-80) is out of scope (never selected by the reference scripts).
+
+Every dense layer runs through the fused GEMM epilogues (bias + relu + dropout) of
+``libllp_b200.so``; activations live in the compute dtype chosen by ``ops.set_compute_dtype``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .sageconv import SAGEConv, _SageBase
+
+
+def _linear(x, lin: nn.Linear, relu: bool, p: float):
+    seed, offset = ops._dropout_seed() if p > 0 else (0, 0)
+    return ops.LinearFn.apply(x, lin.weight, lin.bias, relu, p, seed, offset)
+
+
+class MLP(nn.Module):
+    def __init__(self, num_layers, input_dim, hidden_dim, output_dim, dropout_ratio, norm_type="none"):
+        super().__init__()
+        if norm_type != "none":
+            raise NotImplementedError("norm layers are never enabled by the reference drivers")
+        self.num_layers, self.norm_type = num_layers, norm_type
+        self.dropout = nn.Dropout(dropout_ratio)
+        self.layers, self.norms = nn.ModuleList(), nn.ModuleList()
+        if num_layers == 1:
+            self.layers.append(nn.Linear(input_dim, output_dim))
+        else:
+            self.layers.append(nn.Linear(input_dim, hidden_dim))
+            for _ in range(num_layers - 2):
+                self.layers.append(nn.Linear(hidden_dim, hidden_dim))
+            self.layers.append(nn.Linear(hidden_dim, output_dim))
+
+    def reset_parameters(self):
+        for layer in self.layers:
+            layer.reset_parameters()
+
+    def forward(self, feats):
+        h = ops.to_compute(feats)
+        p = float(self.dropout.p) if self.training else 0.0
+        for l, layer in enumerate(self.layers):
+            last = l == self.num_layers - 1
+            h = _linear(h, layer, relu=not last, p=0.0 if last else p)
+        return h
+
+
+class SAGE(nn.Module):
+    def __init__(self, data_name, in_channels, hidden_channels, out_channels, num_layers, dropout, conv_layer=SAGEConv,
+                 norm_type="none"):
+        super().__init__()
+        if norm_type != "none":
+            raise NotImplementedError("norm layers are never enabled by the reference drivers")
+        self.convs, self.norms, self.norm_type = nn.ModuleList(), nn.ModuleList(), norm_type
+        self.convs.append(conv_layer(in_channels, hidden_channels))
+        for _ in range(num_layers - 2):
+            self.convs.append(conv_layer(hidden_channels, hidden_channels))
+        self.convs.append(conv_layer(hidden_channels, out_channels))
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for conv in self.convs:
+            conv.reset_parameters()
+
+    def forward(self, x, adj_t):
+        graph = adj_t if isinstance(adj_t, ops.Graph) else ops.graph_of(adj_t, x.size(0))
+        x = ops.to_compute(x)
+        for conv in self.convs[:-1]:
+            if not isinstance(conv, _SageBase):
+                raise RuntimeError("SAGE expects the SAGEConv / SAGEConv_updated layers of this package")
+            x = conv(x, graph, _relu=True, _dropout=self.dropout)
+        return self.convs[-1](x, graph)
+
+
+class LinkPredictor(nn.Module):
+    def __init__(self, predictor, in_channels, hidden_channels, out_channels, num_layers, dropout):
+        super().__init__()
+        if predictor not in ("mlp", "inner"):
+            raise ValueError(predictor)
+        self.predictor = predictor
+        self.lins = nn.ModuleList()
+        self.lins.append(nn.Linear(in_channels, hidden_channels))
+        for _ in range(num_layers - 2):
+            self.lins.append(nn.Linear(hidden_channels, hidden_channels))
+        self.lins.append(nn.Linear(hidden_channels, out_channels))
+        self.dropout = dropout
+
+    def reset_parameters(self):
+        for lin in self.lins:
+            lin.reset_parameters()
+
+    def _head(self, z):
+        """z = x_i * x_j rows [M, C] in the compute dtype -> sigmoid scores."""
+        p = float(self.dropout) if self.training else 0.0
+        if self.predictor == "mlp":
+            for lin in self.lins[:-1]:
+                z = _linear(z, lin, relu=True, p=p)
+            last = self.lins[-1]
+            if last.out_features == 1:
+                return ops.ScoreHeadFn.apply(z, last.weight, last.bias).unsqueeze(-1)
+            return torch.sigmoid(_linear(z, last, relu=False, p=0.0).float())
+        ones = torch.ones(1, z.size(1), dtype=torch.float32, device=z.device)
+        return ops.ScoreHeadFn.apply(z, ones, None)  # 'inner': sigmoid(sum(x_i * x_j))
+
+    def forward(self, x_i, x_j):
+        """Reference signature (models.py:139): pre-gathered rows, 2-D ``[M,C]`` or 3-D ``[B,K,C]`` (main.py:186)."""
+        lead = x_i.shape[:-1]
+        z = ops.to_compute((x_i * x_j).reshape(-1, x_i.size(-1)))
+        out = self._head(z)
+        return out.reshape(*lead, 1) if self.predictor == "mlp" else out.reshape(*lead)
+
+    def score(self, h, u, v):
+        """Fused path used by the step functions: scores of the edges ``(u[m], v[m])`` straight from the node
+        embedding matrix ``h`` — same value as ``forward(h[u], h[v])`` without materialising the gathers."""
+        lead = u.shape
+        z = ops.HadamardFn.apply(ops.to_compute(h), u.reshape(-1).contiguous(), v.reshape(-1).contiguous())
+        out = self._head(z)
+        return out.reshape(*lead, 1) if self.predictor == "mlp" else out.reshape(*lead)

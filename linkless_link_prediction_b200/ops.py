@@ -1,0 +1,462 @@
+"""Host-side operators over the C-ABI kernels: thin wrappers + ``torch.autograd.Function``s.
+
+Each function cites the reference call site it stands in for (paths under /root/reference).
+All tensors must live on an sm_100 device; nothing here falls back to ATen or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+# --------------------------------------------------------------------------------------------
+# precision mode
+# --------------------------------------------------------------------------------------------
+_COMPUTE_DTYPE = torch.bfloat16
+
+
+def set_compute_dtype(dt) -> None:
+    """``torch.bfloat16`` (default: bf16 storage + tcgen05 tensor cores, fp32 accumulate; matches the
+    reference within 2e-2) or ``torch.float32`` (fp32 storage + fp32 FFMA GEMMs; matches within 1e-5)."""
+    global _COMPUTE_DTYPE
+    if isinstance(dt, str):
+        dt = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}[dt]
+    if dt not in (torch.bfloat16, torch.float32):
+        raise ValueError("compute dtype must be bfloat16 or float32")
+    _COMPUTE_DTYPE = dt
+
+
+def compute_dtype() -> torch.dtype:
+    return _COMPUTE_DTYPE
+
+
+_ELT = {torch.float32: 4, torch.bfloat16: 2, torch.int64: 8, torch.int32: 4}
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def empty_mat(rows: int, cols: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """[rows, cols] view of a row-padded buffer whose rows are 16-byte multiples (TMA / 128-bit loads)."""
+    ld = _round_up(max(cols, 1), 16 // _ELT[dtype])
+    buf = torch.empty((max(rows, 1), ld), dtype=dtype, device=device)
+    return buf[:rows, :cols]
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# plain wrappers
+# --------------------------------------------------------------------------------------------
+def cast2d(src: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> torch.Tensor:
+    lib = N.require_gpu()
+    rows, cols = src.shape
+    out = empty_mat(cols, rows, dtype, src.device) if transpose else empty_mat(rows, cols, dtype, src.device)
+    sp, lds = N.mat(src)
+    dp, ldd = N.mat(out)
+    N.check(lib.llp_cast2d(N.dtype_id(src.dtype), N.dtype_id(dtype), sp, lds, rows, cols, dp, ldd, int(transpose),
+                           N.stream_ptr()), "llp_cast2d")
+    return out
+
+
+def to_compute(x: torch.Tensor) -> torch.Tensor:
+    """Bring a 2-D activation/feature matrix to the compute dtype with 16-byte-aligned rows."""
+    dt = compute_dtype()
+    if x.dtype == dt and x.dim() == 2 and x.stride(1) == 1 and (x.stride(0) * x.element_size()) % 16 == 0 \
+            and x.data_ptr() % 16 == 0:
+        return x
+    return cast2d(x if x.dim() == 2 else x.reshape(-1, x.size(-1)), dt)
+
+
+def gemm_nt(A1, B1, A2=None, B2=None, bias=None, addend=None, gate=None, gate_scale=1.0, relu=False, dropout_p=0.0,
+            seed=0, offset=0, out_dtype=None, backend=N.GEMM_AUTO) -> torch.Tensor:
+    """D = epi(A1 @ B1.T [+ A2 @ B2.T]) — F.linear and the fused lin_l+lin_r of SAGEConv
+    (models.py:48,143; sageconv_updated.py:71,76)."""
+    lib = N.require_gpu()
+    M, K1 = A1.shape
+    Nn = B1.shape[0]
+    out_dtype = out_dtype or A1.dtype
+    D = empty_mat(M, Nn, out_dtype, A1.device)
+    a = N.GemmNtArgs()
+    a.dtype, a.out_dtype, a.backend, a.relu = N.dtype_id(A1.dtype), N.dtype_id(out_dtype), backend, int(relu)
+    a.M, a.N, a.K1 = M, Nn, K1
+    a.A1, a.lda1 = N.mat(A1)
+    a.B1, a.ldb1 = N.mat(B1)
+    if A2 is not None:
+        a.K2 = A2.shape[1]
+        a.A2, a.lda2 = N.mat(A2)
+        a.B2, a.ldb2 = N.mat(B2)
+    a.bias = N.ptr(bias)
+    if addend is not None:
+        a.addend, a.ldadd = N.mat(addend)
+    if gate is not None:
+        a.gate, a.ldgate = N.mat(gate)
+    a.gate_scale, a.dropout_p, a.seed, a.offset = float(gate_scale), float(dropout_p), int(seed), int(offset)
+    a.D, a.ldd = N.mat(D)
+    N.check(lib.llp_gemm_nt(ctypes.byref(a), N.stream_ptr()), "llp_gemm_nt")
+    return D
+
+
+def gemm_tn(A: torch.Tensor, B: torch.Tensor, backend=N.GEMM_AUTO) -> torch.Tensor:
+    """fp32 [N1,N2] = A[M,N1].T @ B[M,N2] — the weight gradient of a linear layer."""
+    lib = N.require_gpu()
+    M, N1 = A.shape
+    N2 = B.shape[1]
+    D = torch.empty((N1, N2), dtype=torch.float32, device=A.device)
+    nbytes = lib.llp_gemm_tn_workspace_bytes(M, N1, N2)
+    ws = _ws(nbytes, A.device)
+    ap, lda = N.mat(A)
+    bp, ldb = N.mat(B)
+    N.check(lib.llp_gemm_tn(N.dtype_id(A.dtype), backend, M, N1, N2, ap, lda, bp, ldb, D.data_ptr(), N2, 0,
+                            ws.data_ptr(), nbytes, N.stream_ptr()), "llp_gemm_tn")
+    return D
+
+
+def colsum(A: torch.Tensor) -> torch.Tensor:
+    lib = N.require_gpu()
+    M, Nn = A.shape
+    out = torch.empty(Nn, dtype=torch.float32, device=A.device)
+    ws = _ws(lib.llp_colsum_workspace_bytes(Nn), A.device)
+    ap, lda = N.mat(A)
+    N.check(lib.llp_colsum(N.dtype_id(A.dtype), ap, lda, M, Nn, out.data_ptr(), 0, ws.data_ptr(), N.stream_ptr()),
+            "llp_colsum")
+    return out
+
+
+def gate(g: torch.Tensor, y: torch.Tensor, scale: float) -> torch.Tensor:
+    """relu/dropout backward from the saved output: g * scale where y > 0 (models.py:116-117,144-145)."""
+    lib = N.require_gpu()
+    M, Nn = g.shape
+    out = empty_mat(M, Nn, g.dtype, g.device)
+    gp, ldg = N.mat(g)
+    yp, ldy = N.mat(y)
+    op, ldo = N.mat(out)
+    N.check(lib.llp_gate(N.dtype_id(g.dtype), gp, ldg, yp, ldy, M, Nn, float(scale), op, ldo, N.stream_ptr()), "llp_gate")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# graph structure (CSR + transpose + work plan), cached per edge_index tensor
+# --------------------------------------------------------------------------------------------
+class Graph:
+    """Device CSR of the message graph ``edge_index[0] -> edge_index[1]`` and of its transpose.
+    Stands in for PyG's per-call gather/scatter bookkeeping (models.py:113 -> SAGEConv.propagate)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        lib = N.require_gpu()
+        if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
+            raise RuntimeError("edge_index must be a LongTensor of shape [2, E]")
+        if not edge_index.is_cuda:
+            raise RuntimeError("edge_index must be a CUDA tensor (no CPU fallback)")
+        ei = edge_index.contiguous()
+        self.num_nodes, self.num_edges = int(num_nodes), int(ei.size(1))
+        dev = ei.device
+        E, Nn = self.num_edges, self.num_nodes
+        nbytes = lib.llp_csr_build_workspace_bytes(Nn, E)
+        ws = _ws(nbytes, dev)
+        n_chunks = lib.llp_spmm_num_chunks(E)
+
+        def build(val, key, want_inv):
+            rowptr = torch.empty(Nn + 1, dtype=torch.int32, device=dev)
+            col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            inv = torch.empty(max(Nn, 1), dtype=torch.float32, device=dev) if want_inv else None
+            N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, Nn, rowptr.data_ptr(), col.data_ptr(),
+                                      perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
+            plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+            N.check(lib.llp_spmm_plan(rowptr.data_ptr(), Nn, E, plan.data_ptr(), N.stream_ptr()), "llp_spmm_plan")
+            return rowptr, col, perm, inv, plan
+
+        src, dst = ei[0], ei[1]
+        # forward: rows = destinations, cols = sources; inv_deg = 1/max(in-degree, 1)
+        self.rowptr, self.col, self.perm, self.inv_deg, self.plan = build(src, dst, True)
+        # transpose: rows = sources, cols = destinations
+        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan = build(dst, src, False)
+
+    def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        """forward: ``out[d] = mean_{s->d} x[s]``; transpose: ``out[s] = sum_{s->d} x[d] / deg_in(d)``."""
+        lib = N.require_gpu()
+        Nn, E = self.num_nodes, self.num_edges
+        F = x.size(1)
+        out = empty_mat(Nn, F, x.dtype, x.device)
+        ws = _ws(lib.llp_spmm_workspace_bytes(E, F), x.device)
+        xp, ldx = N.mat(x)
+        op, ldo = N.mat(out)
+        if not transpose:
+            rc = lib.llp_spmm(N.dtype_id(x.dtype), self.rowptr.data_ptr(), self.col.data_ptr(), self.plan.data_ptr(), Nn, E,
+                              xp, ldx, F, None, 1, op, ldo, ws.data_ptr(), N.stream_ptr())
+        else:
+            rc = lib.llp_spmm(N.dtype_id(x.dtype), self.t_rowptr.data_ptr(), self.t_col.data_ptr(), self.t_plan.data_ptr(),
+                              Nn, E, xp, ldx, F, self.inv_deg.data_ptr(), 0, op, ldo, ws.data_ptr(), N.stream_ptr())
+        N.check(rc, "llp_spmm")
+        return out
+
+
+_GRAPH_CACHE: Dict[Tuple[int, int, int, int], Tuple[weakref.ref, Graph]] = {}
+
+
+def graph_of(edge_index: torch.Tensor, num_nodes: int) -> Graph:
+    """CSR for ``edge_index``, built once per (tensor, version) — the reference re-derives the structure on
+    every forward (train_teacher_gnn.py:39-45 calls the full-graph encoder per mini-batch)."""
+    key = (edge_index.data_ptr(), edge_index.size(1), int(num_nodes), edge_index._version)
+    hit = _GRAPH_CACHE.get(key)
+    if hit is not None and hit[0]() is edge_index:
+        return hit[1]
+    if len(_GRAPH_CACHE) > 16:
+        _GRAPH_CACHE.clear()
+    g = Graph(edge_index, num_nodes)
+    _GRAPH_CACHE[key] = (weakref.ref(edge_index), g)
+    return g
+
+
+# --------------------------------------------------------------------------------------------
+# dropout RNG: (seed, offset) pairs drawn from torch's CPU generator so seed_everything() controls them
+# --------------------------------------------------------------------------------------------
+def _dropout_seed() -> Tuple[int, int]:
+    s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
+    return int(s[0]), int(s[1]) & 0xFFFFFFFF
+
+
+def _weights(W: torch.Tensor) -> torch.Tensor:
+    dt = compute_dtype()
+    if W.dtype == dt and (W.stride(0) * W.element_size()) % 16 == 0:
+        return W.detach()
+    return cast2d(W.detach(), dt)
+
+
+def _weights_t(W: torch.Tensor) -> torch.Tensor:
+    return cast2d(W.detach(), compute_dtype(), transpose=True)
+
+
+# --------------------------------------------------------------------------------------------
+# autograd functions
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = dropout(relu(x W^T + b)) — nn.Linear + F.relu + F.dropout (models.py:48-53,143-145)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu, p, seed, offset):
+        y = gemm_nt(x, _weights(W), bias=b, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        ctx.save_for_backward(x, W, y if (relu or p > 0) else None)
+        ctx.cfg = (relu, p, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        relu, p, has_b = ctx.cfg
+        g = to_compute(gy)
+        if y is not None:
+            g = gate(g, y, 1.0 / (1.0 - p))
+        gW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
+        gb = colsum(g) if (has_b and ctx.needs_input_grad[2]) else None
+        gx = gemm_nt(g, _weights_t(W)) if ctx.needs_input_grad[0] else None
+        return gx, gW, gb, None, None, None, None
+
+
+class SageConvFn(torch.autograd.Function):
+    """PyG SAGEConv(mean): y = epi(lin_l(mean_{s->d} x[s]) + lin_r(x)) as ONE dual-operand GEMM over
+    [agg | x] with the relu/dropout of SAGE.forward fused into the epilogue (models.py:110-119)."""
+
+    @staticmethod
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset):
+        agg = graph.spmm(x)
+        y = gemm_nt(agg, _weights(Wl), x, _weights(Wr), bias=bl, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        ctx.save_for_backward(x, agg, Wl, Wr, y if (relu or p > 0) else None)
+        ctx.graph, ctx.cfg = graph, (relu, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, agg, Wl, Wr, y = ctx.saved_tensors
+        relu, p = ctx.cfg
+        g = to_compute(gy)
+        if y is not None:
+            g = gate(g, y, 1.0 / (1.0 - p))
+        gWl = gemm_tn(g, agg) if ctx.needs_input_grad[1] else None
+        gbl = colsum(g) if ctx.needs_input_grad[2] else None
+        gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            # A~^T (g W_l) = (A~^T g) W_l : aggregate first, then one dual GEMM writes gx with no add kernel
+            t = ctx.graph.spmm(g, transpose=True)
+            gx = gemm_nt(t, _weights_t(Wl), g, _weights_t(Wr))
+        return gx, gWl, gbl, gWr, None, None, None, None, None
+
+
+class SageConvUpdatedFn(torch.autograd.Function):
+    """SAGEConv_updated (sageconv_updated.py:65-81): y = epi(mean_{s->d}(W_l x[s] + b_l) + W_r x)."""
+
+    @staticmethod
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset):
+        t = gemm_nt(x, _weights(Wl), bias=bl)
+        agg = graph.spmm(t)
+        y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        ctx.save_for_backward(x, Wl, Wr, y if (relu or p > 0) else None)
+        ctx.graph, ctx.cfg = graph, (relu, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, Wl, Wr, y = ctx.saved_tensors
+        relu, p = ctx.cfg
+        g = to_compute(gy)
+        if y is not None:
+            g = gate(g, y, 1.0 / (1.0 - p))
+        gt = ctx.graph.spmm(g, transpose=True)
+        gWl = gemm_tn(gt, x) if ctx.needs_input_grad[1] else None
+        gbl = colsum(gt) if ctx.needs_input_grad[2] else None
+        gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
+        gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr)) if ctx.needs_input_grad[0] else None
+        return gx, gWl, gbl, gWr, None, None, None, None, None
+
+
+class HadamardFn(torch.autograd.Function):
+    """z[m] = h[u[m]] * h[v[m]] — the two fancy-index gathers + mul in front of LinkPredictor
+    (train_teacher_gnn.py:58; main.py:186,214; models.py:140)."""
+
+    @staticmethod
+    def forward(ctx, h, u, v):
+        lib = N.require_gpu()
+        M, F = u.numel(), h.size(1)
+        z = empty_mat(M, F, h.dtype, h.device)
+        hp, ldh = N.mat(h)
+        zp, ldz = N.mat(z)
+        N.check(lib.llp_edge_hadamard(N.dtype_id(h.dtype), hp, ldh, F, u.data_ptr(), v.data_ptr(), M, zp, ldz,
+                                      N.stream_ptr()), "llp_edge_hadamard")
+        ctx.save_for_backward(h, u, v)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        lib = N.require_gpu()
+        h, u, v = ctx.saved_tensors
+        M, F = u.numel(), h.size(1)
+        gz = to_compute(gz) if gz.dtype != h.dtype else gz
+        gh = torch.zeros((h.size(0), _round_up(F, 4)), dtype=torch.float32, device=h.device)
+        hp, ldh = N.mat(h)
+        gp, ldg = N.mat(gz)
+        N.check(lib.llp_edge_hadamard_bwd(N.dtype_id(h.dtype), hp, ldh, F, u.data_ptr(), v.data_ptr(), M, gp, ldg,
+                                          gh.data_ptr(), gh.stride(0), N.stream_ptr()), "llp_edge_hadamard_bwd")
+        gh = gh[:, :F]
+        return (gh if h.dtype == torch.float32 else cast2d(gh, h.dtype)), None, None
+
+
+class ScoreHeadFn(torch.autograd.Function):
+    """prob = sigmoid(y w^T + b) for the 1-output last predictor layer (models.py:146,150)."""
+
+    @staticmethod
+    def forward(ctx, y, w, b):
+        lib = N.require_gpu()
+        M, H = y.shape
+        prob = torch.empty(M, dtype=torch.float32, device=y.device)
+        yp, ldy = N.mat(y)
+        wf = w.detach().reshape(-1).contiguous()
+        N.check(lib.llp_score_head(N.dtype_id(y.dtype), yp, ldy, M, H, wf.data_ptr(), N.ptr(b), prob.data_ptr(),
+                                   N.stream_ptr()), "llp_score_head")
+        ctx.save_for_backward(y, w, prob)
+        ctx.has_b = b is not None
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        lib = N.require_gpu()
+        y, w, prob = ctx.saved_tensors
+        M, H = y.shape
+        need_y, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gy = empty_mat(M, H, y.dtype, y.device) if need_y else None
+        gw = torch.empty(H, dtype=torch.float32, device=y.device) if need_w else None
+        gb = torch.empty(1, dtype=torch.float32, device=y.device) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+        nbytes = lib.llp_score_head_bwd_workspace_bytes(M, H)
+        ws = _ws(nbytes, y.device)
+        yp, ldy = N.mat(y)
+        gyp, ldgy = N.mat(gy) if gy is not None else (None, 0)
+        wf = w.detach().reshape(-1).contiguous()
+        N.check(lib.llp_score_head_bwd(N.dtype_id(y.dtype), yp, ldy, M, H, wf.data_ptr(), prob.data_ptr(),
+                                       dprob.contiguous().data_ptr(), gyp, ldgy, N.ptr(gw), N.ptr(gb), ws.data_ptr(), nbytes,
+                                       N.stream_ptr()), "llp_score_head_bwd")
+        return gy, (gw.reshape(w.shape) if gw is not None else None), gb
+
+
+class _LossFn(torch.autograd.Function):
+    """Shared shape of the fused loss kernels: scalar loss + gradient w.r.t. the first input in one launch."""
+
+    @staticmethod
+    def forward(ctx, kind, s, t, a, b):
+        lib = N.require_gpu()
+        s = s.contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        ds = torch.empty_like(s) if ctx.needs_input_grad[1] else None
+        rows = s.size(0)
+        ws = _ws(lib.llp_loss_workspace_bytes(s.numel() if kind == "bce" else rows), s.device)
+        if kind == "bce":    # a = n_pos
+            rc = lib.llp_bce(s.data_ptr(), s.numel(), int(a), loss.data_ptr(), N.ptr(ds), ws.data_ptr(), N.stream_ptr())
+        elif kind == "kd_d":  # a = temperature
+            rc = lib.llp_kd_d(s.data_ptr(), t.contiguous().data_ptr(), rows, s.size(1), float(a), loss.data_ptr(), N.ptr(ds),
+                              ws.data_ptr(), N.stream_ptr())
+        else:                # kd_r: a = margin
+            rc = lib.llp_kd_r(s.data_ptr(), t.contiguous().data_ptr(), rows, s.size(1), float(a), loss.data_ptr(), N.ptr(ds),
+                              ws.data_ptr(), N.stream_ptr())
+        N.check(rc, f"llp_{kind}")
+        ctx.save_for_backward(ds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (ds,) = ctx.saved_tensors
+        return None, (ds * gl if ds is not None else None), None, None, None
+
+
+def bce_loss(prob: torch.Tensor, n_pos: int) -> torch.Tensor:
+    """nn.BCELoss()(prob, [1]*n_pos + [0]*(n-n_pos)) — train_teacher_gnn.py:57-59."""
+    return _LossFn.apply("bce", prob.float(), None, n_pos, None)
+
+
+def kl_loss(s: torch.Tensor, t: torch.Tensor, T: float) -> torch.Tensor:
+    """LLP_D: main.py:27-31."""
+    return _LossFn.apply("kd_d", s.float(), t.detach().float(), T, None)
+
+
+def rank_loss(s: torch.Tensor, t: torch.Tensor, margin: float) -> torch.Tensor:
+    """LLP_R: main.py:190-203 (all C(K,2) pairs, 3-valued teacher sign, MarginRankingLoss(margin))."""
+    return _LossFn.apply("kd_r", s.float(), t.detach().float(), margin, None)
+
+
+# --------------------------------------------------------------------------------------------
+# Hits@K and sampling
+# --------------------------------------------------------------------------------------------
+def topk_desc(scores: torch.Tensor, kmax: int) -> torch.Tensor:
+    lib = N.require_gpu()
+    scores = scores.float().contiguous()
+    out = torch.empty(kmax, dtype=torch.float32, device=scores.device)
+    nbytes = lib.llp_topk_workspace_bytes(scores.numel(), kmax)
+    ws = _ws(nbytes, scores.device)
+    N.check(lib.llp_topk_desc(scores.data_ptr(), scores.numel(), kmax, out.data_ptr(), ws.data_ptr(), nbytes,
+                              N.stream_ptr()), "llp_topk_desc")
+    return out
+
+
+def count_greater(pos: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
+    lib = N.require_gpu()
+    pos = pos.float().contiguous()
+    thresholds = thresholds.float().contiguous()
+    counts = torch.empty(thresholds.numel(), dtype=torch.int64, device=pos.device)
+    N.check(lib.llp_count_greater(pos.data_ptr(), pos.numel(), thresholds.data_ptr(), thresholds.numel(),
+                                  counts.data_ptr(), N.stream_ptr()), "llp_count_greater")
+    return counts
+
+
+def random_walk_with_rand(rowptr: torch.Tensor, col: torch.Tensor, start: torch.Tensor, rand: torch.Tensor) -> torch.Tensor:
+    lib = N.require_gpu()
+    B, L = rand.shape
+    out = torch.empty((B, L + 1), dtype=torch.int64, device=start.device)
+    N.check(lib.llp_random_walk(rowptr.data_ptr(), col.contiguous().data_ptr(), start.contiguous().data_ptr(),
+                                rand.contiguous().data_ptr(), B, L, out.data_ptr(), N.stream_ptr()), "llp_random_walk")
+    return out

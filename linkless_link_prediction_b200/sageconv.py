@@ -1,0 +1,58 @@
+"""SAGE convolution layers with the reference's module surface.
+
+``SAGEConv`` mirrors ``torch_geometric.nn.SAGEConv(in, out)`` as the reference uses it
+(``train_teacher_gnn.py:381-383``: mean aggregation, root weight, bias on ``lin_l`` only) and
+``SAGEConv_updated`` mirrors ``src/sageconv_updated.py:9-93`` (transform, then aggregate).
+State-dict keys (``lin_l.weight``, ``lin_l.bias``, ``lin_r.weight``; weight ``[out, in]``) and the
+parameter initialisation order are the reference's, so checkpoints interchange.
+``forward(x, edge_index)`` takes the dense ``[2,E]`` LongTensor the drivers pass.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class _SageBase(nn.Module):
+    _fn = None
+
+    def __init__(self, in_channels: int, out_channels: int, normalize: bool = False, root_weight: bool = True,
+                 bias: bool = True, **kwargs):
+        super().__init__()
+        if normalize or not root_weight or not bias:
+            raise NotImplementedError("only the configuration the reference drivers use is built: "
+                                      "normalize=False, root_weight=True, bias=True")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.normalize, self.root_weight = normalize, root_weight
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self):
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+
+    def forward(self, x, edge_index, size=None, *, _relu: bool = False, _dropout: float = 0.0):
+        """``_relu`` / ``_dropout`` are set by ``models.SAGE`` to fuse its relu + dropout into this layer's epilogue."""
+        if isinstance(x, (tuple, list)):
+            x = x[0]
+        graph = edge_index if isinstance(edge_index, ops.Graph) else ops.graph_of(edge_index, x.size(0))
+        x = ops.to_compute(x)
+        p = float(_dropout) if self.training else 0.0
+        seed, offset = ops._dropout_seed() if p > 0 else (0, 0)
+        return type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, bool(_relu), p, seed,
+                                    offset)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
+
+
+class SAGEConv(_SageBase):
+    """``lin_l(mean_{s->d} x[s]) + lin_r(x)`` — aggregate, then transform."""
+    _fn = ops.SageConvFn
+
+
+class SAGEConv_updated(_SageBase):
+    """``mean_{s->d}(lin_l(x)[s]) + lin_r(x)`` — transform, then aggregate (sageconv_updated.py:71-76)."""
+    _fn = ops.SageConvUpdatedFn

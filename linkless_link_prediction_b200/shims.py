@@ -1,0 +1,178 @@
+"""Stand-ins for the third-party entry points the reference drivers import, with the same names,
+arguments and error behaviour, backed by the B200 kernels (torch_geometric / torch_cluster / ogb are
+not installed here and are not needed):
+
+* ``negative_sampling``  — torch_geometric.utils.negative_sampling (train_teacher_gnn.py:50-51, main.py:81,206)
+* ``random_walk``        — torch_cluster.random_walk (main.py:37,43,45)
+* ``Evaluator``          — ogb.linkproppred.Evaluator (train_teacher_gnn.py:394,120-145)
+* ``seed_everything``    — torch_geometric.seed.seed_everything (train_teacher_gnn.py:422, main.py:396)
+* ``Data``               — the attribute bag the step functions read (.x .adj_t .edge_index .edge_label ...)
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def seed_everything(seed: int) -> None:
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+class Data:
+    """Minimal PyG ``Data`` look-alike: attribute container with ``.to(device)`` moving every tensor."""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+    @property
+    def num_features(self):
+        return self.x.size(1)
+
+
+def negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None, num_neg_samples: Optional[int] = None,
+                      method: str = "sparse", force_undirected: bool = False) -> torch.Tensor:
+    """PyG 2.2.0 ``negative_sampling(method='dense')``: the candidate ids come from Python's
+    ``random.sample`` on the host exactly as upstream (bit-exact indices require the CPython
+    MT19937 stream); the N*N-N validity mask and the filtering stay on ``edge_index.device``."""
+    if method != "dense":
+        raise NotImplementedError("the reference only calls method='dense'")
+    if force_undirected:
+        raise NotImplementedError("force_undirected is never set by the reference")
+    if num_nodes is None:
+        num_nodes = int(edge_index.max()) + 1
+    if num_neg_samples is None:
+        num_neg_samples = edge_index.size(1)
+    dev = edge_index.device
+    row, col = edge_index[0].clone(), edge_index[1].clone()
+    keep = row != col
+    row, col = row[keep], col[keep]
+    col[row < col] -= 1
+    idx = row * (num_nodes - 1) + col
+    population = num_nodes * num_nodes - num_nodes
+    if idx.numel() >= population:
+        return edge_index.new_empty((2, 0))
+    prob = 1.0 - idx.numel() / population
+    sample_size = int(1.1 * num_neg_samples / prob)
+    mask = torch.ones(population, dtype=torch.bool, device=dev)
+    mask[idx] = False
+    neg_idx = None
+    for _ in range(3):
+        if population <= sample_size:
+            rnd = torch.arange(population, device=dev)
+        else:
+            rnd = torch.tensor(random.sample(range(population), sample_size), device=dev)
+        rnd = rnd[mask[rnd]]
+        neg_idx = rnd if neg_idx is None else torch.cat([neg_idx, rnd])
+        if neg_idx.numel() >= num_neg_samples:
+            neg_idx = neg_idx[:num_neg_samples]
+            break
+        mask[neg_idx] = False
+    r = neg_idx.div(num_nodes - 1, rounding_mode="floor")
+    c = neg_idx % (num_nodes - 1)
+    c[r <= c] += 1
+    return torch.stack([r, c], dim=0)
+
+
+_RAND_ON_HOST = False
+
+
+def draw_rand_on_host(flag: bool) -> None:
+    """Parity-test switch: draw the walk/negative random numbers with torch's CPU generator (the stream the CPU
+    oracle consumes) instead of the CUDA generator."""
+    global _RAND_ON_HOST
+    _RAND_ON_HOST = bool(flag)
+
+
+def random_walk(row: torch.Tensor, col: torch.Tensor, start: torch.Tensor, walk_length: int, p: float = 1, q: float = 1,
+                coalesced: bool = True, num_nodes: Optional[int] = None, return_edge_indices: bool = False,
+                rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch_cluster 1.6.0 ``random_walk`` (uniform: p == q == 1).  ``rowptr = cumsum(bincount(row))`` and ``col`` is
+    used in the given order when ``coalesced=False``.  ``rand`` optionally supplies the ``[B, L]``
+    uniform numbers (otherwise ``torch.rand`` on the start tensor's device, as upstream)."""
+    if p != 1 or q != 1 or return_edge_indices:
+        raise NotImplementedError("only uniform walks returning node sequences are used by the reference")
+    dev = start.device
+    if num_nodes is None:
+        num_nodes = max(int(row.max()), int(col.max()), int(start.max())) + 1
+    if coalesced:
+        perm = torch.argsort(row * num_nodes + col)
+        row, col = row[perm], col[perm]
+    deg = row.new_zeros(num_nodes)
+    deg.scatter_add_(0, row, torch.ones_like(row))
+    rowptr = row.new_zeros(num_nodes + 1)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    if rand is None:
+        if _RAND_ON_HOST:
+            rand = torch.rand(start.size(0), walk_length).to(dev)
+        else:
+            rand = torch.rand(start.size(0), walk_length, device=dev)
+    return ops.random_walk_with_rand(rowptr, col, start, rand.to(torch.float32))
+
+
+def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence[int], group=None) -> torch.Tensor:
+    """Integer hit counts for every K in ONE pass over the scores (device tensors in, int64 ``[len(Ks)]`` out).
+    With ``group`` (a torch.distributed process group) positives and negatives are rank-local shards: each rank
+    contributes its top-K_max negatives (all-gather of W*K_max floats), thresholds are taken from the merged
+    candidates and the counts are all-reduced — exact and independent of the sharding."""
+    kmax = max(Ks)
+    cand = ops.topk_desc(y_pred_neg, kmax)
+    n_neg = torch.tensor([y_pred_neg.numel()], dtype=torch.int64, device=cand.device)
+    if group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        gathered = [torch.empty_like(cand) for _ in range(world)]
+        dist.all_gather(gathered, cand, group=group)
+        cand = ops.topk_desc(torch.cat(gathered), kmax)
+        dist.all_reduce(n_neg, group=group)
+    # fewer negatives than K  =>  every positive is a hit (ogb: `if len(y_pred_neg) < K: return 1.0`); the top-k
+    # list is padded with -inf in that case, which a strict '>' already treats as "always hit" for finite scores.
+    thr = cand[torch.tensor([k - 1 for k in Ks], device=cand.device)]
+    counts = ops.count_greater(y_pred_pos, thr)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(counts, group=group)
+    n_pos_total = torch.tensor([y_pred_pos.numel()], dtype=torch.int64, device=cand.device)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(n_pos_total, group=group)
+    short = n_neg < torch.tensor(list(Ks), dtype=torch.int64, device=cand.device)
+    return torch.where(short, n_pos_total.expand_as(counts), counts), n_pos_total
+
+
+class Evaluator:
+    """``ogb.linkproppred.Evaluator`` for the hits@K metric family with mutable ``K``
+    (``evaluator.K = K`` at train_teacher_gnn.py:121).  ``eval`` takes the ogb input dict."""
+
+    def __init__(self, name: str = "ogbl-ddi"):
+        self.name = name
+        self.K = 20
+        self.eval_metric = "hits@20"
+
+    def eval(self, input_dict: Dict[str, torch.Tensor]) -> Dict[str, float]:
+        if "y_pred_pos" not in input_dict or "y_pred_neg" not in input_dict:
+            raise RuntimeError("Missing key of y_pred_pos or y_pred_neg")
+        pos, neg = input_dict["y_pred_pos"], input_dict["y_pred_neg"]
+        if len(neg) < self.K:
+            return {f"hits@{self.K}": 1.0}
+        counts, n_pos = hits_counts(pos, neg, [self.K])
+        return {f"hits@{self.K}": float(counts[0].item()) / len(pos)}
