@@ -189,6 +189,10 @@ class Graph:
         ws = _ws(lib.llp_spmm_workspace_bytes(E, F), x.device)
         xp, ldx = N.mat(x)
         op, ldo = N.mat(out)
+        prof = SPMM_PROFILE
+        if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if not transpose:
             rc = lib.llp_spmm(N.dtype_id(x.dtype), self.rowptr.data_ptr(), self.col.data_ptr(), self.plan.data_ptr(), Nn, E,
                               xp, ldx, F, None, 1, op, ldo, ws.data_ptr(), N.stream_ptr())
@@ -196,8 +200,16 @@ class Graph:
             rc = lib.llp_spmm(N.dtype_id(x.dtype), self.t_rowptr.data_ptr(), self.t_col.data_ptr(), self.t_plan.data_ptr(),
                               Nn, E, xp, ldx, F, self.inv_deg.data_ptr(), 0, op, ldo, ws.data_ptr(), N.stream_ptr())
         N.check(rc, "llp_spmm")
+        if prof is not None:
+            ev1.record()
+            # algorithmic bytes: gather E rows + write N rows + int32 col + rowptr (+ fp32 scale on the transpose)
+            s_elt = x.element_size()
+            nbytes = E * F * s_elt + Nn * F * s_elt + 4 * E + 4 * (Nn + 1) + (4 * Nn if transpose else 0)
+            prof.append((ev0, ev1, nbytes))
         return out
 
+
+SPMM_PROFILE = None  # set to a list by bench.py to collect (start_event, end_event, algorithmic_bytes) per SpMM call
 
 _GRAPH_CACHE: Dict[Tuple[int, int, int, int], Tuple[weakref.ref, Graph]] = {}
 

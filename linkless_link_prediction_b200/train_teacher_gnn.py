@@ -54,6 +54,28 @@ def optimizer_tail(model, predictor, optimizer) -> None:
         optimizer.step()
 
 
+def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='sage', transductive='transductive',
+               loss_weight=1.0):
+    """One optimisation step of the reference loop body (train_teacher_gnn.py:37-67) on the positive edges ``edge``
+    and negatives ``neg_edge`` (both ``[2,B]`` device LongTensors): full-graph encoder forward, fused edge scoring,
+    BCE, backward, separate clipping of model / predictor, Adam.  Returns the (device) loss tensor."""
+    optimizer.zero_grad()
+    if encoder_name == 'mlp':
+        h = model(data.x)
+    elif transductive == "transductive":
+        h = model(data.x, data.adj_t)
+    else:
+        h = model(data.x, data.edge_index)
+    train_edges = torch.cat((edge, neg_edge), dim=-1)
+    out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+    loss = ops.bce_loss(out, edge.size(1))
+    if loss_weight != 1.0:
+        loss = loss * loss_weight
+    loss.backward()
+    optimizer_tail(model, predictor, optimizer)
+    return loss.detach()
+
+
 def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_name, dataset, transductive):
     if transductive == "transductive":
         row, col = data.adj_t
@@ -73,15 +95,6 @@ def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_nam
     # every rank draws the same permutation (same seed); a global batch of world*batch_size edges is cut into
     # contiguous per-rank shards, so W ranks reproduce the 1-rank run with --batch_size=W*batch_size
     for perm in shuffled_batches(pos_train_edge.size(0), batch_size * world):  # == DataLoader(range(n), bs, shuffle=True)
-        optimizer.zero_grad()
-
-        if encoder_name == 'mlp':
-            h = model(data.x)
-        elif transductive == "transductive":
-            h = model(data.x, data.adj_t)
-        else:
-            h = model(data.x, data.edge_index)
-
         edge = pos_train_edge[perm.to(device)].t()
         if dataset != "collab":
             neg_edge = negative_sampling(edge_index, num_nodes=data.x.size(0), num_neg_samples=perm.size(0),
@@ -90,19 +103,16 @@ def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_nam
             neg_edge = torch.randint(0, data.x.size()[0], edge.size(), dtype=torch.long, device=device)
 
         n_global = edge.size(1)
-        lo, hi = _shard(n_global, rank, world)
-        nlo, nhi = _shard(neg_edge.size(1), rank, world)
-        edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
-        train_edges = torch.cat((edge, neg_edge), dim=-1)
-        out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
-        loss = ops.bce_loss(out, edge.size(1))
-        if world > 1:  # mean over the global batch = average over ranks of (local mean * local share * W)
-            loss = loss * (train_edges.size(1) * world / float(n_global + perm.size(0)))
-        loss.backward()
+        weight = 1.0
+        if world > 1:
+            lo, hi = _shard(n_global, rank, world)
+            nlo, nhi = _shard(neg_edge.size(1), rank, world)
+            edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
+            # mean over the global batch = average over ranks of (local mean * local share * W)
+            weight = (edge.size(1) + neg_edge.size(1)) * world / float(n_global + perm.size(0))
+        loss = train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name, transductive, weight)
 
-        optimizer_tail(model, predictor, optimizer)
-
-        total_loss += loss.detach() * n_global
+        total_loss += loss * n_global
         total_examples += n_global
 
     if world > 1:

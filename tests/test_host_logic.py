@@ -1,0 +1,131 @@
+"""Host-side logic, the CLI surface and the C-ABI export table — runs without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import linkless_link_prediction_b200 as L
+from linkless_link_prediction_b200 import _native as N
+from linkless_link_prediction_b200 import data as D
+from linkless_link_prediction_b200 import loader, main as student, train_teacher_gnn as teacher
+from oracle import llp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = N.load()
+    header = open(os.path.join(ROOT, "include", "llp_b200.h")).read()
+    declared = set(re.findall(r"\b(llp_[a-z0-9_]+)\s*\(", header))
+    declared.discard("llp_gemm_nt_args")
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/llp_b200.h but not exported"
+        assert name in N.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert lib.llp_version() == 100
+    assert b"no fallback" in lib.llp_error_string(-4)
+    # struct layout must match the C definition (8-byte fields after four ints)
+    assert ctypes.sizeof(N.GemmNtArgs) == 4 * 4 + 8 * 4 + 8 * 8 + 8 + 16 + 16 + 8 + 16 + 16
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        L.ops.gemm_nt(torch.zeros(4, 8), torch.zeros(4, 8))
+    model = L.SAGE("cora", 8, 16, 16, 2, 0.0)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(5, 8), torch.zeros(2, 3, dtype=torch.long))
+
+
+@pytest.mark.parametrize("seed,n,b", [(0, 100, 32), (5, 8976, 65536), (7, 1000, 100), (9, 7, 3)])
+def test_shuffled_batches_equal_dataloader(seed, n, b):
+    from torch.utils.data import DataLoader
+    torch.manual_seed(seed)
+    ref = [p for p in DataLoader(range(n), b, shuffle=True)]
+    after_ref = torch.rand(1)
+    torch.manual_seed(seed)
+    got = list(loader.shuffled_batches(n, b))
+    after_got = torch.rand(1)
+    assert len(ref) == len(got) and all(torch.equal(x, y) for x, y in zip(ref, got))
+    assert torch.equal(after_ref, after_got)  # same number of global-RNG draws
+
+
+def test_state_dict_keys_match_reference_layout(golden):
+    sage = L.SAGE("cora", 24, 32, 16, 3, 0.5, L.SAGEConv)
+    assert list(sage.state_dict().keys()) == list(golden["models"]["sage_sd"].keys())
+    sage.load_state_dict(golden["models"]["sage_sd"], strict=True)
+    sage_u = L.SAGE("coauthor-physics", 24, 32, 16, 2, 0.5, L.SAGEConv_updated)
+    sage_u.load_state_dict(golden["models"]["sage_u_sd"], strict=True)
+    L.MLP(3, 24, 32, 16, 0.5).load_state_dict(golden["models"]["mlp_sd"], strict=True)
+    L.LinkPredictor("mlp", 16, 32, 1, 3, 0.5).load_state_dict(golden["models"]["pred_sd"], strict=True)
+
+
+def test_parameter_init_stream_matches_oracle():
+    torch.manual_seed(3)
+    a = L.SAGE("cora", 12, 8, 8, 2, 0.5)
+    pa = L.LinkPredictor("mlp", 8, 8, 1, 2, 0.5)
+    torch.manual_seed(3)
+    b = O.SAGE("cora", 12, 8, 8, 2, 0.5)
+    pb = O.LinkPredictor("mlp", 8, 8, 1, 2, 0.5)
+    for (k1, v1), (k2, v2) in zip(list(a.state_dict().items()) + list(pa.state_dict().items()),
+                                  list(b.state_dict().items()) + list(pb.state_dict().items())):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_cli_flags_match_reference():
+    t = teacher.build_parser().parse_args([])
+    assert (t.device, t.num_layers, t.hidden_channels, t.dropout, t.batch_size, t.lr, t.epochs, t.runs, t.datasets,
+            t.predictor, t.patience, t.transductive, t.encoder) == (0, 2, 256, 0.5, 65536, 0.005, 20000, 5, "cora",
+                                                                    "mlp", 100, "transductive", "sage")
+    s = student.build_parser().parse_args([])
+    assert (s.True_label, s.KD_RM, s.KD_LM, s.LLP_D, s.LLP_R, s.margin, s.rw_step, s.ns_rate, s.hops, s.ps_method,
+            s.link_batch_size, s.node_batch_size, s.runs, s.datasets) == (0.1, 0, 0, 1, 1, 0.1, 3, 1, 2, "nb", 65536,
+                                                                          65536, 10, "collab")
+    s = student.build_parser().parse_args("--datasets=cora --LLP_D=0.001 --LLP_R=1 --True_label=0.1 --minibatch".split())
+    assert s.minibatch and s.LLP_D == 0.001
+
+
+def test_synthetic_shapes():
+    data, split = D.synthetic_dataset("cora", seed=0)
+    assert data.x.shape == (2708, 1433)
+    e = split["train"]["edge"]
+    assert data.adj_t.shape[0] == 2 and data.adj_t.shape[1] == e.shape[0]
+    assert e.shape[0] % 2 == 0 and abs(e.shape[0] - 8976) <= 4          # both directions of 85% of 5278 pairs
+    assert split["valid"]["edge"].shape[0] == 263 and split["test"]["edge"].shape[0] == 527
+    key = e[:, 0] * 2708 + e[:, 1]
+    assert torch.equal(key, torch.sort(key).values)                      # (row, col)-sorted like to_undirected
+
+
+def test_shard_partition_covers_everything():
+    for n in (0, 1, 7, 64, 1000):
+        for w in (1, 2, 3, 8):
+            parts = [teacher._shard(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+
+
+def test_logger_best_by_validation():
+    lg = L.logger.Logger(1)
+    for r in [(0.1, 0.5), (0.3, 0.2), (0.2, 0.9)]:
+        lg.add_result(0, r)
+    r, arg = lg.best(0)
+    assert arg == 1 and r[arg, 1].item() == pytest.approx(20.0)
+    with pytest.raises(AssertionError):
+        L.logger.ProductionLogger(1).add_result(0, (1, 2))
+
+
+def test_interleaved_loaders_consume_rng_like_reference():
+    # main.py:167-171: the node loader iterator is created first, the link loader drives the loop
+    from torch.utils.data import DataLoader
+    torch.manual_seed(1)
+    nl = iter(DataLoader(range(50), 7, shuffle=True))
+    ref = [(lp, next(nl)) for lp in DataLoader(range(90), 40, shuffle=True)]
+    torch.manual_seed(1)
+    nl2 = loader.shuffled_batches(50, 7)
+    got = [(lp, next(nl2)) for lp in loader.shuffled_batches(90, 40)]
+    assert len(ref) == len(got)
+    for (a, b), (c, d) in zip(ref, got):
+        assert torch.equal(a, c) and torch.equal(b, d)

@@ -1,0 +1,150 @@
+"""The oracle against the fixtures produced by the REFERENCE'S OWN functions (tests/golden/make_golden.py),
+plus first-principles known-answer tests for the third-party semantics it restates."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import llp_oracle as O
+
+RTOL = 1e-5  # fp32 tolerance stated by BASELINE.json north_star
+
+
+def test_models_match_reference(golden):
+    g = golden["models"]
+    mlp = O.MLP(3, 24, 32, 16, 0.5).eval(); mlp.load_state_dict(g["mlp_sd"])
+    sage = O.SAGE("cora", 24, 32, 16, 3, 0.5, O.SAGEConv).eval(); sage.load_state_dict(g["sage_sd"])
+    sage_u = O.SAGE("p", 24, 32, 16, 2, 0.5, O.SAGEConvUpdated).eval(); sage_u.load_state_dict(g["sage_u_sd"])
+    pred = O.LinkPredictor("mlp", 16, 32, 1, 3, 0.5).eval(); pred.load_state_dict(g["pred_sd"])
+    pred_in = O.LinkPredictor("inner", 16, 32, 1, 2, 0.5).eval(); pred_in.load_state_dict(g["pred_in_sd"])
+    with torch.no_grad():
+        torch.testing.assert_close(mlp(g["x"]), g["mlp_out"], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(sage(g["x"], g["edge_index"]), g["sage_out"], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(sage_u(g["x"], g["edge_index"]), g["sage_u_out"], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(pred(g["xi"], g["xj"]), g["pred_out"], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(pred(g["x3i"], g["x3j"]), g["pred_out3"], rtol=RTOL, atol=1e-6)
+        torch.testing.assert_close(pred_in(g["xi"], g["xj"]), g["pred_in_out"], rtol=RTOL, atol=1e-6)
+
+
+def test_kl_and_rank_losses_match_reference(golden):
+    g = golden["kl"]
+    torch.testing.assert_close(O.kl_loss(g["s"], g["t"], 1), g["kl_T1"], rtol=RTOL, atol=1e-7)
+    torch.testing.assert_close(O.kl_loss(g["s"], g["t"], 2.0), g["kl_T2"], rtol=RTOL, atol=1e-7)
+    torch.testing.assert_close(O.cosine_loss(g["s"], g["t"]), g["cos"], rtol=RTOL, atol=1e-7)
+    r = golden["llp_r"]
+    torch.testing.assert_close(O.llp_r_loss(r["s_r"], r["t_r"], r["margin"]), r["loss"], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["teacher_fullbatch", "teacher_minibatch"])
+def test_teacher_epoch_matches_reference(golden, tag):
+    g = golden[tag]
+    x, split, H = g["x"], g["split"], g["H"]
+    adj_t = split["train"]["edge"].t().contiguous()
+    model = O.SAGE("cora", x.size(1), H, H, 2, 0.0, O.SAGEConv)
+    predictor = O.LinkPredictor("mlp", H, H, 1, 2, 0.0)
+    model.load_state_dict(g["sd0"]["gnn"]); predictor.load_state_dict(g["sd0"]["predictor"])
+    opt = torch.optim.Adam(list(model.parameters()) + list(predictor.parameters()), lr=g["lr"])
+    random.seed(g["seed_train"]); np.random.seed(g["seed_train"]); torch.manual_seed(g["seed_train"])
+    losses = [O.teacher_train_epoch(model, predictor, x, adj_t, split["train"]["edge"], opt, g["batch_size"]) for _ in range(2)]
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+    for k, v in model.state_dict().items():
+        torch.testing.assert_close(v, g["sd1"]["gnn"][k], rtol=1e-4, atol=1e-6)
+    results, h = O.test_transductive(model, predictor, x, adj_t, split, g["batch_size"])
+    torch.testing.assert_close(h, g["h"], rtol=1e-4, atol=1e-6)
+    for K in (10, 20, 30, 50):
+        assert results[f"Hits@{K}"] == pytest.approx(g["results"][f"Hits@{K}"], abs=1e-12)
+
+
+def test_student_step_matches_reference(golden):
+    g = golden["student"]
+    a = g["args"]
+    x, split, H, t_h = g["x"], g["split"], g["H"], g["t_h"]
+    model = O.MLP(2, x.size(1), H, H, 0.0); model.load_state_dict(g["sd0"]["mlp"])
+    pred = O.LinkPredictor("mlp", H, H, 1, 2, 0.0); pred.load_state_dict(g["sd0"]["predictor"])
+    t_pred = O.LinkPredictor("mlp", H, H, 1, 2, 0.0); t_pred.load_state_dict(g["teacher_pred_sd"])
+    opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=g["lr"])
+    random.seed(g["seed_train"]); np.random.seed(g["seed_train"]); torch.manual_seed(g["seed_train"])
+    from torch.utils.data import DataLoader
+    row, col = split["train"]["edge"].t()
+    edge_index = torch.stack([col, row], 0)
+    pos = split["train"]["edge"]
+    losses = []
+    for _ in range(2):
+        tot = n = 0
+        node_loader = iter(DataLoader(range(x.size(0)), a["node_batch_size"], shuffle=True))
+        for link_perm in DataLoader(range(pos.size(0)), a["link_batch_size"], shuffle=True):
+            node_perm = next(node_loader)
+            ps, ns = O.neighbor_samplers(row, col, node_perm, x, a["rw_step"], a["ps_method"], a["ns_rate"], a["hops"])
+            samples = torch.cat((ps, ns), 1)
+            edge = pos[link_perm].t()
+            neg = O.negative_sampling_dense(edge_index, x.size(0), link_perm.size(0))
+            l = O.student_step(model, pred, t_h, t_pred, x, samples, edge, neg, node_perm, opt,
+                               a["True_label"], a["LLP_D"], a["LLP_R"], a["KD_RM"], a["KD_LM"], a["margin"])
+            tot += l * edge.size(1); n += edge.size(1)
+        losses.append(tot / n)
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+
+
+# ---- first-principles known answers for the third-party semantics (parity unpinned by the reference) ----
+def test_mean_aggregate_kat():
+    # path 0->1->2, star into 3, isolated 4, duplicate edge 0->1, self loop 2->2
+    ei = torch.tensor([[0, 1, 0, 1, 2, 0, 2], [1, 2, 3, 3, 3, 1, 2]])
+    x = torch.tensor([[1., 10.], [2., 20.], [4., 40.], [8., 80.], [16., 160.]])
+    out = O.mean_aggregate(x, ei)
+    exp = torch.tensor([[0., 0.], [1., 10.], [(2 + 4) / 2, (20 + 40) / 2], [(1 + 2 + 4) / 3, (10 + 20 + 40) / 3], [0., 0.]])
+    torch.testing.assert_close(out, exp)
+    rowptr, col, perm = O.csr_build(ei, 5)
+    assert rowptr.tolist() == [0, 0, 2, 4, 7, 7]
+    assert col.tolist() == [0, 0, 1, 2, 0, 1, 2]          # stable in edge order
+    assert perm.tolist() == [0, 5, 1, 6, 2, 3, 4]
+    torch.testing.assert_close(O.spmm_csr(rowptr, col, x, True), exp)
+
+
+def test_sageconv_isolated_node_bias_quirk():
+    # SAGEConv keeps b_l on isolated nodes, SAGEConv_updated aggregates it away
+    torch.manual_seed(0)
+    ei = torch.tensor([[0], [1]])
+    x = torch.randn(3, 4)
+    a, b = O.SAGEConv(4, 5), O.SAGEConvUpdated(4, 5)
+    b.load_state_dict(a.state_dict())
+    ya, yb = a(x, ei), b(x, ei)
+    torch.testing.assert_close(ya[1], yb[1], rtol=1e-5, atol=1e-6)            # node with a neighbour: identical
+    torch.testing.assert_close(ya[2] - yb[2], a.lin_l.bias.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_hits_at_k_kat():
+    pos = torch.tensor([0.9, 0.5, 0.5, 0.1])
+    neg = torch.tensor([0.5, 0.5, 0.3, 0.2])
+    assert O.hits_at_k(pos, neg, 1) == 0.25     # thr 0.5, strict '>' : only 0.9
+    assert O.hits_at_k(pos, neg, 3) == 0.75     # thr 0.3
+    assert O.hits_at_k(pos, neg, 5) == 1.0      # fewer negatives than K
+    assert O.hits_counts(pos, neg, [1, 3, 5]) == [1, 3, 4]
+
+
+def test_llp_r_margin_constant_term():
+    # teacher ties (|ti-tj| <= m) give y=0 -> each such pair contributes exactly `margin`
+    s = torch.tensor([[0.2, 0.9, 0.4]])
+    t = torch.tensor([[0.5, 0.5, 0.5]])
+    assert O.llp_r_loss(s, t, 0.1).item() == pytest.approx(0.1)
+
+
+def test_random_walk_kat():
+    row = torch.tensor([0, 0, 1, 2, 2, 2])
+    col = torch.tensor([1, 2, 2, 0, 1, 3])
+    rowptr = O.walk_rowptr(row, 4)
+    assert rowptr.tolist() == [0, 2, 3, 6, 6]
+    rand = torch.tensor([[0.0, 0.99, 0.5], [0.7, 0.4, 0.0]])
+    out = O.random_walk_with_rand(rowptr, col, torch.tensor([0, 2]), rand)
+    # walk 0: 0 -(0.0*2=0)-> 1 -(0.99*1=0)-> 2 -(0.5*3=1)-> 1 ; walk 1: 2 -(0.7*3=2)-> 3 (sink) stays, stays
+    assert out.tolist() == [[0, 1, 2, 1], [2, 3, 3, 3]]
+
+
+def test_negative_sampling_never_returns_edges_or_self_loops():
+    ei = O.synthetic_undirected_graph(60, 200, seed=1)
+    random.seed(3)
+    neg = O.negative_sampling_dense(ei, 60, 150)
+    assert neg.shape == (2, 150)
+    assert (neg[0] != neg[1]).all()
+    have = set((ei[0] * 60 + ei[1]).tolist())
+    assert not (set((neg[0] * 60 + neg[1]).tolist()) & have)
