@@ -129,33 +129,37 @@ def random_walk(row: torch.Tensor, col: torch.Tensor, start: torch.Tensor, walk_
     return ops.random_walk_with_rand(rowptr, col, start, rand.to(torch.float32))
 
 
-def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence[int], group=None) -> torch.Tensor:
-    """Integer hit counts for every K in ONE pass over the scores (device tensors in, int64 ``[len(Ks)]`` out).
+def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence[int], group=None, topk_fn=None,
+                count_fn=None):
+    """Integer hit counts for every K in ONE pass over the scores: returns ``(counts int64 [len(Ks)], n_pos int64 [1])``.
     With ``group`` (a torch.distributed process group) positives and negatives are rank-local shards: each rank
     contributes its top-K_max negatives (all-gather of W*K_max floats), thresholds are taken from the merged
-    candidates and the counts are all-reduced — exact and independent of the sharding."""
+    candidates and the counts are all-reduced — exact and independent of the sharding.
+    ``topk_fn`` / ``count_fn`` default to the CUDA kernels (``llp_topk_desc`` / ``llp_count_greater``); they are only
+    injectable so the exchange logic can be exercised by the world_size-2 gloo tests on a CPU-only box."""
+    topk_fn = topk_fn or ops.topk_desc
+    count_fn = count_fn or ops.count_greater
     kmax = max(Ks)
-    cand = ops.topk_desc(y_pred_neg, kmax)
-    n_neg = torch.tensor([y_pred_neg.numel()], dtype=torch.int64, device=cand.device)
+    cand = topk_fn(y_pred_neg, kmax)
+    dev = cand.device
+    n_neg = torch.tensor([y_pred_neg.numel()], dtype=torch.int64, device=dev)
+    n_pos_total = torch.tensor([y_pred_pos.numel()], dtype=torch.int64, device=dev)
     if group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
         gathered = [torch.empty_like(cand) for _ in range(world)]
         dist.all_gather(gathered, cand, group=group)
-        cand = ops.topk_desc(torch.cat(gathered), kmax)
+        cand = topk_fn(torch.cat(gathered), kmax)
         dist.all_reduce(n_neg, group=group)
+        dist.all_reduce(n_pos_total, group=group)
     # fewer negatives than K  =>  every positive is a hit (ogb: `if len(y_pred_neg) < K: return 1.0`); the top-k
     # list is padded with -inf in that case, which a strict '>' already treats as "always hit" for finite scores.
-    thr = cand[torch.tensor([k - 1 for k in Ks], device=cand.device)]
-    counts = ops.count_greater(y_pred_pos, thr)
+    thr = cand[torch.tensor([k - 1 for k in Ks], device=dev)]
+    counts = count_fn(y_pred_pos, thr)
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(counts, group=group)
-    n_pos_total = torch.tensor([y_pred_pos.numel()], dtype=torch.int64, device=cand.device)
-    if group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(n_pos_total, group=group)
-    short = n_neg < torch.tensor(list(Ks), dtype=torch.int64, device=cand.device)
+    short = n_neg < torch.tensor(list(Ks), dtype=torch.int64, device=dev)
     return torch.where(short, n_pos_total.expand_as(counts), counts), n_pos_total
 
 

@@ -1,0 +1,88 @@
+"""Multi-rank host logic on CPU: world_size-2 ``gloo`` processes (the CUDA kernels themselves need a GPU; what is
+covered here is everything around them that changes with the number of ranks — shard arithmetic, the loss weighting
+that makes the averaged gradient equal the global-batch gradient, and the Hits@K candidate exchange)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from linkless_link_prediction_b200 import shims
+from linkless_link_prediction_b200.train_teacher_gnn import _shard
+from oracle import llp_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cpu_topk(x, k):
+    x = x.float()
+    out = torch.full((k,), float("-inf"))
+    v = torch.topk(x, min(k, x.numel())).values if x.numel() else x
+    out[: v.numel()] = v
+    return out
+
+
+def _cpu_count(pos, thr):
+    return (pos.float().unsqueeze(0) > thr.unsqueeze(1)).sum(1).to(torch.int64)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        # ---- Hits@K: sharded == unsharded, including ties and fewer negatives than K ----
+        for n_pos, n_neg, Ks in ((1001, 5003, [10, 50, 100]), (37, 60, [10, 50, 100]), (5, 1, [1, 3])):
+            pos = (torch.rand(n_pos, generator=g) * 50).round() / 50
+            neg = (torch.rand(n_neg, generator=g) * 50).round() / 50
+            lo, hi = _shard(n_pos, rank, world)
+            nlo, nhi = _shard(n_neg, rank, world)
+            counts, n = shims.hits_counts(pos[lo:hi], neg[nlo:nhi], Ks, group=dist.group.WORLD, topk_fn=_cpu_topk,
+                                          count_fn=_cpu_count)
+            assert counts.tolist() == O.hits_counts(pos, neg, Ks), (counts.tolist(), O.hits_counts(pos, neg, Ks))
+            assert int(n) == n_pos
+        # ---- training step: W ranks on shards of a 2B batch == 1 rank on the whole batch ----
+        torch.manual_seed(0)
+        n, f, H, B = 120, 16, 16, 101  # odd batch -> ragged shards
+        ei = O.synthetic_undirected_graph(n, 400, seed=1)
+        x = torch.randn(n, f)
+        model = O.SAGE("t", f, H, H, 2, 0.0)
+        pred = O.LinkPredictor("mlp", H, H, 1, 2, 0.0)
+        edge = ei[:, :B]
+        neg = torch.randint(0, n, (2, B))
+        params = list(model.parameters()) + list(pred.parameters())
+
+        def grads(e, ng, weight):
+            for p in params:
+                p.grad = None
+            h = model(x, ei)
+            te = torch.cat((e, ng), -1)
+            out = pred(h[te[0]], h[te[1]]).squeeze()
+            label = torch.cat((torch.ones(e.size(1)), torch.zeros(ng.size(1))))
+            (O.bce_loss(out, label) * weight).backward()
+            return torch.cat([p.grad.reshape(-1) for p in params])
+
+        full = grads(edge, neg, 1.0)
+        lo, hi = _shard(B, rank, world)
+        weight = ((hi - lo) * 2) * world / float(2 * B)  # the rule in train_teacher_gnn.train
+        local = grads(edge[:, lo:hi], neg[:, lo:hi], weight)
+        dist.all_reduce(local)
+        local /= world  # FusedAdam folds this 1/W into its kernel (grad_scale)
+        torch.testing.assert_close(local, full, rtol=1e-5, atol=1e-7)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))

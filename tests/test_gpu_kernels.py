@@ -135,7 +135,7 @@ def test_gemm_nt(cuda, backend, M, Nn, K1, K2):
     # storage-dtype output path
     D = ops.gemm_nt(c(A1), c(B1), bias=bias.to(cuda), relu=True, backend=backend).float().cpu()
     ref = _ref_gemm(A1, B1, None, None, bias, None, True, None, 1.0)
-    torch.testing.assert_close(D, ref, **(FP32 if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2 * math.sqrt(K1))))
+    torch.testing.assert_close(D, ref, **(dict(rtol=1e-5, atol=2e-5 * math.sqrt(K1)) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2 * math.sqrt(K1))))
 
 
 @pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt", "tcgen05"])
