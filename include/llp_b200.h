@@ -76,6 +76,8 @@ size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
  * its autograd transpose (index_add_).  dtype in {LLP_F32, LLP_BF16}; fp32 accumulation in CSR order.
  * x/out rows must be 4-byte aligned at least; 16-byte aligned rows (ld*elt % 16 == 0) take the
  * 128-bit path.  src_scale may be NULL. */
+/* 0 (default): cp.async.bulk staging kernel for aligned rows <= 1 KB; 1: always the register-gather kernel (tests). */
+void llp_spmm_set_path(int force_register_path);
 int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
              int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
              const float* src_scale, int mean, void* out, int64_t ldo, void* workspace, void* stream);
@@ -140,10 +142,12 @@ int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t feat, c
  * (models.py:146,150 with out_channels == 1.) */
 int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w, const float* b,
                    float* prob, void* stream);
-/* backward of llp_score_head: dlogit = dprob*p*(1-p); gy[m,:] = dlogit[m]*w ; gw (+)= sum_m dlogit*y ; gb (+)= sum dlogit */
+/* backward of llp_score_head: dlogit = dprob*p*(1-p); gy[m,:] = dlogit[m]*w ; gw = sum_m dlogit*y ; gb = sum dlogit.
+ * gate_scale > 0 additionally applies the relu/dropout backward of the layer that produced y:
+ * gy = y > 0 ? gy*gate_scale : 0 (models.py:144-145). */
 int llp_score_head_bwd(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w,
-                       const float* prob, const float* dprob, void* gy, int64_t ldgy, float* gw, float* gb,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       const float* prob, const float* dprob, float gate_scale, void* gy, int64_t ldgy, float* gw,
+                       float* gb, void* workspace, size_t workspace_bytes, void* stream);
 size_t llp_score_head_bwd_workspace_bytes(int64_t M, int64_t H);
 
 /* ---------------------------------------------------------------------------------------

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "llp_spmm_num_chunks": (c_int64, [c_int64]),
     "llp_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "llp_spmm_set_path": (None, [c_int]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                          c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),
@@ -67,8 +68,8 @@ PROTOTYPES = {
                                       c_void_p, c_int64, c_void_p]),
     "llp_score_head": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_score_head_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "llp_score_head_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "llp_score_head_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float,
+                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "llp_loss_workspace_bytes": (c_size_t, [c_int64]),
     "llp_bce": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_kd_d": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -133,12 +133,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr_lo, u
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-decision for element (row, col) of a dropout site: one Philox call covers 4 consecutive columns.
+// Dropout mask: one Philox4x32-10 call covers 8 consecutive columns of a row (16 random bits per element);
+// keep iff u16 >= thr16 with thr16 = p * 65536.  Identical in every kernel that draws or re-draws the mask.
+__host__ __device__ __forceinline__ uint32_t dropout_thr16(float p) {
+  float t = p * 65536.0f;
+  return t >= 65535.0f ? 65535u : (uint32_t)t;
+}
+__device__ __forceinline__ uint32_t dropout_u16(const uint4& r, int idx /*0..7*/) {
+  uint32_t w = (idx >> 1) == 0 ? r.x : (idx >> 1) == 1 ? r.y : (idx >> 1) == 2 ? r.z : r.w;
+  return (idx & 1) ? (w >> 16) : (w & 0xffffu);
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, int64_t row, int64_t col, float p) {
-  uint4 r = philox4x32_10(seed, (uint64_t)row, offset + (uint64_t)(col >> 2));
-  uint32_t w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
-  // uniform in [0,1): keep iff u >= p
-  return (float)(w >> 8) * (1.0f / 16777216.0f) >= p;
+  uint4 r = philox4x32_10(seed, (uint64_t)row, offset + (uint64_t)(col >> 3));
+  return dropout_u16(r, (int)(col & 7)) >= dropout_thr16(p);
 }
 
 // ---- epilogue shared by the SIMT and tcgen05 GEMMs ---------------------------------------------

@@ -155,38 +155,85 @@ int splitk_reduce(const float* partial, int splits, int64_t rows, int64_t cols, 
   return 0;
 }
 
-// ---- column sums -------------------------------------------------------------------------------
-// grid (N/32 strips, S row-splits): 8 warps stride over the split's rows; partials are combined in
-// fixed order by a second tiny kernel => deterministic.
-constexpr int kColsumSplits = 64;
-
-template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ A, int64_t lda, int64_t M, int64_t N, int64_t rows_per_split,
-                                      float* __restrict__ partial) {
-  __shared__ float red[8][33];
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int64_t n = (int64_t)blockIdx.x * 32 + lane;
-  int64_t mb = (int64_t)blockIdx.y * rows_per_split, me = min(M, mb + rows_per_split);
-  float acc = 0.0f;
-  if (n < N)
-    for (int64_t m = mb + w; m < me; m += 8) acc += to_f32(A[m * lda + n]);
-  red[w][lane] = acc;
-  __syncthreads();
-  if (w == 0 && n < N) {
-    float s = 0.0f;
+// ---- column reductions ---------------------------------------------------------------------------
+// out[n] = sum_m w[m] * A[m,n]   (w == nullptr -> plain column sums: the bias gradient).
+// grid (column tiles of 32*VE, row splits); every warp reads whole 16-byte vectors of consecutive rows, so a
+// [M,256] bf16 matrix is streamed with fully coalesced 512-byte rows.  Partials are combined in fixed order by
+// colreduce_final_kernel => deterministic.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256)
+colreduce_partial_kernel(const T* __restrict__ A, int64_t lda, int64_t M, int64_t N, const float* __restrict__ w,
+                         int64_t rows_per_split, float* __restrict__ partial) {
+  constexpr int VE = kVec ? Vec16<T>::n : 1;
+  __shared__ float red[8][32 * VE + 1];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * VE;
+  const int64_t mb = (int64_t)blockIdx.y * rows_per_split, me = min(M, mb + rows_per_split);
+  float acc[VE];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][lane];
-    partial[(int64_t)blockIdx.y * N + n] = s;
+  for (int i = 0; i < VE; ++i) acc[i] = 0.0f;
+  if (c < N) {
+    for (int64_t m = mb + wv; m < me; m += 8) {
+      const float wm = w != nullptr ? __ldg(w + m) : 1.0f;
+      if constexpr (kVec) {
+        float f[VE];
+        unpack16(ldg_nc_v4(A + m * lda + c), f, T());
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = fmaf(wm, f[i], acc[i]);
+      } else {
+        acc[0] = fmaf(wm, to_f32(A[m * lda + c]), acc[0]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VE; ++i) red[wv][lane * VE + i] = acc[i];
+  __syncthreads();
+  for (int t = threadIdx.x; t < 32 * VE; t += 256) {
+    const int64_t n = (int64_t)blockIdx.x * 32 * VE + t;
+    if (n < N) {
+      float s = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][t];
+      partial[(int64_t)blockIdx.y * N + n] = s;
+    }
   }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int splits, int64_t N, float* __restrict__ out,
-                                    int accumulate) {
+__global__ void colreduce_final_kernel(const float* __restrict__ partial, int splits, int64_t N, float* __restrict__ out,
+                                       int accumulate) {
   int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.0f;
   for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * N + n];
   out[n] = accumulate ? out[n] + s : s;
+}
+
+constexpr int kColreduceSplits = 512;
+
+size_t colreduce_workspace_bytes(int64_t N) { return (size_t)kColreduceSplits * (size_t)(N > 0 ? N : 1) * sizeof(float); }
+
+template <typename T>
+static int colreduce_typed(const void* A_, int64_t lda, int64_t M, int64_t N, const float* w, float* out, int accumulate,
+                           float* partial, cudaStream_t stream) {
+  const T* A = reinterpret_cast<const T*>(A_);
+  const bool vec = aligned(A, 16) && (lda * sizeof(T)) % 16 == 0 && N % Vec16<T>::n == 0;
+  const int VE = vec ? Vec16<T>::n : 1;
+  const int splits = (int)imin64(kColreduceSplits, imax64(1, ceil_div(M, 64)));
+  const int64_t rows_per_split = ceil_div(imax64(M, 1), splits);
+  dim3 grid((unsigned)ceil_div(N, 32 * VE), (unsigned)splits);
+  if (vec) colreduce_partial_kernel<T, true><<<grid, 256, 0, stream>>>(A, lda, M, N, w, rows_per_split, partial);
+  else colreduce_partial_kernel<T, false><<<grid, 256, 0, stream>>>(A, lda, M, N, w, rows_per_split, partial);
+  LLP_LAUNCH_OK();
+  colreduce_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(partial, splits, N, out, accumulate);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+int colreduce(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, const float* w, float* out, int accumulate,
+              float* partial, cudaStream_t stream) {
+  if (dtype == LLP_F32) return colreduce_typed<float>(A, lda, M, N, w, out, accumulate, partial, stream);
+  if (dtype == LLP_BF16) return colreduce_typed<__nv_bfloat16>(A, lda, M, N, w, out, accumulate, partial, stream);
+  return LLP_E_BADARG;
 }
 
 // ---- cast / transpose ----------------------------------------------------------------------------
@@ -211,38 +258,52 @@ __global__ void cast2d_kernel(const TS* __restrict__ src, int64_t lds, int64_t r
   }
 }
 
-template <typename T>
+// y = gate > 0 ? g*scale : 0, one 16-byte vector per thread (rows are 16-byte multiples) or scalar fallback
+template <typename T, bool kVec>
 __global__ void gate_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ gate, int64_t ldgate, int64_t M,
                             int64_t N, float scale, T* __restrict__ y, int64_t ldy) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  int64_t m = i / N, n = i % N;
-  float v = to_f32(gate[m * ldgate + n]) > 0.0f ? to_f32(g[m * ldg + n]) * scale : 0.0f;
-  y[m * ldy + n] = from_f32<T>(v);
+  constexpr int VE = kVec ? Vec16<T>::n : 1;
+  const int64_t vec_per_row = (N + VE - 1) / VE;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M * vec_per_row) return;
+  const int64_t m = i / vec_per_row, n = (i % vec_per_row) * VE;
+  if constexpr (kVec) {
+    float a[VE], b[VE];
+    unpack16(ldg_nc_v4(g + m * ldg + n), a, T());
+    unpack16(ldg_nc_v4(gate + m * ldgate + n), b, T());
+#pragma unroll
+    for (int k = 0; k < VE; ++k) a[k] = b[k] > 0.0f ? a[k] * scale : 0.0f;
+    stg_v4(y + m * ldy + n, pack16(a, T()));
+  } else {
+    float v = to_f32(gate[m * ldgate + n]) > 0.0f ? to_f32(g[m * ldg + n]) * scale : 0.0f;
+    y[m * ldy + n] = from_f32<T>(v);
+  }
+}
+
+template <typename T>
+static int gate_typed(const void* g, int64_t ldg, const void* gate, int64_t ldgate, int64_t M, int64_t N, float scale,
+                      void* y, int64_t ldy, cudaStream_t stream) {
+  auto ok = [&](const void* p, int64_t ld) { return aligned(p, 16) && (ld * sizeof(T)) % 16 == 0; };
+  const bool vec = ok(g, ldg) && ok(gate, ldgate) && ok(y, ldy) && N % Vec16<T>::n == 0;
+  const int VE = vec ? Vec16<T>::n : 1;
+  unsigned blocks = (unsigned)ceil_div(M * ceil_div(N, VE), 256);
+  if (vec) gate_kernel<T, true><<<blocks, 256, 0, stream>>>((const T*)g, ldg, (const T*)gate, ldgate, M, N, scale, (T*)y, ldy);
+  else gate_kernel<T, false><<<blocks, 256, 0, stream>>>((const T*)g, ldg, (const T*)gate, ldgate, M, N, scale, (T*)y, ldy);
+  LLP_LAUNCH_OK();
+  return 0;
 }
 
 }  // namespace llp
 
 using namespace llp;
 
-extern "C" size_t llp_colsum_workspace_bytes(int64_t N) { return (size_t)kColsumSplits * (size_t)(N > 0 ? N : 1) * sizeof(float); }
+extern "C" size_t llp_colsum_workspace_bytes(int64_t N) { return colreduce_workspace_bytes(N); }
 
 extern "C" int llp_colsum(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, float* out, int accumulate,
                           void* workspace, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(A && out && workspace && M >= 0 && N > 0 && lda >= N);
   if (int rc = check_device()) return rc;
-  int splits = (int)imin64(kColsumSplits, imax64(1, ceil_div(M, 256)));
-  int64_t rows_per_split = ceil_div(imax64(M, 1), splits);
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)splits);
-  float* partial = reinterpret_cast<float*>(workspace);
-  if (dtype == LLP_F32) colsum_partial_kernel<float><<<grid, 256, 0, stream>>>((const float*)A, lda, M, N, rows_per_split, partial);
-  else if (dtype == LLP_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)A, lda, M, N, rows_per_split, partial);
-  else return LLP_E_BADARG;
-  LLP_LAUNCH_OK();
-  colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(partial, splits, N, out, accumulate);
-  LLP_LAUNCH_OK();
-  return 0;
+  return colreduce(dtype, A, lda, M, N, nullptr, out, accumulate, reinterpret_cast<float*>(workspace), (cudaStream_t)stream_);
 }
 
 extern "C" int llp_cast2d(int src_dtype, int dst_dtype, const void* src, int64_t lds, int64_t rows, int64_t cols,
@@ -272,10 +333,7 @@ extern "C" int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate,
   LLP_CHECK_ARG(g && gate && y && M >= 0 && N >= 0);
   if (int rc = check_device()) return rc;
   if (M * N == 0) return 0;
-  unsigned blocks = (unsigned)ceil_div(M * N, 256);
-  if (dtype == LLP_F32) gate_kernel<float><<<blocks, 256, 0, stream>>>((const float*)g, ldg, (const float*)gate, ldgate, M, N, scale, (float*)y, ldy);
-  else if (dtype == LLP_BF16) gate_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)g, ldg, (const __nv_bfloat16*)gate, ldgate, M, N, scale, (__nv_bfloat16*)y, ldy);
-  else return LLP_E_BADARG;
-  LLP_LAUNCH_OK();
-  return 0;
+  if (dtype == LLP_F32) return gate_typed<float>(g, ldg, gate, ldgate, M, N, scale, y, ldy, stream);
+  if (dtype == LLP_BF16) return gate_typed<__nv_bfloat16>(g, ldg, gate, ldgate, M, N, scale, y, ldy, stream);
+  return LLP_E_BADARG;
 }

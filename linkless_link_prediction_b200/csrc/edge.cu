@@ -84,49 +84,26 @@ score_head_kernel(const T* __restrict__ y, int64_t ldy, int64_t M, int64_t H, co
   }
 }
 
-// dlogit = dprob*p*(1-p); gy[m,:] = dlogit*w
+// dlogit = dprob*p*(1-p); gy[m,:] = dlogit*w, optionally masked by the relu/dropout gate of the layer that produced y
+// (gate_scale > 0: gy = y > 0 ? dlogit*w*gate_scale : 0)
 template <typename T>
 __global__ void __launch_bounds__(256)
-score_head_bwd_kernel(int64_t M, int64_t H, const float* __restrict__ w, const float* __restrict__ prob,
-                      const float* __restrict__ dprob, T* __restrict__ gy, int64_t ldgy, float* __restrict__ dlogit) {
+score_head_bwd_kernel(const T* __restrict__ y, int64_t ldy, int64_t M, int64_t H, const float* __restrict__ w,
+                      const float* __restrict__ prob, const float* __restrict__ dprob, float gate_scale,
+                      T* __restrict__ gy, int64_t ldgy, float* __restrict__ dlogit) {
   int lane = threadIdx.x & 31;
   int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (m >= M) return;
   float p = prob[m];
   float dl = dprob[m] * p * (1.0f - p);
   if (lane == 0) dlogit[m] = dl;
-  if (gy != nullptr)
-    for (int64_t c = lane; c < H; c += 32) gy[m * ldgy + c] = from_f32<T>(dl * __ldg(w + c));
-}
-
-// partial[s][c] = sum_{m in split s} dlogit[m]*y[m,c]
-constexpr int kHeadSplits = 64;
-template <typename T>
-__global__ void score_head_gw_kernel(const T* __restrict__ y, int64_t ldy, int64_t M, int64_t H,
-                                     const float* __restrict__ dlogit, int64_t rows_per_split, float* __restrict__ partial) {
-  __shared__ float red[8][33];
-  int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-  int64_t c = (int64_t)blockIdx.x * 32 + lane;
-  int64_t mb = (int64_t)blockIdx.y * rows_per_split, me = min(M, mb + rows_per_split);
-  float acc = 0.0f;
-  if (c < H)
-    for (int64_t m = mb + wv; m < me; m += 8) acc = fmaf(dlogit[m], to_f32(y[m * ldy + c]), acc);
-  red[wv][lane] = acc;
-  __syncthreads();
-  if (wv == 0 && c < H) {
-    float s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][lane];
-    partial[(int64_t)blockIdx.y * H + c] = s;
+  if (gy != nullptr) {
+    for (int64_t c = lane; c < H; c += 32) {
+      float v = dl * __ldg(w + c);
+      if (gate_scale > 0.0f) v = to_f32(y[m * ldy + c]) > 0.0f ? v * gate_scale : 0.0f;
+      gy[m * ldgy + c] = from_f32<T>(v);
+    }
   }
-}
-
-__global__ void head_final_kernel(const float* __restrict__ partial, int splits, int64_t H, float* __restrict__ gw) {
-  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= H) return;
-  float s = 0.0f;
-  for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * H + c];
-  gw[c] = s;
 }
 
 template <typename T>
@@ -159,15 +136,20 @@ static int hadamard_bwd_launch(const void* h, int64_t ldh, int64_t F, const int6
   return 0;
 }
 
+int colreduce(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, const float* w, float* out, int accumulate,
+              float* partial, cudaStream_t stream);
+size_t colreduce_workspace_bytes(int64_t N);
+
 }  // namespace llp
 
 using namespace llp;
 
 extern "C" int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t F, const int64_t* u, const int64_t* v,
                                  int64_t M, void* z, int64_t ldz, void* stream_) {
-  LLP_CHECK_ARG(h && u && v && z && F > 0 && M >= 0 && ldh >= F && ldz >= F);
+  LLP_CHECK_ARG(F > 0 && M >= 0);
   if (int rc = check_device()) return rc;
   if (M == 0) return 0;
+  LLP_CHECK_ARG(h && u && v && z && ldh >= F && ldz >= F);
   if (dtype == LLP_F32) return hadamard_launch<float>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
   if (dtype == LLP_BF16) return hadamard_launch<__nv_bfloat16>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
   return LLP_E_BADARG;
@@ -176,9 +158,10 @@ extern "C" int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t 
 extern "C" int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t F, const int64_t* u,
                                      const int64_t* v, int64_t M, const void* dz, int64_t lddz, float* gh, int64_t ldgh,
                                      void* stream_) {
-  LLP_CHECK_ARG(h && u && v && dz && gh && F > 0 && M >= 0 && ldh >= F && lddz >= F && ldgh >= F);
+  LLP_CHECK_ARG(F > 0 && M >= 0);
   if (int rc = check_device()) return rc;
   if (M == 0) return 0;
+  LLP_CHECK_ARG(h && u && v && dz && gh && ldh >= F && lddz >= F && ldgh >= F);
   if (dtype == LLP_F32) return hadamard_bwd_launch<float>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
   if (dtype == LLP_BF16) return hadamard_bwd_launch<__nv_bfloat16>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
   return LLP_E_BADARG;
@@ -199,12 +182,12 @@ extern "C" int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, 
 }
 
 extern "C" size_t llp_score_head_bwd_workspace_bytes(int64_t M, int64_t H) {
-  return 8192 + ((size_t)(M > 0 ? M : 1) + (size_t)kHeadSplits * (size_t)(H > 0 ? H : 1)) * sizeof(float);
+  return 8192 + (size_t)(M > 0 ? M : 1) * sizeof(float) + colreduce_workspace_bytes(H);
 }
 
 extern "C" int llp_score_head_bwd(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w,
-                                  const float* prob, const float* dprob, void* gy, int64_t ldgy, float* gw, float* gb,
-                                  void* workspace, size_t workspace_bytes, void* stream_) {
+                                  const float* prob, const float* dprob, float gate_scale, void* gy, int64_t ldgy,
+                                  float* gw, float* gb, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(y && w && prob && dprob && workspace && M > 0 && H > 0 && ldy >= H);
   if (workspace_bytes < llp_score_head_bwd_workspace_bytes(M, H)) return LLP_E_WORKSPACE;
@@ -212,24 +195,15 @@ extern "C" int llp_score_head_bwd(int dtype, const void* y, int64_t ldy, int64_t
   float* dlogit = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 8192);
   float* partial = dlogit + M;
   unsigned blocks = (unsigned)ceil_div(M * 32, 256);
-  int splits = (int)imin64(kHeadSplits, imax64(1, ceil_div(M, 256)));
-  int64_t rows_per_split = ceil_div(M, splits);
-  dim3 grid((unsigned)ceil_div(H, 32), (unsigned)splits);
-  if (dtype == LLP_F32) {
-    score_head_bwd_kernel<float><<<blocks, 256, 0, stream>>>(M, H, w, prob, dprob, (float*)gy, ldgy, dlogit);
-    LLP_LAUNCH_OK();
-    if (gw) { score_head_gw_kernel<float><<<grid, 256, 0, stream>>>((const float*)y, ldy, M, H, dlogit, rows_per_split, partial); LLP_LAUNCH_OK(); }
-  } else if (dtype == LLP_BF16) {
-    score_head_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(M, H, w, prob, dprob, (__nv_bfloat16*)gy, ldgy, dlogit);
-    LLP_LAUNCH_OK();
-    if (gw) { score_head_gw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)y, ldy, M, H, dlogit, rows_per_split, partial); LLP_LAUNCH_OK(); }
-  } else {
+  if (dtype == LLP_F32)
+    score_head_bwd_kernel<float><<<blocks, 256, 0, stream>>>((const float*)y, ldy, M, H, w, prob, dprob, gate_scale, (float*)gy, ldgy, dlogit);
+  else if (dtype == LLP_BF16)
+    score_head_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)y, ldy, M, H, w, prob, dprob, gate_scale, (__nv_bfloat16*)gy, ldgy, dlogit);
+  else
     return LLP_E_BADARG;
-  }
-  if (gw) {
-    head_final_kernel<<<(unsigned)ceil_div(H, 256), 256, 0, stream>>>(partial, splits, H, gw);
-    LLP_LAUNCH_OK();
-  }
+  LLP_LAUNCH_OK();
+  if (gw)
+    if (int rc = colreduce(dtype, y, ldy, M, H, dlogit, gw, 0, partial, stream)) return rc;  // gw = sum_m dlogit[m]*y[m,:]
   if (gb) return sum_f32(dlogit, M, 1.0f, gb, workspace, stream);
   return 0;
 }

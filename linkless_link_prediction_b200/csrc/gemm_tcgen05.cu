@@ -22,7 +22,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // bf16 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;             // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kAccStages = 2;
 constexpr int kSlabBytes = BLOCK_K * 128;  // 64 rows x 128 B: one TMA box of the MN-major layout
 
@@ -128,9 +129,88 @@ struct TcParams {
   int splits;            // TN only: number of K-splits
   int64_t k_per_split;   // TN only: reduction rows per split (multiple of BLOCK_K)
   EpilogueParams ep;
+  int ep_flags;          // kVec*: which epilogue operands may be accessed with 128-bit vectors
   void* D; int64_t ldd;
   float* partial;        // TN: [splits][M][N] fp32
 };
+
+// ---- fused epilogue for one row x 32 columns ------------------------------------------------------------
+// Every option is a warp-uniform branch around fully unrolled register code; bias / addend / gate are read with
+// 128-bit loads when the host verified the alignment (ep_flags), the dropout mask costs one Philox call per 8 columns.
+constexpr int kVecBias = 1, kVecAddend = 2, kVecGate = 4, kVecOut = 8;
+
+template <typename TO>
+__device__ __forceinline__ void load32(const TO* __restrict__ src, bool vec, int valid, float (&v)[32]) {
+  if (vec && valid == 32) {
+    constexpr int VE = Vec16<TO>::n;
+#pragma unroll
+    for (int j = 0; j < 32; j += VE) {
+      float t[VE];
+      unpack16(ldg_v4(src + j), t, TO());
+#pragma unroll
+      for (int i = 0; i < VE; ++i) v[j + i] = t[i];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = j < valid ? to_f32(src[j]) : 0.0f;
+  }
+}
+
+template <typename TO>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t m, int64_t n_base, const TcParams& p) {
+  const EpilogueParams& ep = p.ep;
+  const int valid = (int)(p.N - n_base < 32 ? p.N - n_base : 32);
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+  if (ep.bias != nullptr) {
+    float b[32];
+    load32<float>(ep.bias + n_base, (p.ep_flags & kVecBias) != 0, valid, b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += b[j];
+  }
+  if (ep.addend != nullptr) {
+    float a[32];
+    load32<TO>(reinterpret_cast<const TO*>(ep.addend) + m * ep.ldadd + n_base, (p.ep_flags & kVecAddend) != 0, valid, a);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += a[j];
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+  if (ep.dropout_p > 0.0f) {
+    const uint32_t thr = dropout_thr16(ep.dropout_p);
+    const float scale = 1.0f / (1.0f - ep.dropout_p);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 rnd = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)((n_base >> 3) + q));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[q * 8 + i] = dropout_u16(rnd, i) >= thr ? f[q * 8 + i] * scale : 0.0f;
+    }
+  }
+  if (ep.gate != nullptr) {
+    float g[32];
+    load32<TO>(reinterpret_cast<const TO*>(ep.gate) + m * ep.ldgate + n_base, (p.ep_flags & kVecGate) != 0, valid, g);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = g[j] > 0.0f ? f[j] * ep.gate_scale : 0.0f;
+  }
+  TO* dst = reinterpret_cast<TO*>(p.D) + m * p.ldd + n_base;
+  if ((p.ep_flags & kVecOut) && valid == 32) {
+    constexpr int VE = Vec16<TO>::n;
+#pragma unroll
+    for (int j = 0; j < 32; j += VE) {
+      float g[VE];
+#pragma unroll
+      for (int i = 0; i < VE; ++i) g[i] = f[j + i];
+      stg_v4(dst + j, pack16(g, TO()));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dst[j] = from_f32<TO>(f[j]);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N, bool kTN, typename TO>
@@ -160,7 +240,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
     tma_prefetch_desc(&maps.b1);
     if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_holder), Cfg::kTmemCols);
@@ -250,7 +330,9 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
     }
   } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    const int half = (warp - 2) >> 2;     // which half of the tile's columns
+    constexpr int kColsPerWarp = BLOCK_N / 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int64_t split = tile / (m_tiles * n_tiles);
@@ -261,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       const int64_t m = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -277,25 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
                 if (n0 + c0 + j < p.N) dst[j] = __uint_as_float(r[j]);
             }
           } else {
-            TO* dst = reinterpret_cast<TO*>(p.D) + m * p.ldd + n0 + c0;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              f[j] = (n0 + c0 + j < p.N) ? epilogue_apply<TO>(__uint_as_float(r[j]), m, n0 + c0 + j, p.ep) : 0.0f;
-            const bool vec = (n0 + c0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-            if (vec) {
-              constexpr int VE = Vec16<TO>::n;
-#pragma unroll
-              for (int j = 0; j < 32; j += VE) {
-                float g[VE];
-#pragma unroll
-                for (int i = 0; i < VE; ++i) g[i] = f[j + i];
-                stg_v4(dst + j, pack16(g, TO()));
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (n0 + c0 + j < p.N) dst[j] = from_f32<TO>(f[j]);
-            }
+            epilogue_chunk<TO>(r, m, n0 + c0, p);
           }
         }
       }
@@ -384,6 +448,12 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
+  {
+    const size_t so = a.out_dtype == LLP_BF16 ? 2 : 4;
+    auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * so) % 16 == 0; };
+    p.ep_flags = (a.bias != nullptr && aligned(a.bias, 16) ? kVecBias : 0) | (ok(a.addend, a.ldadd) ? kVecAddend : 0) |
+                 (ok(a.gate, a.ldgate) ? kVecGate : 0) | (ok(a.D, a.ldd) ? kVecOut : 0);
+  }
 #define LLP_TC_NT(BN)                                                                                          \
   if (bn == BN) {                                                                                              \
     if (a.out_dtype == LLP_BF16) return launch<BN, false, __nv_bfloat16>(maps, p, stream);                     \

@@ -14,9 +14,14 @@ from . import ops
 from .sageconv import SAGEConv, _SageBase
 
 
-def _linear(x, lin: nn.Linear, relu: bool, p: float):
+def _linear(x, lin: nn.Linear, relu: bool, p: float, in_gate: float = 0.0, defer_gate: bool = False):
     seed, offset = ops._dropout_seed() if p > 0 else (0, 0)
-    return ops.LinearFn.apply(x, lin.weight, lin.bias, relu, p, seed, offset)
+    return ops.LinearFn.apply(x, lin.weight, lin.bias, relu, p, seed, offset, in_gate, defer_gate)
+
+
+def _gate_scale(p: float) -> float:
+    """Backward factor of relu + dropout(p) taken from the saved output: 1/(1-p) where the output is positive."""
+    return 1.0 / (1.0 - p)
 
 
 class MLP(nn.Module):
@@ -40,11 +45,13 @@ class MLP(nn.Module):
             layer.reset_parameters()
 
     def forward(self, feats):
-        h = ops.to_compute(feats)
+        h = ops.to_compute(feats, cache=True)
         p = float(self.dropout.p) if self.training else 0.0
         for l, layer in enumerate(self.layers):
             last = l == self.num_layers - 1
-            h = _linear(h, layer, relu=not last, p=0.0 if last else p)
+            # every hidden activation is consumed by the next layer, which applies its relu/dropout mask in backward
+            h = _linear(h, layer, relu=not last, p=0.0 if last else p, in_gate=_gate_scale(p) if l > 0 else 0.0,
+                        defer_gate=not last)
         return h
 
 
@@ -67,12 +74,16 @@ class SAGE(nn.Module):
 
     def forward(self, x, adj_t):
         graph = adj_t if isinstance(adj_t, ops.Graph) else ops.graph_of(adj_t, x.size(0))
-        x = ops.to_compute(x)
-        for conv in self.convs[:-1]:
+        x = ops.to_compute(x, cache=True)
+        p = float(self.dropout) if self.training else 0.0
+        n = len(self.convs)
+        for l, conv in enumerate(self.convs):
             if not isinstance(conv, _SageBase):
                 raise RuntimeError("SAGE expects the SAGEConv / SAGEConv_updated layers of this package")
-            x = conv(x, graph, _relu=True, _dropout=self.dropout)
-        return self.convs[-1](x, graph)
+            last = l == n - 1
+            x = conv(x, graph, _relu=not last, _dropout=0.0 if last else self.dropout,
+                     _in_gate=_gate_scale(p) if l > 0 else 0.0, _defer_gate=not last)
+        return x
 
 
 class LinkPredictor(nn.Module):
@@ -96,12 +107,14 @@ class LinkPredictor(nn.Module):
         """z = x_i * x_j rows [M, C] in the compute dtype -> sigmoid scores."""
         p = float(self.dropout) if self.training else 0.0
         if self.predictor == "mlp":
-            for lin in self.lins[:-1]:
-                z = _linear(z, lin, relu=True, p=p)
+            hidden = len(self.lins) - 1
+            for l, lin in enumerate(self.lins[:-1]):
+                z = _linear(z, lin, relu=True, p=p, in_gate=_gate_scale(p) if l > 0 else 0.0, defer_gate=True)
             last = self.lins[-1]
+            gate_in = _gate_scale(p) if hidden > 0 else 0.0
             if last.out_features == 1:
-                return ops.ScoreHeadFn.apply(z, last.weight, last.bias).unsqueeze(-1)
-            return torch.sigmoid(_linear(z, last, relu=False, p=0.0).float())
+                return ops.ScoreHeadFn.apply(z, last.weight, last.bias, gate_in).unsqueeze(-1)
+            return torch.sigmoid(_linear(z, last, relu=False, p=0.0, in_gate=gate_in).float())
         ones = torch.ones(1, z.size(1), dtype=torch.float32, device=z.device)
         return ops.ScoreHeadFn.apply(z, ones, None)  # 'inner': sigmoid(sum(x_i * x_j))
 

@@ -66,12 +66,27 @@ def cast2d(src: torch.Tensor, dtype: torch.dtype, transpose: bool = False) -> to
     return out
 
 
-def to_compute(x: torch.Tensor) -> torch.Tensor:
-    """Bring a 2-D activation/feature matrix to the compute dtype with 16-byte-aligned rows."""
+_FEATURE_CACHE: Dict[Tuple, Tuple] = {}
+
+
+def to_compute(x: torch.Tensor, cache: bool = False) -> torch.Tensor:
+    """Bring a 2-D activation/feature matrix to the compute dtype with 16-byte-aligned rows.  ``cache=True`` (constant
+    node features: the reference feeds the same ``data.x`` to every step) keeps the converted copy keyed on the source
+    tensor's identity and version counter."""
     dt = compute_dtype()
     if x.dtype == dt and x.dim() == 2 and x.stride(1) == 1 and (x.stride(0) * x.element_size()) % 16 == 0 \
             and x.data_ptr() % 16 == 0:
         return x
+    if cache and not x.requires_grad:
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, dt, x._version)
+        hit = _FEATURE_CACHE.get(key)
+        if hit is not None and hit[0]() is x:
+            return hit[1]
+        if len(_FEATURE_CACHE) > 8:
+            _FEATURE_CACHE.clear()
+        out = cast2d(x if x.dim() == 2 else x.reshape(-1, x.size(-1)), dt)
+        _FEATURE_CACHE[key] = (weakref.ref(x), out)
+        return out
     return cast2d(x if x.dim() == 2 else x.reshape(-1, x.size(-1)), dt)
 
 
@@ -250,27 +265,37 @@ def _weights_t(W: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # autograd functions
 # --------------------------------------------------------------------------------------------
+# Gate fusion convention shared by the layer functions below.  ``in_gate`` > 0 says "my input x is the relu/dropout
+# output of the previous fused layer and I apply that layer's backward mask (x > 0 ? g*in_gate : 0) in the epilogue of
+# my input-gradient GEMM"; ``defer_gate`` says "my consumer does that for me, the incoming gradient is already
+# masked".  The modules in models.py set the pair consistently; standalone use keeps the defaults (0, False).
+def _own_gate(g, y, p, defer_gate):
+    if y is None or defer_gate:
+        return g
+    return gate(g, y, 1.0 / (1.0 - p))
+
+
 class LinearFn(torch.autograd.Function):
     """y = dropout(relu(x W^T + b)) — nn.Linear + F.relu + F.dropout (models.py:48-53,143-145)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu, p, seed, offset):
+    def forward(ctx, x, W, b, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
         y = gemm_nt(x, _weights(W), bias=b, relu=relu, dropout_p=p, seed=seed, offset=offset)
-        ctx.save_for_backward(x, W, y if (relu or p > 0) else None)
-        ctx.cfg = (relu, p, b is not None)
+        ctx.save_for_backward(x, W, y if ((relu or p > 0) and not defer_gate) else None)
+        ctx.cfg = (p, b is not None, in_gate, defer_gate)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
-        relu, p, has_b = ctx.cfg
-        g = to_compute(gy)
-        if y is not None:
-            g = gate(g, y, 1.0 / (1.0 - p))
+        p, has_b, in_gate, defer_gate = ctx.cfg
+        g = _own_gate(to_compute(gy), y, p, defer_gate)
         gW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
         gb = colsum(g) if (has_b and ctx.needs_input_grad[2]) else None
-        gx = gemm_nt(g, _weights_t(W)) if ctx.needs_input_grad[0] else None
-        return gx, gW, gb, None, None, None, None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nt(g, _weights_t(W), gate=x if in_gate > 0 else None, gate_scale=in_gate)
+        return gx, gW, gb, None, None, None, None, None, None
 
 
 class SageConvFn(torch.autograd.Function):
@@ -278,20 +303,18 @@ class SageConvFn(torch.autograd.Function):
     [agg | x] with the relu/dropout of SAGE.forward fused into the epilogue (models.py:110-119)."""
 
     @staticmethod
-    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset):
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
         agg = graph.spmm(x)
         y = gemm_nt(agg, _weights(Wl), x, _weights(Wr), bias=bl, relu=relu, dropout_p=p, seed=seed, offset=offset)
-        ctx.save_for_backward(x, agg, Wl, Wr, y if (relu or p > 0) else None)
-        ctx.graph, ctx.cfg = graph, (relu, p)
+        ctx.save_for_backward(x, agg, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
+        ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, agg, Wl, Wr, y = ctx.saved_tensors
-        relu, p = ctx.cfg
-        g = to_compute(gy)
-        if y is not None:
-            g = gate(g, y, 1.0 / (1.0 - p))
+        p, in_gate, defer_gate = ctx.cfg
+        g = _own_gate(to_compute(gy), y, p, defer_gate)
         gWl = gemm_tn(g, agg) if ctx.needs_input_grad[1] else None
         gbl = colsum(g) if ctx.needs_input_grad[2] else None
         gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
@@ -299,35 +322,35 @@ class SageConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # A~^T (g W_l) = (A~^T g) W_l : aggregate first, then one dual GEMM writes gx with no add kernel
             t = ctx.graph.spmm(g, transpose=True)
-            gx = gemm_nt(t, _weights_t(Wl), g, _weights_t(Wr))
-        return gx, gWl, gbl, gWr, None, None, None, None, None
+            gx = gemm_nt(t, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
+        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
 
 
 class SageConvUpdatedFn(torch.autograd.Function):
     """SAGEConv_updated (sageconv_updated.py:65-81): y = epi(mean_{s->d}(W_l x[s] + b_l) + W_r x)."""
 
     @staticmethod
-    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset):
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
         t = gemm_nt(x, _weights(Wl), bias=bl)
         agg = graph.spmm(t)
         y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset)
-        ctx.save_for_backward(x, Wl, Wr, y if (relu or p > 0) else None)
-        ctx.graph, ctx.cfg = graph, (relu, p)
+        ctx.save_for_backward(x, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
+        ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, Wl, Wr, y = ctx.saved_tensors
-        relu, p = ctx.cfg
-        g = to_compute(gy)
-        if y is not None:
-            g = gate(g, y, 1.0 / (1.0 - p))
+        p, in_gate, defer_gate = ctx.cfg
+        g = _own_gate(to_compute(gy), y, p, defer_gate)
         gt = ctx.graph.spmm(g, transpose=True)
         gWl = gemm_tn(gt, x) if ctx.needs_input_grad[1] else None
         gbl = colsum(gt) if ctx.needs_input_grad[2] else None
         gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
-        gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr)) if ctx.needs_input_grad[0] else None
-        return gx, gWl, gbl, gWr, None, None, None, None, None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
+        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
 
 
 class HadamardFn(torch.autograd.Function):
@@ -365,9 +388,10 @@ class ScoreHeadFn(torch.autograd.Function):
     """prob = sigmoid(y w^T + b) for the 1-output last predictor layer (models.py:146,150)."""
 
     @staticmethod
-    def forward(ctx, y, w, b):
+    def forward(ctx, y, w, b, in_gate=0.0):
         lib = N.require_gpu()
         M, H = y.shape
+        ctx.in_gate = float(in_gate)
         prob = torch.empty(M, dtype=torch.float32, device=y.device)
         yp, ldy = N.mat(y)
         wf = w.detach().reshape(-1).contiguous()
@@ -392,9 +416,9 @@ class ScoreHeadFn(torch.autograd.Function):
         gyp, ldgy = N.mat(gy) if gy is not None else (None, 0)
         wf = w.detach().reshape(-1).contiguous()
         N.check(lib.llp_score_head_bwd(N.dtype_id(y.dtype), yp, ldy, M, H, wf.data_ptr(), prob.data_ptr(),
-                                       dprob.contiguous().data_ptr(), gyp, ldgy, N.ptr(gw), N.ptr(gb), ws.data_ptr(), nbytes,
-                                       N.stream_ptr()), "llp_score_head_bwd")
-        return gy, (gw.reshape(w.shape) if gw is not None else None), gb
+                                       dprob.contiguous().data_ptr(), ctx.in_gate, gyp, ldgy, N.ptr(gw), N.ptr(gb),
+                                       ws.data_ptr(), nbytes, N.stream_ptr()), "llp_score_head_bwd")
+        return gy, (gw.reshape(w.shape) if gw is not None else None), gb, None
 
 
 class _LossFn(torch.autograd.Function):

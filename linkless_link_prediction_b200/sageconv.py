@@ -33,16 +33,18 @@ class _SageBase(nn.Module):
         self.lin_l.reset_parameters()
         self.lin_r.reset_parameters()
 
-    def forward(self, x, edge_index, size=None, *, _relu: bool = False, _dropout: float = 0.0):
-        """``_relu`` / ``_dropout`` are set by ``models.SAGE`` to fuse its relu + dropout into this layer's epilogue."""
+    def forward(self, x, edge_index, size=None, *, _relu: bool = False, _dropout: float = 0.0, _in_gate: float = 0.0,
+                _defer_gate: bool = False):
+        """``_relu`` / ``_dropout`` are set by ``models.SAGE`` to fuse its relu + dropout into this layer's epilogue;
+        ``_in_gate`` / ``_defer_gate`` move the relu/dropout backward mask into the consumer's GEMM epilogue (ops.py)."""
         if isinstance(x, (tuple, list)):
             x = x[0]
         graph = edge_index if isinstance(edge_index, ops.Graph) else ops.graph_of(edge_index, x.size(0))
-        x = ops.to_compute(x)
+        x = ops.to_compute(x, cache=True)
         p = float(_dropout) if self.training else 0.0
         seed, offset = ops._dropout_seed() if p > 0 else (0, 0)
         return type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, bool(_relu), p, seed,
-                                    offset)
+                                    offset, float(_in_gate), bool(_defer_gate))
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"

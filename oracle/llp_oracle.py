@@ -312,6 +312,9 @@ def random_walk_with_rand(rowptr: Tensor, col: Tensor, start: Tensor, rand: Tens
         deg = re - rs
         off = (rand[:, l].float() * deg.float()).long()
         e = rs + off
+        if col.numel() == 0:  # no edges at all: every walker stays where it is
+            out[:, l + 1] = cur
+            continue
         nxt = col[torch.where(deg > 0, e, torch.zeros_like(e))]
         cur = torch.where(deg > 0, nxt, cur)
         out[:, l + 1] = cur

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks at the collab (C4) sizes: CUDA-event timing on the launching stream, L2 flushed
+between iterations (a 512 MB memset), achieved GB/s / TFLOP/s against MEASURED_PEAKS.json.  Development tool."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from linkless_link_prediction_b200 import _native as N  # noqa: E402
+from linkless_link_prediction_b200 import ops  # noqa: E402
+from linkless_link_prediction_b200.data import undirected_graph  # noqa: E402
+
+dev = torch.device("cuda:0")
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e3  # us
+
+
+def report(name, us, nbytes=None, flops=None):
+    s = f"{name:58s} {us:9.1f} us"
+    if nbytes:
+        g = nbytes / us / 1e3
+        s += f"  {g:8.0f} GB/s ({100 * g / PEAK['hbm_gbs']:5.1f}% of measured HBM)"
+    if flops:
+        t = flops / us / 1e6
+        s += f"  {t:7.1f} TFLOP/s ({100 * t / PEAK['bf16_tflops']:5.1f}% of measured bf16)"
+    print(s, flush=True)
+
+
+def main():
+    which = set(sys.argv[1:]) or {"spmm", "gemm", "misc"}
+    n, E = 235868, 2358104
+    ei = undirected_graph(n, 1179052, 0, True, unique=False).to(dev)
+    g = ops.Graph(ei, n)
+    if "spmm" in which:
+        for dt in (torch.bfloat16, torch.float32):
+            for F in (128, 256):
+                x = torch.randn(n, F, device=dev).to(dt)
+                s = x.element_size()
+                nb = E * F * s + n * F * s + 4 * E + 4 * (n + 1)
+                report(f"spmm fwd  {dt} F={F}", timeit(lambda: g.spmm(x)), nbytes=nb)
+                report(f"spmm bwd  {dt} F={F}", timeit(lambda: g.spmm(x, transpose=True)), nbytes=nb + 4 * n)
+    if "gemm" in which:
+        H = 256
+        for M, K1, K2, kw, tag in ((n, 128, 128, dict(relu=True, dropout_p=0.5, seed=1), "L1 fwd relu+drop"),
+                                   (n, 256, 256, dict(relu=True, dropout_p=0.5, seed=1), "L2 fwd relu+drop"),
+                                   (n, 256, 256, dict(), "L3 fwd / dgrad"),
+                                   (n, 256, 256, dict(relu=True), "L2 fwd relu only"),
+                                   (131072, 256, 0, dict(relu=True, dropout_p=0.5, seed=1), "pred fwd relu+drop"),
+                                   (131072, 256, 0, dict(), "pred dgrad")):
+            A1 = torch.randn(M, K1, device=dev).bfloat16(); B1 = torch.randn(H, K1, device=dev).bfloat16()
+            A2 = torch.randn(M, K2, device=dev).bfloat16() if K2 else None
+            B2 = torch.randn(H, K2, device=dev).bfloat16() if K2 else None
+            bias = torch.randn(H, device=dev)
+            us = timeit(lambda: ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw))
+            report(f"gemm_nt M={M} K={K1}+{K2} {tag}", us, nbytes=M * (K1 + K2) * 2 + M * H * 2, flops=2 * M * H * (K1 + K2))
+        for M, N1, N2 in ((n, 256, 256), (n, 256, 128), (131072, 256, 256)):
+            A = torch.randn(M, N1, device=dev).bfloat16(); B = torch.randn(M, N2, device=dev).bfloat16()
+            report(f"gemm_tn M={M} {N1}x{N2}", timeit(lambda: ops.gemm_tn(A, B)), nbytes=M * (N1 + N2) * 2, flops=2 * M * N1 * N2)
+    if "misc" in which:
+        H = 256
+        a = torch.randn(n, H, device=dev).bfloat16(); b = torch.randn(n, H, device=dev).bfloat16()
+        report("gate [N,256] bf16", timeit(lambda: ops.gate(a, b, 2.0)), nbytes=3 * n * H * 2)
+        report("colsum [N,256] bf16", timeit(lambda: ops.colsum(a)), nbytes=n * H * 2)
+        xf = torch.randn(n, 128, device=dev)
+        report("cast2d fp32->bf16 [N,128]", timeit(lambda: ops.cast2d(xf, torch.bfloat16)), nbytes=n * 128 * 6)
+        M = 131072
+        u = torch.randint(0, n, (M,), device=dev); v = torch.randint(0, n, (M,), device=dev)
+        report("edge_hadamard M=131072", timeit(lambda: ops.HadamardFn.apply(a, u, v)), nbytes=3 * M * H * 2)
+        z = torch.randn(M, H, device=dev).bfloat16()
+        hh = a.clone().requires_grad_(True)
+        def hb():
+            zz = ops.HadamardFn.apply(hh, u, v)
+            zz.backward(z)
+            hh.grad = None
+        report("edge_hadamard fwd+bwd (atomics + zero + cast)", timeit(hb), nbytes=(3 + 3) * M * H * 2 + n * H * 10)
+        w = torch.randn(1, H, device=dev); bb = torch.randn(1, device=dev)
+        report("score_head fwd M=131072", timeit(lambda: ops.ScoreHeadFn.apply(z, w, bb)), nbytes=M * H * 2)
+
+
+if __name__ == "__main__":
+    main()
