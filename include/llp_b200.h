@@ -50,6 +50,8 @@ const char* llp_error_string(int code);
 int llp_device_supported(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t llp_launch_count(void);
+/* development knob (benchmark sweeps only; results never depend on it): key 0 = SpMM occupancy/register variant */
+void llp_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------
  * Graph structure.  Replaces: PyG MessagePassing.__collect__/aggregate over a dense [2,E]
@@ -76,8 +78,6 @@ size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
  * its autograd transpose (index_add_).  dtype in {LLP_F32, LLP_BF16}; fp32 accumulation in CSR order.
  * x/out rows must be 4-byte aligned at least; 16-byte aligned rows (ld*elt % 16 == 0) take the
  * 128-bit path.  src_scale may be NULL. */
-/* 0 (default): cp.async.bulk staging kernel for aligned rows <= 1 KB; 1: always the register-gather kernel (tests). */
-void llp_spmm_set_path(int force_register_path);
 int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
              int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
              const float* src_scale, int mean, void* out, int64_t ldo, void* workspace, void* stream);

@@ -44,13 +44,13 @@ PROTOTYPES = {
     "llp_error_string": (c_char_p, [c_int]),
     "llp_device_supported": (c_int, []),
     "llp_launch_count": (c_int64, []),
+    "llp_set_tuning": (None, [c_int, c_int]),
     "llp_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_csr_build": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "llp_spmm_num_chunks": (c_int64, [c_int64]),
     "llp_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
-    "llp_spmm_set_path": (None, [c_int]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                          c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),

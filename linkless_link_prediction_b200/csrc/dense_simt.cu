@@ -199,16 +199,19 @@ colreduce_partial_kernel(const T* __restrict__ A, int64_t lda, int64_t M, int64_
   }
 }
 
+// one warp per output column: lanes stride over the splits, then a shuffle tree (fixed order => deterministic)
 __global__ void colreduce_final_kernel(const float* __restrict__ partial, int splits, int64_t N, float* __restrict__ out,
                                        int accumulate) {
-  int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
   float s = 0.0f;
-  for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * N + n];
-  out[n] = accumulate ? out[n] + s : s;
+  for (int i = lane; i < splits; i += 32) s += partial[(int64_t)i * N + n];
+  s = warp_sum(s);
+  if (lane == 0) out[n] = accumulate ? out[n] + s : s;
 }
 
-constexpr int kColreduceSplits = 512;
+constexpr int kColreduceSplits = 256;
 
 size_t colreduce_workspace_bytes(int64_t N) { return (size_t)kColreduceSplits * (size_t)(N > 0 ? N : 1) * sizeof(float); }
 
@@ -224,7 +227,7 @@ static int colreduce_typed(const void* A_, int64_t lda, int64_t M, int64_t N, co
   if (vec) colreduce_partial_kernel<T, true><<<grid, 256, 0, stream>>>(A, lda, M, N, w, rows_per_split, partial);
   else colreduce_partial_kernel<T, false><<<grid, 256, 0, stream>>>(A, lda, M, N, w, rows_per_split, partial);
   LLP_LAUNCH_OK();
-  colreduce_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(partial, splits, N, out, accumulate);
+  colreduce_final_kernel<<<(unsigned)ceil_div(N * 32, 256), 256, 0, stream>>>(partial, splits, N, out, accumulate);
   LLP_LAUNCH_OK();
   return 0;
 }

@@ -43,20 +43,12 @@ def test_csr_build_bit_exact(cuda, n, e, hub):
     assert torch.equal(g.inv_deg.cpu(), 1.0 / deg)
 
 
-@pytest.fixture(params=["bulk", "register"])
-def spmm_path(request):
-    """Both SpMM implementations: the cp.async.bulk staging kernel (default) and the register-gather kernel."""
-    N.load().llp_spmm_set_path(1 if request.param == "register" else 0)
-    yield request.param
-    N.load().llp_spmm_set_path(0)
-
-
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("n,e,f,hub", [(64, 0, 16, None), (200, 1500, 128, None), (500, 4000, 256, None),
                                        (300, 12000, 256, 5000), (120, 700, 1433, None), (90, 500, 7, None),
                                        (2000, 30000, 64, 1500), (3000, 50000, 512, 3000), (50, 3000, 8, 2000),
                                        (1, 1, 128, None), (700, 128 * 5, 32, None)])
-def test_spmm_forward_and_transpose(cuda, spmm_path, dtype, n, e, f, hub):
+def test_spmm_forward_and_transpose(cuda, dtype, n, e, f, hub):
     ei = rand_graph(n, e, 2, hub)
     x = torch.randn(n, f, generator=torch.Generator().manual_seed(3))
     xq = x.to(dtype).float()  # what the kernel actually reads
@@ -73,7 +65,7 @@ def test_spmm_forward_and_transpose(cuda, spmm_path, dtype, n, e, f, hub):
     torch.testing.assert_close(gx, xo.grad, **(FP32 if dtype == torch.float32 else dict(rtol=2e-2, atol=6e-2)))
 
 
-def test_spmm_fp32_is_bit_exact_in_edge_order(cuda, spmm_path):
+def test_spmm_fp32_is_bit_exact_in_edge_order(cuda):
     # no hub rows: the kernel sums each row in CSR (= original edge) order like index_add_ on the CPU
     ei = rand_graph(400, 3000, 5)
     x = torch.randn(400, 128, generator=torch.Generator().manual_seed(6))
@@ -83,7 +75,7 @@ def test_spmm_fp32_is_bit_exact_in_edge_order(cuda, spmm_path):
     assert torch.equal(out, O.spmm_csr(rp, col, x, True))
 
 
-def test_spmm_collab_size_properties(cuda, spmm_path):
+def test_spmm_collab_size_properties(cuda):
     # BASELINE config C4 size: checked through size-independent properties (no CPU oracle at this size)
     n, f = 235868, 256
     from linkless_link_prediction_b200.data import undirected_graph

@@ -48,6 +48,28 @@ def main():
     n, E = 235868, 2358104
     ei = undirected_graph(n, 1179052, 0, True, unique=False).to(dev)
     g = ops.Graph(ei, n)
+    if "spmmsweep" in which:
+        for variant in (0, 1, 2, 3):
+            N.load().llp_set_tuning(0, variant)
+            for dt, F in ((torch.bfloat16, 256), (torch.bfloat16, 128), (torch.float32, 256)):
+                x = torch.randn(n, F, device=dev).to(dt)
+                s = x.element_size()
+                nb = E * F * s + n * F * s + 4 * E + 4 * (n + 1)
+                report(f"variant {variant}: spmm fwd {dt} F={F}", timeit(lambda: g.spmm(x)), nbytes=nb)
+                report(f"variant {variant}: spmm bwd {dt} F={F}", timeit(lambda: g.spmm(x, transpose=True)), nbytes=nb)
+        N.load().llp_set_tuning(0, 0)
+    if "spmmexp" in which:
+        N.load().llp_set_tuning(0, 1)
+        x = torch.randn(n, 256, device=dev).bfloat16()
+        nb = E * 512 + n * 512 + 4 * E + 4 * (n + 1)
+        for div in (1, 2, 4, 8):
+            N.load().llp_set_tuning(1, div)
+            report(f"chunk_div={div} (1/{div} of the chunks) bf16 F=256", timeit(lambda: g.spmm(x)), nbytes=nb / div)
+        N.load().llp_set_tuning(1, 1)
+        N.load().llp_set_tuning(2, 1)
+        report("sequential sources (e mod N) bf16 F=256", timeit(lambda: g.spmm(x)), nbytes=nb)
+        N.load().llp_set_tuning(2, 0)
+        N.load().llp_set_tuning(0, 0)
     if "spmm" in which:
         for dt in (torch.bfloat16, torch.float32):
             for F in (128, 256):
