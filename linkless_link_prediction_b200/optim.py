@@ -19,7 +19,7 @@ class FusedAdam(torch.optim.Optimizer):
     launches regardless of the number of tensors and the DP gradient sync is one all-reduce."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None):
+                 process_group=None, distributed: bool = True):
         params = list(params)
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._params: List[torch.nn.Parameter] = [p for g in self.param_groups for p in g["params"]]
@@ -42,6 +42,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self._step = 0
         self.process_group = process_group
+        self.distributed = distributed  # False: never all-reduce (single-rank reference runs inside a DP job)
         lib = N.load()
         self._ws = torch.empty(max(lib.llp_clip_adam_workspace_bytes(8), 256), dtype=torch.uint8, device=dev)
         self.group_norms = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -78,8 +79,9 @@ class FusedAdam(torch.optim.Optimizer):
         (the reference clips model and predictor separately)."""
         lib = N.require_gpu()
         grad_scale = 1.0
-        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                              and torch.distributed.get_world_size() > 1):
+        if self.distributed and (self.process_group is not None or (
+                torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1)):
             import torch.distributed as dist
             world = dist.get_world_size(self.process_group)
             if world > 1:
