@@ -70,7 +70,8 @@ int llp_csr_build(const int64_t* edge_val, const int64_t* edge_key, int64_t num_
 /* Edge-balanced work plan for llp_spmm: chunk c owns rows [first_row[c], first_row[c+1]). */
 int64_t llp_spmm_num_chunks(int64_t num_edges);
 int llp_spmm_plan(const int32_t* rowptr, int64_t num_nodes, int64_t num_edges,
-                  int32_t* chunk_first_row /*[num_chunks+1]*/, void* stream);
+                  int32_t* chunk_first_row /*[num_chunks+1]*/, int32_t* hub_list /*[num_chunks] out*/,
+                  int32_t* num_hubs /*[1] device out: rows longer than the split threshold*/, void* stream);
 size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 
 /* CSR gather-reduce SpMM: out[r,:] = (mean ? 1/max(deg r,1) : 1) * sum_{e in row r} scale[col e] * x[col e,:]
@@ -80,7 +81,8 @@ size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
  * 128-bit path.  src_scale may be NULL. */
 int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
              int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
-             const float* src_scale, int mean, void* out, int64_t ldo, void* workspace, void* stream);
+             const float* src_scale, int mean, void* out, int64_t ldo, void* workspace,
+             const int32_t* hub_list, int64_t num_hubs /* from llp_spmm_plan (host copy of *num_hubs) */, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Dense layers.  Replaces cuBLAS SGEMM behind F.linear (sageconv_updated.py:71,76; PyG

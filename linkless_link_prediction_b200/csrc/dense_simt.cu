@@ -173,14 +173,34 @@ colreduce_partial_kernel(const T* __restrict__ A, int64_t lda, int64_t M, int64_
 #pragma unroll
   for (int i = 0; i < VE; ++i) acc[i] = 0.0f;
   if (c < N) {
-    for (int64_t m = mb + wv; m < me; m += 8) {
-      const float wm = w != nullptr ? __ldg(w + m) : 1.0f;
-      if constexpr (kVec) {
+    if constexpr (kVec) {
+      int64_t m = mb + wv;
+      for (; m + 24 < me; m += 32) {  // 4 independent 128-bit loads in flight per lane
+        uint4 v[4];
+        float wm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = ldg_nc_v4(A + (m + 8 * u) * lda + c);
+          wm[u] = w != nullptr ? __ldg(w + m + 8 * u) : 1.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[VE];
+          unpack16(v[u], f, T());
+#pragma unroll
+          for (int i = 0; i < VE; ++i) acc[i] = fmaf(wm[u], f[i], acc[i]);
+        }
+      }
+      for (; m < me; m += 8) {
+        const float wm = w != nullptr ? __ldg(w + m) : 1.0f;
         float f[VE];
         unpack16(ldg_nc_v4(A + m * lda + c), f, T());
 #pragma unroll
         for (int i = 0; i < VE; ++i) acc[i] = fmaf(wm, f[i], acc[i]);
-      } else {
+      }
+    } else {
+      for (int64_t m = mb + wv; m < me; m += 8) {
+        const float wm = w != nullptr ? __ldg(w + m) : 1.0f;
         acc[0] = fmaf(wm, to_f32(A[m * lda + c]), acc[0]);
       }
     }
@@ -211,7 +231,7 @@ __global__ void colreduce_final_kernel(const float* __restrict__ partial, int sp
   if (lane == 0) out[n] = accumulate ? out[n] + s : s;
 }
 
-constexpr int kColreduceSplits = 256;
+constexpr int kColreduceSplits = 2048;
 
 size_t colreduce_workspace_bytes(int64_t N) { return (size_t)kColreduceSplits * (size_t)(N > 0 ? N : 1) * sizeof(float); }
 
@@ -221,7 +241,7 @@ static int colreduce_typed(const void* A_, int64_t lda, int64_t M, int64_t N, co
   const T* A = reinterpret_cast<const T*>(A_);
   const bool vec = aligned(A, 16) && (lda * sizeof(T)) % 16 == 0 && N % Vec16<T>::n == 0;
   const int VE = vec ? Vec16<T>::n : 1;
-  const int splits = (int)imin64(kColreduceSplits, imax64(1, ceil_div(M, 64)));
+  const int splits = (int)imin64(kColreduceSplits, imax64(1, ceil_div(M, 96)));
   const int64_t rows_per_split = ceil_div(imax64(M, 1), splits);
   dim3 grid((unsigned)ceil_div(N, 32 * VE), (unsigned)splits);
   if (vec) colreduce_partial_kernel<T, true><<<grid, 256, 0, stream>>>(A, lda, M, N, w, rows_per_split, partial);

@@ -23,9 +23,21 @@
 
 namespace llp {
 
-constexpr int kEPW = 128;   // nominal edges per warp-chunk
-constexpr int kHub = 256;   // rows with more edges than this are split along the chunk grid (must be >= kEPW)
+constexpr int kEPW = 64;    // nominal edges per warp-chunk
+constexpr int kHub = 128;   // rows with more edges than this are split along the chunk grid (must be >= kEPW)
 constexpr int kSpmmThreads = 128;
+
+// Hub list: chunk c is appended when it is the FIRST continuation chunk of a row longer than kHub (that row started in
+// chunk c-1).  One entry per hub row; the order of the list does not matter (every hub is combined independently).
+__global__ void spmm_hub_list_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
+                                     int64_t n_chunks, int32_t* __restrict__ hub_list, int32_t* __restrict__ num_hubs) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x + 1;
+  if (c >= n_chunks) return;
+  const int r0 = first_row[c];
+  if (r0 == 0) return;
+  const int ps = rowptr[r0 - 1], pe = rowptr[r0];
+  if (pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1) hub_list[atomicAdd(num_hubs, 1)] = (int32_t)c;
+}
 
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N, int64_t n_chunks,
                                  int32_t* __restrict__ first_row) {
@@ -39,6 +51,49 @@ __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N, 
     if ((int64_t)rowptr[mid] < target) lo = mid + 1; else hi = mid;
   }
   first_row[c] = (int32_t)lo;
+}
+
+// ---- lane vectors: 16 bytes (VE = 4 fp32 / 8 bf16), 8 bytes (2 fp32 / 4 bf16: rows of <= 256 bytes keep all 32 lanes
+// busy that way) or one element (unaligned fallback) ------------------------------------------------------------------
+template <typename T, int VE>
+__device__ __forceinline__ uint4 load_vec(const T* p) {
+  if constexpr (VE * sizeof(T) == 16) {
+    return ldg_nc_v4(p);
+  } else if constexpr (VE * sizeof(T) == 8) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return make_uint4(r.x, r.y, 0, 0);
+  } else {
+    return make_uint4(__float_as_uint(to_f32(*p)), 0, 0, 0);
+  }
+}
+template <typename T, int VE>
+__device__ __forceinline__ void unpack_vec(const uint4& v, float (&f)[VE]) {
+  if constexpr (VE == 1) {
+    f[0] = __uint_as_float(v.x);
+  } else if constexpr (sizeof(T) == 4) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    if constexpr (VE == 4) { f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w); }
+  } else {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    if constexpr (VE == 8) {
+      f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+      f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    }
+  }
+}
+template <typename T, int VE>
+__device__ __forceinline__ void store_vec(T* p, const float (&f)[VE]) {
+  if constexpr (VE == 1) {
+    *p = from_f32<T>(f[0]);
+  } else if constexpr (sizeof(T) == 4) {
+    if constexpr (VE == 4) *reinterpret_cast<uint4*>(p) = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    else *reinterpret_cast<uint2*>(p) = make_uint2(__float_as_uint(f[0]), __float_as_uint(f[1]));
+  } else {
+    if constexpr (VE == 8) *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    else *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+  }
 }
 
 // ---- per-lane accumulator over NV vectors of VE elements --------------------------------------------
@@ -60,12 +115,7 @@ __device__ __forceinline__ void load_row(const T* __restrict__ x, int64_t ldx, i
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = col0 + (k * 32 + lane) * VE;
-    if constexpr (VE * sizeof(T) == 16) {
-      v[k] = (c < F) ? ldg_nc_v4(row + k * 32 * VE) : make_uint4(0, 0, 0, 0);
-    } else {  // scalar path: one element per lane
-      float f = (c < F) ? to_f32(row[k * 32]) : 0.0f;
-      v[k] = make_uint4(__float_as_uint(f), 0, 0, 0);
-    }
+    v[k] = (c < F) ? load_vec<T, VE>(row + k * 32 * VE) : make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -73,15 +123,10 @@ template <typename T, int VE, int NV, bool kScale>
 __device__ __forceinline__ void add_row(RowAcc<VE, NV>& acc, const uint4 (&v)[NV], float scale) {
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    if constexpr (VE * sizeof(T) == 16) {
-      float f[VE];
-      unpack16(v[k], f, T());
+    float f[VE];
+    unpack_vec<T, VE>(v[k], f);
 #pragma unroll
-      for (int i = 0; i < VE; ++i) acc.a[k][i] = kScale ? fmaf(f[i], scale, acc.a[k][i]) : acc.a[k][i] + f[i];
-    } else {
-      const float f = __uint_as_float(v[k].x);
-      acc.a[k][0] = kScale ? fmaf(f, scale, acc.a[k][0]) : acc.a[k][0] + f;
-    }
+    for (int i = 0; i < VE; ++i) acc.a[k][i] = kScale ? fmaf(f[i], scale, acc.a[k][i]) : acc.a[k][i] + f[i];
   }
 }
 
@@ -116,11 +161,7 @@ __device__ __noinline__ void close_row(const RowAcc<VE, NV>& acc, T* __restrict_
     float f[VE];
 #pragma unroll
     for (int i = 0; i < VE; ++i) f[i] = sizeof(T) == 4 ? __fdiv_rn(acc.a[k][i], d) : acc.a[k][i] * inv;
-    if constexpr (VE * sizeof(T) == 16) {
-      stg_v4(row + col, pack16(f, T()));
-    } else {
-      row[col] = from_f32<T>(f[0]);
-    }
+    store_vec<T, VE>(row + col, f);
   }
 }
 
@@ -160,10 +201,23 @@ template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks>
 __global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
 spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ first_row,
             int n_chunks, const T* __restrict__ x, int64_t ldx, int F, const float* __restrict__ src_scale, int mean,
-            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n) {
+            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int zero_rows_per_warp) {
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (c >= n_chunks) return;
+  // Rows without edges get zeros.  They are spread over the warps by row index (not by edge ownership), so a long run
+  // of isolated nodes cannot pile up on one warp.
+  for (int rb = c * zero_rows_per_warp; rb < min(n_rows, (c + 1) * zero_rows_per_warp); rb += 32) {
+    const int rr = rb + lane;
+    const bool empty = rr < min(n_rows, (c + 1) * zero_rows_per_warp) && rowptr[rr + 1] == rowptr[rr];
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      T* row = out + (int64_t)(rb + j) * ldo;
+      for (int f = lane; f < F; f += 32) row[f] = from_f32<T>(0.0f);
+    }
+  }
   const ChunkRange cr = chunk_range(rowptr, first_row, c);
   if (cr.ee <= cr.eb) return;
   const int cb = c * kEPW;
@@ -230,73 +284,57 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
   }
 }
 
-// Fix-up: (a) combine hub-row partials in chunk order, (b) zero-fill rows without edges.
+// Fix-up: one block per hub row adds the row's fp32 partials.  Warp w sums the partials w, w+8, ... (8 x 16 bytes in
+// flight per lane), the eight warp sums are combined in warp order through shared memory: a fixed association, so the
+// result is deterministic, and a 12k-edge hub (200 partials) costs a few microseconds instead of one long serial chain.
+constexpr int kFixTile = 1024;  // floats per column tile (8 warps x 4 KB of shared memory)
 template <typename T>
 __global__ void __launch_bounds__(256)
-spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row, int n_chunks, int N, int F,
-                  int mean, T* __restrict__ out, int64_t ldo, const float* __restrict__ partial) {
-  const int lane = threadIdx.x & 31;
-  const int w = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  const int n_warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  // (a) chunk c is the FIRST continuation chunk of hub row rp  <=>  rp started in chunk c-1
-  for (int c = w + 1; c < n_chunks; c += n_warps) {
-    const int r0 = first_row[c];
-    if (r0 == 0) continue;
-    const int rp = r0 - 1;
-    const int ps = rowptr[rp], pe = rowptr[rp + 1];
-    if (!(pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1)) continue;
-    const int c_last = (pe - 1) / kEPW;
-    const float divisor = mean ? (float)(pe - ps) : 1.0f;
-    const float* first = partial + ((int64_t)(c - 1) * 2 + 1) * F;  // slot 1 of the owner chunk
-    if (F % 4 == 0) {  // 128-bit loads, 8 partials in flight per lane, added in chunk order
-      for (int f = lane * 4; f < F; f += 128) {
-        float4 acc = *reinterpret_cast<const float4*>(first + f);
-        int cc = c;
-        for (; cc + 8 <= c_last + 1; cc += 8) {
-          float4 t[8];
+spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
+                  const int32_t* __restrict__ hub_list, int F, int mean, T* __restrict__ out, int64_t ldo,
+                  const float* __restrict__ partial) {
+  __shared__ float red[8][kFixTile];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = hub_list[blockIdx.x];
+  const int rp = first_row[c] - 1;
+  const int ps = rowptr[rp], pe = rowptr[rp + 1];
+  const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
+  const float divisor = mean ? (float)(pe - ps) : 1.0f;
+  auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
+  for (int f0 = 0; f0 < F; f0 += kFixTile) {
+    const int fw = min(kFixTile, F - f0);
+    for (int f = lane; f < fw; f += 32) {
+      float acc = 0.0f;
+      int k = w;
+      for (; k + 56 < n_part; k += 64) {
+        float t[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(partial + ((int64_t)(cc + i) * 2) * F + f));
+        for (int i = 0; i < 8; ++i) t[i] = __ldg(part_ptr(k + 8 * i) + f0 + f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
-        }
-        for (; cc <= c_last; ++cc) {
-          float4 t = __ldg(reinterpret_cast<const float4*>(partial + ((int64_t)cc * 2) * F + f));
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-        T* o = out + (int64_t)rp * ldo + f;
-        o[0] = from_f32<T>(__fdiv_rn(acc.x, divisor)); o[1] = from_f32<T>(__fdiv_rn(acc.y, divisor));
-        o[2] = from_f32<T>(__fdiv_rn(acc.z, divisor)); o[3] = from_f32<T>(__fdiv_rn(acc.w, divisor));
+        for (int i = 0; i < 8; ++i) acc += t[i];
       }
-    } else {
-      for (int f = lane; f < F; f += 32) {
-        float acc = first[f];
-        for (int cc = c; cc <= c_last; ++cc) acc += partial[((int64_t)cc * 2) * F + f];
-        out[(int64_t)rp * ldo + f] = from_f32<T>(__fdiv_rn(acc, divisor));
-      }
+      for (; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
+      red[w][f] = acc;
     }
-  }
-  // (b) zero rows: each warp inspects 32 rows at a time
-  for (int rb = w * 32; rb < N; rb += n_warps * 32) {
-    const int r = rb + lane;
-    const bool empty = (r < N) && (rowptr[r + 1] == rowptr[r]);
-    unsigned m = __ballot_sync(0xffffffffu, empty);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      T* row = out + (int64_t)(rb + j) * ldo;
-      for (int f = lane; f < F; f += 32) row[f] = from_f32<T>(0.0f);
+    __syncthreads();
+    for (int f = threadIdx.x; f < fw; f += 256) {
+      float acc = red[0][f];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) acc += red[i][f];
+      out[(int64_t)rp * ldo + f0 + f] = from_f32<T>(__fdiv_rn(acc, divisor));
     }
+    __syncthreads();
   }
 }
 
-int g_spmm_variant = 0;
+int g_spmm_variant = 1;  // 6 blocks/SM (<= 80 registers, no spills) measured fastest on B200 (tools/kbench.py spmmsweep)
 int g_spmm_chunk_div = 1;  // experiment: process only the first n_chunks/div chunks
 int g_spmm_fake_seq = 0;   // experiment: gather row (edge id mod N) instead of col[e]
 
 template <typename T, bool kScale>
 static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t* first_row, int64_t N, int64_t E,
                        const void* x_, int64_t ldx, int64_t F, const float* src_scale, int mean, void* out_,
-                       int64_t ldo, void* ws, cudaStream_t stream) {
+                       int64_t ldo, void* ws, const int32_t* hub_list, int num_hubs, cudaStream_t stream) {
   const T* x = reinterpret_cast<const T*>(x_);
   T* out = reinterpret_cast<T*>(out_);
   float* partial = reinterpret_cast<float*>(ws);
@@ -307,9 +345,13 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
   if (E > 0) {
 #define LLP_SPMM_LAUNCH(VE_, NV_, U_, MB_) \
-  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, n_chunks / g_spmm_chunk_div, x, ldx, (int)F, src_scale, mean, out, ldo, partial, g_spmm_fake_seq ? (int)N : 0)
+  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, n_chunks / g_spmm_chunk_div, x, ldx, (int)F, src_scale, mean, out, ldo, partial, g_spmm_fake_seq ? (int)N : 0, (int)N, (int)ceil_div(N, n_chunks))
     const int variant = g_spmm_variant;  // occupancy/register trade-off (llp_set_tuning(0, v)): 0 = 8 blocks/SM (<=64 regs)
-    if (vec) {
+    const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
+                      F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
+    if (vec8) {
+      if (variant == 0) LLP_SPMM_LAUNCH(VE / 2, 1, 8, 8); else LLP_SPMM_LAUNCH(VE / 2, 1, 8, 6);
+    } else if (vec) {
       if (F * (int64_t)sizeof(T) <= 512) {
         if (variant == 1) LLP_SPMM_LAUNCH(VE, 1, 8, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 1, 8, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 1, 4, 8); else LLP_SPMM_LAUNCH(VE, 1, 8, 8);
       } else {
@@ -321,10 +363,12 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
 #undef LLP_SPMM_LAUNCH
     LLP_LAUNCH_OK();
   }
-  const int64_t fix_warps = imax64(n_chunks, ceil_div(N, 32));
-  const int64_t fix_blocks = imin64(ceil_div(fix_warps * 32, 256), (int64_t)kNumSMs * 8);
-  spmm_fixup_kernel<T><<<(unsigned)imax64(fix_blocks, 1), 256, 0, stream>>>(rowptr, first_row, n_chunks, (int)N, (int)F, mean, out, ldo, partial);
-  LLP_LAUNCH_OK();
+  if (E > 0 && num_hubs > 0) {
+    spmm_fixup_kernel<T><<<(unsigned)num_hubs, 256, 0, stream>>>(rowptr, first_row, hub_list, (int)F, mean, out, ldo, partial);
+    LLP_LAUNCH_OK();
+  } else if (E == 0) {
+    LLP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(T), 0, (size_t)F * sizeof(T), (size_t)N, stream));
+  }
   return 0;
 }
 
@@ -340,13 +384,19 @@ extern "C" void llp_set_tuning(int key, int value) {
 
 extern "C" int64_t llp_spmm_num_chunks(int64_t E) { return E <= 0 ? 1 : ceil_div(E, kEPW); }
 
-extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_t* chunk_first_row, void* stream_) {
+extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_t* chunk_first_row, int32_t* hub_list,
+                             int32_t* num_hubs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0);
+  LLP_CHECK_ARG(rowptr && chunk_first_row && hub_list && num_hubs && N >= 0 && E >= 0);
   if (int rc = check_device()) return rc;
   int64_t n_chunks = llp_spmm_num_chunks(E);
   spmm_plan_kernel<<<(unsigned)ceil_div(n_chunks + 1, 256), 256, 0, stream>>>(rowptr, N, n_chunks, chunk_first_row);
   LLP_LAUNCH_OK();
+  LLP_CUDA(cudaMemsetAsync(num_hubs, 0, sizeof(int32_t), stream));
+  if (n_chunks > 1) {
+    spmm_hub_list_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(rowptr, chunk_first_row, n_chunks, hub_list, num_hubs);
+    LLP_LAUNCH_OK();
+  }
   return 0;
 }
 
@@ -356,17 +406,17 @@ extern "C" size_t llp_spmm_workspace_bytes(int64_t E, int64_t F) {
 
 extern "C" int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
                         int64_t N, int64_t E, const void* x, int64_t ldx, int64_t F, const float* src_scale, int mean,
-                        void* out, int64_t ldo, void* workspace, void* stream_) {
+                        void* out, int64_t ldo, void* workspace, const int32_t* hub_list, int64_t num_hubs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0 && F > 0 && ldx >= F && ldo >= F);
-  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out));
+  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (num_hubs == 0 || hub_list));
   LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && F < (1 << 24));
   if (int rc = check_device()) return rc;
   if (N == 0) return 0;
 #define LLP_SPMM(T)                                                                                                     \
   return src_scale != nullptr                                                                                           \
-             ? spmm_launch<T, true>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, stream)  \
-             : spmm_launch<T, false>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, stream)
+             ? spmm_launch<T, true>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)  \
+             : spmm_launch<T, false>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)
   if (dtype == LLP_F32) { LLP_SPMM(float); }
   if (dtype == LLP_BF16) { LLP_SPMM(__nv_bfloat16); }
 #undef LLP_SPMM

@@ -186,14 +186,18 @@ class Graph:
             N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, Nn, rowptr.data_ptr(), col.data_ptr(),
                                       perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
             plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
-            N.check(lib.llp_spmm_plan(rowptr.data_ptr(), Nn, E, plan.data_ptr(), N.stream_ptr()), "llp_spmm_plan")
-            return rowptr, col, perm, inv, plan
+            hub_list = torch.empty(n_chunks, dtype=torch.int32, device=dev)
+            n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
+            N.check(lib.llp_spmm_plan(rowptr.data_ptr(), Nn, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),
+                                      N.stream_ptr()), "llp_spmm_plan")
+            n_hubs = int(n_hubs.item())  # the one host sync per graph, at build time
+            return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs)
 
         src, dst = ei[0], ei[1]
         # forward: rows = destinations, cols = sources; inv_deg = 1/max(in-degree, 1)
-        self.rowptr, self.col, self.perm, self.inv_deg, self.plan = build(src, dst, True)
+        self.rowptr, self.col, self.perm, self.inv_deg, self.plan, self.hubs = build(src, dst, True)
         # transpose: rows = sources, cols = destinations
-        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan = build(dst, src, False)
+        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan, self.t_hubs = build(dst, src, False)
 
     def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
         """forward: ``out[d] = mean_{s->d} x[s]``; transpose: ``out[s] = sum_{s->d} x[d] / deg_in(d)``."""
@@ -210,10 +214,11 @@ class Graph:
             ev0.record()
         if not transpose:
             rc = lib.llp_spmm(N.dtype_id(x.dtype), self.rowptr.data_ptr(), self.col.data_ptr(), self.plan.data_ptr(), Nn, E,
-                              xp, ldx, F, None, 1, op, ldo, ws.data_ptr(), N.stream_ptr())
+                              xp, ldx, F, None, 1, op, ldo, ws.data_ptr(), self.hubs[0].data_ptr(), self.hubs[1], N.stream_ptr())
         else:
             rc = lib.llp_spmm(N.dtype_id(x.dtype), self.t_rowptr.data_ptr(), self.t_col.data_ptr(), self.t_plan.data_ptr(),
-                              Nn, E, xp, ldx, F, self.inv_deg.data_ptr(), 0, op, ldo, ws.data_ptr(), N.stream_ptr())
+                              Nn, E, xp, ldx, F, self.inv_deg.data_ptr(), 0, op, ldo, ws.data_ptr(), self.t_hubs[0].data_ptr(),
+                              self.t_hubs[1], N.stream_ptr())
         N.check(rc, "llp_spmm")
         if prof is not None:
             ev1.record()

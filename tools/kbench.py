@@ -69,7 +69,7 @@ def main():
         N.load().llp_set_tuning(2, 1)
         report("sequential sources (e mod N) bf16 F=256", timeit(lambda: g.spmm(x)), nbytes=nb)
         N.load().llp_set_tuning(2, 0)
-        N.load().llp_set_tuning(0, 0)
+        N.load().llp_set_tuning(0, 1)
     if "spmm" in which:
         for dt in (torch.bfloat16, torch.float32):
             for F in (128, 256):

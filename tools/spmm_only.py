@@ -4,8 +4,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from linkless_link_prediction_b200 import ops
 from linkless_link_prediction_b200.data import undirected_graph
 dev = torch.device("cuda:0")
-from linkless_link_prediction_b200 import _native as N
-N.load().llp_spmm_set_path(int(os.environ.get("SPMM_REGISTER", "0")))
 n = 235868
 g = ops.Graph(undirected_graph(n, 1179052, 0, True, unique=False).to(dev), n)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
