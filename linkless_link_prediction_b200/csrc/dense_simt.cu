@@ -282,6 +282,34 @@ __global__ void cast2d_kernel(const TS* __restrict__ src, int64_t lds, int64_t r
 }
 
 // y = gate > 0 ? g*scale : 0, one 16-byte vector per thread (rows are 16-byte multiples) or scalar fallback
+// plain (non-transposing) cast: one 16-byte output vector per thread when rows allow it
+template <typename TS, typename TD>
+__global__ void cast_rows_kernel(const TS* __restrict__ src, int64_t lds, int64_t rows, int64_t cols, TD* __restrict__ dst,
+                                 int64_t ldd) {
+  constexpr int VE = Vec16<TD>::n;  // elements per 16-byte output vector
+  const int64_t vec_per_row = cols / VE;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows * vec_per_row) return;
+  const int64_t r = i / vec_per_row, c = (i % vec_per_row) * VE;
+  float f[VE];
+  if constexpr (sizeof(TS) == 4) {
+#pragma unroll
+    for (int k = 0; k < VE; k += 4) {
+      const uint4 v = ldg_nc_v4(src + r * lds + c + k);
+      f[k] = __uint_as_float(v.x); f[k + 1] = __uint_as_float(v.y); f[k + 2] = __uint_as_float(v.z); f[k + 3] = __uint_as_float(v.w);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VE; k += 8) {
+      float t[8];
+      unpack16(ldg_nc_v4(src + r * lds + c + k), t, TS());
+#pragma unroll
+      for (int q = 0; q < 8 && k + q < VE; ++q) f[k + q] = t[q];
+    }
+  }
+  stg_v4(dst + r * ldd + c, pack16(f, TD()));
+}
+
 template <typename T, bool kVec>
 __global__ void gate_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ gate, int64_t ldgate, int64_t M,
                             int64_t N, float scale, T* __restrict__ y, int64_t ldy) {
@@ -336,6 +364,21 @@ extern "C" int llp_cast2d(int src_dtype, int dst_dtype, const void* src, int64_t
   if (int rc = check_device()) return rc;
   if (rows == 0 || cols == 0) return 0;
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
+  {  // fast path: fp32 -> bf16 / bf16 -> fp32 without transposition on 16-byte-aligned rows (cols % 8 == 0)
+    const size_t ss = src_dtype == LLP_BF16 ? 2 : 4, ds = dst_dtype == LLP_BF16 ? 2 : 4;
+    const bool ok = !transpose && cols % 8 == 0 && aligned(src, 16) && aligned(dst, 16) && (lds * ss) % 16 == 0 &&
+                    (ldd * ds) % 16 == 0;
+    if (ok && src_dtype == LLP_F32 && dst_dtype == LLP_BF16) {
+      cast_rows_kernel<float, __nv_bfloat16><<<(unsigned)ceil_div(rows * (cols / 8), 256), 256, 0, stream>>>((const float*)src, lds, rows, cols, (__nv_bfloat16*)dst, ldd);
+      LLP_LAUNCH_OK();
+      return 0;
+    }
+    if (ok && src_dtype == LLP_BF16 && dst_dtype == LLP_F32) {
+      cast_rows_kernel<__nv_bfloat16, float><<<(unsigned)ceil_div(rows * (cols / 4), 256), 256, 0, stream>>>((const __nv_bfloat16*)src, lds, rows, cols, (float*)dst, ldd);
+      LLP_LAUNCH_OK();
+      return 0;
+    }
+  }
 #define LLP_CAST_CASE(SD, DD, TS, TD)                                                                             \
   if (src_dtype == SD && dst_dtype == DD) {                                                                       \
     cast2d_kernel<TS, TD><<<grid, block, 0, stream>>>((const TS*)src, lds, rows, cols, (TD*)dst, ldd, transpose); \

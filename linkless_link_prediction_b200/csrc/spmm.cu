@@ -303,18 +303,29 @@ spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
   for (int f0 = 0; f0 < F; f0 += kFixTile) {
     const int fw = min(kFixTile, F - f0);
-    for (int f = lane; f < fw; f += 32) {
-      float acc = 0.0f;
-      int k = w;
-      for (; k + 56 < n_part; k += 64) {
-        float t[8];
+    if (F % 4 == 0) {  // 128-bit loads: a 256-float row is two passes of the warp
+      for (int f = lane * 4; f < fw; f += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = w;
+        for (; k + 56 < n_part; k += 64) {
+          float4 t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = __ldg(part_ptr(k + 8 * i) + f0 + f);
+          for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(part_ptr(k + 8 * i) + f0 + f));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc += t[i];
+          for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+        }
+        for (; k < n_part; k += 8) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(part_ptr(k) + f0 + f));
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        *reinterpret_cast<float4*>(&red[w][f]) = acc;
       }
-      for (; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
-      red[w][f] = acc;
+    } else {
+      for (int f = lane; f < fw; f += 32) {
+        float acc = 0.0f;
+        for (int k = w; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
+        red[w][f] = acc;
+      }
     }
     __syncthreads();
     for (int f = threadIdx.x; f < fw; f += 256) {
