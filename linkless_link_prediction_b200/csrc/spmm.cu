@@ -133,10 +133,9 @@ __device__ __forceinline__ void add_row(RowAcc<VE, NV>& acc, const uint4 (&v)[NV
 // A row [rs, re) is done for this chunk.  Rows of up to kHub edges were streamed whole and go to `out` (mean: divided
 // by the degree — an exact IEEE division in fp32 so the result is bit-identical to scatter-mean's true_divide, a
 // reciprocal multiply for bf16 outputs).  The slice of a longer (hub) row goes to this chunk's fp32 partial slot
-// (0: the row started in an earlier chunk, 1: it starts here).  Not inlined on purpose: it runs once per row, and
-// keeping it out of the streaming loop keeps that loop small enough for the instruction cache.
+// (0: the row started in an earlier chunk, 1: it starts here).
 template <typename T, int VE, int NV>
-__device__ __noinline__ void close_row(const RowAcc<VE, NV>& acc, T* __restrict__ out, int64_t ldo, int F, int r, int col0,
+__device__ __forceinline__ void close_row(const RowAcc<VE, NV>& acc, T* __restrict__ out, int64_t ldo, int F, int r, int col0,
                                        int lane, int mean, int rs, int re, int cb, int c, float* __restrict__ partial) {
   const int deg = re - rs;
   if (deg > kHub) {
@@ -197,11 +196,16 @@ __device__ __forceinline__ ChunkRange chunk_range(const int32_t* __restrict__ ro
   return cr;
 }
 
+// Row-run traversal: the warp walks its edge range row by row; inside a row, edges are consumed in groups of up to U
+// whose gathers are all issued before the first one is used.  Every branch is warp-uniform and there is no per-edge
+// boundary test: a group never crosses a row end (or the 32-wide index batch held in registers), so the inner body is
+// load / unpack / add only.  Column indices are fetched one batch ahead.
 template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks>
 __global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
 spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ first_row,
-            int n_chunks, const T* __restrict__ x, int64_t ldx, int F, const float* __restrict__ src_scale, int mean,
-            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int zero_rows_per_warp) {
+            int n_chunks, const T* __restrict__ x, int ldx, int F, const float* __restrict__ src_scale, int mean,
+            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int zero_rows_per_warp,
+            int n_edges) {
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (c >= n_chunks) return;
@@ -222,61 +226,69 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
   if (cr.ee <= cr.eb) return;
   const int cb = c * kEPW;
   constexpr int kColsPerPass = 32 * VE * NV;
+  const uint32_t ld_bytes = (uint32_t)ldx * (uint32_t)sizeof(T);
 
   for (int col0 = 0; col0 < F; col0 += kColsPerPass) {
+    const char* xlane = reinterpret_cast<const char*>(x + col0 + lane * VE);
+    bool lane_ok[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) lane_ok[k] = col0 + (k * 32 + lane) * VE < F;
     RowAcc<VE, NV> acc;
     acc.zero();
     int r = cr.r0;
     int row_start = cr.row_start;
     int row_end = rowptr[r + 1];
-    for (int base = cr.eb; base < cr.ee; base += 32) {
-      const int cnt = min(32, cr.ee - base);
-      int my = (lane < cnt) ? __ldg(col + base + lane) : 0;
-      if (fake_seq_n > 0) my = (base + lane) % fake_seq_n;
-      float mys = 1.0f;
-      if constexpr (kScale) mys = (lane < cnt) ? __ldg(src_scale + my) : 0.0f;
-      int j0 = 0;
-      // full groups of U edges: U independent row gathers in flight, no per-edge predicates
-      for (; j0 + U <= cnt; j0 += U) {
+    int e = cr.eb;
+    // index batches are 32-aligned in edge space: lane i of batch `base` holds col[base + i]
+    int base = e & ~31;
+    auto fetch_idx = [&](int b) {
+      const int i = b + lane;
+      int v = (i < n_edges) ? __ldg(col + i) : 0;
+      if (fake_seq_n > 0) v = i % fake_seq_n;
+      return v;
+    };
+    int my = fetch_idx(base), my_next = fetch_idx(base + 32);
+    float mys = 1.0f, mys_next = 1.0f;
+    if constexpr (kScale) { mys = __ldg(src_scale + my); mys_next = __ldg(src_scale + my_next); }
+
+    while (e < cr.ee) {
+      while (row_end == e) {  // close finished rows, skip rows without edges
+        if (row_end > row_start) {
+          close_row<T, VE, NV>(acc, out, ldo, F, r, col0, lane, mean, row_start, row_end, cb, c, partial);
+          acc.zero();
+        }
+        ++r;
+        row_start = row_end;
+        row_end = rowptr[r + 1];
+      }
+      const int run_end = min(row_end, cr.ee);
+      while (e < run_end) {
+        if (e >= base + 32) {  // next index batch (already in registers), prefetch the one after
+          base += 32;
+          my = my_next;
+          my_next = fetch_idx(base + 32);
+          if constexpr (kScale) { mys = mys_next; mys_next = __ldg(src_scale + my_next); }
+        }
+        const int o = e - base;                             // position inside the batch
+        const int cnt = min(min(U, run_end - e), 32 - o);  // group: same row, same batch
         uint4 v[U][NV];
 #pragma unroll
-        for (int u = 0; u < U; ++u) load_row<T, VE, NV>(x, ldx, F, __shfl_sync(0xffffffffu, my, j0 + u), col0, lane, v[u]);
-        const int e0 = base + j0;
-        if (e0 + U <= row_end) {  // warp-uniform fast path: the whole group lies inside the open row
+        for (int u = 0; u < U; ++u) {
+          const int src = __shfl_sync(0xffffffffu, my, (o + u) & 31);
+          if (u < cnt) {
+            const char* row = xlane + (uint64_t)((uint32_t)src) * ld_bytes;
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            add_row<T, VE, NV, kScale>(acc, v[u], kScale ? __shfl_sync(0xffffffffu, mys, j0 + u) : 1.0f);
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            while (e0 + u == row_end) {  // close finished rows, skip rows without edges
-              if (row_end > row_start) {
-                close_row<T, VE, NV>(acc, out, ldo, F, r, col0, lane, mean, row_start, row_end, cb, c, partial);
-                acc.zero();
-              }
-              ++r;
-              row_start = row_end;
-              row_end = rowptr[r + 1];
-            }
-            add_row<T, VE, NV, kScale>(acc, v[u], kScale ? __shfl_sync(0xffffffffu, mys, j0 + u) : 1.0f);
+            for (int k = 0; k < NV; ++k)
+              v[u][k] = lane_ok[k] ? load_vec<T, VE>(reinterpret_cast<const T*>(row) + k * 32 * VE) : make_uint4(0, 0, 0, 0);
           }
         }
-      }
-      // tail of the batch, one edge at a time
-      for (; j0 < cnt; ++j0) {
-        uint4 v[NV];
-        load_row<T, VE, NV>(x, ldx, F, __shfl_sync(0xffffffffu, my, j0), col0, lane, v);
-        const int e = base + j0;
-        while (e == row_end) {
-          if (row_end > row_start) {
-            close_row<T, VE, NV>(acc, out, ldo, F, r, col0, lane, mean, row_start, row_end, cb, c, partial);
-            acc.zero();
-          }
-          ++r;
-          row_start = row_end;
-          row_end = rowptr[r + 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float sc = 1.0f;
+          if constexpr (kScale) sc = __shfl_sync(0xffffffffu, mys, (o + u) & 31);
+          if (u < cnt) add_row<T, VE, NV, kScale>(acc, v[u], sc);
         }
-        add_row<T, VE, NV, kScale>(acc, v, kScale ? __shfl_sync(0xffffffffu, mys, j0) : 1.0f);
+        e += cnt;
       }
     }
     // the last open row: complete (it ends exactly at ee) or a hub slice
@@ -338,7 +350,7 @@ spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   }
 }
 
-int g_spmm_variant = 1;  // 6 blocks/SM (<= 80 registers, no spills) measured fastest on B200 (tools/kbench.py spmmsweep)
+int g_spmm_variant = 0;  // 0 = 8 blocks/SM (<= 64 registers): fastest for the row-run kernel (tools/kbench.py spmmsweep)
 int g_spmm_chunk_div = 1;  // experiment: process only the first n_chunks/div chunks
 int g_spmm_fake_seq = 0;   // experiment: gather row (edge id mod N) instead of col[e]
 
@@ -356,7 +368,7 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
   if (E > 0) {
 #define LLP_SPMM_LAUNCH(VE_, NV_, U_, MB_) \
-  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, n_chunks / g_spmm_chunk_div, x, ldx, (int)F, src_scale, mean, out, ldo, partial, g_spmm_fake_seq ? (int)N : 0, (int)N, (int)ceil_div(N, n_chunks))
+  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, n_chunks / g_spmm_chunk_div, x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, g_spmm_fake_seq ? (int)N : 0, (int)N, (int)ceil_div(N, n_chunks), (int)E)
     const int variant = g_spmm_variant;  // occupancy/register trade-off (llp_set_tuning(0, v)): 0 = 8 blocks/SM (<=64 regs)
     const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
                       F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
@@ -421,7 +433,7 @@ extern "C" int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, co
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0 && F > 0 && ldx >= F && ldo >= F);
   LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (num_hubs == 0 || hub_list));
-  LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && F < (1 << 24));
+  LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && F < (1 << 24) && ldx * 4 < (int64_t)UINT32_MAX);
   if (int rc = check_device()) return rc;
   if (N == 0) return 0;
 #define LLP_SPMM(T)                                                                                                     \
