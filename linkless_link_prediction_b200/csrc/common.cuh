@@ -133,8 +133,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint64_t ctr_lo, u
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// Dropout mask: one Philox4x32-10 call covers 8 consecutive columns of a row (16 random bits per element);
-// keep iff u16 >= thr16 with thr16 = p * 65536.  Identical in every kernel that draws or re-draws the mask.
+// Dropout mask from Philox4x32-10, a pure function of (seed, offset, row, col) shared by every kernel that draws it.
+//   p == 0.5 (the reference default, train_teacher_gnn.py:277): ONE random bit per element — a Philox call covers 128
+//             consecutive columns of a row (call index col/128, word (col/32)%4, bit col%32), keep iff the bit is set;
+//   other p : 16 random bits per element — a call covers 8 columns, keep iff u16 >= p * 65536.
 __host__ __device__ __forceinline__ uint32_t dropout_thr16(float p) {
   float t = p * 65536.0f;
   return t >= 65535.0f ? 65535u : (uint32_t)t;
@@ -143,7 +145,14 @@ __device__ __forceinline__ uint32_t dropout_u16(const uint4& r, int idx /*0..7*/
   uint32_t w = (idx >> 1) == 0 ? r.x : (idx >> 1) == 1 ? r.y : (idx >> 1) == 2 ? r.z : r.w;
   return (idx & 1) ? (w >> 16) : (w & 0xffffu);
 }
+__device__ __forceinline__ uint32_t dropout_word(const uint4& r, int idx /*0..3*/) {
+  return idx == 0 ? r.x : idx == 1 ? r.y : idx == 2 ? r.z : r.w;
+}
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, int64_t row, int64_t col, float p) {
+  if (p == 0.5f) {
+    uint4 r = philox4x32_10(seed, (uint64_t)row, offset + (uint64_t)(col >> 7));
+    return (dropout_word(r, (int)((col >> 5) & 3)) >> (col & 31)) & 1u;
+  }
   uint4 r = philox4x32_10(seed, (uint64_t)row, offset + (uint64_t)(col >> 3));
   return dropout_u16(r, (int)(col & 7)) >= dropout_thr16(p);
 }

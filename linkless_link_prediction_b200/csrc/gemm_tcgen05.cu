@@ -157,7 +157,8 @@ __device__ __forceinline__ void load32(const TO* __restrict__ src, bool vec, int
 }
 
 template <typename TO>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t m, int64_t n_base, const TcParams& p) {
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t m, int64_t n_base, const TcParams& p,
+                                               const uint4& rnd128) {
   const EpilogueParams& ep = p.ep;
   const int valid = (int)(p.N - n_base < 32 ? p.N - n_base : 32);
   float f[32];
@@ -179,7 +180,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t 
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   }
-  if (ep.dropout_p > 0.0f) {
+  if (ep.dropout_p == 0.5f) {  // one random bit per element: this chunk is one 32-bit word of the row's Philox block
+    const uint32_t bits = dropout_word(rnd128, (int)((n_base >> 5) & 3));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = ((bits >> j) & 1u) ? f[j] * 2.0f : 0.0f;
+  } else if (ep.dropout_p > 0.0f) {
     const uint32_t thr = dropout_thr16(ep.dropout_p);
     const float scale = 1.0f / (1.0f - ep.dropout_p);
 #pragma unroll
@@ -342,9 +347,17 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       tcgen05_fence_after();
       const int64_t m = m0 + quad * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      uint4 rnd128 = make_uint4(0, 0, 0, 0);
+      uint32_t rnd_group = 0xffffffffu;  // which 128-column Philox block rnd128 holds (p == 0.5 fast path)
 #pragma unroll 1
       for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
+        if constexpr (!kTN) {
+          if (p.ep.dropout_p == 0.5f && (uint32_t)((n0 + c0) >> 7) != rnd_group) {
+            rnd_group = (uint32_t)((n0 + c0) >> 7);
+            rnd128 = philox4x32_10(p.ep.seed, (uint64_t)m, p.ep.offset + (uint64_t)rnd_group);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         if (m < p.M) {
@@ -359,7 +372,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
                 if (n0 + c0 + j < p.N) dst[j] = __uint_as_float(r[j]);
             }
           } else {
-            epilogue_chunk<TO>(r, m, n0 + c0, p);
+            epilogue_chunk<TO>(r, m, n0 + c0, p, rnd128);
           }
         }
       }

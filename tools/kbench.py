@@ -59,7 +59,7 @@ def main():
                 report(f"variant {variant}: spmm bwd {dt} F={F}", timeit(lambda: g.spmm(x, transpose=True)), nbytes=nb)
         N.load().llp_set_tuning(0, 0)
     if "spmmexp" in which:
-        N.load().llp_set_tuning(0, 1)
+        N.load().llp_set_tuning(0, 0)
         x = torch.randn(n, 256, device=dev).bfloat16()
         nb = E * 512 + n * 512 + 4 * E + 4 * (n + 1)
         for div in (1, 2, 4, 8):
@@ -69,7 +69,7 @@ def main():
         N.load().llp_set_tuning(2, 1)
         report("sequential sources (e mod N) bf16 F=256", timeit(lambda: g.spmm(x)), nbytes=nb)
         N.load().llp_set_tuning(2, 0)
-        N.load().llp_set_tuning(0, 1)
+        N.load().llp_set_tuning(0, 0)
     if "spmm" in which:
         for dt in (torch.bfloat16, torch.float32):
             for F in (128, 256):
