@@ -105,7 +105,9 @@ typedef struct llp_gemm_nt_args {
                                         (backward of relu+dropout from the saved output)      */
   float gate_scale;
   float dropout_p;              /* 0 = off; keep-prob 1-p, survivors scaled by 1/(1-p)        */
-  uint64_t seed, offset;        /* Philox4x32-10 stream for the dropout mask                  */
+  uint64_t seed, offset;        /* Philox4x32-10 stream for the dropout mask (offset < 2^44)  */
+  const uint64_t* rng_state;    /* device {seed, step} or NULL: mixed into the stream, so a
+                                   captured CUDA graph draws a fresh mask on every replay       */
   void* D; int64_t ldd;         /* [M,N]                                                      */
 } llp_gemm_nt_args;
 int llp_gemm_nt(const llp_gemm_nt_args* host_args, void* stream);
@@ -191,10 +193,13 @@ int llp_random_walk(const int64_t* rowptr, const int64_t* col, const int64_t* st
  * (train_teacher_gnn.py:63-67; main.py:226-230) on flat fp32 buffers.  Groups are
  * contiguous ranges [group_begin[g], group_begin[g+1]) clipped separately to max_norm.
  * ------------------------------------------------------------------------------------- */
+/* state[1] += 1 (one launch per training step; llp_gemm_nt_args.rng_state points at `state`). */
+int llp_rng_advance(uint64_t* state, void* stream);
 size_t llp_clip_adam_workspace_bytes(int num_groups);
 int llp_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   const int64_t* host_group_begin, int num_groups, float max_norm, float grad_scale, float lr,
-                  float beta1, float beta2, float eps, int64_t step, void* bf16_copy /*[n] or NULL*/,
+                  float beta1, float beta2, float eps, int64_t step, int64_t* device_step /*NULL, or a device counter
+                  that is incremented and used instead of `step` (CUDA-graph safe)*/, void* bf16_copy /*[n] or NULL*/,
                   float* group_norms /*[num_groups] out*/, void* workspace, void* stream);
 
 /* Deterministic sum of n floats (double accumulate): out[0] = scale * sum(in). */

@@ -34,6 +34,7 @@ class GemmNtArgs(ctypes.Structure):
         ("gate", c_void_p), ("ldgate", c_int64),
         ("gate_scale", c_float), ("dropout_p", c_float),
         ("seed", c_uint64), ("offset", c_uint64),
+        ("rng_state", c_void_p),
         ("D", c_void_p), ("ldd", c_int64),
     ]
 
@@ -78,10 +79,11 @@ PROTOTYPES = {
     "llp_topk_desc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "llp_count_greater": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "llp_random_walk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "llp_rng_advance": (c_int, [c_void_p, c_void_p]),
     "llp_clip_adam_workspace_bytes": (c_size_t, [c_int]),
     "llp_clip_adam": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, ctypes.POINTER(c_int64), c_int, c_float,
                               c_float, c_float, c_float, c_float, c_float, c_int64, c_void_p, c_void_p, c_void_p,
-                              c_void_p]),
+                              c_void_p, c_void_p]),
     "llp_sum": (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
 }
 

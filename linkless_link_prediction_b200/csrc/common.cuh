@@ -166,7 +166,21 @@ struct EpilogueParams {
   int relu;
   float dropout_p;
   uint64_t seed, offset;
+  const uint64_t* rng_state;  // device {seed, step}: when set, the mask stream also depends on it (CUDA-graph safe)
 };
+
+// Effective Philox key / counter base of a dropout site.  By value: key = seed, base = offset << 20.  With a device
+// rng_state {s, step}: key = seed ^ s, base = (step << 32) + (offset << 20); `offset` is then the site id (< 4096), the
+// low 20 bits are left for the column-group index.
+__device__ __forceinline__ void resolve_rng(EpilogueParams& ep) {
+  uint64_t key = ep.seed, base = ep.offset << 20;
+  if (ep.rng_state != nullptr) {
+    key ^= ep.rng_state[0];
+    base += ep.rng_state[1] << 32;
+  }
+  ep.seed = key;
+  ep.offset = base;
+}
 
 template <typename TO>
 __device__ __forceinline__ float epilogue_apply(float acc, int64_t m, int64_t n, const EpilogueParams& ep) {

@@ -38,6 +38,7 @@ gemm_simt_kernel(int64_t M, int64_t N, StridedOperand a1, StridedOperand b1, Str
                  int64_t k_per_split, EpilogueParams ep, TO* __restrict__ D, int64_t ldd, float* __restrict__ partial) {
   __shared__ float As[kTK][kTM + 1];
   __shared__ float Bs[kTK][kTN + 1];
+  if (ep.dropout_p > 0.0f) resolve_rng(ep);
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int64_t m0 = (int64_t)blockIdx.y * kTM, n0 = (int64_t)blockIdx.x * kTN;
   float acc[4][4] = {};
@@ -99,7 +100,7 @@ static int gemm_nt_simt_typed(const llp_gemm_nt_args& a, cudaStream_t stream) {
   StridedOperand a1{a.A1, a.lda1, 1, a.K1}, b1{a.B1, a.ldb1, 1, a.K1};
   StridedOperand a2{a.A2, a.lda2, 1, a.K2}, b2{a.B2, a.ldb2, 1, a.K2};
   if (a.A2 == nullptr || a.K2 == 0) a2.p = b2.p = nullptr;
-  EpilogueParams ep{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset};
+  EpilogueParams ep{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   dim3 grid((unsigned)ceil_div(a.N, kTN), (unsigned)ceil_div(a.M, kTM), 1);
   gemm_simt_kernel<T, TO, false><<<grid, kSimtThreads, 0, stream>>>(a.M, a.N, a1, b1, a2, b2, 0, ep,
                                                                   reinterpret_cast<TO*>(a.D), a.ldd, nullptr);

@@ -335,6 +335,8 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
     }
   } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    TcParams pe = p;                      // thread-local copy: the dropout stream is resolved once (device rng_state)
+    if (pe.ep.dropout_p > 0.0f) resolve_rng(pe.ep);
     const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
     constexpr int kColsPerWarp = BLOCK_N / 2;
@@ -353,9 +355,9 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         if constexpr (!kTN) {
-          if (p.ep.dropout_p == 0.5f && (uint32_t)((n0 + c0) >> 7) != rnd_group) {
+          if (pe.ep.dropout_p == 0.5f && (uint32_t)((n0 + c0) >> 7) != rnd_group) {
             rnd_group = (uint32_t)((n0 + c0) >> 7);
-            rnd128 = philox4x32_10(p.ep.seed, (uint64_t)m, p.ep.offset + (uint64_t)rnd_group);
+            rnd128 = philox4x32_10(pe.ep.seed, (uint64_t)m, pe.ep.offset + (uint64_t)rnd_group);
           }
         }
         uint32_t r[32];
@@ -372,7 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
                 if (n0 + c0 + j < p.N) dst[j] = __uint_as_float(r[j]);
             }
           } else {
-            epilogue_chunk<TO>(r, m, n0 + c0, p, rnd128);
+            epilogue_chunk<TO>(r, m, n0 + c0, pe, rnd128);
           }
         }
       }
@@ -459,7 +461,7 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   }
   TcParams p{};
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
-  p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset};
+  p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
   {
     const size_t so = a.out_dtype == LLP_BF16 ? 2 : 4;

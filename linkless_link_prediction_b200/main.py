@@ -83,6 +83,7 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
     node_loader = shuffled_batches(data.x.size(0), args.node_batch_size * world)
     for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size * world):
         optimizer.zero_grad()
+        ops.advance_rng(dev)
         node_perm = next(node_loader).to(dev)
         h = model(data.x)
         edge = pos_train_edge[link_perm.to(dev)].t()
@@ -160,6 +161,7 @@ def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, 
     node_loader = shuffled_batches(x.size(0), args.node_batch_size)
     for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size):
         optimizer.zero_grad()
+        ops.advance_rng(device)
         node_perm = next(node_loader).to(device)
         edge = pos_train_edge[link_perm.to(device)].t()
         if args.datasets != "collab":

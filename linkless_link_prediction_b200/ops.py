@@ -91,7 +91,7 @@ def to_compute(x: torch.Tensor, cache: bool = False) -> torch.Tensor:
 
 
 def gemm_nt(A1, B1, A2=None, B2=None, bias=None, addend=None, gate=None, gate_scale=1.0, relu=False, dropout_p=0.0,
-            seed=0, offset=0, out_dtype=None, backend=N.GEMM_AUTO) -> torch.Tensor:
+            seed=0, offset=0, out_dtype=None, backend=N.GEMM_AUTO, rng_state=None) -> torch.Tensor:
     """D = epi(A1 @ B1.T [+ A2 @ B2.T]) — F.linear and the fused lin_l+lin_r of SAGEConv
     (models.py:48,143; sageconv_updated.py:71,76)."""
     lib = N.require_gpu()
@@ -114,6 +114,7 @@ def gemm_nt(A1, B1, A2=None, B2=None, bias=None, addend=None, gate=None, gate_sc
     if gate is not None:
         a.gate, a.ldgate = N.mat(gate)
     a.gate_scale, a.dropout_p, a.seed, a.offset = float(gate_scale), float(dropout_p), int(seed), int(offset)
+    a.rng_state = N.ptr(rng_state)
     a.D, a.ldd = N.mat(D)
     N.check(lib.llp_gemm_nt(ctypes.byref(a), N.stream_ptr()), "llp_gemm_nt")
     return D
@@ -210,7 +211,10 @@ class Graph:
         op, ldo = N.mat(out)
         prof = SPMM_PROFILE
         if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # inside a stream capture the events become event-record NODES (external=True), re-recorded by every replay
+            ext = torch.cuda.is_current_stream_capturing()
+            ev0 = torch.cuda.Event(enable_timing=True, external=ext)
+            ev1 = torch.cuda.Event(enable_timing=True, external=ext)
             ev0.record()
         if not transpose:
             rc = lib.llp_spmm(N.dtype_id(x.dtype), self.rowptr.data_ptr(), self.col.data_ptr(), self.plan.data_ptr(), Nn, E,
@@ -249,11 +253,41 @@ def graph_of(edge_index: torch.Tensor, num_nodes: int) -> Graph:
 
 
 # --------------------------------------------------------------------------------------------
-# dropout RNG: (seed, offset) pairs drawn from torch's CPU generator so seed_everything() controls them
+# dropout RNG.  The mask of a dropout site is Philox(key = seed ^ state[0], counter = (row, (state[1] << 32) + (site << 20)
+# + column group)).  ``state`` = {seed, step} lives on the DEVICE and ``advance_rng()`` (one tiny launch per training
+# step) bumps the step, so a CUDA graph that captured the launches draws a fresh mask at every replay; ``site`` is a
+# host-side counter that distinguishes the dropout layers of one step.
 # --------------------------------------------------------------------------------------------
+_RNG_STATE: Dict[int, torch.Tensor] = {}
+_SITE = [0]
+
+
+def rng_state(device) -> torch.Tensor:
+    idx = torch.device(device).index or 0
+    st = _RNG_STATE.get(idx)
+    if st is None:
+        st = torch.zeros(2, dtype=torch.int64, device=device)
+        st[0] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        _RNG_STATE[idx] = st
+    return st
+
+
+def seed_dropout(seed: int) -> None:
+    """Re-key every device's dropout stream (called by ``shims.seed_everything``) and restart the site counter."""
+    _SITE[0] = 0
+    for st in _RNG_STATE.values():
+        st.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def advance_rng(device) -> None:
+    lib = N.require_gpu()
+    N.check(lib.llp_rng_advance(rng_state(device).data_ptr(), N.stream_ptr()), "llp_rng_advance")
+
+
 def _dropout_seed() -> Tuple[int, int]:
-    s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
-    return int(s[0]), int(s[1]) & 0xFFFFFFFF
+    """(seed, site) of the next dropout layer; the seed part is 0 (the key comes from the device state)."""
+    _SITE[0] = (_SITE[0] + 1) % 4096
+    return 0, _SITE[0]
 
 
 def _weights(W: torch.Tensor) -> torch.Tensor:
@@ -285,7 +319,8 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
-        y = gemm_nt(x, _weights(W), bias=b, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        y = gemm_nt(x, _weights(W), bias=b, relu=relu, dropout_p=p, seed=seed, offset=offset,
+                    rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, W, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.cfg = (p, b is not None, in_gate, defer_gate)
         return y
@@ -310,7 +345,8 @@ class SageConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
         agg = graph.spmm(x)
-        y = gemm_nt(agg, _weights(Wl), x, _weights(Wr), bias=bl, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        y = gemm_nt(agg, _weights(Wl), x, _weights(Wr), bias=bl, relu=relu, dropout_p=p, seed=seed, offset=offset,
+                    rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, agg, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
         return y
@@ -338,7 +374,8 @@ class SageConvUpdatedFn(torch.autograd.Function):
     def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
         t = gemm_nt(x, _weights(Wl), bias=bl)
         agg = graph.spmm(t)
-        y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset)
+        y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset,
+                    rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
         return y

@@ -41,6 +41,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.data = view
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self._step = 0
+        self._dev_step = torch.zeros(1, dtype=torch.int64, device=dev)  # the step counter the kernel uses (graph safe)
         self.process_group = process_group
         self.distributed = distributed  # False: never all-reduce (single-rank reference runs inside a DP job)
         lib = N.load()
@@ -50,6 +51,7 @@ class FusedAdam(torch.optim.Optimizer):
     def reset_state(self) -> None:
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
+        self._dev_step.zero_()
         self._step = 0
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # grads stay views of the flat bucket
@@ -94,6 +96,7 @@ class FusedAdam(torch.optim.Optimizer):
         N.check(lib.llp_clip_adam(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
                                   self.exp_avg_sq.data_ptr(), self.flat_param.numel(), arr, len(bounds) - 1, float(max_norm),
                                   grad_scale, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                  self._step, None, self.group_norms.data_ptr(), self._ws.data_ptr(), N.stream_ptr()),
+                                  self._step, self._dev_step.data_ptr(), None, self.group_norms.data_ptr(), self._ws.data_ptr(),
+                                  N.stream_ptr()),
                 "llp_clip_adam")
         return None

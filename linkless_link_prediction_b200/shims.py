@@ -25,6 +25,7 @@ def seed_everything(seed: int) -> None:
     torch.manual_seed(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(seed)
+    ops.seed_dropout(seed)
 
 
 class Data:

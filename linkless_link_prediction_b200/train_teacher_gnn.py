@@ -60,6 +60,7 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     and negatives ``neg_edge`` (both ``[2,B]`` device LongTensors): full-graph encoder forward, fused edge scoring,
     BCE, backward, separate clipping of model / predictor, Adam.  Returns the (device) loss tensor."""
     optimizer.zero_grad()
+    ops.advance_rng(data.x.device)  # new dropout masks for this step (device-side counter: CUDA-graph safe)
     if encoder_name == 'mlp':
         h = model(data.x)
     elif transductive == "transductive":
@@ -74,6 +75,81 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     loss.backward()
     optimizer_tail(model, predictor, optimizer)
     return loss.detach()
+
+
+USE_CUDA_GRAPH = True   # replay whole training steps as one CUDA graph once their shapes have been seen twice
+_EAGER_STEPS_BEFORE_CAPTURE = 2
+
+
+class CapturedTrainStep:
+    """``train_step`` for a fixed batch shape as ONE CUDA-graph replay (zero_grad, encoder forward/backward, scoring,
+    BCE, gradient all-reduce, clip, Adam: ~65 launches whose host enqueue time otherwise exceeds their GPU time).
+
+    The first ``_EAGER_STEPS_BEFORE_CAPTURE`` calls run eagerly (they are real optimisation steps and double as the
+    warm-up a capture needs: CSR/plan built, feature cast cached).  The next call captures the step on a side stream and
+    every call from then on copies the batch into static buffers and replays.  Everything that varies between steps
+    lives on the device: the dropout stream (``ops.advance_rng``) and Adam's bias-correction step counter
+    (``llp_clip_adam(device_step=...)``), so replays are ordinary, distinct optimisation steps.  The returned loss is a
+    static tensor that the next replay overwrites."""
+
+    def __init__(self, model, predictor, data, optimizer, encoder_name='sage', transductive='transductive',
+                 loss_weight=1.0, eager_steps=_EAGER_STEPS_BEFORE_CAPTURE, profile_spmm=False):
+        self.model, self.predictor, self.data, self.optimizer = model, predictor, data, optimizer
+        self.encoder_name, self.transductive, self.loss_weight = encoder_name, transductive, loss_weight
+        self.eager_left = int(eager_steps)
+        self.graph = None
+        self.edge = self.neg = self.loss = None
+        self.launches_per_replay = 0
+        self.replays = 0
+        self.profile_spmm = bool(profile_spmm)  # bench.py: event-record nodes around every SpMM launch of the graph
+        self.spmm_events = []
+
+    def _eager(self, edge, neg_edge):
+        return train_step(self.model, self.predictor, self.data, edge, neg_edge, self.optimizer, self.encoder_name,
+                          self.transductive, self.loss_weight)
+
+    def _capture(self, edge, neg_edge):
+        from . import _native as N
+        self.edge, self.neg = edge.clone(), neg_edge.clone()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = N.launch_count()
+        saved_profile = ops.SPMM_PROFILE
+        if self.profile_spmm:
+            ops.SPMM_PROFILE = self.spmm_events = []
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager(self.edge, self.neg)
+        finally:
+            ops.SPMM_PROFILE = saved_profile
+        self.launches_per_replay = N.launch_count() - n0
+
+    def __call__(self, edge, neg_edge):
+        if not (self.model.training and self.predictor.training):
+            raise RuntimeError("CapturedTrainStep replays a training-mode step: call model.train() first")
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            return self._eager(edge, neg_edge)
+        if self.graph is None:
+            self._capture(edge, neg_edge)
+        else:
+            if edge.shape != self.edge.shape or neg_edge.shape != self.neg.shape:
+                raise RuntimeError("CapturedTrainStep: batch shape changed; build a new instance per shape")
+            self.edge.copy_(edge, non_blocking=True)
+            self.neg.copy_(neg_edge, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.loss
+
+
+def _captured_step_for(optimizer, key, make):
+    """Per-optimizer cache of captured steps keyed on the batch shape (a new optimizer = a new run = new graphs)."""
+    cache = optimizer.__dict__.setdefault("_llp_captured_steps", {})
+    step = cache.get(key)
+    if step is None:
+        if len(cache) >= 4:  # full batches + the ragged tail of an epoch; anything beyond that stays eager
+            return None
+        step = cache[key] = make()
+    return step
 
 
 def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_name, dataset, transductive):
@@ -110,7 +186,16 @@ def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_nam
             edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
             # mean over the global batch = average over ranks of (local mean * local share * W)
             weight = (edge.size(1) + neg_edge.size(1)) * world / float(n_global + perm.size(0))
-        loss = train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name, transductive, weight)
+        step = None
+        if USE_CUDA_GRAPH and isinstance(optimizer, FusedAdam):
+            key = (id(model), id(predictor), id(data), tuple(edge.shape), tuple(neg_edge.shape), encoder_name,
+                   transductive, float(weight), ops.compute_dtype())
+            step = _captured_step_for(optimizer, key, lambda: CapturedTrainStep(
+                model, predictor, data, optimizer, encoder_name, transductive, weight))
+        if step is not None:
+            loss = step(edge, neg_edge)
+        else:
+            loss = train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name, transductive, weight)
 
         total_loss += loss * n_global
         total_examples += n_global

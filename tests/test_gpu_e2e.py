@@ -185,7 +185,7 @@ def test_fused_gate_equals_explicit_gate(cuda):
             for m in (c1, c2, lin):
                 m.zero_grad()
             c1.train(); c2.train()
-            seed_all(2)  # identical dropout (seed, offset) draws in both variants
+            ops.seed_dropout(2)  # identical dropout streams (key, step, site ids) in both variants
             h1 = c1(x, ei, _relu=True, _dropout=0.4, _in_gate=0.0, _defer_gate=fused)
             h2 = c2(h1, ei, _relu=True, _dropout=0.4, _in_gate=(1.0 / 0.6) if fused else 0.0, _defer_gate=fused)
             p = ops.ScoreHeadFn.apply(h2, lin.weight, lin.bias, (1.0 / 0.6) if fused else 0.0)
@@ -195,3 +195,58 @@ def test_fused_gate_equals_explicit_gate(cuda):
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
     finally:
         ops.set_compute_dtype(torch.bfloat16)
+
+
+def _teacher_pair(cuda, dropout, seed=0, n=600, f=48, H=64):
+    seed_all(seed)
+    ei = O.synthetic_undirected_graph(n, 2500, seed=5)
+    data = shims.Data(x=torch.randn(n, f), adj_t=ei).to(cuda)
+    model = L.SAGE("c", f, H, H, 2, dropout).to(cuda)
+    pred = L.LinkPredictor("mlp", H, H, 1, 2, dropout).to(cuda)
+    model.train(); pred.train()
+    return data, ei, model, pred
+
+
+def test_captured_step_matches_eager_steps(cuda, mode):
+    """CUDA-graph replays of the training step are the same optimisation steps as eager calls (dropout 0): same
+    losses, same parameters, including Adam's bias correction from the device-side step counter."""
+    batches = None
+    outs = []
+    for captured in (False, True):
+        data, ei, model, pred = _teacher_pair(cuda, 0.0)
+        opt = L.FusedAdam(list(model.parameters()) + list(pred.parameters()), lr=0.01)
+        if batches is None:
+            g = torch.Generator().manual_seed(7)
+            batches = [(ei[:, torch.randint(0, ei.size(1), (512,), generator=g)].to(cuda),
+                        torch.randint(0, 600, (2, 512), generator=g).to(cuda)) for _ in range(7)]
+        step = teacher.CapturedTrainStep(model, pred, data, opt, eager_steps=2) if captured else \
+            (lambda e, n_: teacher.train_step(model, pred, data, e, n_, opt))
+        losses = [float(step(e, n_).item()) for e, n_ in batches]
+        if captured:
+            assert step.graph is not None and step.replays == 5 and step.launches_per_replay > 10
+        outs.append((losses, [p.detach().clone() for p in list(model.parameters()) + list(pred.parameters())]))
+    rt = 1e-5 if mode == torch.float32 else 2e-2
+    np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=rt)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        torch.testing.assert_close(b, a, rtol=1e-3, atol=2e-5 if mode == torch.float32 else 3e-3)
+
+
+def test_captured_step_draws_new_dropout_masks(cuda):
+    """The dropout stream is keyed on a device-side step counter, so every replay of the captured graph sees new
+    masks: with lr = 0 (parameters frozen) and one fixed batch, the per-replay losses must differ from each other,
+    and re-seeding must reproduce the sequence."""
+    data, ei, model, pred = _teacher_pair(cuda, 0.5)
+    opt = L.FusedAdam(list(model.parameters()) + list(pred.parameters()), lr=0.0)
+    e, n_ = ei[:, :512].contiguous().to(cuda), torch.randint(0, 600, (2, 512)).to(cuda)
+    step = teacher.CapturedTrainStep(model, pred, data, opt, eager_steps=1)
+    shims.seed_everything(11)
+    a = [float(step(e, n_).item()) for _ in range(6)]
+    assert step.replays == 5
+    assert len({round(v, 7) for v in a[1:]}) == 5, a
+    ops.seed_dropout(11)
+    b = [float(step(e, n_).item()) for _ in range(5)]
+    # replays 0..4 after re-seeding use device steps 1..5 again -> a[0] was the eager step 1 with other site ids
+    assert len({round(v, 7) for v in b}) == 5
+    ops.seed_dropout(11)
+    c = [float(step(e, n_).item()) for _ in range(5)]
+    np.testing.assert_allclose(b, c, rtol=1e-6)

@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.llp_version() == 100
     assert b"no fallback" in lib.llp_error_string(-4)
     # struct layout must match the C definition (8-byte fields after four ints)
-    assert ctypes.sizeof(N.GemmNtArgs) == 4 * 4 + 8 * 4 + 8 * 8 + 8 + 16 + 16 + 8 + 16 + 16
+    assert ctypes.sizeof(N.GemmNtArgs) == 4 * 4 + 8 * 4 + 8 * 8 + 8 + 16 + 16 + 8 + 16 + 8 + 16
 
 
 def test_no_cpu_fallback():
