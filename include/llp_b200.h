@@ -119,6 +119,16 @@ int llp_gemm_tn(int dtype, int backend, int64_t M, int64_t N1, int64_t N2, const
                 const void* B, int64_t ldb, float* D, int64_t ldd, int accumulate, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Fused weight gradient of one layer, everything the backward of `lin_l(agg) + lin_r(x)` (PyG SAGEConv;
+ * sageconv_updated.py:71-76) or of one nn.Linear (models.py:48,143) needs from the output gradient G[M,N1]:
+ *     dWa[N1,N2a] (+)= G^T A[M,N2a]     dWb[N1,N2b] (+)= G^T B[M,N2b]  (N2b = 0: none)     dbias[N1] (+)= colsum(G)
+ * bf16 with N2a, N2b <= 256: ONE tcgen05 kernel that reads G, A and B once (split over M, deterministic reduce);
+ * otherwise the separate kernels above.  dbias may be NULL.  accumulate != 0 adds into the outputs. */
+size_t llp_wgrad_workspace_bytes(int64_t M, int64_t N1, int64_t N2a, int64_t N2b);
+int llp_wgrad(int dtype, int backend, int64_t M, int64_t N1, const void* G, int64_t ldg, int64_t N2a, const void* A,
+              int64_t lda, float* dWa, int64_t ldwa, int64_t N2b, const void* B, int64_t ldb, float* dWb, int64_t ldwb,
+              float* dbias, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Column sums (bias gradient): out[n] (+)= sum_m A[m,n].  Deterministic. */
 size_t llp_colsum_workspace_bytes(int64_t N);
 int llp_colsum(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, float* out, int accumulate,
@@ -138,10 +148,19 @@ int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ld
 /* z[m,:] = h[u[m],:] * h[v[m],:] */
 int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t feat, const int64_t* u, const int64_t* v,
                       int64_t num_edges, void* z, int64_t ldz, void* stream);
-/* gh[u[m],:] += dz[m,:]*h[v[m],:]; gh[v[m],:] += dz[m,:]*h[u[m],:]   (gh fp32 [N,feat], pre-zeroed) */
-int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t feat, const int64_t* u,
-                          const int64_t* v, int64_t num_edges, const void* dz, int64_t lddz, float* gh,
-                          int64_t ldgh, void* stream);
+/* Incidence plan of an edge batch: the 2*num_edges (node, edge) incidences stably sorted by node.
+ * rowptr[n] = first sorted position of node n (int32[num_nodes+1]); meta[2p], meta[2p+1] = (edge m, OTHER endpoint of m)
+ * of sorted position p (int32[4*num_edges]).  Depends only on u and v: callers run it early / on a side stream. */
+size_t llp_edge_plan_workspace_bytes(int64_t num_edges);
+int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t num_edges, int64_t num_nodes, int32_t* rowptr, int32_t* meta,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the gather: gh[n,:] = sum_{u[m]==n} dz[m,:]*h[v[m],:] + sum_{v[m]==n} dz[m,:]*h[u[m],:] for EVERY node row
+ * n < num_nodes (rows no edge touches are written as zeros), gh in the activation dtype.  Gather-reduce over the plan:
+ * no atomics, bit-reproducible. */
+size_t llp_edge_hadamard_bwd_workspace_bytes(int64_t num_edges);
+int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t feat, int64_t num_edges, const void* dz,
+                          int64_t lddz, int64_t num_nodes, const int32_t* rowptr, const int32_t* meta, void* gh,
+                          int64_t ldgh, void* workspace, size_t workspace_bytes, void* stream);
 /* Final predictor layer with one output: logit[m] = y[m,:].w + b ; p = sigmoid(logit).
  * (models.py:146,150 with out_channels == 1.) */
 int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w, const float* b,

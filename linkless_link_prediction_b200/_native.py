@@ -58,6 +58,9 @@ PROTOTYPES = {
     "llp_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "llp_gemm_tn": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                             c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "llp_wgrad_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    "llp_wgrad": (c_int, [c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                          c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "llp_colsum_workspace_bytes": (c_size_t, [c_int64]),
     "llp_colsum": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "llp_cast2d": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
@@ -65,8 +68,11 @@ PROTOTYPES = {
                          c_void_p]),
     "llp_edge_hadamard": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                   c_void_p]),
-    "llp_edge_hadamard_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
-                                      c_void_p, c_int64, c_void_p]),
+    "llp_edge_plan_workspace_bytes": (c_size_t, [c_int64]),
+    "llp_edge_plan": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "llp_edge_hadamard_bwd_workspace_bytes": (c_size_t, [c_int64]),
+    "llp_edge_hadamard_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "llp_score_head": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_score_head_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_score_head_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float,

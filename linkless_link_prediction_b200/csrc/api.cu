@@ -4,6 +4,7 @@
 namespace llp {
 
 std::atomic<int64_t> g_launch_count{0};
+int g_tuning[32] = {0};
 
 int check_device() {
   static thread_local int cached_dev = -1;

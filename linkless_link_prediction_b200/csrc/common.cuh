@@ -192,6 +192,8 @@ __device__ __forceinline__ float epilogue_apply(float acc, int64_t m, int64_t n,
   return acc;
 }
 
+extern int g_tuning[32];  // experiment knobs (llp_set_tuning), 0 = default
+
 int check_device();  // 0 if the current device is sm_100, LLP_E_DEVICE otherwise (cached)
 
 // Deterministic reduction helpers implemented in loss.cu

@@ -1,5 +1,6 @@
 // Edge scoring kernels: gather-Hadamard z = h[u]*h[v] (train_teacher_gnn.py:58,97; main.py:186,214;
-// models.py:140), its scatter backward, and the 1-output predictor head + sigmoid (models.py:146,150).
+// models.py:140) and the 1-output predictor head + sigmoid (models.py:146,150).  The backward of the gather is in
+// edge_bwd.cu.
 #include "common.cuh"
 
 namespace llp {
@@ -27,43 +28,6 @@ edge_hadamard_kernel(const T* __restrict__ h, int64_t ldh, int64_t F, const int6
     }
   } else {
     for (int64_t c = lane; c < F; c += 32) zr[c] = from_f32<T>(to_f32(hu[c]) * to_f32(hv[c]));
-  }
-}
-
-// gh[u] += dz*h[v]; gh[v] += dz*h[u]  — fp32 vector reductions into L2 (red.global.add.v4.f32)
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(256)
-edge_hadamard_bwd_kernel(const T* __restrict__ h, int64_t ldh, int64_t F, const int64_t* __restrict__ u,
-                         const int64_t* __restrict__ v, int64_t M, const T* __restrict__ dz, int64_t lddz,
-                         float* __restrict__ gh, int64_t ldgh) {
-  int lane = threadIdx.x & 31;
-  int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (m >= M) return;
-  int64_t um = u[m], vm = v[m];
-  const T* hu = h + um * ldh;
-  const T* hv = h + vm * ldh;
-  const T* dr = dz + m * lddz;
-  float* gu = gh + um * ldgh;
-  float* gv = gh + vm * ldgh;
-  if constexpr (kVec) {
-    constexpr int VE = Vec16<T>::n;
-    for (int64_t c = lane * VE; c < F; c += 32 * VE) {
-      float a[VE], b[VE], d[VE];
-      unpack16(ldg_v4(hu + c), a, T());
-      unpack16(ldg_v4(hv + c), b, T());
-      unpack16(ldg_v4(dr + c), d, T());
-#pragma unroll
-      for (int i = 0; i < VE; i += 4) {
-        atomicAdd(reinterpret_cast<float4*>(gu + c + i), make_float4(d[i] * b[i], d[i + 1] * b[i + 1], d[i + 2] * b[i + 2], d[i + 3] * b[i + 3]));
-        atomicAdd(reinterpret_cast<float4*>(gv + c + i), make_float4(d[i] * a[i], d[i + 1] * a[i + 1], d[i + 2] * a[i + 2], d[i + 3] * a[i + 3]));
-      }
-    }
-  } else {
-    for (int64_t c = lane; c < F; c += 32) {
-      float d = to_f32(dr[c]);
-      atomicAdd(gu + c, d * to_f32(hv[c]));
-      atomicAdd(gv + c, d * to_f32(hu[c]));
-    }
   }
 }
 
@@ -123,19 +87,6 @@ static int hadamard_launch(const void* h, int64_t ldh, int64_t F, const int64_t*
   return 0;
 }
 
-template <typename T>
-static int hadamard_bwd_launch(const void* h, int64_t ldh, int64_t F, const int64_t* u, const int64_t* v, int64_t M,
-                               const void* dz, int64_t lddz, float* gh, int64_t ldgh, cudaStream_t stream) {
-  unsigned blocks = (unsigned)ceil_div(M * 32, 256);
-  bool vec = rows_vec_ok<T>(h, ldh, F) && rows_vec_ok<T>(dz, lddz, F) && aligned(gh, 16) && (ldgh % 4) == 0;
-  if (vec)
-    edge_hadamard_bwd_kernel<T, true><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (const T*)dz, lddz, gh, ldgh);
-  else
-    edge_hadamard_bwd_kernel<T, false><<<blocks, 256, 0, stream>>>((const T*)h, ldh, F, u, v, M, (const T*)dz, lddz, gh, ldgh);
-  LLP_LAUNCH_OK();
-  return 0;
-}
-
 int colreduce(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, const float* w, float* out, int accumulate,
               float* partial, cudaStream_t stream);
 size_t colreduce_workspace_bytes(int64_t N);
@@ -152,18 +103,6 @@ extern "C" int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t 
   LLP_CHECK_ARG(h && u && v && z && ldh >= F && ldz >= F);
   if (dtype == LLP_F32) return hadamard_launch<float>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
   if (dtype == LLP_BF16) return hadamard_launch<__nv_bfloat16>(h, ldh, F, u, v, M, z, ldz, (cudaStream_t)stream_);
-  return LLP_E_BADARG;
-}
-
-extern "C" int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t F, const int64_t* u,
-                                     const int64_t* v, int64_t M, const void* dz, int64_t lddz, float* gh, int64_t ldgh,
-                                     void* stream_) {
-  LLP_CHECK_ARG(F > 0 && M >= 0);
-  if (int rc = check_device()) return rc;
-  if (M == 0) return 0;
-  LLP_CHECK_ARG(h && u && v && dz && gh && ldh >= F && lddz >= F && ldgh >= F);
-  if (dtype == LLP_F32) return hadamard_bwd_launch<float>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
-  if (dtype == LLP_BF16) return hadamard_bwd_launch<__nv_bfloat16>(h, ldh, F, u, v, M, dz, lddz, gh, ldgh, (cudaStream_t)stream_);
   return LLP_E_BADARG;
 }
 

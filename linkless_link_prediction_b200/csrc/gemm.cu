@@ -12,6 +12,15 @@ int gemm_tn_tcgen05(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t ld
 int tn_splits(int64_t M, int64_t N1, int64_t N2);
 void tn_split_plan(int64_t M, int64_t N1, int64_t N2, int* splits, int64_t* k_per_split);
 
+bool wgrad_tcgen05_supported(int64_t M, int64_t N1, int64_t n2a, int64_t n2b);
+size_t wgrad_tcgen05_workspace_bytes(int64_t M, int64_t N1, int64_t n2a, int64_t n2b);
+int wgrad_tcgen05(int64_t M, int64_t N1, const void* G, int64_t ldg, int64_t n2a, const void* A, int64_t lda, float* dWa,
+                  int64_t ldwa, int64_t n2b, const void* B, int64_t ldb, float* dWb, int64_t ldwb, float* dbias,
+                  int accumulate, float* ws, cudaStream_t stream);
+size_t colreduce_workspace_bytes(int64_t N);
+int colreduce(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, const float* w, float* out, int accumulate,
+              float* partial, cudaStream_t stream);
+
 static bool tma_ok(const void* p, int64_t ld) { return p != nullptr && aligned(p, 16) && (ld * 2) % 16 == 0; }
 }  // namespace llp
 
@@ -64,4 +73,52 @@ extern "C" int llp_gemm_tn(int dtype, int backend, int64_t M, int64_t N1, int64_
   if (backend == LLP_GEMM_SIMT)
     return gemm_tn_simt(dtype, M, N1, N2, A, lda, B, ldb, D, ldd, accumulate, reinterpret_cast<float*>(workspace), stream);
   return LLP_E_BADARG;
+}
+
+// ---- fused weight gradient of one layer ------------------------------------------------------------
+extern "C" size_t llp_wgrad_workspace_bytes(int64_t M, int64_t N1, int64_t N2a, int64_t N2b) {
+  if (M <= 0 || N1 <= 0 || N2a <= 0 || N2b < 0) return 256;
+  size_t fused = wgrad_tcgen05_supported(M, N1, N2a, N2b) ? wgrad_tcgen05_workspace_bytes(M, N1, N2a, N2b) : 0;
+  size_t sep = llp_gemm_tn_workspace_bytes(M, N1, N2a);
+  if (N2b > 0) {
+    size_t t = llp_gemm_tn_workspace_bytes(M, N1, N2b);
+    sep = t > sep ? t : sep;
+  }
+  size_t cs = colreduce_workspace_bytes(N1);
+  sep = cs > sep ? cs : sep;
+  return fused > sep ? fused : sep;
+}
+
+extern "C" int llp_wgrad(int dtype, int backend, int64_t M, int64_t N1, const void* G, int64_t ldg, int64_t N2a,
+                         const void* A, int64_t lda, float* dWa, int64_t ldwa, int64_t N2b, const void* B, int64_t ldb,
+                         float* dWb, int64_t ldwb, float* dbias, int accumulate, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(G && A && dWa && workspace && M > 0 && N1 > 0 && N2a > 0 && N2b >= 0);
+  LLP_CHECK_ARG(ldg >= N1 && lda >= N2a && ldwa >= N2a);
+  LLP_CHECK_ARG(N2b == 0 || (B && dWb && ldb >= N2b && ldwb >= N2b));
+  if (workspace_bytes < llp_wgrad_workspace_bytes(M, N1, N2a, N2b)) return LLP_E_WORKSPACE;
+  if (int rc = check_device()) return rc;
+  float* ws = reinterpret_cast<float*>(workspace);
+  if (backend == LLP_GEMM_AUTO) {
+    const bool ok = dtype == LLP_BF16 && wgrad_tcgen05_supported(M, N1, N2a, N2b) && tma_ok(G, ldg) && tma_ok(A, lda) &&
+                    (N2b == 0 || tma_ok(B, ldb));
+    backend = ok ? LLP_GEMM_TCGEN05 : LLP_GEMM_SIMT;
+  }
+  if (backend == LLP_GEMM_TCGEN05) {
+    if (dtype != LLP_BF16 || !wgrad_tcgen05_supported(M, N1, N2a, N2b)) return LLP_E_SHAPE;
+    return wgrad_tcgen05(M, N1, G, ldg, N2a, A, lda, dWa, ldwa, N2b, B, ldb, dWb, ldwb, dbias, accumulate, ws, stream);
+  }
+  if (backend != LLP_GEMM_SIMT) return LLP_E_BADARG;
+  // separate launches: fp32-parity mode (CUDA-core GEMMs) and shapes the fused kernel does not take (N2 > 256)
+  const bool tc = dtype == LLP_BF16 && tma_ok(G, ldg);
+  auto one = [&](const void* X, int64_t ldx, int64_t n2, float* dW, int64_t ldw) -> int {
+    if (tc && tma_ok(X, ldx)) return gemm_tn_tcgen05(M, N1, n2, G, ldg, X, ldx, dW, ldw, accumulate, ws, stream);
+    return gemm_tn_simt(dtype, M, N1, n2, G, ldg, X, ldx, dW, ldw, accumulate, ws, stream);
+  };
+  if (int rc = one(A, lda, N2a, dWa, ldwa)) return rc;
+  if (N2b > 0)
+    if (int rc = one(B, ldb, N2b, dWb, ldwb)) return rc;
+  if (dbias != nullptr) return colreduce(dtype, G, ldg, M, N1, nullptr, dbias, accumulate, ws, stream);
+  return 0;
 }

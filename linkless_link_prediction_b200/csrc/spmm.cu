@@ -400,6 +400,7 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
 using namespace llp;
 
 extern "C" void llp_set_tuning(int key, int value) {
+  if (key >= 0 && key < 32) g_tuning[key] = value;
   if (key == 0) g_spmm_variant = value;
   if (key == 1) g_spmm_chunk_div = value < 1 ? 1 : value;
   if (key == 2) g_spmm_fake_seq = value;

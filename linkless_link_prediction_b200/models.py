@@ -125,10 +125,11 @@ class LinkPredictor(nn.Module):
         out = self._head(z)
         return out.reshape(*lead, 1) if self.predictor == "mlp" else out.reshape(*lead)
 
-    def score(self, h, u, v):
+    def score(self, h, u, v, plan=None):
         """Fused path used by the step functions: scores of the edges ``(u[m], v[m])`` straight from the node
-        embedding matrix ``h`` — same value as ``forward(h[u], h[v])`` without materialising the gathers."""
+        embedding matrix ``h`` — same value as ``forward(h[u], h[v])`` without materialising the gathers.
+        ``plan``: optional ``ops.EdgePlan`` of (u, v) built ahead of time for the backward."""
         lead = u.shape
-        z = ops.HadamardFn.apply(ops.to_compute(h), u.reshape(-1).contiguous(), v.reshape(-1).contiguous())
+        z = ops.HadamardFn.apply(ops.to_compute(h), u.reshape(-1).contiguous(), v.reshape(-1).contiguous(), plan)
         out = self._head(z)
         return out.reshape(*lead, 1) if self.predictor == "mlp" else out.reshape(*lead)

@@ -135,6 +135,55 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, backend=N.GEMM_AUTO) -> torch.Tens
     return D
 
 
+FUSE_GRAD_ACCUMULATION = True  # weight gradients are added straight into existing fp32 ``.grad`` buffers (FusedAdam's flat
+# bucket) by the kernel's split reduce instead of being returned to autograd and added by a separate launch each
+
+
+def _grad_target(P):
+    if not FUSE_GRAD_ACCUMULATION or P is None:
+        return None
+    g = P.grad
+    if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
+        return None
+    return g
+
+
+def wgrad(g: torch.Tensor, a: torch.Tensor, Wa, b: Optional[torch.Tensor] = None, Wb=None, bias=None,
+          backend=N.GEMM_AUTO):
+    """Weight gradients of one layer from its output gradient ``g [M,N1]`` in one pass (``llp_wgrad``):
+    ``dWa = g^T a``, ``dWb = g^T b`` (optional), ``dbias = colsum(g)`` (optional).  ``Wa / Wb / bias`` are the parameters
+    (or None when that gradient is not wanted).  Returns ``(dWa, dWb, dbias)``; an entry is None when the gradient was
+    accumulated directly into the parameter's ``.grad`` (see FUSE_GRAD_ACCUMULATION) or was not wanted."""
+    lib = N.require_gpu()
+    if Wa is None:  # only the second operand / bias wanted: degenerate, use the separate kernels
+        return (None, gemm_tn(g, b) if Wb is not None else None, colsum(g) if bias is not None else None)
+    M, N1 = g.shape
+    n2a = a.shape[1]
+    n2b = b.shape[1] if (b is not None and Wb is not None) else 0
+    wanted = [Wa] + ([Wb] if n2b else []) + ([bias] if bias is not None else [])
+    targets = [_grad_target(P) for P in wanted]
+    direct = all(t is not None for t in targets)
+    dev = g.device
+    if direct:
+        dWa = Wa.grad
+        dWb = Wb.grad if n2b else None
+        db = bias.grad if bias is not None else None
+    else:
+        dWa = torch.empty((N1, n2a), dtype=torch.float32, device=dev)
+        dWb = torch.empty((N1, n2b), dtype=torch.float32, device=dev) if n2b else None
+        db = torch.empty(N1, dtype=torch.float32, device=dev) if bias is not None else None
+    nbytes = lib.llp_wgrad_workspace_bytes(M, N1, n2a, n2b)
+    ws = _ws(nbytes, dev)
+    gp, ldg = N.mat(g)
+    ap, lda = N.mat(a)
+    bp, ldb = N.mat(b) if n2b else (None, 0)
+    N.check(lib.llp_wgrad(N.dtype_id(g.dtype), backend, M, N1, gp, ldg, n2a, ap, lda, dWa.data_ptr(), n2a, n2b, bp, ldb,
+                          N.ptr(dWb), n2b, N.ptr(db), int(direct), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_wgrad")
+    if direct:
+        return None, None, None
+    return dWa, dWb, db
+
+
 def colsum(A: torch.Tensor) -> torch.Tensor:
     lib = N.require_gpu()
     M, Nn = A.shape
@@ -323,15 +372,17 @@ class LinearFn(torch.autograd.Function):
                     rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, W, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.cfg = (p, b is not None, in_gate, defer_gate)
+        ctx.params = (W, b)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, W, y = ctx.saved_tensors
         p, has_b, in_gate, defer_gate = ctx.cfg
+        Wp, bp = ctx.params
         g = _own_gate(to_compute(gy), y, p, defer_gate)
-        gW = gemm_tn(g, x) if ctx.needs_input_grad[1] else None
-        gb = colsum(g) if (has_b and ctx.needs_input_grad[2]) else None
+        gW, _, gb = wgrad(g, x, Wp if ctx.needs_input_grad[1] else None,
+                          bias=bp if (has_b and ctx.needs_input_grad[2]) else None)
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_nt(g, _weights_t(W), gate=x if in_gate > 0 else None, gate_scale=in_gate)
@@ -349,16 +400,21 @@ class SageConvFn(torch.autograd.Function):
                     rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, agg, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
+        ctx.params = (Wl, bl, Wr)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, agg, Wl, Wr, y = ctx.saved_tensors
         p, in_gate, defer_gate = ctx.cfg
+        Pl, Pb, Pr = ctx.params
         g = _own_gate(to_compute(gy), y, p, defer_gate)
-        gWl = gemm_tn(g, agg) if ctx.needs_input_grad[1] else None
-        gbl = colsum(g) if ctx.needs_input_grad[2] else None
-        gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
+        need = ctx.needs_input_grad
+        if need[1]:  # one pass over g, agg and x: dW_l, dW_r and db_l
+            gWl, gWr, gbl = wgrad(g, agg, Pl, x, Pr if need[3] else None, bias=Pb if need[2] else None)
+        else:
+            gWl, gWr, gbl = wgrad(g, x, Pr if need[3] else None, bias=Pb if need[2] else None)
+            gWl, gWr = None, gWl
         gx = None
         if ctx.needs_input_grad[0]:
             # A~^T (g W_l) = (A~^T g) W_l : aggregate first, then one dual GEMM writes gx with no add kernel
@@ -378,29 +434,88 @@ class SageConvUpdatedFn(torch.autograd.Function):
                     rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
+        ctx.params = (Wl, bl, Wr)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, Wl, Wr, y = ctx.saved_tensors
         p, in_gate, defer_gate = ctx.cfg
+        Pl, Pb, Pr = ctx.params
         g = _own_gate(to_compute(gy), y, p, defer_gate)
         gt = ctx.graph.spmm(g, transpose=True)
-        gWl = gemm_tn(gt, x) if ctx.needs_input_grad[1] else None
-        gbl = colsum(gt) if ctx.needs_input_grad[2] else None
-        gWr = gemm_tn(g, x) if ctx.needs_input_grad[3] else None
+        need = ctx.needs_input_grad
+        gWl, _, gbl = wgrad(gt, x, Pl if need[1] else None, bias=Pb if need[2] else None)
+        gWr = wgrad(g, x, Pr)[0] if need[3] else None
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
         return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    idx = torch.device(device).index or 0
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
+class EdgePlan:
+    """Incidence plan of one edge batch ``(u[m], v[m])``: the 2M (node, edge) incidences stably sorted by node, which
+    turns the backward of the gathers ``h[u] * h[v]`` (PyTorch: ``index_put_`` with atomics) into an atomic-free
+    gather-reduce.  It depends only on ``u`` and ``v``, so with ``side_stream=True`` the sort runs on a second stream
+    (a parallel branch of a captured CUDA graph) while the encoder works; ``wait()`` joins it back."""
+
+    def __init__(self, u: torch.Tensor, v: torch.Tensor, num_nodes: int, side_stream: bool = False):
+        lib = N.require_gpu()
+        if u.dtype != torch.int64 or v.dtype != torch.int64 or not u.is_cuda or not v.is_cuda:
+            raise RuntimeError("edge endpoints must be CUDA LongTensors (no CPU fallback)")
+        self.u, self.v = u.reshape(-1).contiguous(), v.reshape(-1).contiguous()
+        self.num_edges, self.num_nodes = int(self.u.numel()), int(num_nodes)
+        dev = u.device
+        self.rowptr = torch.empty(self.num_nodes + 1, dtype=torch.int32, device=dev)
+        self.meta = torch.empty(max(4 * self.num_edges, 2), dtype=torch.int32, device=dev)
+        nbytes = lib.llp_edge_plan_workspace_bytes(self.num_edges)
+        self._ws = _ws(nbytes, dev)   # kept alive until the plan dies (the side stream may still be using it)
+        self._event = None
+
+        def launch(stream_ptr):
+            N.check(lib.llp_edge_plan(self.u.data_ptr(), self.v.data_ptr(), self.num_edges, self.num_nodes,
+                                      self.rowptr.data_ptr(), self.meta.data_ptr(), self._ws.data_ptr(), nbytes, stream_ptr),
+                    "llp_edge_plan")
+
+        if side_stream:
+            cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                launch(side.cuda_stream)
+                self._event = torch.cuda.Event()
+                self._event.record(side)
+        else:
+            launch(N.stream_ptr())
+
+    def matches(self, u: torch.Tensor, v: torch.Tensor, num_nodes: int) -> bool:
+        return self.num_edges == u.numel() and self.num_nodes == num_nodes and self.u.data_ptr() == u.data_ptr() \
+            and self.v.data_ptr() == v.data_ptr()
+
+    def wait(self) -> None:
+        """Make the current stream wait for the plan (joins the side branch)."""
+        if self._event is not None:
+            torch.cuda.current_stream(self.rowptr.device).wait_event(self._event)
+            self._event = None
+
+
 class HadamardFn(torch.autograd.Function):
     """z[m] = h[u[m]] * h[v[m]] — the two fancy-index gathers + mul in front of LinkPredictor
-    (train_teacher_gnn.py:58; main.py:186,214; models.py:140)."""
+    (train_teacher_gnn.py:58; main.py:186,214; models.py:140).  ``plan``: an ``EdgePlan`` of (u, v) built ahead of time
+    (optional; built here when the backward will need one)."""
 
     @staticmethod
-    def forward(ctx, h, u, v):
+    def forward(ctx, h, u, v, plan=None):
         lib = N.require_gpu()
         M, F = u.numel(), h.size(1)
         z = empty_mat(M, F, h.dtype, h.device)
@@ -408,22 +523,31 @@ class HadamardFn(torch.autograd.Function):
         zp, ldz = N.mat(z)
         N.check(lib.llp_edge_hadamard(N.dtype_id(h.dtype), hp, ldh, F, u.data_ptr(), v.data_ptr(), M, zp, ldz,
                                       N.stream_ptr()), "llp_edge_hadamard")
-        ctx.save_for_backward(h, u, v)
+        if ctx.needs_input_grad[0]:
+            if plan is None or not plan.matches(u, v, h.size(0)):
+                plan = EdgePlan(u, v, h.size(0))
+            ctx.plan = plan
+        ctx.save_for_backward(h)
         return z
 
     @staticmethod
     def backward(ctx, gz):
         lib = N.require_gpu()
-        h, u, v = ctx.saved_tensors
-        M, F = u.numel(), h.size(1)
+        (h,) = ctx.saved_tensors
+        plan = ctx.plan
+        M, F, Nn = plan.num_edges, h.size(1), h.size(0)
         gz = to_compute(gz) if gz.dtype != h.dtype else gz
-        gh = torch.zeros((h.size(0), _round_up(F, 4)), dtype=torch.float32, device=h.device)
+        gh = empty_mat(Nn, F, h.dtype, h.device)
+        nbytes = lib.llp_edge_hadamard_bwd_workspace_bytes(M)
+        ws = _ws(nbytes, h.device)
         hp, ldh = N.mat(h)
         gp, ldg = N.mat(gz)
-        N.check(lib.llp_edge_hadamard_bwd(N.dtype_id(h.dtype), hp, ldh, F, u.data_ptr(), v.data_ptr(), M, gp, ldg,
-                                          gh.data_ptr(), gh.stride(0), N.stream_ptr()), "llp_edge_hadamard_bwd")
-        gh = gh[:, :F]
-        return (gh if h.dtype == torch.float32 else cast2d(gh, h.dtype)), None, None
+        op, ldo = N.mat(gh)
+        plan.wait()
+        N.check(lib.llp_edge_hadamard_bwd(N.dtype_id(h.dtype), hp, ldh, F, M, gp, ldg, Nn, plan.rowptr.data_ptr(),
+                                          plan.meta.data_ptr(), op, ldo, ws.data_ptr(), nbytes, N.stream_ptr()),
+                "llp_edge_hadamard_bwd")
+        return gh, None, None, None
 
 
 class ScoreHeadFn(torch.autograd.Function):

@@ -61,18 +61,23 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     BCE, backward, separate clipping of model / predictor, Adam.  Returns the (device) loss tensor."""
     optimizer.zero_grad()
     ops.advance_rng(data.x.device)  # new dropout masks for this step (device-side counter: CUDA-graph safe)
+    train_edges = torch.cat((edge, neg_edge), dim=-1)
+    u, v = train_edges[0].contiguous(), train_edges[1].contiguous()
+    # the sort behind the gather backward only needs (u, v): it runs on a side stream under the encoder forward
+    plan = ops.EdgePlan(u, v, data.x.size(0), side_stream=True) if torch.is_grad_enabled() else None
     if encoder_name == 'mlp':
         h = model(data.x)
     elif transductive == "transductive":
         h = model(data.x, data.adj_t)
     else:
         h = model(data.x, data.edge_index)
-    train_edges = torch.cat((edge, neg_edge), dim=-1)
-    out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+    out = predictor.score(h, u, v, plan=plan).reshape(-1)
     loss = ops.bce_loss(out, edge.size(1))
     if loss_weight != 1.0:
         loss = loss * loss_weight
     loss.backward()
+    if plan is not None:
+        plan.wait()  # no-op when the backward consumed it; otherwise re-join the side stream
     optimizer_tail(model, predictor, optimizer)
     return loss.detach()
 

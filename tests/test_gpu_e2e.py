@@ -228,7 +228,7 @@ def test_captured_step_matches_eager_steps(cuda, mode):
     rt = 1e-5 if mode == torch.float32 else 2e-2
     np.testing.assert_allclose(outs[1][0], outs[0][0], rtol=rt)
     for a, b in zip(outs[0][1], outs[1][1]):
-        torch.testing.assert_close(b, a, rtol=1e-3, atol=2e-5 if mode == torch.float32 else 3e-3)
+        torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-4 if mode == torch.float32 else 3e-3)
 
 
 def test_captured_step_draws_new_dropout_masks(cuda):

@@ -154,6 +154,53 @@ def test_gemm_tn(cuda, backend, M, N1, N2):
     torch.testing.assert_close(D, ref, **tol)
 
 
+@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt_fp32", "tcgen05_bf16"])
+@pytest.mark.parametrize("M,N1,n2a,n2b,bias", [(1, 8, 8, 0, True), (77, 64, 128, 128, True), (1000, 256, 256, 256, True),
+                                              (5000, 256, 128, 128, False), (4099, 200, 136, 72, True),
+                                              (30000, 256, 256, 0, True), (3000, 384, 64, 256, True),
+                                              (700, 256, 1440, 0, True)])
+def test_wgrad_fused(cuda, backend, M, N1, n2a, n2b, bias):
+    """llp_wgrad: dWa = G^T A, dWb = G^T B, dbias = colsum(G) in one pass, fresh outputs and accumulation into
+    existing fp32 .grad buffers (autograd of lin_l(agg) + lin_r(x): two mm's and a sum(0))."""
+    dtype = torch.bfloat16 if backend == N.GEMM_TCGEN05 else torch.float32
+    if backend == N.GEMM_TCGEN05 and max(n2a, n2b) > 256:
+        backend = N.GEMM_AUTO  # wider than the fused kernel's TMEM tile: the library takes the separate tcgen05 kernels
+    gen = torch.Generator().manual_seed(M + N1 + n2a)
+    G = torch.randn(M, N1, generator=gen).to(dtype)
+    A = torch.randn(M, n2a, generator=gen).to(dtype)
+    B = torch.randn(M, n2b, generator=gen).to(dtype) if n2b else None
+    Gd, Ad = ops.cast2d(G.to(cuda), dtype), ops.cast2d(A.to(cuda), dtype)
+    Bd = ops.cast2d(B.to(cuda), dtype) if n2b else None
+    Wa = torch.nn.Parameter(torch.zeros(N1, n2a, device=cuda))
+    Wb = torch.nn.Parameter(torch.zeros(N1, n2b, device=cuda)) if n2b else None
+    bp = torch.nn.Parameter(torch.zeros(N1, device=cuda)) if bias else None
+    tol = dict(rtol=1e-5, atol=2e-5 * math.sqrt(M)) if dtype == torch.float32 else dict(rtol=1e-3, atol=1e-3 * math.sqrt(M))
+    ref_a = (G.double().t() @ A.double()).float()
+    ref_b = (G.double().t() @ B.double()).float() if n2b else None
+    ref_bias = G.double().sum(0).float()
+    dWa, dWb, db = ops.wgrad(Gd, Ad, Wa, Bd, Wb, bias=bp, backend=backend)   # no .grad yet: fresh outputs
+    torch.testing.assert_close(dWa.cpu(), ref_a, **tol)
+    if n2b:
+        torch.testing.assert_close(dWb.cpu(), ref_b, **tol)
+    if bias:
+        torch.testing.assert_close(db.cpu(), ref_bias, **tol)
+    Wa.grad = torch.full_like(Wa, 1.0)
+    if n2b:
+        Wb.grad = torch.full_like(Wb, 2.0)
+    if bias:
+        bp.grad = torch.full_like(bp, 3.0)
+    assert ops.wgrad(Gd, Ad, Wa, Bd, Wb, bias=bp, backend=backend) == (None, None, None)  # accumulated in place
+    torch.testing.assert_close(Wa.grad.cpu(), ref_a + 1.0, **tol)
+    if n2b:
+        torch.testing.assert_close(Wb.grad.cpu(), ref_b + 2.0, **tol)
+    if bias:
+        torch.testing.assert_close(bp.grad.cpu(), ref_bias + 3.0, **tol)
+    # deterministic: same bits on a second run
+    Wa.grad = None
+    again = ops.wgrad(Gd, Ad, Wa, Bd, Wb if n2b else None, bias=None, backend=backend)[0]
+    assert torch.equal(again, dWa)
+
+
 def test_tcgen05_matches_simt_on_identical_bf16_inputs(cuda):
     g = torch.Generator().manual_seed(0)
     A, B = torch.randn(777, 320, generator=g).bfloat16().to(cuda), torch.randn(256, 320, generator=g).bfloat16().to(cuda)

@@ -95,6 +95,35 @@ def main():
         for M, N1, N2 in ((n, 256, 256), (n, 256, 128), (131072, 256, 256)):
             A = torch.randn(M, N1, device=dev).bfloat16(); B = torch.randn(M, N2, device=dev).bfloat16()
             report(f"gemm_tn M={M} {N1}x{N2}", timeit(lambda: ops.gemm_tn(A, B)), nbytes=M * (N1 + N2) * 2, flops=2 * M * N1 * N2)
+    if "wgrad" in which or "gemm" in which:
+        for M, N1, n2a, n2b, tag in ((n, 256, 256, 256, "L2/L3"), (n, 256, 128, 128, "L1"), (131072, 256, 256, 0, "predictor")):
+            G = torch.randn(M, N1, device=dev).bfloat16(); A = torch.randn(M, n2a, device=dev).bfloat16()
+            B = torch.randn(M, n2b, device=dev).bfloat16() if n2b else None
+            Wa = torch.nn.Parameter(torch.zeros(N1, n2a, device=dev)); Wa.grad = torch.zeros_like(Wa)
+            Wb = torch.nn.Parameter(torch.zeros(N1, max(n2b, 1), device=dev)); Wb.grad = torch.zeros_like(Wb)
+            bp = torch.nn.Parameter(torch.zeros(N1, device=dev)); bp.grad = torch.zeros_like(bp)
+            us = timeit(lambda: ops.wgrad(G, A, Wa, B, Wb if n2b else None, bias=bp))
+            report(f"wgrad fused M={M} {N1}x({n2a}+{n2b})+bias {tag}", us, nbytes=M * (N1 + n2a + n2b) * 2,
+                   flops=2 * M * N1 * (n2a + n2b))
+    if "wgradexp" in which:
+        lib = N.load()
+        M, N1 = n, 256
+        G = torch.randn(M, N1, device=dev).bfloat16(); A = torch.randn(M, 256, device=dev).bfloat16()
+        B = torch.randn(M, 256, device=dev).bfloat16()
+        Wa = torch.nn.Parameter(torch.zeros(N1, 256, device=dev)); Wa.grad = torch.zeros_like(Wa)
+        Wb = torch.nn.Parameter(torch.zeros(N1, 256, device=dev)); Wb.grad = torch.zeros_like(Wb)
+        bp = torch.nn.Parameter(torch.zeros(N1, device=dev)); bp.grad = torch.zeros_like(bp)
+        nb = M * 768 * 2
+        for tag, knobs, bias in (("default", {}, True), ("no bias warp", {}, False), ("stages=3", {10: 3}, True),
+                                 ("stages=2", {10: 2}, True), ("skip mma", {11: 1}, True), ("skip mma, no bias", {11: 1}, False),
+                                 ("BK=64 (2 stages)", {12: 64}, True), ("BK=64 skip mma no bias", {12: 64, 11: 1}, False),
+                                 ("wide un-swizzled boxes, skip mma, no bias", {13: 1}, False),
+                                 ("wide boxes BK=64", {13: 1, 12: 64}, False)):
+            for k in (10, 11, 12, 13):
+                lib.llp_set_tuning(k, knobs.get(k, 0))
+            report(f"wgrad 256x(256+256) {tag}", timeit(lambda: ops.wgrad(G, A, Wa, B, Wb, bias=bp if bias else None)), nbytes=nb)
+        for k in (10, 11, 12, 13):
+            lib.llp_set_tuning(k, 0)
     if "misc" in which:
         H = 256
         a = torch.randn(n, H, device=dev).bfloat16(); b = torch.randn(n, H, device=dev).bfloat16()
@@ -111,7 +140,14 @@ def main():
             zz = ops.HadamardFn.apply(hh, u, v)
             zz.backward(z)
             hh.grad = None
-        report("edge_hadamard fwd+bwd (atomics + zero + cast)", timeit(hb), nbytes=(3 + 3) * M * H * 2 + n * H * 10)
+        report("edge_hadamard fwd + plan (sort) + gather-reduce bwd", timeit(hb), nbytes=(3 + 3) * M * H * 2 + n * H * 10)
+        plan = ops.EdgePlan(u, v, n)
+        def hb2():
+            zz = ops.HadamardFn.apply(hh, u, v, plan)
+            zz.backward(z)
+            hh.grad = None
+        report("edge_hadamard fwd + gather-reduce bwd (plan prebuilt)", timeit(hb2), nbytes=(3 + 3) * M * H * 2 + n * H * 2)
+        report("edge plan (incidence sort) M=131072", timeit(lambda: ops.EdgePlan(u, v, n)))
         w = torch.randn(1, H, device=dev); bb = torch.randn(1, device=dev)
         report("score_head fwd M=131072", timeit(lambda: ops.ScoreHeadFn.apply(z, w, bb)), nbytes=M * H * 2)
 
