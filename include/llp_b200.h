@@ -52,6 +52,8 @@ int llp_device_supported(void);
 int64_t llp_launch_count(void);
 /* development knob (benchmark sweeps only; results never depend on it): key 0 = SpMM occupancy/register variant */
 void llp_set_tuning(int key, int value);
+/* development aid: copy n (<= 4096) int64 of the instrumentation scratch to the host (synchronises the device) */
+int llp_debug_read(int64_t* host_out, int n);
 
 /* ---------------------------------------------------------------------------------------
  * Graph structure.  Replaces: PyG MessagePassing.__collect__/aggregate over a dense [2,E]

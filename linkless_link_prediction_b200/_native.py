@@ -46,6 +46,7 @@ PROTOTYPES = {
     "llp_device_supported": (c_int, []),
     "llp_launch_count": (c_int64, []),
     "llp_set_tuning": (None, [c_int, c_int]),
+    "llp_debug_read": (c_int, [c_void_p, c_int]),
     "llp_csr_build_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_csr_build": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),

@@ -6,6 +6,15 @@ namespace llp {
 std::atomic<int64_t> g_launch_count{0};
 int g_tuning[32] = {0};
 
+long long* debug_buffer() {
+  static long long* buf = nullptr;
+  if (buf == nullptr) {
+    if (cudaMalloc(&buf, 4096 * sizeof(long long)) != cudaSuccess) { cudaGetLastError(); buf = nullptr; return nullptr; }
+    cudaMemset(buf, 0, 4096 * sizeof(long long));
+  }
+  return buf;
+}
+
 int check_device() {
   static thread_local int cached_dev = -1;
   static thread_local int cached_rc = 0;
@@ -46,4 +55,15 @@ extern "C" const char* llp_error_string(int code) {
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "llp: unknown error";
+}
+
+// development aid: copy the instrumentation scratch (see debug_buffer) to the host; synchronises the device
+extern "C" int llp_debug_read(int64_t* host_out, int n) {
+  if (host_out == nullptr || n < 0 || n > 4096) return LLP_E_BADARG;
+  long long* buf = llp::debug_buffer();
+  if (buf == nullptr) return LLP_E_DEVICE;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemcpy(host_out, buf, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? 0 : (int)e;
 }

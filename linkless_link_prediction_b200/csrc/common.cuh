@@ -103,6 +103,20 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 __device__ __forceinline__ uint4 ldg_v4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg_v4(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per lane and instruction
+struct alignas(32) U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ldg_v8(const void* p) {
+  U32x8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_v8(void* p, const U32x8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -192,7 +206,8 @@ __device__ __forceinline__ float epilogue_apply(float acc, int64_t m, int64_t n,
   return acc;
 }
 
-extern int g_tuning[32];  // experiment knobs (llp_set_tuning), 0 = default
+extern int g_tuning[32];
+long long* debug_buffer();   // lazily allocated device scratch of 4096 int64 for instrumented runs (llp_debug_read)  // experiment knobs (llp_set_tuning), 0 = default
 
 int check_device();  // 0 if the current device is sm_100, LLP_E_DEVICE otherwise (cached)
 

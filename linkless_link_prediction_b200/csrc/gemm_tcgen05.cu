@@ -47,16 +47,35 @@ struct TcParams {
   int ep_flags;          // kVec*: which epilogue operands may be accessed with 128-bit vectors
   void* D; int64_t ldd;
   float* partial;        // TN: [splits][M][N] fp32
+  long long* dbg;        // instrumentation (llp_set_tuning(15, 1)): per CTA {issue loop ns, operand wait ns, accumulator wait ns}
 };
 
 // ---- fused epilogue for one row x 32 columns ------------------------------------------------------------
 // Every option is a warp-uniform branch around fully unrolled register code; bias / addend / gate are read with
 // 128-bit loads when the host verified the alignment (ep_flags), the dropout mask costs one Philox call per 8 columns.
 constexpr int kVecBias = 1, kVecAddend = 2, kVecGate = 4, kVecOut = 8;
+constexpr int kVec32Addend = 16, kVec32Gate = 32, kVec32Out = 64;  // 32-byte alignment: 256-bit accesses
 
+// 32 consecutive elements of a row -> fp32.  wide: 256-bit loads (32-byte aligned rows), vec: 128-bit loads.
 template <typename TO>
-__device__ __forceinline__ void load32(const TO* __restrict__ src, bool vec, int valid, float (&v)[32]) {
-  if (vec && valid == 32) {
+__device__ __forceinline__ void load32(const TO* __restrict__ src, bool wide, bool vec, int valid, float (&v)[32]) {
+  if (wide && valid == 32) {
+    constexpr int E = 32 / sizeof(TO);  // elements per 256-bit load: 8 fp32 / 16 bf16
+#pragma unroll
+    for (int j = 0; j < 32; j += E) {
+      const U32x8 r = ldg_v8(src + j);
+      if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j + i] = __uint_as_float(r.v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[j + 2 * i] = __uint_as_float(r.v[i] << 16);
+          v[j + 2 * i + 1] = __uint_as_float(r.v[i] & 0xffff0000u);
+        }
+      }
+    }
+  } else if (vec && valid == 32) {
     constexpr int VE = Vec16<TO>::n;
 #pragma unroll
     for (int j = 0; j < 32; j += VE) {
@@ -81,13 +100,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t 
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
   if (ep.bias != nullptr) {
     float b[32];
-    load32<float>(ep.bias + n_base, (p.ep_flags & kVecBias) != 0, valid, b);
+    load32<float>(ep.bias + n_base, false, (p.ep_flags & kVecBias) != 0, valid, b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] += b[j];
   }
   if (ep.addend != nullptr) {
     float a[32];
-    load32<TO>(reinterpret_cast<const TO*>(ep.addend) + m * ep.ldadd + n_base, (p.ep_flags & kVecAddend) != 0, valid, a);
+    load32<TO>(reinterpret_cast<const TO*>(ep.addend) + m * ep.ldadd + n_base, (p.ep_flags & kVec32Addend) != 0,
+               (p.ep_flags & kVecAddend) != 0, valid, a);
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] += a[j];
   }
@@ -111,12 +131,27 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], int64_t 
   }
   if (ep.gate != nullptr) {
     float g[32];
-    load32<TO>(reinterpret_cast<const TO*>(ep.gate) + m * ep.ldgate + n_base, (p.ep_flags & kVecGate) != 0, valid, g);
+    load32<TO>(reinterpret_cast<const TO*>(ep.gate) + m * ep.ldgate + n_base, (p.ep_flags & kVec32Gate) != 0,
+               (p.ep_flags & kVecGate) != 0, valid, g);
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = g[j] > 0.0f ? f[j] * ep.gate_scale : 0.0f;
   }
   TO* dst = reinterpret_cast<TO*>(p.D) + m * p.ldd + n_base;
-  if ((p.ep_flags & kVecOut) && valid == 32) {
+  if ((p.ep_flags & kVec32Out) && valid == 32) {  // full 32-byte sectors per lane: half the store instructions
+    constexpr int E = 32 / sizeof(TO);
+#pragma unroll
+    for (int j = 0; j < 32; j += E) {
+      U32x8 r;
+      if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = __float_as_uint(f[j + i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = pack_bf16x2(f[j + 2 * i], f[j + 2 * i + 1]);
+      }
+      stg_v8(dst + j, r);
+    }
+  } else if ((p.ep_flags & kVecOut) && valid == 32) {
     constexpr int VE = Vec16<TO>::n;
 #pragma unroll
     for (int j = 0; j < 32; j += VE) {
@@ -169,8 +204,8 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int64_t split = tile / (m_tiles * n_tiles);
@@ -186,6 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (elect_one_sync()) {
         const uint32_t bar = smem_u32(&full_bar[stage]);
         mbar_expect_tx(bar, Cfg::kStageBytes);
         const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes), sb = smem_u32(smem_b + stage * Cfg::kBBytes);
@@ -202,14 +238,25 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
           tma_load_2d(sa, second ? &maps.a2 : &maps.a1, k0, m0, bar);
           tma_load_2d(sb, second ? &maps.b2 : &maps.b1, k0, n0, bar);
         }
+        }
+        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer (single thread) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the pipeline, one elected lane issues) =====================
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, kTN);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    // K-major SW128: LBO 16 B, one UMMA_K step = 32 B inside the swizzle row.  MN-major SW128: LBO = distance between
+    // 64-element MN slabs, one UMMA_K step = 16 reduction rows = 2048 B.  SBO = 8 rows (1024 B) in both.
+    constexpr uint32_t kStep = (kTN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), kTN ? kSlabBytes : 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(smem_b), kTN ? kSlabBytes : 16);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    long long t_begin = 0, w_full = 0, w_acc = 0, t0 = 0;
+    auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (p.dbg) t_begin = now();
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int num_kb;
       if constexpr (kTN) {
@@ -220,33 +267,34 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       } else {
         num_kb = kb1 + kb2;
       }
+      if (p.dbg) t0 = now();
       mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      if (p.dbg) w_acc += now() - t0;
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.dbg) t0 = now();
         mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (p.dbg) w_full += now() - t0;
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes), sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (Cfg::kABytes >> 4), b_lo = b_lo0 + (uint32_t)stage * (Cfg::kBBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          uint64_t adesc, bdesc;
-          if constexpr (kTN) {
-            // MN-major, SW128: LBO = distance between 64-element MN slabs, SBO = 8 reduction rows (1024 B);
-            // one UMMA_K step = 16 reduction rows = 2048 B
-            adesc = make_smem_desc(sa + k * (UMMA_K * 128), kSlabBytes, 1024);
-            bdesc = make_smem_desc(sb + k * (UMMA_K * 128), kSlabBytes, 1024);
-          } else {
-            // K-major, SW128: rows of 128 B, SBO = 8 rows (1024 B); one UMMA_K step = 32 B inside the swizzle row
-            adesc = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            bdesc = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-          }
-          umma_bf16(tmem_d, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_d, desc_from(a_lo + k * kStep, kHi), desc_from(b_lo + k * kStep, kHi), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs retire
         }
-        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs retire
+        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(smem_u32(&tmem_full[acc]));      // accumulator ready for the epilogue
+      if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc]));      // accumulator ready for the epilogue
+      __syncwarp();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 4 + 0] = now() - t_begin;
+      p.dbg[blockIdx.x * 4 + 1] = w_full;
+      p.dbg[blockIdx.x * 4 + 2] = w_acc;
     }
   } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -308,6 +356,189 @@ gemm_tcgen05_kernel(const __grid_constant__ Maps maps, const TcParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NT with the weight operand RESIDENT in shared memory.  The plain kernel above re-reads the whole [N, K] weight
+// matrix from L2 for every 128-row tile (256 KB of B per 128 KB of A at K = 512), which makes tall-skinny layer GEMMs
+// L2->SM-traffic bound.  Here a persistent CTA owns ONE column tile of the output: its B operand (all K blocks, <= 128 KB)
+// is loaded once, the ring only streams A tiles, and the CTA walks the row tiles m = first, first + stride, ...
+// (N = 256, K = 512: two column tiles of 128, so A is read twice -- the second read hits L2 because the two CTAs of a
+// row tile run side by side -- instead of B 1843 times.)
+template <int BLOCK_N, typename TO>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_nt_resb_kernel(const __grid_constant__ Maps maps, const TcParams p, const int stages, long long* dbg) {
+  constexpr int kABytes = BLOCK_M * 128, kBBytes = BLOCK_N * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kb1 = (int)((p.K1 + BLOCK_K - 1) / BLOCK_K), kb2 = (int)((p.K2 + BLOCK_K - 1) / BLOCK_K);
+  const int num_kb = kb1 + kb2;
+  uint8_t* smem_b = smem;                                   // [num_kb][BLOCK_N rows x 128 B], resident
+  uint8_t* smem_a = smem + (size_t)num_kb * kBBytes;        // [stages][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)stages * kABytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + stages;           // [stages]
+  uint64_t* tmem_full = bars + 2 * stages;       // [kAccStages]
+  uint64_t* tmem_empty = tmem_full + kAccStages; // [kAccStages]
+  uint64_t* b_full = tmem_empty + kAccStages;    // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
+  constexpr int kTmemCols = kAccStages * BLOCK_N;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (int)((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int n0 = (int)(blockIdx.x % n_tiles) * BLOCK_N;
+  const int64_t m_first = blockIdx.x / n_tiles, m_stride = gridDim.x / n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
+    for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps); }
+    mbar_init(smem_u32(b_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer: B once, then the A ring =====================
+    if (m_first < m_tiles && elect_one_sync()) {
+      mbar_expect_tx(smem_u32(b_full), (uint32_t)(num_kb * kBBytes));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const bool second = kb >= kb1;
+        tma_load_2d(smem_u32(smem_b + (size_t)kb * kBBytes), second ? &maps.b2 : &maps.b1, (second ? kb - kb1 : kb) * BLOCK_K,
+                    n0, smem_u32(b_full));
+      }
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t mt = m_first; mt < m_tiles; mt += m_stride) {
+      const int m0 = (int)mt * BLOCK_M;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(bar, kABytes);
+          const bool second = kb >= kb1;
+          tma_load_2d(smem_u32(smem_a + (size_t)stage * kABytes), second ? &maps.a2 : &maps.a1,
+                      (second ? kb - kb1 : kb) * BLOCK_K, m0, bar);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, false);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16), b_lo0 = desc_lo(smem_u32(smem_b), 16);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    long long t_begin = 0, w_full = 0, w_acc = 0, t0 = 0, t1 = 0;
+    auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (dbg) t_begin = now();
+    if (m_first < m_tiles) {
+      mbar_wait(smem_u32(b_full), 0);
+      tcgen05_fence_after();
+    }
+    for (int64_t mt = m_first; mt < m_tiles; mt += m_stride) {
+      if (dbg) t0 = now();
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      if (dbg) w_acc += now() - t0;
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (dbg) t1 = now();
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (dbg) w_full += now() - t1;
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kABytes >> 4), b_lo = b_lo0 + (uint32_t)kb * (kBBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_d, desc_from(a_lo + k * 2, kHi), desc_from(b_lo + k * 2, kHi), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc]));
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (dbg && lane == 0) {
+      dbg[blockIdx.x * 4 + 0] = now() - t_begin;   // issue-loop time of this CTA
+      dbg[blockIdx.x * 4 + 1] = w_full;            // waiting for operands (load-bound)
+      dbg[blockIdx.x * 4 + 2] = w_acc;             // waiting for a free accumulator (epilogue-bound)
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue =====================
+    TcParams pe = p;
+    if (pe.ep.dropout_p > 0.0f) resolve_rng(pe.ep);
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BLOCK_N / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t mt = m_first; mt < m_tiles; mt += m_stride) {
+      const int64_t m0 = mt * BLOCK_M;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int64_t m = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      uint4 rnd128 = make_uint4(0, 0, 0, 0);
+      uint32_t rnd_group = 0xffffffffu;
+#pragma unroll 1
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
+        if (n0 + c0 >= p.N) break;
+        if (pe.ep.dropout_p == 0.5f && (uint32_t)((n0 + c0) >> 7) != rnd_group) {
+          rnd_group = (uint32_t)((n0 + c0) >> 7);
+          rnd128 = philox4x32_10(pe.ep.seed, (uint64_t)m, pe.ep.offset + (uint64_t)rnd_group);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        if (m < p.M) epilogue_chunk<TO>(r, m, n0 + c0, pe, rnd128);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+constexpr int kResBBudget = 128 * 1024;   // bytes of shared memory the resident B operand may take
+constexpr int kResBSmemMax = 226 * 1024;
+
+template <int BLOCK_N, typename TO>
+static int launch_resb(const Maps& maps, const TcParams& p, int num_kb, cudaStream_t stream) {
+  auto kern = gemm_nt_resb_kernel<BLOCK_N, TO>;
+  static bool configured = false;
+  if (!configured) {
+    LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBSmemMax));
+    configured = true;
+  }
+  const int b_bytes = num_kb * BLOCK_N * 128;
+  int stages = (kResBSmemMax - 1024 - 512 - b_bytes) / (BLOCK_M * 128);
+  if (stages > 8) stages = 8;
+  if (g_tuning[17] > 0 && g_tuning[17] < stages) stages = g_tuning[17];
+  const int smem = b_bytes + stages * BLOCK_M * 128 + 1024 + 512;
+  const int n_tiles = (int)ceil_div(p.N, BLOCK_N);
+  const unsigned grid = (unsigned)(kNumSMs / n_tiles * n_tiles);
+  kern<<<grid, kThreads, smem, stream>>>(maps, p, stages, g_tuning[15] ? debug_buffer() : nullptr);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
 template <int BLOCK_N, bool kTN, typename TO>
 static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
   using Cfg = Config<BLOCK_N>;
@@ -333,7 +564,15 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   using namespace tc;
   if (a.dtype != LLP_BF16) return LLP_E_SHAPE;
   const bool dual = a.A2 != nullptr && a.K2 > 0;
-  const int bn = pick_block_n(a.N);
+  int bn = pick_block_n(a.N);
+  // resident-B variant: tall problems whose weight column tile (all K blocks) fits in 128 KB of shared memory
+  const int num_kb = (int)(ceil_div(a.K1, BLOCK_K) + (dual ? ceil_div(a.K2, BLOCK_K) : 0));
+  int res_bn = 0;
+  if (g_tuning[16] == 0 && a.M >= (int64_t)BLOCK_M * kNumSMs * 2 && a.N >= 128) {
+    if (a.N > 128 && num_kb * 256 * 128 <= kResBBudget) res_bn = 256;
+    else if (g_tuning[18] && num_kb * 128 * 128 <= kResBBudget) res_bn = 128;  // half-rate MMAs (N = 128): experiment only
+  }
+  if (res_bn) bn = res_bn;
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   if (int rc = make_map(&maps.a1, a.A1, a.M, a.K1, a.lda1, BLOCK_K, BLOCK_M)) return rc;
@@ -346,11 +585,26 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
+  p.dbg = g_tuning[15] ? debug_buffer() : nullptr;
   {
     const size_t so = a.out_dtype == LLP_BF16 ? 2 : 4;
     auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * so) % 16 == 0; };
+    auto ok32 = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 32) && (ld * so) % 32 == 0; };
     p.ep_flags = (a.bias != nullptr && aligned(a.bias, 16) ? kVecBias : 0) | (ok(a.addend, a.ldadd) ? kVecAddend : 0) |
-                 (ok(a.gate, a.ldgate) ? kVecGate : 0) | (ok(a.D, a.ldd) ? kVecOut : 0);
+                 (ok(a.gate, a.ldgate) ? kVecGate : 0) | (ok(a.D, a.ldd) ? kVecOut : 0) |
+                 (ok32(a.addend, a.ldadd) ? kVec32Addend : 0) | (ok32(a.gate, a.ldgate) ? kVec32Gate : 0) |
+                 (ok32(a.D, a.ldd) ? kVec32Out : 0);
+    if (g_tuning[19]) p.ep_flags &= ~(kVec32Addend | kVec32Gate | kVec32Out);  // experiment: 128-bit epilogue accesses
+  }
+  if (res_bn == 256) {
+    if (a.out_dtype == LLP_BF16) return launch_resb<256, __nv_bfloat16>(maps, p, num_kb, stream);
+    if (a.out_dtype == LLP_F32) return launch_resb<256, float>(maps, p, num_kb, stream);
+    return LLP_E_BADARG;
+  }
+  if (res_bn == 128) {
+    if (a.out_dtype == LLP_BF16) return launch_resb<128, __nv_bfloat16>(maps, p, num_kb, stream);
+    if (a.out_dtype == LLP_F32) return launch_resb<128, float>(maps, p, num_kb, stream);
+    return LLP_E_BADARG;
   }
 #define LLP_TC_NT(BN)                                                                                          \
   if (bn == BN) {                                                                                              \

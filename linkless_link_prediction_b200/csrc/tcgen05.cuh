@@ -12,6 +12,19 @@ constexpr int UMMA_K = 16;  // bf16: 16 reduction elements per tcgen05.mma
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (elect.sync).  tcgen05.mma / TMA issue code must be reached through this, with the
+// whole warp executing the surrounding loop: behind a plain `lane == 0` branch ptxas cannot prove the descriptor operands
+// uniform and wraps every UTCHMMA in a per-active-thread loop (~230 cycles per instruction instead of the pipe rate).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -83,6 +96,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// Lean descriptor arithmetic for issue loops: the high word of a SW128 descriptor is a constant, the low word is
+// (address >> 4) | (LBO >> 4) << 16, so stepping through stages / K slices is ONE 32-bit add per operand (a single
+// thread issues every MMA: each dependent ALU instruction in front of it costs issue slots of the tensor pipe).
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return (saddr >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 // Instruction descriptor: c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), a/b major bits 15/16, N>>3 at 17, M>>4 at 24.

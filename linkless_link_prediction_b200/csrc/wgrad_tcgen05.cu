@@ -28,6 +28,8 @@ constexpr int kSmemBudget = 220 * 1024;
 struct Params {
   int64_t M, N1;
   int debug_skip_mma, debug_wide_box;
+  long long* debug_times;        // nullptr, or [grid][4] globaltimer stamps (start, accumulators ready, epilogue done)
+  int strided;                   // k-blocks of a split: 0 = one contiguous slice of M, 1 = every splits-th block
   int slabs_a, slabs_b;          // 64-column slabs of A and B (B may have 0)
   int64_t n2a, n2b;              // logical widths
   int splits;
@@ -59,9 +61,19 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int n1_tiles = (int)((p.N1 + kTileN1 - 1) / kTileN1);
   const int tile = blockIdx.x % n1_tiles, split = blockIdx.x / n1_tiles;
   const int n1_0 = tile * kTileN1;
-  const int64_t m_begin = (int64_t)split * p.rows_per_split;
-  const int64_t m_end = m_begin + p.rows_per_split < p.M ? m_begin + p.rows_per_split : p.M;
-  const int num_kb = m_end > m_begin ? (int)((m_end - m_begin + kBK - 1) / kBK) : 0;
+  int64_t m_begin, kb_stride;
+  int num_kb;
+  if (p.strided) {  // block kb of this CTA = global k-block (split + kb * splits): all CTAs sweep M together
+    const int64_t total_kb = (p.M + kBK - 1) / kBK;
+    m_begin = (int64_t)split * kBK;
+    kb_stride = (int64_t)p.splits * kBK;
+    num_kb = total_kb > split ? (int)((total_kb - split + p.splits - 1) / p.splits) : 0;
+  } else {
+    m_begin = (int64_t)split * p.rows_per_split;
+    const int64_t m_end = m_begin + p.rows_per_split < p.M ? m_begin + p.rows_per_split : p.M;
+    kb_stride = kBK;
+    num_kb = m_end > m_begin ? (int)((m_end - m_begin + kBK - 1) / kBK) : 0;
+  }
   const bool want_bias = p.partial_bias != nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -81,15 +93,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+      if (elect_one_sync()) {
       const uint32_t bar = smem_u32(&full_bar[stage]);
       mbar_expect_tx(bar, (uint32_t)stage_bytes);
       const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
-      const int k0 = (int)(m_begin + (int64_t)kb * kBK);
+      const int k0 = (int)(m_begin + (int64_t)kb * kb_stride);
       if (p.debug_wide_box) {  // load-rate experiment only: un-swizzled full-row boxes (layout unusable by the MMA)
         tma_load_2d(s0, &maps.g, n1_0, k0, bar);
         tma_load_2d(s0 + 2 * kSlab, &maps.a, 0, k0, bar);
@@ -100,32 +113,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       for (int j = 0; j < p.slabs_a; ++j) tma_load_2d(s0 + (2 + j) * kSlab, &maps.a, j * 64, k0, bar);
       for (int j = 0; j < p.slabs_b; ++j) tma_load_2d(s0 + (2 + p.slabs_a + j) * kSlab, &maps.b, j * 64, k0, bar);
       }
+      }
+      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the ring, one elected lane issues) =====================
+    // MN-major SW128 operands: LBO = slab stride, SBO = 8 reduction rows (1024 B), one UMMA_K step = 16 rows = 2048 B
     const uint32_t idesc_a = make_idesc(kTileN1, p.slabs_a * 64, true);
     const uint32_t idesc_b = make_idesc(kTileN1, p.slabs_b * 64, true);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    constexpr uint32_t kStep = (UMMA_K * 128) >> 4;
+    const uint32_t g_lo0 = desc_lo(smem_u32(smem), kSlab);
+    const uint32_t a_off = (uint32_t)(2 * kSlab) >> 4, b_off = (uint32_t)((2 + p.slabs_a) * kSlab) >> 4;
+    const uint32_t tmem_b = tmem_base + (uint32_t)(p.slabs_a * 64);
+    const bool has_b = p.slabs_b > 0;
     int stage = 0; uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(smem_u32(&full_bar[stage]), phase);
       tcgen05_fence_after();
-      const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
+      if (elect_one_sync()) {
+        const uint32_t g_lo = g_lo0 + (uint32_t)stage * ((uint32_t)stage_bytes >> 4);
 #pragma unroll
-      for (int k = 0; k < (p.debug_skip_mma ? 0 : kBK / UMMA_K); ++k) {
-        // MN-major SW128 operands: LBO = slab stride, SBO = 8 reduction rows (1024 B), one UMMA_K step = 2048 B
-        const uint64_t gdesc = make_smem_desc(s0 + k * (UMMA_K * 128), kSlab, 1024);
-        const uint64_t adesc = make_smem_desc(s0 + 2 * kSlab + k * (UMMA_K * 128), kSlab, 1024);
-        umma_bf16(tmem_base, gdesc, adesc, idesc_a, (uint32_t)((kb | k) != 0));
-        if (p.slabs_b > 0) {
-          const uint64_t bdesc = make_smem_desc(s0 + (2 + p.slabs_a) * kSlab + k * (UMMA_K * 128), kSlab, 1024);
-          umma_bf16(tmem_base + (uint32_t)(p.slabs_a * 64), gdesc, bdesc, idesc_b, (uint32_t)((kb | k) != 0));
+        for (int k = 0; k < kBK / UMMA_K; ++k) {
+          if (p.debug_skip_mma) break;
+          const uint64_t gdesc = desc_from(g_lo + k * kStep, kHi);
+          umma_bf16(tmem_base, gdesc, desc_from(g_lo + a_off + k * kStep, kHi), idesc_a, (uint32_t)((kb | k) != 0));
+          if (has_b) umma_bf16(tmem_b, gdesc, desc_from(g_lo + b_off + k * kStep, kHi), idesc_b, (uint32_t)((kb | k) != 0));
         }
+        umma_commit(smem_u32(&empty_bar[stage]));
       }
-      umma_commit(smem_u32(&empty_bar[stage]));
+      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    umma_commit(smem_u32(tmem_full));
+    if (elect_one_sync()) umma_commit(smem_u32(tmem_full));
+    __syncwarp();
   } else if (warp == 2 && want_bias) {
     // ===================== bias gradient: column sums of the G slabs, from shared memory =====================
     // lane -> (row half, slab, 16-byte chunk): 8 consecutive columns of G, one half of the rows of every stage
@@ -169,8 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       first = ew >= 4 ? 1 : 0;
     }
     const int ncols = 64 * (p.slabs_a + p.slabs_b);
+    long long t_start = 0, t_ready = 0;
+    if (p.debug_times != nullptr && warp == 3 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     mbar_wait(smem_u32(tmem_full), 0);
     tcgen05_fence_after();
+    if (p.debug_times != nullptr && warp == 3 && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ready));
     const int64_t row = n1_0 + quad * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int c0 = first * 32; c0 < ncols; c0 += 64) {
@@ -187,6 +212,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       }
     }
     tcgen05_fence_before();
+    if (p.debug_times != nullptr && warp == 3 && lane == 0) {
+      long long t_done;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_done));
+      p.debug_times[blockIdx.x * 4 + 0] = t_start;
+      p.debug_times[blockIdx.x * 4 + 1] = t_ready;
+      p.debug_times[blockIdx.x * 4 + 2] = t_done;
+    }
   }
 
   tcgen05_fence_before();
@@ -272,6 +304,8 @@ static void plan(int64_t M, int64_t N1, int64_t n2a, int64_t n2b, Params* p, int
   if (g_tuning[10] > 0 && g_tuning[10] < p->stages) p->stages = g_tuning[10];
   p->debug_skip_mma = g_tuning[11];
   p->debug_wide_box = g_tuning[13];
+  p->strided = g_tuning[14];
+  p->debug_times = g_tuning[15] ? debug_buffer() : nullptr;
   const int cols = 64 * (p->slabs_a + p->slabs_b);
   p->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
 }

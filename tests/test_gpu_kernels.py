@@ -139,6 +139,36 @@ def test_gemm_nt(cuda, backend, M, Nn, K1, K2):
     torch.testing.assert_close(D, ref, **(dict(rtol=1e-5, atol=2e-5 * math.sqrt(K1)) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2 * math.sqrt(K1))))
 
 
+@pytest.mark.parametrize("M,Nn,K1,K2", [(40000, 256, 256, 256), (38011, 256, 256, 0), (50001, 200, 128, 128),
+                                        (45000, 128, 256, 256), (39999, 256, 192, 64)])
+def test_gemm_nt_resident_weights(cuda, M, Nn, K1, K2):
+    """Tall problems take the resident-B tcgen05 kernel (weights loaded into shared memory once per CTA): same
+    results as the streaming kernel (bit-identical: same MMA order per output element) and as the fp64 reference."""
+    g = torch.Generator().manual_seed(M + Nn + K1)
+    r = lambda *s: torch.randn(*s, generator=g)
+    A1, B1 = r(M, K1).bfloat16(), r(Nn, K1).bfloat16()
+    A2, B2 = (r(M, K2).bfloat16(), r(Nn, K2).bfloat16()) if K2 else (None, None)
+    bias, gate = r(Nn), r(M, Nn).bfloat16()
+    c = lambda t: None if t is None else ops.cast2d(t.to(cuda), t.dtype)
+    dA1, dB1, dA2, dB2, dgate = c(A1), c(B1), c(A2), c(B2), c(gate)
+    lib = N.load()
+    outs = []
+    for streaming in (0, 1):
+        lib.llp_set_tuning(16, streaming)   # 1 = force the streaming kernel
+        try:
+            plain = ops.gemm_nt(dA1, dB1, dA2, dB2, bias=bias.to(cuda), relu=True, out_dtype=torch.float32,
+                                backend=N.GEMM_TCGEN05)
+            gated = ops.gemm_nt(dA1, dB1, dA2, dB2, gate=dgate, gate_scale=2.0, backend=N.GEMM_TCGEN05)
+            drop = ops.gemm_nt(dA1, dB1, dA2, dB2, relu=True, dropout_p=0.5, seed=5, offset=3, backend=N.GEMM_TCGEN05)
+        finally:
+            lib.llp_set_tuning(16, 0)
+        outs.append((plain, gated, drop))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    ref = _ref_gemm(A1, B1, A2, B2, bias, None, True, None, 1.0)
+    torch.testing.assert_close(outs[0][0].cpu(), ref, rtol=1e-3, atol=1e-3 * math.sqrt(K1 + K2))
+
+
 @pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("M,N1,N2", [(64, 8, 8), (1000, 256, 256), (5000, 256, 1433), (333, 200, 36), (20000, 256, 512),
                                      (100, 1, 256)])

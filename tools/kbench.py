@@ -105,6 +105,34 @@ def main():
             us = timeit(lambda: ops.wgrad(G, A, Wa, B, Wb if n2b else None, bias=bp))
             report(f"wgrad fused M={M} {N1}x({n2a}+{n2b})+bias {tag}", us, nbytes=M * (N1 + n2a + n2b) * 2,
                    flops=2 * M * N1 * (n2a + n2b))
+    if "gemmexp" in which:
+        import ctypes
+        lib = N.load()
+        H = 256
+        for M, K1, K2, kw, tag in ((n, 256, 256, dict(relu=True, dropout_p=0.5, seed=1), "L2 fwd relu+drop"),
+                                   (n, 256, 256, dict(), "L3 fwd"), (131072, 256, 0, dict(relu=True, dropout_p=0.5, seed=1), "pred fwd"),
+                                   (n, 128, 128, dict(relu=True, dropout_p=0.5, seed=1), "L1 fwd relu+drop"),
+                                   (n, 128, 128, dict(), "L1-shaped, plain epilogue"), (131072, 256, 0, dict(), "pred dgrad")):
+            A1 = torch.randn(M, K1, device=dev).bfloat16(); B1 = torch.randn(H, K1, device=dev).bfloat16()
+            A2 = torch.randn(M, K2, device=dev).bfloat16() if K2 else None
+            B2 = torch.randn(H, K2, device=dev).bfloat16() if K2 else None
+            bias = torch.randn(H, device=dev)
+            for vtag, knobs in (("auto", {}), ("streaming", {16: 1})):
+                for k_ in (16, 18):
+                    lib.llp_set_tuning(k_, knobs.get(k_, 0))
+                report(f"gemm_nt [{vtag}] M={M} K={K1}+{K2} {tag}",
+                       timeit(lambda: ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw)), nbytes=M * (K1 + K2) * 2 + M * H * 2)
+                lib.llp_set_tuning(15, 1)
+                flush.zero_()
+                ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw)
+                buf = (ctypes.c_int64 * (148 * 4))()
+                lib.llp_debug_read(buf, 148 * 4)
+                lib.llp_set_tuning(15, 0)
+                tot = sorted(buf[4 * i] for i in range(148)); wf = sorted(buf[4 * i + 1] for i in range(148)); wa = sorted(buf[4 * i + 2] for i in range(148))
+                print(f"   MMA issue loop (ns) min/med/max {tot[0]}/{tot[74]}/{tot[-1]}; waiting for operands med/max {wf[74]}/{wf[-1]}; "
+                      f"waiting for a free accumulator med/max {wa[74]}/{wa[-1]}", flush=True)
+            for k_ in (16, 18):
+                lib.llp_set_tuning(k_, 0)
     if "wgradexp" in which:
         lib = N.load()
         M, N1 = n, 256
@@ -118,11 +146,35 @@ def main():
                                  ("stages=2", {10: 2}, True), ("skip mma", {11: 1}, True), ("skip mma, no bias", {11: 1}, False),
                                  ("BK=64 (2 stages)", {12: 64}, True), ("BK=64 skip mma no bias", {12: 64, 11: 1}, False),
                                  ("wide un-swizzled boxes, skip mma, no bias", {13: 1}, False),
-                                 ("wide boxes BK=64", {13: 1, 12: 64}, False)):
-            for k in (10, 11, 12, 13):
+                                 ("wide boxes BK=64", {13: 1, 12: 64}, False),
+                                 ("strided k-blocks", {14: 1}, True), ("strided k-blocks BK=64", {14: 1, 12: 64}, True),
+                                 ("strided k-blocks, 3 stages", {14: 1, 10: 3}, True)):
+            for k in (10, 11, 12, 13, 14):
                 lib.llp_set_tuning(k, knobs.get(k, 0))
             report(f"wgrad 256x(256+256) {tag}", timeit(lambda: ops.wgrad(G, A, Wa, B, Wb, bias=bp if bias else None)), nbytes=nb)
-        for k in (10, 11, 12, 13):
+        for k in (10, 11, 12, 13, 14):
+            lib.llp_set_tuning(k, 0)
+        # phase stamps (globaltimer, ns) of every CTA of one launch: main loop vs epilogue
+        import ctypes
+        lib.llp_set_tuning(15, 1)
+        ops.wgrad(G, A, Wa, B, Wb, bias=bp)
+        buf = (ctypes.c_int64 * (148 * 4))()
+        lib.llp_debug_read(buf, 148 * 4)
+        lib.llp_set_tuning(15, 0)
+        st = [(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2]) for i in range(148)]
+        t0 = min(s_[0] for s_ in st)
+        main = sorted(s_[1] - s_[0] for s_ in st); epi = sorted(s_[2] - s_[1] for s_ in st)
+        print(f"wgrad phases (ns): start skew {max(s_[0] for s_ in st) - t0}, main loop min/med/max {main[0]}/{main[74]}/{main[-1]}, "
+              f"epilogue min/med/max {epi[0]}/{epi[74]}/{epi[-1]}, last CTA done at {max(s_[2] for s_ in st) - t0}", flush=True)
+        # no duplicated reads: a single N1 tile (G is [M,128]) => every byte is fetched by exactly one CTA
+        G1 = torch.randn(M, 128, device=dev).bfloat16()
+        Wa1 = torch.nn.Parameter(torch.zeros(128, 256, device=dev)); Wa1.grad = torch.zeros_like(Wa1)
+        Wb1 = torch.nn.Parameter(torch.zeros(128, 256, device=dev)); Wb1.grad = torch.zeros_like(Wb1)
+        for tag, knobs in (("default", {}), ("skip mma", {11: 1}), ("strided k-blocks", {14: 1})):
+            for k in (10, 11, 12, 13, 14):
+                lib.llp_set_tuning(k, knobs.get(k, 0))
+            report(f"wgrad 128x(256+256) single N1 tile, {tag}", timeit(lambda: ops.wgrad(G1, A, Wa1, B, Wb1)), nbytes=M * 640 * 2)
+        for k in (10, 11, 12, 13, 14):
             lib.llp_set_tuning(k, 0)
     if "misc" in which:
         H = 256
