@@ -138,6 +138,15 @@ int llp_colsum(int dtype, const void* A, int64_t lda, int64_t M, int64_t N, floa
 /* dst[c,r] = (dst dtype) src[r,c]; also plain cast when transpose == 0. */
 int llp_cast2d(int src_dtype, int dst_dtype, const void* src, int64_t lds, int64_t rows, int64_t cols,
                void* dst, int64_t ldd, int transpose, void* stream);
+/* bf16 working copies of fp32 master weights, all matrices in ONE launch: dst[rows, cols] (ld) = bf16(src) and/or
+ * dst_t[cols, rows] (ld_t) = bf16(src)^T.  src is contiguous [rows, cols].  Run once per optimiser step instead of a
+ * cast / transpose launch per weight and use (F.linear / its autograd read the same weights several times per step). */
+typedef struct llp_weight_desc {
+  const float* src; int64_t rows, cols;
+  void* dst; int64_t ld;        /* may be NULL */
+  void* dst_t; int64_t ld_t;    /* may be NULL */
+} llp_weight_desc;
+int llp_weights_prep(int count, const llp_weight_desc* host_descs, void* stream);
 /* y = gate>0 ? g*scale : 0  (relu/dropout backward from the saved forward output). */
 int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ldgate, int64_t M, int64_t N,
              float scale, void* y, int64_t ldy, void* stream);

@@ -39,6 +39,13 @@ class GemmNtArgs(ctypes.Structure):
     ]
 
 
+class WeightDesc(ctypes.Structure):
+    """Mirror of ``llp_weight_desc`` (include/llp_b200.h)."""
+
+    _fields_ = [("src", c_void_p), ("rows", c_int64), ("cols", c_int64), ("dst", c_void_p), ("ld", c_int64),
+                ("dst_t", c_void_p), ("ld_t", c_int64)]
+
+
 # name -> (restype, argtypes); the single source for both binding and the "exports every symbol" test
 PROTOTYPES = {
     "llp_version": (c_int, []),
@@ -65,6 +72,7 @@ PROTOTYPES = {
     "llp_colsum_workspace_bytes": (c_size_t, [c_int64]),
     "llp_colsum": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "llp_cast2d": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "llp_weights_prep": (c_int, [c_int, ctypes.POINTER(WeightDesc), c_void_p]),
     "llp_gate": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64,
                          c_void_p]),
     "llp_edge_hadamard": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

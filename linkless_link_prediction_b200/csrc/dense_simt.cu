@@ -282,6 +282,41 @@ __global__ void cast2d_kernel(const TS* __restrict__ src, int64_t lds, int64_t r
   }
 }
 
+// ---- low-precision copies of all weight matrices in one launch ------------------------------------
+// After every optimiser step the fp32 master weights are re-materialised as bf16 [rows, cols] (the B operand of the
+// forward GEMMs) and bf16 [cols, rows] (the B operand of the input-gradient GEMMs) for up to kMaxPrep matrices by ONE
+// grid of 32x32 tiles, instead of a cast or transpose launch per weight and use.
+constexpr int kMaxPrep = 16;
+struct PrepTable {
+  int count;
+  int tile_begin[kMaxPrep + 1];
+  llp_weight_desc d[kMaxPrep];
+};
+
+__global__ void weights_prep_kernel(const PrepTable t) {
+  __shared__ float tile[32][33];
+  int k = 0;
+  while (k + 1 < t.count && (int)blockIdx.x >= t.tile_begin[k + 1]) ++k;
+  const llp_weight_desc d = t.d[k];
+  const int local = blockIdx.x - t.tile_begin[k];
+  const int tiles_x = (int)((d.cols + 31) / 32);
+  const int64_t r0 = (int64_t)(local / tiles_x) * 32, c0 = (int64_t)(local % tiles_x) * 32;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(d.dst);
+  __nv_bfloat16* dst_t = reinterpret_cast<__nv_bfloat16*>(d.dst_t);
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    const float v = (r < d.rows && c < d.cols) ? d.src[r * d.cols + c] : 0.0f;
+    tile[i][threadIdx.x] = v;
+    if (dst != nullptr && r < d.rows && c < d.cols) dst[r * d.ld + c] = __float2bfloat16_rn(v);
+  }
+  if (dst_t == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;  // dst_t[c, r]
+    if (r < d.rows && c < d.cols) dst_t[c * d.ld_t + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
 // y = gate > 0 ? g*scale : 0, one 16-byte vector per thread (rows are 16-byte multiples) or scalar fallback
 // plain (non-transposing) cast: one 16-byte output vector per thread when rows allow it
 template <typename TS, typename TD>
@@ -403,4 +438,28 @@ extern "C" int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate,
   if (dtype == LLP_F32) return gate_typed<float>(g, ldg, gate, ldgate, M, N, scale, y, ldy, stream);
   if (dtype == LLP_BF16) return gate_typed<__nv_bfloat16>(g, ldg, gate, ldgate, M, N, scale, y, ldy, stream);
   return LLP_E_BADARG;
+}
+
+extern "C" int llp_weights_prep(int count, const llp_weight_desc* host_descs, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(count >= 0 && (count == 0 || host_descs != nullptr));
+  if (int rc = check_device()) return rc;
+  for (int base = 0; base < count; base += kMaxPrep) {
+    PrepTable t;
+    t.count = count - base < kMaxPrep ? count - base : kMaxPrep;
+    int tiles = 0;
+    for (int i = 0; i < t.count; ++i) {
+      const llp_weight_desc& d = host_descs[base + i];
+      LLP_CHECK_ARG(d.src && d.rows > 0 && d.cols > 0 && (d.dst == nullptr || d.ld >= d.cols) &&
+                    (d.dst_t == nullptr || d.ld_t >= d.rows));
+      t.d[i] = d;
+      t.tile_begin[i] = tiles;
+      tiles += (int)(ceil_div(d.rows, 32) * ceil_div(d.cols, 32));
+    }
+    t.tile_begin[t.count] = tiles;
+    if (tiles == 0) continue;
+    weights_prep_kernel<<<(unsigned)tiles, dim3(32, 8), 0, stream>>>(t);
+    LLP_LAUNCH_OK();
+  }
+  return 0;
 }

@@ -18,7 +18,7 @@ namespace llp {
 namespace eb {
 
 constexpr int kHubThreshold = 48;
-constexpr int kHubWarps = 8;
+constexpr int kHubWarpsMax = 32;  // warps of a hub block (fewer when F is wide: [warps][F] floats of shared memory)
 constexpr int kRowsPerWarp = 16;
 
 __global__ void incidence_keys_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M,
@@ -174,12 +174,13 @@ __global__ void __launch_bounds__(256) hadamard_bwd_rows_kernel(const RowArgs<T>
   }
 }
 
-// one block per hub row: warp w adds sorted positions p0+w, p0+w+8, ...; the 8 partial rows are combined in warp order
+// one block per hub row: warp w of nw adds sorted positions p0+w, p0+w+nw, ...; the nw partial rows are combined in warp
+// order (deterministic for a given F, which fixes nw)
 template <typename T>
-__global__ void __launch_bounds__(32 * kHubWarps) hadamard_bwd_hubs_kernel(const RowArgs<T> a) {
+__global__ void __launch_bounds__(32 * kHubWarpsMax) hadamard_bwd_hubs_kernel(const RowArgs<T> a) {
   constexpr int VE = Vec16<T>::n;
-  extern __shared__ float part[];  // [kHubWarps][F]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  extern __shared__ float part[];  // [nw][F]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int n_hubs = *a.hub_count;
   for (int i = blockIdx.x; i < n_hubs; i += gridDim.x) {
     const int64_t r = a.hub_list[i];
@@ -188,18 +189,17 @@ __global__ void __launch_bounds__(32 * kHubWarps) hadamard_bwd_hubs_kernel(const
       float acc[VE];
 #pragma unroll
       for (int k = 0; k < VE; ++k) acc[k] = 0.0f;
-      accumulate<T, VE>(a, p0 + w, p1, kHubWarps, c, acc);
+      accumulate<T, VE>(a, p0 + w, p1, nw, c, acc);
 #pragma unroll
       for (int k = 0; k < VE; ++k) part[w * a.F + c + k] = acc[k];
     }
     __syncthreads();
-    for (int c = threadIdx.x * VE; c < a.F; c += 32 * kHubWarps * VE) {
+    for (int c = threadIdx.x * VE; c < a.F; c += blockDim.x * VE) {
       float s[VE];
 #pragma unroll
       for (int k = 0; k < VE; ++k) {
         float t = 0.0f;
-#pragma unroll
-        for (int q = 0; q < kHubWarps; ++q) t += part[q * a.F + c + k];
+        for (int q = 0; q < nw; ++q) t += part[q * a.F + c + k];
         s[k] = t;
       }
       stg_v4(a.gh + r * a.ldgh + c, pack16(s, T()));
@@ -274,9 +274,11 @@ static int run(const void* h, int64_t ldh, int64_t F, int64_t M, const void* dz,
   }
   hadamard_bwd_rows_kernel<T><<<(unsigned)ceil_div(ceil_div(N, kRowsPerWarp) * 32, 256), 256, 0, stream>>>(a);
   LLP_LAUNCH_OK();
-  const size_t smem = (size_t)kHubWarps * F * sizeof(float);
-  if (smem > 48 * 1024) return LLP_E_SHAPE;
-  hadamard_bwd_hubs_kernel<T><<<kNumSMs * 2, 32 * kHubWarps, smem, stream>>>(a);
+  int hub_warps = (int)((48 * 1024) / (F * sizeof(float)));
+  hub_warps = hub_warps > kHubWarpsMax ? kHubWarpsMax : hub_warps;
+  if (hub_warps < 1) return LLP_E_SHAPE;
+  const size_t smem = (size_t)hub_warps * F * sizeof(float);
+  hadamard_bwd_hubs_kernel<T><<<kNumSMs * 2, 32 * hub_warps, smem, stream>>>(a);
   LLP_LAUNCH_OK();
   return 0;
 }

@@ -339,15 +339,52 @@ def _dropout_seed() -> Tuple[int, int]:
     return 0, _SITE[0]
 
 
+def _lowp(W: torch.Tensor):
+    """bf16 working copies ``(W, W^T)`` kept by ``FusedAdam`` (``prepare_weights``), valid while nothing but the
+    optimiser has written the parameter since (torch-level writes bump ``_version``)."""
+    c = getattr(W, "_llp_lowp", None)
+    if c is not None and c[0] == W._version and compute_dtype() == torch.bfloat16:
+        return c
+    return None
+
+
 def _weights(W: torch.Tensor) -> torch.Tensor:
     dt = compute_dtype()
     if W.dtype == dt and (W.stride(0) * W.element_size()) % 16 == 0:
         return W.detach()
+    c = _lowp(W)
+    if c is not None:
+        return c[1]
     return cast2d(W.detach(), dt)
 
 
 def _weights_t(W: torch.Tensor) -> torch.Tensor:
+    c = _lowp(W)
+    if c is not None:
+        return c[2]
     return cast2d(W.detach(), compute_dtype(), transpose=True)
+
+
+def prepare_weights(params: Sequence[torch.nn.Parameter]) -> None:
+    """(Re)build the bf16 ``[out, in]`` and ``[in, out]`` copies of every 2-D fp32 parameter in one launch and attach
+    them to the parameter (``_llp_lowp``).  Called by ``FusedAdam`` after each step; the buffers are allocated once."""
+    lib = N.require_gpu()
+    todo = [p for p in params if p.dim() == 2 and p.dtype == torch.float32 and p.is_cuda and p.is_contiguous()]
+    if not todo:
+        return
+    arr = (N.WeightDesc * len(todo))()
+    for i, p in enumerate(todo):
+        c = getattr(p, "_llp_lowp", None)
+        if c is None or c[1].shape != p.shape:
+            w = empty_mat(p.size(0), p.size(1), torch.bfloat16, p.device)
+            wt = empty_mat(p.size(1), p.size(0), torch.bfloat16, p.device)
+        else:
+            w, wt = c[1], c[2]
+        arr[i].src, arr[i].rows, arr[i].cols = p.data_ptr(), p.size(0), p.size(1)
+        arr[i].dst, arr[i].ld = N.mat(w)
+        arr[i].dst_t, arr[i].ld_t = N.mat(wt)
+        p._llp_lowp = (p._version, w, wt)
+    N.check(lib.llp_weights_prep(len(todo), arr, N.stream_ptr()), "llp_weights_prep")
 
 
 # --------------------------------------------------------------------------------------------

@@ -99,4 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
                                   self._step, self._dev_step.data_ptr(), None, self.group_norms.data_ptr(), self._ws.data_ptr(),
                                   N.stream_ptr()),
                 "llp_clip_adam")
+        from . import ops
+        if ops.compute_dtype() == torch.bfloat16:
+            ops.prepare_weights(self._params)  # bf16 W and W^T of every weight matrix for the next step: one launch
         return None
