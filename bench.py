@@ -286,10 +286,20 @@ def main():
     ms_eval = max_over_ranks(e0.elapsed_time(e1))
     model.train(); predictor.train()
 
-    if rank != 0:
+    def finish():
+        """Leave without NCCL teardown: a CUDA graph that captured the gradient all-reduce is still alive, and
+        destroying the communicator under it can block forever.  Everything has been synchronised by now."""
         if world > 1:
             import torch.distributed as dist
-            dist.destroy_process_group()
+            step.graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     line = {
@@ -317,9 +327,7 @@ def main():
         res = run_cpu(args, data_cpu, split, budget_s=args.cpu_baseline_seconds, max_steps=3, warmup=1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
