@@ -172,6 +172,27 @@ size_t llp_edge_hadamard_bwd_workspace_bytes(int64_t num_edges);
 int llp_edge_hadamard_bwd(int dtype, const void* h, int64_t ldh, int64_t feat, int64_t num_edges, const void* dz,
                           int64_t lddz, int64_t num_nodes, const int32_t* rowptr, const int32_t* meta, void* gh,
                           int64_t ldgh, void* workspace, size_t workspace_bytes, void* stream);
+/* Fused edge scorer, bf16 (the gather-Hadamard is the A-operand producer of the first predictor GEMM):
+ *   z[m,:] = h[u[m],:]*h[v[m],:] ; y[m,:] = dropout(relu(z[m,:] W1^T + bias1)) ; prob[m] = sigmoid(y[m,:].w2 + b2)
+ * (models.py:139-150 with num_layers == 2 and out_channels == 1) in one tcgen05 kernel.  z and y are optional outputs
+ * (training keeps them for the backward pass; evaluation leaves them NULL: two row gathers in, four bytes out per
+ * edge); prob is optional when y is wanted.  The dropout stream is the one llp_gemm_nt draws (same seed / offset /
+ * rng_state => same mask).  K % 64 == 0, N % 8 == 0, N <= 256, W1 column tile <= 128 KB (llp_edge_mlp_supported). */
+typedef struct llp_edge_mlp_args {
+  const void* h; int64_t ldh;           /* bf16 [num_nodes, K] */
+  const int64_t* u; const int64_t* v;   /* [M] */
+  int64_t M, K, N;
+  const void* W1; int64_t ldw1;         /* bf16 [N, K] */
+  const float* bias1;                   /* [N] or NULL */
+  int relu; float dropout_p;
+  uint64_t seed, offset; const uint64_t* rng_state;
+  void* z; int64_t ldz;                 /* bf16 [M, K] or NULL */
+  void* y; int64_t ldy;                 /* bf16 [M, N] or NULL */
+  const float* w2; const float* b2;     /* [N], [1] (b2 may be NULL) */
+  float* prob;                          /* [M] or NULL */
+} llp_edge_mlp_args;
+int llp_edge_mlp_supported(int64_t K, int64_t N);
+int llp_edge_mlp_fused(const llp_edge_mlp_args* host_args, void* stream);
 /* Final predictor layer with one output: logit[m] = y[m,:].w + b ; p = sigmoid(logit).
  * (models.py:146,150 with out_channels == 1.) */
 int llp_score_head(int dtype, const void* y, int64_t ldy, int64_t M, int64_t H, const float* w, const float* b,

@@ -39,6 +39,19 @@ class GemmNtArgs(ctypes.Structure):
     ]
 
 
+class EdgeMlpArgs(ctypes.Structure):
+    """Mirror of ``llp_edge_mlp_args`` (include/llp_b200.h)."""
+
+    _fields_ = [
+        ("h", c_void_p), ("ldh", c_int64), ("u", c_void_p), ("v", c_void_p),
+        ("M", c_int64), ("K", c_int64), ("N", c_int64),
+        ("W1", c_void_p), ("ldw1", c_int64), ("bias1", c_void_p),
+        ("relu", c_int), ("dropout_p", c_float), ("seed", c_uint64), ("offset", c_uint64), ("rng_state", c_void_p),
+        ("z", c_void_p), ("ldz", c_int64), ("y", c_void_p), ("ldy", c_int64),
+        ("w2", c_void_p), ("b2", c_void_p), ("prob", c_void_p),
+    ]
+
+
 class WeightDesc(ctypes.Structure):
     """Mirror of ``llp_weight_desc`` (include/llp_b200.h)."""
 
@@ -82,6 +95,8 @@ PROTOTYPES = {
     "llp_edge_hadamard_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "llp_edge_hadamard_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "llp_edge_mlp_supported": (c_int, [c_int64, c_int64]),
+    "llp_edge_mlp_fused": (c_int, [ctypes.POINTER(EdgeMlpArgs), c_void_p]),
     "llp_score_head": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_score_head_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_score_head_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float,

@@ -1,0 +1,338 @@
+// Fused edge scorer (sm_100a, tcgen05): for a batch of edges (u[m], v[m])
+//
+//     z[m,:]  = h[u[m],:] * h[v[m],:]                       (the two fancy-index gathers + mul, models.py:140)
+//     y[m,:]  = dropout(relu(z[m,:] W1^T + b1))             (first predictor layer, models.py:143-145)
+//     prob[m] = sigmoid(y[m,:] . w2 + b2)                   (1-output last layer + sigmoid, models.py:146,150)
+//
+// in ONE kernel: the gather-Hadamard is the A-operand PRODUCER of the first predictor GEMM.  Four
+// producer warps gather the two embedding rows of every edge of a 128-edge tile with 128-bit loads, multiply them and
+// write the bf16 products straight into the 128B-swizzled K-major shared-memory stage the tensor core reads (and, for
+// training, also to `z`, which the weight gradient needs); W1 (<= 128 KB) is loaded into shared memory once per CTA by
+// TMA; one elected lane issues tcgen05.mma into a double-buffered TMEM accumulator; eight epilogue warps apply
+// bias + relu + Philox dropout, store `y` (training) and reduce the row against w2 for the sigmoid score.  With z and y
+// switched off (evaluation) a scored edge costs two row gathers and four bytes of output.
+#include "tcgen05.cuh"
+
+namespace llp {
+namespace em {
+
+using namespace tc;
+
+constexpr int kTileM = 128;
+constexpr int kBK = 64;                 // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kGatherWarps = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kGatherWarps + kEpiWarps);
+constexpr int kAccStages = 2;
+constexpr int kABytes = kTileM * 128;   // one A stage: 128 rows x 128 B
+constexpr int kSmemMax = 226 * 1024;
+
+struct Params {
+  const __nv_bfloat16* h; int64_t ldh;
+  const int64_t* u; const int64_t* v;
+  int64_t M; int K, N;
+  const float* bias1;
+  int relu; float dropout_p; uint64_t seed, offset; const uint64_t* rng_state;
+  __nv_bfloat16* z; int64_t ldz;
+  __nv_bfloat16* y; int64_t ldy;
+  const float* w2; const float* b2; float* prob;
+  int stages;
+};
+
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_constant__ CUtensorMap map_w, const Params p) {
+  constexpr int kBBytes = BLOCK_N * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int num_kb = p.K / kBK;
+  uint8_t* smem_b = smem;                                   // [num_kb][BLOCK_N rows x 128 B], resident
+  uint8_t* smem_a = smem + (size_t)num_kb * kBBytes;        // [stages][128 rows x 128 B]
+  float* head_part = reinterpret_cast<float*>(smem_a + (size_t)p.stages * kABytes);  // [kAccStages][2][kTileM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(head_part + kAccStages * 2 * kTileM);
+  uint64_t* full_bar = bars;                       // [stages], one arrival per gather warp
+  uint64_t* empty_bar = bars + p.stages;           // [stages]
+  uint64_t* tmem_full = bars + 2 * p.stages;       // [kAccStages]
+  uint64_t* tmem_empty = tmem_full + kAccStages;   // [kAccStages]
+  uint64_t* w_full = tmem_empty + kAccStages;      // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
+  constexpr int kTmemCols = kAccStages * BLOCK_N;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (p.M + kTileM - 1) / kTileM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), kGatherWarps); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps); }
+    mbar_init(smem_u32(w_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== W1: all K blocks, once =====================
+    if ((int64_t)blockIdx.x < m_tiles && elect_one_sync()) {
+      mbar_expect_tx(smem_u32(w_full), (uint32_t)(num_kb * kBBytes));
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_u32(smem_b + (size_t)kb * kBBytes), &map_w, kb * kBK, 0, smem_u32(w_full));
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(kTileM, BLOCK_N, false);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16), b_lo0 = desc_lo(smem_u32(smem_b), 16);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    if ((int64_t)blockIdx.x < m_tiles) {
+      mbar_wait(smem_u32(w_full), 0);
+      tcgen05_fence_after();
+    }
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kABytes >> 4), b_lo = b_lo0 + (uint32_t)kb * (kBBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBK / UMMA_K; ++k)
+            umma_bf16(tmem_d, desc_from(a_lo + k * 2, kHi), desc_from(b_lo + k * 2, kHi), idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) umma_commit(smem_u32(&tmem_full[acc]));
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp < 2 + kGatherWarps) {
+    // ===================== gather producers: z = h[u] * h[v] straight into the swizzled A stage =====================
+    const int gw = warp - 2;                      // rows [32 gw, 32 gw + 32) of the tile
+    const int sub = lane >> 3, j = lane & 7;      // 8 lanes per row (one 128-byte K slice), 4 rows per instruction
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      const int64_t m_lane = mt * kTileM + gw * 32 + lane;
+      int64_t uu = 0, vv = 0;
+      if (m_lane < p.M) { uu = __ldg(p.u + m_lane); vv = __ldg(p.v + m_lane); }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        uint8_t* sa = smem_a + (size_t)stage * kABytes;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint4 a[4], b[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = (half * 4 + it) * 4 + sub;       // row inside this warp's 32
+            const int64_t ur = __shfl_sync(0xffffffffu, uu, rl), vr = __shfl_sync(0xffffffffu, vv, rl);
+            a[it] = ldg_v4(p.h + ur * p.ldh + kb * kBK + j * 8);
+            b[it] = ldg_v4(p.h + vr * p.ldh + kb * kBK + j * 8);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = (half * 4 + it) * 4 + sub;
+            const int row = gw * 32 + rl;                    // row inside the tile
+            const int64_t m = mt * kTileM + row;
+            uint4 z;
+            z.x = mul_bf16x2(a[it].x, b[it].x); z.y = mul_bf16x2(a[it].y, b[it].y);
+            z.z = mul_bf16x2(a[it].z, b[it].z); z.w = mul_bf16x2(a[it].w, b[it].w);
+            if (m >= p.M) z = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sa + row * 128 + ((j ^ (row & 7)) << 4)) = z;   // SWIZZLE_128B, K-major
+            if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb * kBK + j * 8, z);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: bias + relu + dropout -> y, row . w2 -> sigmoid =====================
+    const int ew = warp - (2 + kGatherWarps);
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                  // which half of the columns
+    constexpr int kColsPerWarp = BLOCK_N / 2;
+    EpilogueParams ep{};
+    ep.dropout_p = p.dropout_p; ep.seed = p.seed; ep.offset = p.offset; ep.rng_state = p.rng_state;
+    if (ep.dropout_p > 0.0f) resolve_rng(ep);
+    const bool y32 = p.y != nullptr && (reinterpret_cast<uintptr_t>(p.y) % 32) == 0 && (p.ldy * 2) % 32 == 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int row = quad * 32 + lane;
+      const int64_t m = mt * kTileM + row;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      uint4 rnd128 = make_uint4(0, 0, 0, 0);
+      uint32_t rnd_group = 0xffffffffu;
+      float dot = 0.0f;
+#pragma unroll 1
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
+        if (c0 >= p.N) break;
+        if (ep.dropout_p == 0.5f && (uint32_t)(c0 >> 7) != rnd_group) {
+          rnd_group = (uint32_t)(c0 >> 7);
+          rnd128 = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)rnd_group);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        const int valid = p.N - c0 < 32 ? p.N - c0 : 32;
+        float f[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(r[q]);
+        if (p.bias1 != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            if (q < valid) {   // N is a multiple of 8 (TMA rows): whole float4s
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + c0 + q));
+              f[q] += b.x; f[q + 1] += b.y; f[q + 2] += b.z; f[q + 3] += b.w;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.0f);
+        }
+        if (ep.dropout_p == 0.5f) {
+          const uint32_t bits = dropout_word(rnd128, (c0 >> 5) & 3);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) f[q] = ((bits >> q) & 1u) ? f[q] * 2.0f : 0.0f;
+        } else if (ep.dropout_p > 0.0f) {
+          const uint32_t thr = dropout_thr16(ep.dropout_p);
+          const float scale = 1.0f / (1.0f - ep.dropout_p);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 rnd = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)((c0 >> 3) + g));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[g * 8 + i] = dropout_u16(rnd, i) >= thr ? f[g * 8 + i] * scale : 0.0f;
+          }
+        }
+        // y is stored (and scored) as bf16: round once, use the rounded values for the head like the unfused path
+        uint32_t packed[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) packed[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
+        if (p.y != nullptr && m < p.M) {
+          __nv_bfloat16* dst = p.y + m * p.ldy + c0;
+          if (y32 && valid == 32) {
+            U32x8 lo, hi;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { lo.v[q] = packed[q]; hi.v[q] = packed[8 + q]; }
+            stg_v8(dst, lo);
+            stg_v8(dst + 16, hi);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (q < valid) dst[q] = __float2bfloat16_rn(f[q]);
+          }
+        }
+        if (p.prob != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (2 * q < valid) {
+              const float2 w = __ldg(reinterpret_cast<const float2*>(p.w2 + c0 + 2 * q));
+              dot = fmaf(__uint_as_float(packed[q] << 16), w.x, dot);
+              dot = fmaf(__uint_as_float(packed[q] & 0xffff0000u), w.y, dot);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));   // accumulator drained: the MMA warp may reuse it
+      if (p.prob != nullptr) {
+        float* part = head_part + acc * 2 * kTileM;
+        part[half * kTileM + row] = dot;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // the 8 epilogue warps only
+        if (half == 0 && m < p.M) {
+          const float logit = part[row] + part[kTileM + row] + (p.b2 != nullptr ? __ldg(p.b2) : 0.0f);
+          p.prob[m] = 1.0f / (1.0f + expf(-logit));
+        }
+        // the next tile uses the other head_part slot; the slot after that is separated from this read by a bar.sync
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BLOCK_N>
+static int launch(const CUtensorMap& map_w, Params& p, cudaStream_t stream) {
+  auto kern = edge_mlp_kernel<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    configured = true;
+  }
+  const int num_kb = p.K / kBK;
+  const int b_bytes = num_kb * BLOCK_N * 128;
+  const int fixed = 1024 + kAccStages * 2 * kTileM * 4 + 512;
+  int stages = (kSmemMax - fixed - b_bytes) / kABytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return LLP_E_SHAPE;
+  p.stages = stages;
+  const int smem = b_bytes + stages * kABytes + fixed;
+  const int64_t m_tiles = ceil_div(p.M, kTileM);
+  const unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
+  kern<<<grid, kThreads, smem, stream>>>(map_w, p);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace em
+}  // namespace llp
+
+using namespace llp;
+
+extern "C" int llp_edge_mlp_supported(int64_t K, int64_t N) {
+  return (K > 0 && K % em::kBK == 0 && N > 0 && N % 8 == 0 && N <= 256 && K * ((N > 128) ? 256 : (N > 64 ? 128 : 64)) * 2 <= 128 * 1024)
+             ? 1 : 0;
+}
+
+extern "C" int llp_edge_mlp_fused(const llp_edge_mlp_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(a != nullptr && a->M >= 0);
+  if (int rc = check_device()) return rc;
+  if (a->M == 0) return 0;
+  LLP_CHECK_ARG(a->h && a->u && a->v && a->W1 && a->ldh >= a->K && a->ldw1 >= a->K);
+  LLP_CHECK_ARG(a->z == nullptr || a->ldz >= a->K);
+  LLP_CHECK_ARG(a->y == nullptr || a->ldy >= a->N);
+  LLP_CHECK_ARG(a->prob == nullptr || a->w2 != nullptr);
+  LLP_CHECK_ARG(a->y != nullptr || a->prob != nullptr);
+  LLP_CHECK_ARG(a->dropout_p >= 0.0f && a->dropout_p < 1.0f);
+  if (!llp_edge_mlp_supported(a->K, a->N)) return LLP_E_SHAPE;
+  if (!aligned(a->h, 16) || (a->ldh * 2) % 16 != 0 || (a->z && (!aligned(a->z, 16) || (a->ldz * 2) % 16 != 0)) ||
+      (a->bias1 && !aligned(a->bias1, 16)) || (a->w2 && !aligned(a->w2, 8)))
+    return LLP_E_ALIGN;
+  const int bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  CUtensorMap map_w;
+  memset(&map_w, 0, sizeof(map_w));
+  if (int rc = tc::make_map(&map_w, a->W1, a->N, a->K, a->ldw1, em::kBK, bn)) return rc;
+  em::Params p{};
+  p.h = reinterpret_cast<const __nv_bfloat16*>(a->h); p.ldh = a->ldh;
+  p.u = a->u; p.v = a->v; p.M = a->M; p.K = (int)a->K; p.N = (int)a->N;
+  p.bias1 = a->bias1; p.relu = a->relu; p.dropout_p = a->dropout_p; p.seed = a->seed; p.offset = a->offset;
+  p.rng_state = a->rng_state;
+  p.z = reinterpret_cast<__nv_bfloat16*>(a->z); p.ldz = a->ldz;
+  p.y = reinterpret_cast<__nv_bfloat16*>(a->y); p.ldy = a->ldy;
+  p.w2 = a->w2; p.b2 = a->b2; p.prob = a->prob;
+  if (bn == 256) return em::launch<256>(map_w, p, stream);
+  if (bn == 128) return em::launch<128>(map_w, p, stream);
+  return em::launch<64>(map_w, p, stream);
+}

@@ -204,7 +204,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       if (row < p.N1 && num_kb > 0) {
         float* dst = p.partial + ((int64_t)split * p.N1 + row) * ncols + c0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        for (int j = 0; j < 32; j += 8) {
+          U32x8 v;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v.v[q] = r[j + q];
+          stg_v8(dst + j, v);   // the workspace is 256-byte aligned and every row is a multiple of 64 floats
+        }
       } else if (row < p.N1) {
         float* dst = p.partial + ((int64_t)split * p.N1 + row) * ncols + c0;
 #pragma unroll
@@ -229,60 +234,67 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   }
 }
 
-// Sum of the split partials in split order (four independent running sums of every fourth split, combined in a fixed
-// order => deterministic).  One thread per 4 consecutive columns of a row (or per bias element).
-__global__ void __launch_bounds__(256)
+// Sum of the split partials.  A block = 64 output quads (4 consecutive columns of a row, or bias elements) x 4 split
+// groups: group g adds the splits g, g+4, g+8, ... (8 loads in flight per thread), the four group sums are combined in
+// group order through shared memory.  A fixed association => deterministic; four times the loads in flight of a
+// one-thread-per-output reduce (the partials are L2-resident, the reduce is latency-bound).
+constexpr int kRedQuads = 64, kRedGroups = 4;
+__global__ void __launch_bounds__(kRedQuads * kRedGroups)
 wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ partial_bias, int splits, int64_t N1,
                     int ncols, int slabs_a, int64_t n2a, int64_t n2b, float* __restrict__ dWa, int64_t ldwa,
                     float* __restrict__ dWb, int64_t ldwb, float* __restrict__ dbias, int accumulate) {
+  __shared__ float4 red[kRedGroups][kRedQuads];
   const int quads = ncols / 4;
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x % kRedQuads, g = threadIdx.x / kRedQuads;
+  const int64_t i = blockIdx.x * (int64_t)kRedQuads + tx;
+  const int64_t n_quads = N1 * quads;
   const int64_t stride = N1 * (int64_t)ncols;
-  if (i < N1 * quads) {
-    const int64_t row = i / quads;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool is_bias = false;
+  int64_t row = 0, j = 0, width = 0;
+  bool in_a = true, live = false;
+  if (i < n_quads) {
+    row = i / quads;
     const int col = (int)(i % quads) * 4;
-    const bool in_a = col < slabs_a * 64;
-    const int64_t j = in_a ? col : col - slabs_a * 64;      // column inside dWa / dWb
-    const int64_t width = in_a ? n2a : n2b;
-    if (j >= width) return;                                    // zero padding of the last slab
-    const float* src = partial + row * ncols + col;
-    float4 acc[4];
+    in_a = col < slabs_a * 64;
+    j = in_a ? col : col - slabs_a * 64;
+    width = in_a ? n2a : n2b;
+    live = j < width;  // not the zero padding of the last slab
+    if (live) {
+      const float* src = partial + row * ncols + col;
+      int k = g;
+      for (; k + 7 * kRedGroups < splits; k += 8 * kRedGroups) {
+        float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int k = 0;
-    for (; k + 8 <= splits; k += 8) {
-      float4 v[8];
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(k + u * kRedGroups) * stride));
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(k + u) * stride));
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        acc[u & 3].x += v[u].x; acc[u & 3].y += v[u].y; acc[u & 3].z += v[u].z; acc[u & 3].w += v[u].w;
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+      }
+      for (; k < splits; k += kRedGroups) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)k * stride));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
-    for (; k < splits; ++k) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)k * stride));
-      acc[k & 3].x += v.x; acc[k & 3].y += v.y; acc[k & 3].z += v.z; acc[k & 3].w += v.w;
-    }
-    float s[4] = {(acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y),
-                  (acc[0].z + acc[1].z) + (acc[2].z + acc[3].z), (acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)};
-    float* dst = (in_a ? dWa + row * ldwa : dWb + row * ldwb) + j;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (j + q < width) dst[q] = accumulate ? dst[q] + s[q] : s[q];
-  } else if (dbias != nullptr && i < N1 * quads + N1) {
-    const int64_t row = i - N1 * quads;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = 0;
-    for (; k + 4 <= splits; k += 4) {
-      a0 += partial_bias[(int64_t)k * N1 + row];
-      a1 += partial_bias[(int64_t)(k + 1) * N1 + row];
-      a2 += partial_bias[(int64_t)(k + 2) * N1 + row];
-      a3 += partial_bias[(int64_t)(k + 3) * N1 + row];
-    }
-    for (; k < splits; ++k) a0 += partial_bias[(int64_t)k * N1 + row];
-    const float s = (a0 + a1) + (a2 + a3);
-    dbias[row] = accumulate ? dbias[row] + s : s;
+  } else if (dbias != nullptr && i < n_quads + N1) {
+    is_bias = live = true;
+    row = i - n_quads;
+    for (int k = g; k < splits; k += kRedGroups) acc.x += partial_bias[(int64_t)k * N1 + row];
   }
+  red[g][tx] = acc;
+  __syncthreads();
+  if (g != 0 || !live) return;
+  float4 s = red[0][tx];
+#pragma unroll
+  for (int q = 1; q < kRedGroups; ++q) { s.x += red[q][tx].x; s.y += red[q][tx].y; s.z += red[q][tx].z; s.w += red[q][tx].w; }
+  if (is_bias) {
+    dbias[row] = accumulate ? dbias[row] + s.x : s.x;
+    return;
+  }
+  float* dst = (in_a ? dWa + row * ldwa : dWb + row * ldwb) + j;
+  const float v4[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (j + q < width) dst[q] = accumulate ? dst[q] + v4[q] : v4[q];
 }
 
 static void plan(int64_t M, int64_t N1, int64_t n2a, int64_t n2b, Params* p, int kBK) {
@@ -361,7 +373,7 @@ int wgrad_tcgen05(int64_t M, int64_t N1, const void* G, int64_t ldg, int64_t n2a
   else wgrad_kernel<32><<<grid, kThreads, smem, stream>>>(maps, p);
   LLP_LAUNCH_OK();
   const int64_t work = N1 * (ncols / 4) + (dbias != nullptr ? N1 : 0);
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, stream>>>(
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(work, kRedQuads), kRedQuads * kRedGroups, 0, stream>>>(
       p.partial, p.partial_bias, p.splits, N1, ncols, p.slabs_a, n2a, n2b, dWa, ldwa, dWb, ldwb, dbias, accumulate);
   LLP_LAUNCH_OK();
   return 0;

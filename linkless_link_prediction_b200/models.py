@@ -19,6 +19,9 @@ def _linear(x, lin: nn.Linear, relu: bool, p: float, in_gate: float = 0.0, defer
     return ops.LinearFn.apply(x, lin.weight, lin.bias, relu, p, seed, offset, in_gate, defer_gate)
 
 
+FUSE_EDGE_MLP = True  # LinkPredictor.score: gather + lin1 + head as one tcgen05 kernel when the shapes allow it
+
+
 def _gate_scale(p: float) -> float:
     """Backward factor of relu + dropout(p) taken from the saved output: 1/(1-p) where the output is positive."""
     return 1.0 / (1.0 - p)
@@ -130,6 +133,15 @@ class LinkPredictor(nn.Module):
         embedding matrix ``h`` — same value as ``forward(h[u], h[v])`` without materialising the gathers.
         ``plan``: optional ``ops.EdgePlan`` of (u, v) built ahead of time for the backward."""
         lead = u.shape
-        z = ops.HadamardFn.apply(ops.to_compute(h), u.reshape(-1).contiguous(), v.reshape(-1).contiguous(), plan)
+        hc, uf, vf = ops.to_compute(h), u.reshape(-1).contiguous(), v.reshape(-1).contiguous()
+        if self.predictor == "mlp" and len(self.lins) == 2 and self.lins[1].out_features == 1 and FUSE_EDGE_MLP \
+                and ops.edge_mlp_supported(hc, self.lins[0].in_features, self.lins[0].out_features):
+            # one kernel: gather-Hadamard -> lin1 (+bias, relu, dropout) -> lin2 -> sigmoid
+            p = float(self.dropout) if self.training else 0.0
+            _, site = ops._dropout_seed() if p > 0 else (0, 0)
+            l1, l2 = self.lins[0], self.lins[1]
+            out = ops.EdgeMlpFn.apply(hc, uf, vf, l1.weight, l1.bias, l2.weight, l2.bias, p, site, plan)
+            return out.reshape(*lead, 1)
+        z = ops.HadamardFn.apply(hc, uf, vf, plan)
         out = self._head(z)
         return out.reshape(*lead, 1) if self.predictor == "mlp" else out.reshape(*lead)

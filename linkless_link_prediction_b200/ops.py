@@ -569,22 +569,26 @@ class HadamardFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gz):
-        lib = N.require_gpu()
         (h,) = ctx.saved_tensors
-        plan = ctx.plan
-        M, F, Nn = plan.num_edges, h.size(1), h.size(0)
-        gz = to_compute(gz) if gz.dtype != h.dtype else gz
-        gh = empty_mat(Nn, F, h.dtype, h.device)
-        nbytes = lib.llp_edge_hadamard_bwd_workspace_bytes(M)
-        ws = _ws(nbytes, h.device)
-        hp, ldh = N.mat(h)
-        gp, ldg = N.mat(gz)
-        op, ldo = N.mat(gh)
-        plan.wait()
-        N.check(lib.llp_edge_hadamard_bwd(N.dtype_id(h.dtype), hp, ldh, F, M, gp, ldg, Nn, plan.rowptr.data_ptr(),
-                                          plan.meta.data_ptr(), op, ldo, ws.data_ptr(), nbytes, N.stream_ptr()),
-                "llp_edge_hadamard_bwd")
-        return gh, None, None, None
+        return hadamard_bwd(h, ctx.plan, gz), None, None, None
+
+
+def hadamard_bwd(h: torch.Tensor, plan: "EdgePlan", gz: torch.Tensor) -> torch.Tensor:
+    """gh[n] = sum of gz[m] * h[other endpoint of m] over the incidences of node n (atomic-free gather-reduce)."""
+    lib = N.require_gpu()
+    M, F, Nn = plan.num_edges, h.size(1), h.size(0)
+    gz = to_compute(gz) if gz.dtype != h.dtype else gz
+    gh = empty_mat(Nn, F, h.dtype, h.device)
+    nbytes = lib.llp_edge_hadamard_bwd_workspace_bytes(M)
+    ws = _ws(nbytes, h.device)
+    hp, ldh = N.mat(h)
+    gp, ldg = N.mat(gz)
+    op, ldo = N.mat(gh)
+    plan.wait()
+    N.check(lib.llp_edge_hadamard_bwd(N.dtype_id(h.dtype), hp, ldh, F, M, gp, ldg, Nn, plan.rowptr.data_ptr(),
+                                      plan.meta.data_ptr(), op, ldo, ws.data_ptr(), nbytes, N.stream_ptr()),
+            "llp_edge_hadamard_bwd")
+    return gh
 
 
 class ScoreHeadFn(torch.autograd.Function):
@@ -606,22 +610,91 @@ class ScoreHeadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dprob):
-        lib = N.require_gpu()
         y, w, prob = ctx.saved_tensors
-        M, H = y.shape
-        need_y, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gy = empty_mat(M, H, y.dtype, y.device) if need_y else None
-        gw = torch.empty(H, dtype=torch.float32, device=y.device) if need_w else None
-        gb = torch.empty(1, dtype=torch.float32, device=y.device) if (ctx.has_b and ctx.needs_input_grad[2]) else None
-        nbytes = lib.llp_score_head_bwd_workspace_bytes(M, H)
-        ws = _ws(nbytes, y.device)
-        yp, ldy = N.mat(y)
-        gyp, ldgy = N.mat(gy) if gy is not None else (None, 0)
-        wf = w.detach().reshape(-1).contiguous()
-        N.check(lib.llp_score_head_bwd(N.dtype_id(y.dtype), yp, ldy, M, H, wf.data_ptr(), prob.data_ptr(),
-                                       dprob.contiguous().data_ptr(), ctx.in_gate, gyp, ldgy, N.ptr(gw), N.ptr(gb),
-                                       ws.data_ptr(), nbytes, N.stream_ptr()), "llp_score_head_bwd")
-        return gy, (gw.reshape(w.shape) if gw is not None else None), gb, None
+        gy, gw, gb = score_head_bwd(y, w, prob, dprob, ctx.in_gate, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    ctx.has_b and ctx.needs_input_grad[2])
+        return gy, gw, gb, None
+
+
+def score_head_bwd(y, w, prob, dprob, in_gate, need_y=True, need_w=True, need_b=True):
+    """Backward of ``sigmoid(y w^T + b)``: ``gy`` (masked by the relu/dropout gate of the layer that produced ``y`` when
+    ``in_gate`` > 0), ``gw`` (shaped like ``w``) and ``gb`` in one pass over ``y``."""
+    lib = N.require_gpu()
+    M, H = y.shape
+    gy = empty_mat(M, H, y.dtype, y.device) if need_y else None
+    gw = torch.empty(H, dtype=torch.float32, device=y.device) if need_w else None
+    gb = torch.empty(1, dtype=torch.float32, device=y.device) if need_b else None
+    nbytes = lib.llp_score_head_bwd_workspace_bytes(M, H)
+    ws = _ws(nbytes, y.device)
+    yp, ldy = N.mat(y)
+    gyp, ldgy = N.mat(gy) if gy is not None else (None, 0)
+    wf = w.detach().reshape(-1).contiguous()
+    N.check(lib.llp_score_head_bwd(N.dtype_id(y.dtype), yp, ldy, M, H, wf.data_ptr(), prob.data_ptr(),
+                                   dprob.contiguous().data_ptr(), float(in_gate), gyp, ldgy, N.ptr(gw), N.ptr(gb),
+                                   ws.data_ptr(), nbytes, N.stream_ptr()), "llp_score_head_bwd")
+    return gy, (gw.reshape(w.shape) if gw is not None else None), gb
+
+
+def edge_mlp_supported(h: torch.Tensor, in_channels: int, hidden: int) -> bool:
+    """Can ``EdgeMlpFn`` (the fused gather + first predictor GEMM + score head kernel) take this problem?"""
+    if compute_dtype() != torch.bfloat16 or not h.is_cuda or h.dim() != 2:
+        return False
+    return bool(N.require_gpu().llp_edge_mlp_supported(int(in_channels), int(hidden)))
+
+
+class EdgeMlpFn(torch.autograd.Function):
+    """``sigmoid(lin2(dropout(relu(lin1(h[u] * h[v])))))`` for a 2-layer LinkPredictor with one output (models.py:139-150
+    on ``predictor(h[edge[0]], h[edge[1]])``, train_teacher_gnn.py:58,97) as ONE kernel: the gather-Hadamard feeds the
+    tensor core directly (``llp_edge_mlp_fused``).  Training keeps ``z`` and ``y`` for the backward pass, which is the
+    same sequence of kernels the unfused modules run; without grad nothing but the scores is written."""
+
+    @staticmethod
+    def forward(ctx, h, u, v, W1, b1, w2, b2, p, site, plan):
+        lib = N.require_gpu()
+        M, K, H = u.numel(), h.size(1), W1.size(0)
+        need_grad = any(ctx.needs_input_grad)
+        dev = h.device
+        z = empty_mat(M, K, h.dtype, dev) if need_grad else None
+        y = empty_mat(M, H, h.dtype, dev) if need_grad else None
+        prob = torch.empty(M, dtype=torch.float32, device=dev)
+        Wc = _weights(W1)
+        a = N.EdgeMlpArgs()
+        a.h, a.ldh = N.mat(h)
+        a.u, a.v, a.M, a.K, a.N = u.data_ptr(), v.data_ptr(), M, K, H
+        a.W1, a.ldw1 = N.mat(Wc)
+        a.bias1 = N.ptr(b1)
+        a.relu, a.dropout_p, a.seed, a.offset = 1, float(p), 0, int(site)
+        a.rng_state = N.ptr(rng_state(dev)) if p > 0 else None
+        if z is not None:
+            a.z, a.ldz = N.mat(z)
+            a.y, a.ldy = N.mat(y)
+        w2f = w2.detach().reshape(-1).contiguous()
+        a.w2, a.b2, a.prob = w2f.data_ptr(), N.ptr(b2), prob.data_ptr()
+        N.check(lib.llp_edge_mlp_fused(ctypes.byref(a), N.stream_ptr()), "llp_edge_mlp_fused")
+        if need_grad:
+            if ctx.needs_input_grad[0] and (plan is None or not plan.matches(u, v, h.size(0))):
+                plan = EdgePlan(u, v, h.size(0))
+            ctx.plan, ctx.p = plan, float(p)
+            ctx.params = (W1, b1)
+            ctx.save_for_backward(h, z, y, W1, w2, prob)
+            ctx.has_b2 = b2 is not None
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        h, z, y, W1, w2, prob = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        W1p, b1p = ctx.params
+        gate_scale = 1.0 / (1.0 - ctx.p)   # relu + dropout backward from the saved y: 1/(1-p) where y > 0
+        gy, gw2, gb2 = score_head_bwd(y, w2, prob, dprob, gate_scale, True, need[5], ctx.has_b2 and need[6])
+        gW1, _, gb1 = wgrad(gy, z, W1p if need[3] else None, bias=b1p if (b1p is not None and need[4]) else None)
+        gh = None
+        if need[0]:
+            gz = gemm_nt(gy, _weights_t(W1p))
+            gh = hadamard_bwd(h, ctx.plan, gz)
+        return gh, None, None, gW1, gb1, gw2, gb2, None, None, None
+
+
 
 
 class _LossFn(torch.autograd.Function):

@@ -250,3 +250,49 @@ def test_captured_step_draws_new_dropout_masks(cuda):
     ops.seed_dropout(11)
     c = [float(step(e, n_).item()) for _ in range(5)]
     np.testing.assert_allclose(b, c, rtol=1e-6)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5, 0.3])
+@pytest.mark.parametrize("n,f,H,m", [(500, 64, 64, 1000), (3000, 256, 256, 20000), (700, 128, 200, 777)])
+def test_fused_edge_scorer_equals_unfused(cuda, p, n, f, H, m):
+    """LinkPredictor.score through the single fused kernel (gather-Hadamard as the A-operand producer of the first
+    predictor GEMM + bias/relu/dropout + score head) == the separate kernels: same dropout masks, same bf16 roundings of
+    z and y, scores and every gradient agree; the no-grad (evaluation) path writes only the scores."""
+    from linkless_link_prediction_b200 import models
+    seed_all(3)
+    h0 = (torch.randn(n, f) * 0.5).to(cuda)
+    u, v = torch.randint(0, n, (m,)).to(cuda), torch.randint(0, n, (m,)).to(cuda)
+    pred = L.LinkPredictor("mlp", f, H, 1, 2, p).to(cuda)
+    pred.train()
+    dp = torch.randn(m).to(cuda)
+    outs = []
+    for fused in (True, False):
+        models.FUSE_EDGE_MLP = fused
+        try:
+            for q in pred.parameters():
+                q.grad = None
+            ops.seed_dropout(5)
+            ops.advance_rng(cuda)
+            h = ops.cast2d(h0, torch.bfloat16).requires_grad_(True)
+            prob = pred.score(h, u, v).reshape(-1)
+            prob.backward(dp)
+            with torch.no_grad():
+                pred.eval()
+                ev = pred.score(h.detach(), u, v).reshape(-1)
+                pred.train()
+            outs.append((prob.detach(), h.grad.float(), [q.grad.clone() for q in pred.parameters()], ev))
+        finally:
+            models.FUSE_EDGE_MLP = True
+    (pa, ga, qa, ea), (pb, gb, qb, eb) = outs
+    torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ea, eb, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ga, gb, rtol=2e-2, atol=2e-3)
+    for a, b in zip(qa, qb):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-3)
+    # and against the fp32 oracle formula at p = 0
+    if p == 0.0:
+        w1, b1, w2, b2 = [q.detach().float().cpu() for q in pred.parameters()]
+        hf = ops.cast2d(h0, torch.bfloat16).float().cpu()
+        z = hf[u.cpu()] * hf[v.cpu()]
+        ref = torch.sigmoid(torch.relu(z @ w1.t() + b1) @ w2.t() + b2).reshape(-1)
+        torch.testing.assert_close(ea.cpu(), ref, rtol=2e-2, atol=2e-2)
