@@ -20,10 +20,16 @@ using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kBK = 64;                 // bf16 elements per K block = one 128-byte swizzle row
-constexpr int kGatherWarps = 4;
+constexpr int kGatherWarps = 8;         // split over the K blocks of a tile
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kGatherWarps + kEpiWarps);
+constexpr int kCtrlWarps = 1;            // warp 0: W1 loader, TMEM allocator and MMA issuer
+constexpr int kThreads = 32 * (kCtrlWarps + kGatherWarps + kEpiWarps);
 constexpr int kAccStages = 2;
+#ifndef LLP_EM_GROUP_ROWS
+#define LLP_EM_GROUP_ROWS 16
+#endif
+constexpr int kGroupRows = LLP_EM_GROUP_ROWS;   // rows per load group of a producer warp: 2 x (rows / 4) 128-bit loads in flight
+                                                // per lane (32 was measured too: 68 us vs 64 us for the M = 131072 issue loop)
 constexpr int kABytes = kTileM * 128;   // one A stage: 128 rows x 128 B
 constexpr int kSmemMax = 226 * 1024;
 
@@ -37,6 +43,7 @@ struct Params {
   __nv_bfloat16* y; int64_t ldy;
   const float* w2; const float* b2; float* prob;
   int stages;
+  long long* dbg;   // instrumentation (llp_set_tuning(15, 1)): per CTA {issue loop ns, operand wait ns, accumulator wait ns}
 };
 
 __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
@@ -53,7 +60,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
   uint8_t* smem_b = smem;                                   // [num_kb][BLOCK_N rows x 128 B], resident
   uint8_t* smem_a = smem + (size_t)num_kb * kBBytes;        // [stages][128 rows x 128 B]
   float* head_part = reinterpret_cast<float*>(smem_a + (size_t)p.stages * kABytes);  // [kAccStages][2][kTileM]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(head_part + kAccStages * 2 * kTileM);
+  float* s_bias = head_part + kAccStages * 2 * kTileM;     // [256] bias1 (zeros when absent)
+  float* s_w2 = s_bias + 256;                              // [256] w2 (zeros when absent)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w2 + 256);
   uint64_t* full_bar = bars;                       // [stages], one arrival per gather warp
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tmem_full = bars + 2 * p.stages;       // [kAccStages]
@@ -67,41 +76,50 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), kGatherWarps); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), kGatherWarps / num_kb); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps); }
     mbar_init(smem_u32(w_full), 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {   // epilogue vectors: shared-memory broadcasts, not global loads
+    s_bias[i] = (p.bias1 != nullptr && i < p.N) ? __ldg(p.bias1 + i) : 0.0f;
+    s_w2[i] = (p.w2 != nullptr && i < p.N) ? __ldg(p.w2 + i) : 0.0f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===================== W1: all K blocks, once =====================
+    // ===================== W1: all K blocks, once; then the MMA issue loop =====================
     if ((int64_t)blockIdx.x < m_tiles && elect_one_sync()) {
       mbar_expect_tx(smem_u32(w_full), (uint32_t)(num_kb * kBBytes));
       for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_u32(smem_b + (size_t)kb * kBBytes), &map_w, kb * kBK, 0, smem_u32(w_full));
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(kTileM, BLOCK_N, false);
     constexpr uint32_t kHi = desc_hi_sw128(1024);
     const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16), b_lo0 = desc_lo(smem_u32(smem_b), 16);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    long long t_begin = 0, w_full_ns = 0, w_acc_ns = 0, t0 = 0;
+    auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (p.dbg) t_begin = now();
     if ((int64_t)blockIdx.x < m_tiles) {
       mbar_wait(smem_u32(w_full), 0);
       tcgen05_fence_after();
     }
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      if (p.dbg) t0 = now();
       mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      if (p.dbg) w_acc_ns += now() - t0;
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.dbg) t0 = now();
         mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (p.dbg) w_full_ns += now() - t0;
         tcgen05_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kABytes >> 4), b_lo = b_lo0 + (uint32_t)kb * (kBBytes >> 4);
@@ -117,50 +135,66 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
       __syncwarp();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp < 2 + kGatherWarps) {
-    // ===================== gather producers: z = h[u] * h[v] straight into the swizzled A stage =====================
-    const int gw = warp - 2;                      // rows [32 gw, 32 gw + 32) of the tile
-    const int sub = lane >> 3, j = lane & 7;      // 8 lanes per row (one 128-byte K slice), 4 rows per instruction
-    int stage = 0; uint32_t phase = 0;
-    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      const int64_t m_lane = mt * kTileM + gw * 32 + lane;
-      int64_t uu = 0, vv = 0;
-      if (m_lane < p.M) { uu = __ldg(p.u + m_lane); vv = __ldg(p.v + m_lane); }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        uint8_t* sa = smem_a + (size_t)stage * kABytes;
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 4 + 0] = now() - t_begin;
+      p.dbg[blockIdx.x * 4 + 1] = w_full_ns;
+      p.dbg[blockIdx.x * 4 + 2] = w_acc_ns;
+    }
+  } else if (warp < kCtrlWarps + kGatherWarps) {
+    // ===================== gather producers: z = h[u] * h[v] straight into the swizzled A stages =====================
+    // The 8 warps are split over the K blocks of the tile (8 / num_kb warps per K block, each owning a slice of the
+    // 128 rows), so every pipeline stage has its own producers: the stage of K block k of the NEXT tile is refilled as
+    // soon as the tensor core has consumed it, while later K blocks of the current tile are still being multiplied.
+    // 8 lanes cover one 128-byte K slice of a row (a full L2 line), 4 rows per instruction, 16 row loads in flight
+    // per lane batch (8 x (h[u], h[v])).
+    const int gw = warp - kCtrlWarps;
+    const int wpk = kGatherWarps / num_kb;               // warps per K block (num_kb in {1, 2, 4})
+    const int kb_mine = gw % num_kb, part = gw / num_kb;
+    const int rows_mine = kTileM / wpk;                  // 16, 32 or 64 rows per warp
+    const int sub = lane >> 3, j = lane & 7;
+    int64_t slot = kb_mine;                              // ring position of my K block: stage = slot % stages
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, slot += num_kb) {
+      const int stage = (int)(slot % p.stages);
+      mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)(((slot / p.stages) & 1) ^ 1));
+      uint8_t* sa = smem_a + (size_t)stage * kABytes;
+      for (int r0 = 0; r0 < rows_mine; r0 += 32) {       // batches of up to 32 rows
+        const int batch = rows_mine - r0 < 32 ? rows_mine - r0 : 32;
+        const int row_l = part * rows_mine + r0 + lane;  // the row whose endpoints this lane fetches
+        const int64_t m_l = mt * kTileM + row_l;
+        int uu = 0, vv = 0;
+        if (lane < batch && m_l < p.M) { uu = (int)__ldg(p.u + m_l); vv = (int)__ldg(p.v + m_l); }
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint4 a[4], b[4];
+        for (int g0 = 0; g0 < 32; g0 += kGroupRows) {
+          if (g0 >= batch) break;
+          constexpr int kIt = kGroupRows / 4;
+          uint4 a[kIt], b[kIt];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = (half * 4 + it) * 4 + sub;       // row inside this warp's 32
-            const int64_t ur = __shfl_sync(0xffffffffu, uu, rl), vr = __shfl_sync(0xffffffffu, vv, rl);
-            a[it] = ldg_v4(p.h + ur * p.ldh + kb * kBK + j * 8);
-            b[it] = ldg_v4(p.h + vr * p.ldh + kb * kBK + j * 8);
+          for (int it = 0; it < kIt; ++it) {
+            const int rl = g0 + it * 4 + sub;            // row inside the batch
+            const int ur = __shfl_sync(0xffffffffu, uu, rl), vr = __shfl_sync(0xffffffffu, vv, rl);
+            a[it] = ldg_v4(p.h + (int64_t)ur * p.ldh + kb_mine * kBK + j * 8);
+            b[it] = ldg_v4(p.h + (int64_t)vr * p.ldh + kb_mine * kBK + j * 8);
           }
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = (half * 4 + it) * 4 + sub;
-            const int row = gw * 32 + rl;                    // row inside the tile
+          for (int it = 0; it < kIt; ++it) {
+            const int row = part * rows_mine + r0 + g0 + it * 4 + sub;   // row inside the tile
             const int64_t m = mt * kTileM + row;
             uint4 z;
             z.x = mul_bf16x2(a[it].x, b[it].x); z.y = mul_bf16x2(a[it].y, b[it].y);
             z.z = mul_bf16x2(a[it].z, b[it].z); z.w = mul_bf16x2(a[it].w, b[it].w);
             if (m >= p.M) z = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(sa + row * 128 + ((j ^ (row & 7)) << 4)) = z;   // SWIZZLE_128B, K-major
-            if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb * kBK + j * 8, z);
+            if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb_mine * kBK + j * 8, z);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
     }
   } else {
     // ===================== epilogue: bias + relu + dropout -> y, row . w2 -> sigmoid =====================
-    const int ew = warp - (2 + kGatherWarps);
+    const int ew = warp - (kCtrlWarps + kGatherWarps);
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int half = ew >> 2;                  // which half of the columns
     constexpr int kColsPerWarp = BLOCK_N / 2;
@@ -188,40 +222,43 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         const int valid = p.N - c0 < 32 ? p.N - c0 : 32;
-        float f[32];
+        const uint32_t bits = ep.dropout_p == 0.5f ? dropout_word(rnd128, (c0 >> 5) & 3) : 0u;
+        const uint32_t thr = dropout_thr16(ep.dropout_p);
+        const float scale = 1.0f / (1.0f - ep.dropout_p);
+        uint32_t packed[16];
+        // 8 columns at a time: bias (smem broadcast), relu, dropout, round to bf16, head dot on the rounded values
 #pragma unroll
-        for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(r[q]);
-        if (p.bias1 != nullptr) {
+        for (int g = 0; g < 4; ++g) {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
+          float f[8] = {__uint_as_float(r[g * 8 + 0]) + b0.x, __uint_as_float(r[g * 8 + 1]) + b0.y, __uint_as_float(r[g * 8 + 2]) + b0.z,
+                        __uint_as_float(r[g * 8 + 3]) + b0.w, __uint_as_float(r[g * 8 + 4]) + b1.x, __uint_as_float(r[g * 8 + 5]) + b1.y,
+                        __uint_as_float(r[g * 8 + 6]) + b1.z, __uint_as_float(r[g * 8 + 7]) + b1.w};
+          if (p.relu) {
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            if (q < valid) {   // N is a multiple of 8 (TMA rows): whole float4s
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + c0 + q));
-              f[q] += b.x; f[q + 1] += b.y; f[q + 2] += b.z; f[q + 3] += b.w;
-            }
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
           }
-        }
-        if (p.relu) {
+          if (ep.dropout_p == 0.5f) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.0f);
-        }
-        if (ep.dropout_p == 0.5f) {
-          const uint32_t bits = dropout_word(rnd128, (c0 >> 5) & 3);
-#pragma unroll
-          for (int q = 0; q < 32; ++q) f[q] = ((bits >> q) & 1u) ? f[q] * 2.0f : 0.0f;
-        } else if (ep.dropout_p > 0.0f) {
-          const uint32_t thr = dropout_thr16(ep.dropout_p);
-          const float scale = 1.0f / (1.0f - ep.dropout_p);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
+            for (int i = 0; i < 8; ++i) f[i] = ((bits >> (g * 8 + i)) & 1u) ? f[i] * 2.0f : 0.0f;
+          } else if (ep.dropout_p > 0.0f) {
             const uint4 rnd = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)((c0 >> 3) + g));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[g * 8 + i] = dropout_u16(rnd, i) >= thr ? f[g * 8 + i] * scale : 0.0f;
+            for (int i = 0; i < 8; ++i) f[i] = dropout_u16(rnd, i) >= thr ? f[i] * scale : 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) packed[g * 4 + i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          if (p.prob != nullptr) {   // columns >= N carry zero weights (and zero accumulators: W1 rows are zero-filled)
+            const float4 w0 = *reinterpret_cast<const float4*>(s_w2 + c0 + g * 8), w1 = *reinterpret_cast<const float4*>(s_w2 + c0 + g * 8 + 4);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 0] << 16), w0.x, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 0] & 0xffff0000u), w0.y, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 1] << 16), w0.z, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 1] & 0xffff0000u), w0.w, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 2] << 16), w1.x, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 2] & 0xffff0000u), w1.y, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 3] << 16), w1.z, dot);
+            dot = fmaf(__uint_as_float(packed[g * 4 + 3] & 0xffff0000u), w1.w, dot);
           }
         }
-        // y is stored (and scored) as bf16: round once, use the rounded values for the head like the unfused path
-        uint32_t packed[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) packed[q] = pack_bf16x2(f[2 * q], f[2 * q + 1]);
         if (p.y != nullptr && m < p.M) {
           __nv_bfloat16* dst = p.y + m * p.ldy + c0;
           if (y32 && valid == 32) {
@@ -232,17 +269,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
             stg_v8(dst + 16, hi);
           } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (q < valid) dst[q] = __float2bfloat16_rn(f[q]);
-          }
-        }
-        if (p.prob != nullptr) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            if (2 * q < valid) {
-              const float2 w = __ldg(reinterpret_cast<const float2*>(p.w2 + c0 + 2 * q));
-              dot = fmaf(__uint_as_float(packed[q] << 16), w.x, dot);
-              dot = fmaf(__uint_as_float(packed[q] & 0xffff0000u), w.y, dot);
+            for (int q = 0; q < 16; ++q) {
+              if (2 * q < valid) {   // N is a multiple of 8: pairs are whole
+                __nv_bfloat162 v2 = *reinterpret_cast<__nv_bfloat162*>(&packed[q]);
+                *reinterpret_cast<__nv_bfloat162*>(dst + 2 * q) = v2;
+              }
             }
           }
         }
@@ -266,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -282,7 +313,7 @@ static int launch(const CUtensorMap& map_w, Params& p, cudaStream_t stream) {
   }
   const int num_kb = p.K / kBK;
   const int b_bytes = num_kb * BLOCK_N * 128;
-  const int fixed = 1024 + kAccStages * 2 * kTileM * 4 + 512;
+  const int fixed = 1024 + kAccStages * 2 * kTileM * 4 + 2 * 256 * 4 + 512;
   int stages = (kSmemMax - fixed - b_bytes) / kABytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return LLP_E_SHAPE;
@@ -301,7 +332,7 @@ static int launch(const CUtensorMap& map_w, Params& p, cudaStream_t stream) {
 using namespace llp;
 
 extern "C" int llp_edge_mlp_supported(int64_t K, int64_t N) {
-  return (K > 0 && K % em::kBK == 0 && N > 0 && N % 8 == 0 && N <= 256 && K * ((N > 128) ? 256 : (N > 64 ? 128 : 64)) * 2 <= 128 * 1024)
+  return ((K == 64 || K == 128 || K == 256) && N > 0 && N % 8 == 0 && N <= 256 && K * ((N > 128) ? 256 : (N > 64 ? 128 : 64)) * 2 <= 128 * 1024)
              ? 1 : 0;
 }
 
@@ -332,6 +363,7 @@ extern "C" int llp_edge_mlp_fused(const llp_edge_mlp_args* a, void* stream_) {
   p.z = reinterpret_cast<__nv_bfloat16*>(a->z); p.ldz = a->ldz;
   p.y = reinterpret_cast<__nv_bfloat16*>(a->y); p.ldy = a->ldy;
   p.w2 = a->w2; p.b2 = a->b2; p.prob = a->prob;
+  p.dbg = g_tuning[15] ? debug_buffer() : nullptr;
   if (bn == 256) return em::launch<256>(map_w, p, stream);
   if (bn == 128) return em::launch<128>(map_w, p, stream);
   return em::launch<64>(map_w, p, stream);

@@ -133,6 +133,31 @@ def main():
                       f"waiting for a free accumulator med/max {wa[74]}/{wa[-1]}", flush=True)
             for k_ in (16, 18):
                 lib.llp_set_tuning(k_, 0)
+    if "edgemlp" in which:
+        import ctypes
+        import linkless_link_prediction_b200 as L
+        lib = N.load()
+        H, M = 256, 131072
+        hN = torch.randn(n, H, device=dev).bfloat16()
+        u = torch.randint(0, n, (M,), device=dev); v = torch.randint(0, n, (M,), device=dev)
+        pred = L.LinkPredictor("mlp", H, H, 1, 2, 0.5).to(dev)
+        for tag, train in (("eval (scores only)", False), ("train forward (z, y, prob; dropout)", True)):
+            pred.train(train)
+            hh = hN.clone().requires_grad_(train)
+            def fwd():
+                with torch.set_grad_enabled(train):
+                    return pred.score(hh, u, v)
+            nb = M * 2 * H * 2 + (M * 2 * H * 2 if train else 0) + 4 * M
+            report(f"fused edge scorer M={M} H={H} {tag}", timeit(fwd), nbytes=nb, flops=2 * M * H * H)
+            lib.llp_set_tuning(15, 1)
+            flush.zero_()
+            fwd()
+            buf = (ctypes.c_int64 * (148 * 4))()
+            lib.llp_debug_read(buf, 148 * 4)
+            lib.llp_set_tuning(15, 0)
+            tot = sorted(buf[4 * i] for i in range(148)); wf = sorted(buf[4 * i + 1] for i in range(148)); wa = sorted(buf[4 * i + 2] for i in range(148))
+            print(f"   MMA issue loop (ns) min/med/max {tot[0]}/{tot[74]}/{tot[-1]}; waiting for operands med/max {wf[74]}/{wf[-1]}; "
+                  f"waiting for a free accumulator med/max {wa[74]}/{wa[-1]}", flush=True)
     if "wgradexp" in which:
         lib = N.load()
         M, N1 = n, 256
