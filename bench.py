@@ -27,11 +27,30 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HIDDEN, LAYERS, BATCH, DROPOUT, LR = 256, 3, 65536, 0.5, 0.005
-# dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch (mean of the step's five launches) from the committed
-# `ncu --set full` capture of this same command; algorithmic bytes per launch are 1.2 GB, the rest are L2 hits
-SPMM_TRAFFIC_BYTES_PER_LAUNCH = (201.3e6 + 804.8e6 + 804.5e6 + 822.4e6 + 821.8e6) / 5
+HIDDEN, LAYERS, BATCH, DROPOUT, LR = 256, 3, 65536, 0.5, 0.005   # LAYERS is per workload: see layers_of()
+
+
+def layers_of(workload):
+    """collab: SAGE 128->256->256->256 (scripts/supervised_transductive.sh); the synthetic power-law config
+    (BASELINE.json configs[4]) is 256->256->256."""
+    return 3 if workload == "collab" else 2
+
+# dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch (mean of one step's five launches) from the committed
+# `ncu --set full` capture of this same command (tools/ncu_summary.py); algorithmic bytes per launch are 1.2 GB, the rest
+# are L2 hits.  Only meaningful for the collab workload the capture was taken on.
 SPMM_TRAFFIC_SOURCE = "profiles/r01_spmm_ncu_full_summary.json"
+
+
+def spmm_traffic(workload):
+    path = os.path.join(ROOT, SPMM_TRAFFIC_SOURCE)
+    if workload != "collab" or not os.path.exists(path):
+        return None
+    try:
+        t = [l["traffic_bytes"] for l in json.load(open(path))["launches"] if "spmm_kernel" in l["kernel"] and "traffic_bytes" in l]
+        return sum(t) / len(t) if t else None
+    except (OSError, ValueError, KeyError):
+        return None
+
 
 
 def parse():
@@ -103,12 +122,12 @@ def build_workload(args, seed=0):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference step on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_runner(data, split, batch):
+def cpu_step_runner(data, split, batch, layers):
     from oracle import llp_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     x, adj = data.x, data.adj_t
-    model = O.SAGE("collab", x.size(1), HIDDEN, HIDDEN, LAYERS, DROPOUT)
+    model = O.SAGE("collab", x.size(1), HIDDEN, HIDDEN, layers, DROPOUT)
     pred = O.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT)
     opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=LR)
     pos = split["train"]["edge"]
@@ -125,7 +144,7 @@ def cpu_step_runner(data, split, batch):
 
 
 def run_cpu(args, data, split, budget_s, max_steps, warmup=1):
-    step = cpu_step_runner(data, split, BATCH)
+    step = cpu_step_runner(data, split, BATCH, layers_of(args.workload))
     for _ in range(warmup):
         step()
     t0, n = time.perf_counter(), 0
@@ -144,8 +163,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"{args.workload}-shaped teacher train step (BASELINE.json configs[3])", "nodes": None,
-              "messages": None, "feat": None, "hidden": HIDDEN, "layers": LAYERS, "batch_pos_edges_per_gpu": BATCH,
+    which = "configs[3]" if args.workload == "collab" else ("configs[4], scaled by %g" % args.scale if args.workload == "powerlaw-10m" else "shape table in data.py")
+    config = {"workload": f"{args.workload}-shaped teacher train step (BASELINE.json {which})", "nodes": None,
+              "messages": None, "feat": None, "hidden": HIDDEN, "layers": layers_of(args.workload), "batch_pos_edges_per_gpu": BATCH,
               "dropout": DROPOUT, "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2"}
 
     if args.impl == "reference":
@@ -180,7 +200,7 @@ def main():
     config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1))
     data = shims.Data(x=data_cpu.x, adj_t=data_cpu.adj_t).to(dev)
     shims.seed_everything(0)
-    model = L.SAGE(args.workload, data.x.size(1), HIDDEN, HIDDEN, LAYERS, DROPOUT).to(dev)
+    model = L.SAGE(args.workload, data.x.size(1), HIDDEN, HIDDEN, layers_of(args.workload), DROPOUT).to(dev)
     predictor = L.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT).to(dev)
     optimizer = L.FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=LR)
     model.train(); predictor.train()
@@ -313,7 +333,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "spmm_kernel (+fix-up), SAGE mean aggregation fwd + transpose-bwd",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-                     "traffic": SPMM_TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": SPMM_TRAFFIC_SOURCE,
+                     "traffic": spmm_traffic(args.workload), "traffic_source": SPMM_TRAFFIC_SOURCE,
                      "launches_timed": spmm_launches, "share_of_step": spmm_share,
                      "algorithmic_bytes_per_launch": spmm_bytes_step / max(len(prof), 1),
                      "algorithmic_bytes_per_step": spmm_bytes_step,

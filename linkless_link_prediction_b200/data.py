@@ -24,6 +24,8 @@ SHAPES = {
     "amazon-computers": (13752, 245861, 767, True, 0.35),
     "amazon-photos": (7650, 119081, 745, True, 0.35),
     "collab": (235868, 1179052, 128, True, None),
+    # BASELINE.json configs[4]: synthetic power-law graph, 10M nodes / 100M undirected pairs (200M messages), 256-d
+    "powerlaw-10m": (10_000_000, 100_000_000, 256, True, None),
 }
 
 
