@@ -65,5 +65,6 @@ extern "C" int llp_debug_read(int64_t* host_out, int n) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return (int)e;
   e = cudaMemcpy(host_out, buf, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(buf, 0, 4096 * sizeof(long long));  // next instrumented launch starts clean
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -539,6 +539,267 @@ static int launch_resb(const Maps& maps, const TcParams& p, int num_kb, cudaStre
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// NT on a CTA PAIR (cta_group::2): one 256 x 256 output tile per pair of SMs, the weight operand resident ACROSS the
+// pair.  tcgen05.mma.cta_group::2 reads the A operand (128 rows) from each CTA's own shared memory and the B operand
+// split along N: CTA r holds the rows [128 r, 128 r + 128) of W for every K block (K <= 512: 128 KB), loaded once.
+// So the ring only streams A tiles and nothing is read twice: L2 -> SM traffic = the activations (the streaming
+// kernel above re-reads the 256 KB weight matrix for every 128-row tile: 2/3 of its traffic at K = 512).
+// Roles per CTA: warp 0 TMA producer (its own A rows / W half; completions are signalled on the LEADER's barriers),
+// warp 1 TMEM allocator (both CTAs) and, in the leader CTA only, the MMA issuer (tcgen05.commit multicasts the stage
+// release and the accumulator-ready arrival to both CTAs), warps 2..9 epilogue of the CTA's own 128 rows (they release
+// the accumulator on the leader's barrier).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the issued MMAs have retired) on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+constexpr int kPairN = 256;                 // output columns of the pair tile
+constexpr int kPairHalfBytes = 128 * 128;   // one K block of a CTA's W half / one A stage: 128 rows x 128 B
+
+template <typename TO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_nt_pair_kernel(const __grid_constant__ Maps maps, const TcParams p, const int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int kb1 = (int)((p.K1 + BLOCK_K - 1) / BLOCK_K), kb2 = (int)((p.K2 + BLOCK_K - 1) / BLOCK_K);
+  const int num_kb = kb1 + kb2;
+  uint8_t* smem_b = smem;                                        // [num_kb][128 rows of W x 128 B], resident
+  uint8_t* smem_a = smem + (size_t)num_kb * kPairHalfBytes;      // [stages][128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)stages * kPairHalfBytes);
+  uint64_t* full_bar = bars;                     // [stages]   (the leader's are used)
+  uint64_t* empty_bar = bars + stages;           // [stages]
+  uint64_t* tmem_full = bars + 2 * stages;       // [kAccStages]
+  uint64_t* tmem_empty = tmem_full + kAccStages; // [kAccStages] (the leader's are used)
+  uint64_t* b_full = tmem_empty + kAccStages;    // [1]   my W half has landed
+  uint64_t* peer_full = b_full + 1;              // [stages] leader only: the peer's stage has landed (forwarded arrival)
+  uint64_t* b_peer = peer_full + stages;         // [1]   leader only: the peer's W half has landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_peer + 1);
+  constexpr int kTmemCols = kAccStages * kPairN;  // 512
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t pair_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int64_t pt_first = blockIdx.x >> 1, pt_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); mbar_init(smem_u32(&peer_full[s]), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 2 * kEpiWarps); }
+    mbar_init(smem_u32(b_full), 1);
+    mbar_init(smem_u32(b_peer), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(tmem_holder), kTmemCols);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer: my W half once, then my A rows =====================
+    if (pt_first < pair_tiles && elect_one_sync()) {
+      const uint32_t bar = smem_u32(b_full);
+      mbar_expect_tx(bar, (uint32_t)(num_kb * kPairHalfBytes));
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const bool second = kb >= kb1;
+        tma_load_2d(smem_u32(smem_b + (size_t)kb * kPairHalfBytes), second ? &maps.b2 : &maps.b1,
+                    (second ? kb - kb1 : kb) * BLOCK_K, (int)rank * 128, bar);
+      }
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t pt = pt_first; pt < pair_tiles; pt += pt_stride) {
+      const int m0 = (int)(pt * 2 * BLOCK_M) + (int)rank * BLOCK_M;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(bar, kPairHalfBytes);
+          const bool second = kb >= kb1;
+          tma_load_2d(smem_u32(smem_a + (size_t)stage * kPairHalfBytes), second ? &maps.a2 : &maps.a1,
+                      (second ? kb - kb1 : kb) * BLOCK_K, m0, bar);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA) =====================
+    constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, kPairN, false);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem_a), 16), b_lo0 = desc_lo(smem_u32(smem_b), 16);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    long long t_begin = 0, w_full = 0, w_acc = 0, t0 = 0;
+    auto now = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (p.dbg) t_begin = now();
+    if (pt_first < pair_tiles) {
+      mbar_wait(smem_u32(b_full), 0);
+      mbar_wait(smem_u32(b_peer), 0);
+      tcgen05_fence_after();
+    }
+    for (int64_t pt = pt_first; pt < pair_tiles; pt += pt_stride) {
+      if (p.dbg) t0 = now();
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      if (p.dbg) w_acc += now() - t0;
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kPairN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.dbg) t0 = now();
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        mbar_wait(smem_u32(&peer_full[stage]), phase);
+        if (p.dbg) w_full += now() - t0;
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kPairHalfBytes >> 4), b_lo = b_lo0 + (uint32_t)kb * (kPairHalfBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            if (p.splits == -1) break;   // experiment (llp_set_tuning(11, 1)): no MMAs, pure load pipeline
+            umma_bf16_pair(tmem_d, desc_from(a_lo + k * 2, kHi), desc_from(b_lo + k * 2, kHi), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit_pair(smem_u32(&empty_bar[stage]), 3);   // both CTAs' stage is free once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) umma_commit_pair(smem_u32(&tmem_full[acc]), 3);
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 4 + 0] = now() - t_begin;
+      p.dbg[blockIdx.x * 4 + 1] = w_full;
+      p.dbg[blockIdx.x * 4 + 2] = w_acc;
+    }
+  } else if (warp == 1) {
+    // ===================== peer CTA: forward "my stage has landed" to the leader =====================
+    // (TMA completions stay on local barriers; one remote arrive per stage crosses the pair)
+    if (pt_first < pair_tiles) {
+      mbar_wait(smem_u32(b_full), 0);
+      if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(b_peer), 0));
+      __syncwarp();
+    }
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t pt = pt_first; pt < pair_tiles; pt += pt_stride) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&peer_full[stage]), 0));
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue of this CTA's 128 rows =====================
+    TcParams pe = p;
+    if (pe.ep.dropout_p > 0.0f) resolve_rng(pe.ep);
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = kPairN / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t pt = pt_first; pt < pair_tiles; pt += pt_stride) {
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tcgen05_fence_after();
+      const int64_t m = pt * 2 * BLOCK_M + (int64_t)rank * BLOCK_M + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kPairN);
+      uint4 rnd128 = make_uint4(0, 0, 0, 0);
+      uint32_t rnd_group = 0xffffffffu;
+#pragma unroll 1
+      for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
+        if (c0 >= p.N) break;
+        if (pe.ep.dropout_p == 0.5f && (uint32_t)(c0 >> 7) != rnd_group) {
+          rnd_group = (uint32_t)(c0 >> 7);
+          rnd128 = philox4x32_10(pe.ep.seed, (uint64_t)m, pe.ep.offset + (uint64_t)rnd_group);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        if (m < p.M) epilogue_chunk<TO>(r, m, c0, pe, rnd128);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(smem_u32(&tmem_empty[acc]));
+        else mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still signal its barriers / read its operands
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+template <typename TO>
+static int launch_pair(const Maps& maps, const TcParams& p, int num_kb, cudaStream_t stream) {
+  auto kern = gemm_nt_pair_kernel<TO>;
+  static bool configured = false;
+  if (!configured) {
+    LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBSmemMax));
+    configured = true;
+  }
+  const int b_bytes = num_kb * kPairHalfBytes;
+  int stages = (kResBSmemMax - 1024 - 512 - b_bytes) / kPairHalfBytes;
+  if (stages > 8) stages = 8;
+  const int smem = b_bytes + stages * kPairHalfBytes + 1024 + 512;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(kNumSMs / 2 * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  LLP_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, p, stages));   // cluster dims come from __cluster_dims__
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
 template <int BLOCK_N, bool kTN, typename TO>
 static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
   using Cfg = Config<BLOCK_N>;
@@ -573,19 +834,27 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
     else if (g_tuning[18] && num_kb * 128 * 128 <= kResBBudget) res_bn = 128;  // half-rate MMAs (N = 128): experiment only
   }
   if (res_bn) bn = res_bn;
+  // CTA-pair kernel (opt-in, llp_set_tuning(20, 2)): N in (128, 256], weights of all K blocks fit in 2 x 128 KB, tall M.
+  // Bit-identical to the streaming kernel and it removes all weight re-reads, but on B200 it is SLOWER for the layer
+  // shapes of this workload (112 us vs 73 us at M = 235,868, K = 512): the tensor pipe is fine (tools/mmabench.cu: 128
+  // clk per 256 x 256 x 16 MMA, multicast commits included) and so is the remote signalling scheme (two were tried); what
+  // is left is a ~5 us stage round trip across the pair with only 96 KB of A stages per CTA beside the resident weights.
+  const bool pair = g_tuning[20] == 2 && !res_bn && a.M >= (int64_t)BLOCK_M * kNumSMs * 2 && a.N > 128 && a.N <= 256 &&
+                    num_kb * kPairHalfBytes <= kResBBudget;
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   if (int rc = make_map(&maps.a1, a.A1, a.M, a.K1, a.lda1, BLOCK_K, BLOCK_M)) return rc;
-  if (int rc = make_map(&maps.b1, a.B1, a.N, a.K1, a.ldb1, BLOCK_K, bn)) return rc;
+  if (int rc = make_map(&maps.b1, a.B1, a.N, a.K1, a.ldb1, BLOCK_K, pair ? 128 : bn)) return rc;
   if (dual) {
     if (int rc = make_map(&maps.a2, a.A2, a.M, a.K2, a.lda2, BLOCK_K, BLOCK_M)) return rc;
-    if (int rc = make_map(&maps.b2, a.B2, a.N, a.K2, a.ldb2, BLOCK_K, bn)) return rc;
+    if (int rc = make_map(&maps.b2, a.B2, a.N, a.K2, a.ldb2, BLOCK_K, pair ? 128 : bn)) return rc;
   }
   TcParams p{};
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
   p.dbg = g_tuning[15] ? debug_buffer() : nullptr;
+  if (g_tuning[11]) p.splits = -1;  // experiment knob read by the pair kernel only
   {
     const size_t so = a.out_dtype == LLP_BF16 ? 2 : 4;
     auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * so) % 16 == 0; };
@@ -595,6 +864,11 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
                  (ok32(a.addend, a.ldadd) ? kVec32Addend : 0) | (ok32(a.gate, a.ldgate) ? kVec32Gate : 0) |
                  (ok32(a.D, a.ldd) ? kVec32Out : 0);
     if (g_tuning[19]) p.ep_flags &= ~(kVec32Addend | kVec32Gate | kVec32Out);  // experiment: 128-bit epilogue accesses
+  }
+  if (pair) {
+    if (a.out_dtype == LLP_BF16) return launch_pair<__nv_bfloat16>(maps, p, num_kb, stream);
+    if (a.out_dtype == LLP_F32) return launch_pair<float>(maps, p, num_kb, stream);
+    return LLP_E_BADARG;
   }
   if (res_bn == 256) {
     if (a.out_dtype == LLP_BF16) return launch_resb<256, __nv_bfloat16>(maps, p, num_kb, stream);

@@ -140,10 +140,12 @@ def test_gemm_nt(cuda, backend, M, Nn, K1, K2):
 
 
 @pytest.mark.parametrize("M,Nn,K1,K2", [(40000, 256, 256, 256), (38011, 256, 256, 0), (50001, 200, 128, 128),
-                                        (45000, 128, 256, 256), (39999, 256, 192, 64)])
+                                        (45000, 128, 256, 256), (39999, 256, 192, 64), (41003, 200, 320, 192),
+                                        (75777, 256, 512, 0)])
 def test_gemm_nt_resident_weights(cuda, M, Nn, K1, K2):
-    """Tall problems take the resident-B tcgen05 kernel (weights loaded into shared memory once per CTA): same
-    results as the streaming kernel (bit-identical: same MMA order per output element) and as the fp64 reference."""
+    """Tall problems take the resident-weight tcgen05 kernels (K <= 256: weights loaded into shared memory once per CTA;
+    K <= 512: once per CTA PAIR, tcgen05.mma.cta_group::2): same results as the streaming kernel (bit-identical: same MMA
+    order per output element) and as the fp64 reference."""
     g = torch.Generator().manual_seed(M + Nn + K1)
     r = lambda *s: torch.randn(*s, generator=g)
     A1, B1 = r(M, K1).bfloat16(), r(Nn, K1).bfloat16()
@@ -155,6 +157,7 @@ def test_gemm_nt_resident_weights(cuda, M, Nn, K1, K2):
     outs = []
     for streaming in (0, 1):
         lib.llp_set_tuning(16, streaming)   # 1 = force the streaming kernel
+        lib.llp_set_tuning(20, 0 if streaming else 2)   # 2 = allow the (opt-in) CTA-pair kernel for K <= 512
         try:
             plain = ops.gemm_nt(dA1, dB1, dA2, dB2, bias=bias.to(cuda), relu=True, out_dtype=torch.float32,
                                 backend=N.GEMM_TCGEN05)
@@ -162,6 +165,7 @@ def test_gemm_nt_resident_weights(cuda, M, Nn, K1, K2):
             drop = ops.gemm_nt(dA1, dB1, dA2, dB2, relu=True, dropout_p=0.5, seed=5, offset=3, backend=N.GEMM_TCGEN05)
         finally:
             lib.llp_set_tuning(16, 0)
+            lib.llp_set_tuning(20, 0)
         outs.append((plain, gated, drop))
     for a, b in zip(*outs):
         assert torch.equal(a, b)

@@ -117,8 +117,9 @@ def main():
             A2 = torch.randn(M, K2, device=dev).bfloat16() if K2 else None
             B2 = torch.randn(H, K2, device=dev).bfloat16() if K2 else None
             bias = torch.randn(H, device=dev)
-            for vtag, knobs in (("auto", {}), ("streaming", {16: 1})):
-                for k_ in (16, 18):
+            for vtag, knobs in (("auto", {}), ("CTA pair (opt-in)", {20: 2}), ("CTA pair, no MMAs (load pipeline only)", {20: 2, 11: 1}),
+                                ("streaming", {16: 1})):
+                for k_ in (11, 16, 18, 20):
                     lib.llp_set_tuning(k_, knobs.get(k_, 0))
                 report(f"gemm_nt [{vtag}] M={M} K={K1}+{K2} {tag}",
                        timeit(lambda: ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw)), nbytes=M * (K1 + K2) * 2 + M * H * 2)
@@ -128,10 +129,14 @@ def main():
                 buf = (ctypes.c_int64 * (148 * 4))()
                 lib.llp_debug_read(buf, 148 * 4)
                 lib.llp_set_tuning(15, 0)
-                tot = sorted(buf[4 * i] for i in range(148)); wf = sorted(buf[4 * i + 1] for i in range(148)); wa = sorted(buf[4 * i + 2] for i in range(148))
-                print(f"   MMA issue loop (ns) min/med/max {tot[0]}/{tot[74]}/{tot[-1]}; waiting for operands med/max {wf[74]}/{wf[-1]}; "
-                      f"waiting for a free accumulator med/max {wa[74]}/{wa[-1]}", flush=True)
-            for k_ in (16, 18):
+                act = [i for i in range(148) if buf[4 * i] > 0]   # (the pair kernel reports from leader CTAs only)
+                tot = sorted(buf[4 * i] for i in act); wf = sorted(buf[4 * i + 1] for i in act); wa = sorted(buf[4 * i + 2] for i in act)
+                h_ = len(act) // 2
+                print(f"   MMA issue loop (ns) min/med/max {tot[0]}/{tot[h_]}/{tot[-1]}; waiting for operands med/max {wf[h_]}/{wf[-1]}; "
+                      f"waiting for a free accumulator med/max {wa[h_]}/{wa[-1]} ({len(act)} issuing CTAs)", flush=True)
+                for i in range(148 * 4):
+                    buf[i] = 0
+            for k_ in (11, 16, 18, 20):
                 lib.llp_set_tuning(k_, 0)
     if "edgemlp" in which:
         import ctypes

@@ -64,6 +64,59 @@ __global__ void __launch_bounds__(128, 1) mma_rate(int N, int mode, int iters, i
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// cta_group::2: a CTA pair issues 256 x N x 16 MMAs (A: 128 rows from each CTA, B: N/2 rows from each CTA)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_rate_pair(int N, int iters, int mask, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[8];
+  __shared__ uint32_t holder;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&holder)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  tcgen05_fence_after();
+  const uint32_t tmem = holder;
+  if (warp == 1 && rank == 0) {
+    const uint32_t idesc = make_idesc(256, N, false);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32 * 1024);
+    uint64_t ad[4], bd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ad[k] = make_smem_desc(sa + k * 32, 16, 1024); bd[k] = make_smem_desc(sb + k * 32, 16, 1024); }
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int slot = it & 7;
+      if (it >= 8) mbar_wait(smem_u32(&bars[slot]), (uint32_t)(((it >> 3) - 1) & 1));
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tmem), "l"(ad[k]), "l"(bd[k]), "r"(idesc), "r"(1u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bars[slot])), "h"((uint16_t)mask) : "memory");
+      }
+      __syncwarp();
+    }
+    for (int it = iters - 8; it < iters; ++it) mbar_wait(smem_u32(&bars[it & 7]), (uint32_t)((it >> 3) & 1));
+    long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x >> 1] = t1 - t0;
+  }
+  tcgen05_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
 int main() {
   long long* out;
   CK(cudaMalloc(&out, 148 * sizeof(long long)));
@@ -88,5 +141,20 @@ int main() {
         printf("%s M=128 N=%3d K=16, %d accumulator(s)%s: %7.1f clk per MMA  -> %7.0f FLOP/clk/SM (%.0f%% of 8192)\n",
                mode == 0 ? "K-major " : "MN-major", N, accs, per_mma ? " alternating per MMA" : "", per_mma_clk, flop_clk, 100.0 * flop_clk / 8192.0);
       }
+  CK(cudaFuncSetAttribute(mma_rate_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int cfg = 0; cfg < 4; ++cfg) {
+    const int N = (cfg & 1) ? 256 : 128, mask = (cfg & 2) ? 3 : 1;
+    const int iters = 4096;
+    for (int rep = 0; rep < 2; ++rep) {
+      mma_rate_pair<<<148, 128, 100 * 1024>>>(N, iters, mask, out);
+      CK(cudaDeviceSynchronize());
+    }
+    CK(cudaMemcpy(h, out, 74 * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long mx = 0;
+    for (int i = 0; i < 74; ++i) mx = h[i] > mx ? h[i] : mx;
+    const double clk = (double)mx / ((double)iters * 4);
+    printf("cta_group::2 K-major M=256 N=%3d K=16, commit mask %d: %7.1f clk per MMA -> %7.0f FLOP/clk per SM (%.0f%% of 8192)\n", N, mask, clk,
+           2.0 * 256 * N * 16 / clk / 2, 100.0 * (2.0 * 256 * N * 16 / clk / 2) / 8192.0);
+  }
   return 0;
 }
