@@ -94,10 +94,17 @@ __device__ __forceinline__ uint4 pack16(const float (&f)[8], __nv_bfloat16) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {   // streaming data: read once, keep it out of L1
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// gathered embedding rows: allowed to allocate in L1 — the hub rows of a power-law graph repeat within a CTA's lifetime
+// (measured on the C4 SpMM: 224 us vs 235 us forward, 249 us vs 261 us transpose)
+__device__ __forceinline__ uint4 ldg_gather_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint4 ldg_v4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void accumulate(const RowArgs<T>& a, int p0, int p1, 
     for (int q = 0; q < 4; ++q) {
       const int2 e = __ldg(a.meta + p + q * step);
       dv[q] = ldg_nc_v4(a.dz + (int64_t)e.x * a.lddz + c);
-      hv[q] = ldg_nc_v4(a.h + (int64_t)e.y * a.ldh + c);
+      hv[q] = ldg_gather_v4(a.h + (int64_t)e.y * a.ldh + c);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -83,7 +83,7 @@ __device__ __forceinline__ void accumulate(const RowArgs<T>& a, int p0, int p1, 
     const int2 e = __ldg(a.meta + p);
     float d[VE], x[VE];
     unpack16(ldg_nc_v4(a.dz + (int64_t)e.x * a.lddz + c), d, T());
-    unpack16(ldg_nc_v4(a.h + (int64_t)e.y * a.ldh + c), x, T());
+    unpack16(ldg_gather_v4(a.h + (int64_t)e.y * a.ldh + c), x, T());
 #pragma unroll
     for (int i = 0; i < VE; ++i) acc[i] = fmaf(d[i], x[i], acc[i]);
   }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) hadamard_bwd_rows_kernel(const RowArgs<T>
           const int m = __shfl_sync(kFull, mine.x, jj), o = __shfl_sync(kFull, mine.y, jj);
           if (active) {
             dv[q] = ldg_nc_v4(a.dz + (int64_t)m * a.lddz + c);
-            hv[q] = ldg_nc_v4(a.h + (int64_t)o * a.ldh + c);
+            hv[q] = ldg_gather_v4(a.h + (int64_t)o * a.ldh + c);
           }
         }
 #pragma unroll

@@ -58,10 +58,10 @@ __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N, 
 template <typename T, int VE>
 __device__ __forceinline__ uint4 load_vec(const T* p) {
   if constexpr (VE * sizeof(T) == 16) {
-    return ldg_nc_v4(p);
+    return ldg_gather_v4(p);
   } else if constexpr (VE * sizeof(T) == 8) {
     uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return make_uint4(r.x, r.y, 0, 0);
   } else {
     return make_uint4(__float_as_uint(to_f32(*p)), 0, 0, 0);
