@@ -23,8 +23,8 @@
 
 namespace llp {
 
-constexpr int kEPW = 64;    // nominal edges per warp-chunk
-constexpr int kHub = 128;   // rows with more edges than this are split along the chunk grid (must be >= kEPW)
+constexpr int kEPW = 64;    // nominal edges per warp-chunk (32 and 128 were measured: slower on the C4 graph)
+constexpr int kHub = 64;    // rows with more edges than this are split along the chunk grid (>= kEPW; 128 and 256 measured: longer warp tails)
 constexpr int kSpmmThreads = 128;
 
 // Hub list: chunk c is appended when it is the FIRST continuation chunk of a row longer than kHub (that row started in
