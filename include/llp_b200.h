@@ -233,6 +233,16 @@ int llp_count_greater(const float* pos, int64_t n_pos, const float* thresholds, 
                       int64_t* counts /*[n_thr]*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ROC-AUC.  Replaces sklearn.metrics.roc_auc_score on host copies of the scores
+ * (train_teacher_gnn.py:147-153,251-266).  pairs[0] = #{(p,n): neg_n < pos_p}, pairs[1] = #{(p,n): neg_n == pos_p}
+ * (-0.0 == +0.0); AUC = (pairs[0] + 0.5*pairs[1]) / (n_pos*n_neg).  Integer counts: bit-exact, additive over shards of
+ * the positives (the multi-GPU exchange all-gathers the negatives and all-reduces `pairs`).  n_neg < 2^31.
+ * ------------------------------------------------------------------------------------- */
+size_t llp_auc_workspace_bytes(int64_t n_neg);
+int llp_auc_pairs(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, int64_t* pairs /*[2]*/,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Context sampling.  Replaces torch_cluster.random_walk(coalesced=False) uniform kernel
  * (main.py:37,43,45).  rand is the [B,L] fp32 torch.rand tensor; out is [B,L+1] int64.
  * ------------------------------------------------------------------------------------- */

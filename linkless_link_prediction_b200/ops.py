@@ -765,6 +765,19 @@ def count_greater(pos: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+def auc_pairs(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    """int64 ``[#(neg < pos) pairs, #(neg == pos) pairs]`` (``llp_auc_pairs``): the integer content of ROC-AUC."""
+    lib = N.require_gpu()
+    pos = pos.float().contiguous()
+    neg = neg.float().contiguous()
+    pairs = torch.empty(2, dtype=torch.int64, device=pos.device)
+    nbytes = lib.llp_auc_workspace_bytes(neg.numel())
+    ws = _ws(nbytes, pos.device)
+    N.check(lib.llp_auc_pairs(pos.data_ptr(), pos.numel(), neg.data_ptr(), neg.numel(), pairs.data_ptr(), ws.data_ptr(),
+                              nbytes, N.stream_ptr()), "llp_auc_pairs")
+    return pairs
+
+
 def random_walk_with_rand(rowptr: torch.Tensor, col: torch.Tensor, start: torch.Tensor, rand: torch.Tensor) -> torch.Tensor:
     lib = N.require_gpu()
     B, L = rand.shape

@@ -164,6 +164,41 @@ def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence
     return torch.where(short, n_pos_total.expand_as(counts), counts), n_pos_total
 
 
+def roc_auc_score_device(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, group=None, pairs_fn=None) -> float:
+    """``sklearn.metrics.roc_auc_score(cat(ones, zeros), cat(pos, neg))`` of train_teacher_gnn.py:147-153,251-266
+    without copying the scores to the host: ``llp_auc_pairs`` counts the (positive, negative) pairs ordered correctly
+    and the tied pairs as integers; the only floating-point operation is the final division (in double).
+    With ``group`` the scores are rank-local shards: the negatives are all-gathered (ragged shards padded with +inf,
+    which no finite positive exceeds or ties), every rank counts its own positives against all of them and the two
+    counters are all-reduced — exact and independent of the sharding.  ``pairs_fn`` is injectable for the gloo tests."""
+    pairs_fn = pairs_fn or ops.auc_pairs
+    dev = y_pred_pos.device
+    neg = y_pred_neg.float().reshape(-1)
+    pos = y_pred_pos.float().reshape(-1)
+    n = torch.tensor([pos.numel(), neg.numel()], dtype=torch.int64, device=dev)
+    if group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, n[1:2].clone(), group=group)
+        cap = max(int(max(s.item() for s in sizes)), 1)
+        padded = torch.full((cap,), float("inf"), dtype=torch.float32, device=dev)
+        padded[:neg.numel()] = neg
+        gathered = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(gathered, padded, group=group)
+        neg = torch.cat([g[:int(s.item())] for g, s in zip(gathered, sizes)])
+        dist.all_reduce(n, group=group)
+    pairs = pairs_fn(pos, neg)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(pairs, group=group)
+    n_pos, n_neg = (int(t) for t in n.tolist())
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    less, equal = (int(t) for t in pairs.tolist())
+    return (2 * less + equal) / (2.0 * n_pos * n_neg)
+
+
 class Evaluator:
     """``ogb.linkproppred.Evaluator`` for the hits@K metric family with mutable ``K``
     (``evaluator.K = K`` at train_teacher_gnn.py:121).  ``eval`` takes the ogb input dict."""

@@ -26,7 +26,7 @@ from .logger import Logger, ProductionLogger
 from .models import MLP, SAGE, LinkPredictor
 from .optim import FusedAdam
 from .sageconv import SAGEConv, SAGEConv_updated
-from .shims import Evaluator, hits_counts, negative_sampling, seed_everything
+from .shims import Evaluator, hits_counts, negative_sampling, roc_auc_score_device, seed_everything
 
 
 def _dist():
@@ -239,12 +239,14 @@ def _hits(pairs, Ks, world):
     return out
 
 
-def _auc(pos: torch.Tensor, neg: torch.Tensor) -> float:
-    """``roc_auc_score`` of the reference (:147-153).  Host-side (sklearn) — outside the hot path."""
-    from sklearn.metrics import roc_auc_score
-    y = torch.cat((torch.ones(pos.numel()), torch.zeros(neg.numel()))).numpy()
-    s = torch.cat((pos, neg)).float().cpu().numpy()
-    return float(roc_auc_score(y, s))
+def _auc(pos: torch.Tensor, neg: torch.Tensor, world: int = 1) -> float:
+    """``roc_auc_score`` of the reference (:147-153, :251-266) on the device (``llp_auc_pairs``): the
+    scores never leave HBM, only two int64 pair counters do.  ``pos`` / ``neg`` are this rank's shards."""
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        group = dist.group.WORLD
+    return roc_auc_score_device(pos, neg, group=group)
 
 
 @torch.no_grad()
@@ -267,8 +269,8 @@ def test_transductive(model, predictor, data, split_edge, evaluator, batch_size,
     Ks = [10, 20, 30, 50] if dataset != "collab" else [10, 50, 100]
     (valid_hits, test_hits) = _hits([(pos_valid_pred, neg_valid_pred), (pos_test_pred, neg_test_pred)], Ks, world)
     results = {f'Hits@{K}': (valid_hits[i], test_hits[i]) for i, K in enumerate(Ks)}
-    if getattr(args, "compute_auc", True) and world == 1:
-        results['AUC'] = (_auc(pos_valid_pred, neg_valid_pred), _auc(pos_test_pred, neg_test_pred))
+    if getattr(args, "compute_auc", True):
+        results['AUC'] = (_auc(pos_valid_pred, neg_valid_pred, world), _auc(pos_test_pred, neg_test_pred, world))
     return results, h
 
 
@@ -304,8 +306,7 @@ def test_production(model, predictor, val_data, inference_data, test_edge_bundle
              (old_new_pred, neg_test_pred), (new_new_pred, neg_test_pred)]
     per_pair = _hits(pairs, Ks, world)
     results = {f'Hits@{K}': tuple(per_pair[j][i] for j in range(5)) for i, K in enumerate(Ks)}
-    if world == 1:
-        results['AUC'] = tuple(_auc(p, n) for p, n in pairs)
+    results['AUC'] = tuple(_auc(p, n, world) for p, n in pairs)
     return results, saved_h
 
 

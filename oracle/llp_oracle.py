@@ -369,6 +369,27 @@ def hits_counts(y_pred_pos: Tensor, y_pred_neg: Tensor, Ks: Sequence[int]) -> Li
     return out
 
 
+# --------------------------------------------------------------------------------------
+# N2: ROC-AUC (sklearn.metrics.roc_auc_score, ``train_teacher_gnn.py:147-153,251-266``) [3P]
+# --------------------------------------------------------------------------------------
+def auc_pairs(y_pred_pos: Tensor, y_pred_neg: Tensor) -> Tuple[int, int]:
+    """``(#{(p,n): neg_n < pos_p}, #{(p,n): neg_n == pos_p})`` — the integer content of the binary ROC-AUC.
+    sklearn integrates the ROC curve (thresholds at the distinct scores) with the trapezoid rule, which equals the
+    Mann-Whitney statistic with ties at half weight; ``tests/test_oracle_golden.py`` pins this against sklearn."""
+    pos = y_pred_pos.detach().to(torch.float32).numpy() + np.float32(0.0)
+    neg = np.sort(y_pred_neg.detach().to(torch.float32).numpy() + np.float32(0.0))
+    lb = np.searchsorted(neg, pos, side="left").astype(np.int64)
+    ub = np.searchsorted(neg, pos, side="right").astype(np.int64)
+    return int(lb.sum()), int((ub - lb).sum())
+
+
+def roc_auc(y_pred_pos: Tensor, y_pred_neg: Tensor) -> float:
+    if len(y_pred_pos) == 0 or len(y_pred_neg) == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    less, equal = auc_pairs(y_pred_pos, y_pred_neg)
+    return (2 * less + equal) / (2.0 * len(y_pred_pos) * len(y_pred_neg))
+
+
 class Evaluator:
     """Stand-in for ``ogb.linkproppred.Evaluator(name='ogbl-ddi')`` with mutable ``K``
     (``train_teacher_gnn.py:394,120-121``)."""
@@ -457,7 +478,7 @@ def teacher_train_epoch(model, predictor, x, adj_t, pos_train_edge, optimizer, b
 @torch.no_grad()
 def test_transductive(model, predictor, x, adj_t, split_edge, batch_size, encoder_name="sage",
                       dataset="cora") -> Tuple[Dict[str, Tuple[float, float]], Tensor]:
-    """``train_teacher_gnn.py:76-155`` without the AUC row (AUC is a "next" item)."""
+    """``train_teacher_gnn.py:76-155`` including the AUC row (:147-153)."""
     model.eval()
     predictor.eval()
     h = model(x) if encoder_name == "mlp" else model(x, adj_t)
@@ -468,6 +489,7 @@ def test_transductive(model, predictor, x, adj_t, split_edge, batch_size, encode
     results = {}
     for K in ([10, 20, 30, 50] if dataset != "collab" else [10, 50, 100]):
         results[f"Hits@{K}"] = (hits_at_k(pv, nv, K), hits_at_k(pt, nt, K))
+    results["AUC"] = (roc_auc(pv, nv), roc_auc(pt, nt))
     return results, h
 
 

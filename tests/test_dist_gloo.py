@@ -32,6 +32,10 @@ def _cpu_count(pos, thr):
     return (pos.float().unsqueeze(0) > thr.unsqueeze(1)).sum(1).to(torch.int64)
 
 
+def _cpu_pairs(pos, neg):
+    return torch.tensor(O.auc_pairs(pos, neg), dtype=torch.int64)
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -47,6 +51,14 @@ def _worker(rank, world, port, ret):
                                           count_fn=_cpu_count)
             assert counts.tolist() == O.hits_counts(pos, neg, Ks), (counts.tolist(), O.hits_counts(pos, neg, Ks))
             assert int(n) == n_pos
+        # ---- ROC-AUC: sharded pair counts == unsharded (ragged shards, ties, an empty shard) ----
+        for n_pos, n_neg in ((1001, 5003), (37, 60), (5, 1)):
+            pos = (torch.rand(n_pos, generator=g) * 50).round() / 50
+            neg = (torch.rand(n_neg, generator=g) * 50).round() / 50
+            lo, hi = _shard(n_pos, rank, world)
+            nlo, nhi = _shard(n_neg, rank, world)
+            auc = shims.roc_auc_score_device(pos[lo:hi], neg[nlo:nhi], group=dist.group.WORLD, pairs_fn=_cpu_pairs)
+            assert auc == O.roc_auc(pos, neg), (auc, O.roc_auc(pos, neg))
         # ---- training step: W ranks on shards of a 2B batch == 1 rank on the whole batch ----
         torch.manual_seed(0)
         n, f, H, B = 120, 16, 16, 101  # odd batch -> ragged shards

@@ -99,7 +99,7 @@ def test_teacher_epochs_match_reference_golden(cuda, golden, mode, tag):
         torch.testing.assert_close(h.float().cpu(), g["h"], rtol=1e-3, atol=1e-5)
         for K in (10, 20, 30, 50):  # reference-matching Hits@K (scores agree to ~1e-6, no near-ties in this fixture)
             assert results[f"Hits@{K}"] == pytest.approx(g["results"][f"Hits@{K}"], abs=1e-12)
-        assert results["AUC"] == pytest.approx(g["results"]["AUC"], abs=5e-4)  # host-side sklearn; one flipped pair = 8e-5
+        assert results["AUC"] == pytest.approx(g["results"]["AUC"], abs=5e-4)  # device pair counts (llp_auc_pairs) vs the reference's sklearn; one flipped pair = 8e-5
         for k, v in model.state_dict().items():
             torch.testing.assert_close(v.cpu(), g["sd1"]["gnn"][k], rtol=1e-3, atol=1e-5)
 

@@ -389,6 +389,32 @@ def test_hits_counts_bit_exact(cuda, n_pos, n_neg, Ks):
         assert torch.equal(ops.topk_desc(neg.to(cuda), max(Ks)).cpu(), torch.topk(neg, max(Ks)).values)
 
 
+@pytest.mark.parametrize("n_pos,n_neg,q", [(1000, 5000, 200), (60084, 100000, 0), (46329, 100000, 1000), (50, 30, 3),
+                                           (1, 1, 0), (777, 1, 10), (0, 10, 0), (10, 0, 0), (300000, 1000000, 0)])
+def test_auc_pairs_bit_exact(cuda, n_pos, n_neg, q):
+    """N2: ROC-AUC as integer pair counts (llp_auc_pairs) == the oracle's, == sklearn within 1e-12 after the one
+    division; heavy ties (q quantisation levels), the collab eval sizes, empty sides."""
+    from linkless_link_prediction_b200.shims import roc_auc_score_device
+    g = torch.Generator().manual_seed(9)
+    pos = torch.sigmoid(torch.randn(n_pos, generator=g) * 3 + 0.3)
+    neg = torch.sigmoid(torch.randn(n_neg, generator=g) * 3)
+    if q:
+        pos, neg = (pos * q).round() / q, (neg * q).round() / q
+    pairs = ops.auc_pairs(pos.to(cuda), neg.to(cuda))
+    assert tuple(pairs.tolist()) == O.auc_pairs(pos, neg)
+    if n_pos and n_neg:
+        assert roc_auc_score_device(pos.to(cuda), neg.to(cuda)) == O.roc_auc(pos, neg)
+    else:
+        with pytest.raises(ValueError):
+            roc_auc_score_device(pos.to(cuda), neg.to(cuda))
+
+
+def test_auc_signed_zero_and_negative_scores(cuda):
+    pos = torch.tensor([-0.0, 0.0, -1.5, 2.0, 1e-30, -1e-30] * 40)
+    neg = torch.tensor([0.0, -0.0, -1.0, 2.0, -7.0, 1e-30] * 33)
+    assert tuple(ops.auc_pairs(pos.to(cuda), neg.to(cuda)).tolist()) == O.auc_pairs(pos, neg)
+
+
 def test_topk_with_negative_scores_and_zeros(cuda):
     x = torch.tensor([-1.0, 0.0, -0.0, 3.5, -7.0, 3.5, 1e-30, -1e-30] * 50)
     assert torch.equal(ops.topk_desc(x.to(cuda), 130).cpu(), torch.topk(x, 130).values)

@@ -54,6 +54,8 @@ def test_teacher_epoch_matches_reference(golden, tag):
     torch.testing.assert_close(h, g["h"], rtol=1e-4, atol=1e-6)
     for K in (10, 20, 30, 50):
         assert results[f"Hits@{K}"] == pytest.approx(g["results"][f"Hits@{K}"], abs=1e-12)
+    # the golden AUC is sklearn's roc_auc_score called by the reference's own test_transductive (:153)
+    assert results["AUC"] == pytest.approx(g["results"]["AUC"], abs=1e-4)  # one flipped pair of 263 x 263 = 1.4e-5 (CPU reductions are not run-to-run deterministic)
 
 
 def test_student_step_matches_reference(golden):
@@ -120,6 +122,29 @@ def test_hits_at_k_kat():
     assert O.hits_at_k(pos, neg, 3) == 0.75     # thr 0.3
     assert O.hits_at_k(pos, neg, 5) == 1.0      # fewer negatives than K
     assert O.hits_counts(pos, neg, [1, 3, 5]) == [1, 3, 4]
+
+
+def test_roc_auc_matches_sklearn_and_kat():
+    """N2: the integer pair-count form of ROC-AUC against sklearn's trapezoid (the reference's call,
+    train_teacher_gnn.py:147-153), including heavy ties, -0.0 == +0.0 and the one-class error."""
+    from sklearn.metrics import roc_auc_score
+    pos = torch.tensor([0.9, 0.5, 0.5, 0.1])
+    neg = torch.tensor([0.5, 0.5, 0.3, 0.2])
+    # pairs neg<pos: 0.9 -> 4, 0.5 -> 2 each, 0.1 -> 0 ; ties: 0.5 x 0.5 -> 2 each
+    assert O.auc_pairs(pos, neg) == (8, 4)
+    assert O.roc_auc(pos, neg) == (8 + 2) / 16
+    assert O.auc_pairs(torch.tensor([-0.0, 0.0]), torch.tensor([0.0, -0.0, -1.0])) == (2, 4)
+    g = torch.Generator().manual_seed(11)
+    for n_pos, n_neg, q in ((1, 1, 0), (50, 3000, 0), (2000, 1500, 100), (4000, 4000, 7), (263, 263, 0)):
+        p = torch.sigmoid(torch.randn(n_pos, generator=g) * 3 + 0.5)
+        n = torch.sigmoid(torch.randn(n_neg, generator=g) * 3)
+        if q:
+            p, n = (p * q).round() / q, (n * q).round() / q
+        y = np.concatenate((np.ones(n_pos), np.zeros(n_neg)))
+        ref = roc_auc_score(y, torch.cat((p, n)).numpy())
+        assert abs(O.roc_auc(p, n) - ref) <= 1e-12, (n_pos, n_neg, q)
+    with pytest.raises(ValueError):
+        O.roc_auc(torch.zeros(0), neg)
 
 
 def test_llp_r_margin_constant_term():
