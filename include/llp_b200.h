@@ -147,6 +147,11 @@ typedef struct llp_weight_desc {
   void* dst_t; int64_t ld_t;    /* may be NULL */
 } llp_weight_desc;
 int llp_weights_prep(int count, const llp_weight_desc* host_descs, void* stream);
+/* y = dropout(relu(a + addend + bias)): the llp_gemm_nt epilogue as a stand-alone pass, same dropout stream
+ * (sageconv_updated.py:71-81 + models.py:116-117: the pre-activation is aggregate(lin_l x) + lin_r x). */
+int llp_add_act(int dtype, const void* a, int64_t lda, const void* addend, int64_t ldadd, const float* bias, int64_t M,
+                int64_t N, int relu, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t* rng_state, void* y,
+                int64_t ldy, void* stream);
 /* y = gate>0 ? g*scale : 0  (relu/dropout backward from the saved forward output). */
 int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ldgate, int64_t M, int64_t N,
              float scale, void* y, int64_t ldy, void* stream);

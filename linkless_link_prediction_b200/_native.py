@@ -86,6 +86,8 @@ PROTOTYPES = {
     "llp_colsum": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "llp_cast2d": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "llp_weights_prep": (c_int, [c_int, ctypes.POINTER(WeightDesc), c_void_p]),
+    "llp_add_act": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_uint64,
+                            c_uint64, c_void_p, c_void_p, c_int64, c_void_p]),
     "llp_gate": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p, c_int64,
                          c_void_p]),
     "llp_edge_hadamard": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

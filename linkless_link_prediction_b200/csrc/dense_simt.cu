@@ -440,6 +440,89 @@ extern "C" int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate,
   return LLP_E_BADARG;
 }
 
+// y = epi(a): the GEMM epilogue (bias, addend, relu, dropout from the same Philox stream) as a stand-alone pass, for
+// layers whose pre-activation is not the direct output of a GEMM (SAGEConv_updated: mean-aggregate of lin_l + lin_r).
+template <typename T>
+__global__ void add_act_kernel(const T* __restrict__ a, int64_t lda, int64_t M, int64_t N, EpilogueParams ep,
+                               T* __restrict__ y, int64_t ldy) {
+  resolve_rng(ep);
+  const int64_t total = M * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N, n = i - m * N;
+    y[m * ldy + n] = from_f32<T>(epilogue_apply<T>(to_f32(a[m * lda + n]), m, n, ep));
+  }
+}
+
+// 8 bf16 columns per thread (128-bit accesses); one Philox call yields the thread's eight keep decisions
+__global__ void add_act_vec8_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int64_t M, int64_t N, EpilogueParams ep,
+                                    __nv_bfloat16* __restrict__ y, int64_t ldy) {
+  resolve_rng(ep);
+  const int64_t groups = N >> 3, total = M * groups;
+  const __nv_bfloat16* addend = reinterpret_cast<const __nv_bfloat16*>(ep.addend);
+  const float keep_scale = ep.dropout_p > 0.0f ? 1.0f / (1.0f - ep.dropout_p) : 1.0f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / groups, n = (i - m * groups) << 3;
+    float v[8], w[8];
+    unpack16(ldg_nc_v4(a + m * lda + n), v, __nv_bfloat16());
+    if (ep.bias) {  // same operation order as epilogue_apply: bias, addend, relu, dropout
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += __ldg(ep.bias + n + k);
+    }
+    if (addend) {
+      unpack16(ldg_nc_v4(addend + m * ep.ldadd + n), w, __nv_bfloat16());
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += w[k];
+    }
+    if (ep.relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.0f);
+    }
+    if (ep.dropout_p > 0.0f) {
+      uint32_t keep = 0;
+      if (ep.dropout_p == 0.5f) {
+        uint4 r = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)(n >> 7));
+        keep = (dropout_word(r, (int)((n >> 5) & 3)) >> (n & 31)) & 0xffu;
+      } else {
+        uint4 r = philox4x32_10(ep.seed, (uint64_t)m, ep.offset + (uint64_t)(n >> 3));
+        const uint32_t thr = dropout_thr16(ep.dropout_p);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) keep |= (dropout_u16(r, k) >= thr ? 1u : 0u) << k;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ((keep >> k) & 1u) ? v[k] * keep_scale : 0.0f;
+    }
+    stg_v4(y + m * ldy + n, pack16(v, __nv_bfloat16()));
+  }
+}
+
+extern "C" int llp_add_act(int dtype, const void* a, int64_t lda, const void* addend, int64_t ldadd, const float* bias,
+                           int64_t M, int64_t N, int relu, float dropout_p, uint64_t seed, uint64_t offset,
+                           const uint64_t* rng_state, void* y, int64_t ldy, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(M >= 0 && N >= 0 && dropout_p >= 0.0f && dropout_p < 1.0f);
+  if (int rc = check_device()) return rc;
+  if (M * N == 0) return 0;
+  LLP_CHECK_ARG(a && y && lda >= N && ldy >= N && (addend == nullptr || ldadd >= N));
+  EpilogueParams ep{bias, addend, ldadd, nullptr, 0, 1.0f, relu, dropout_p, seed, offset, rng_state};
+  unsigned blocks = (unsigned)imin64(ceil_div(M * N, 256), (int64_t)kNumSMs * 16);
+  if (dtype == LLP_F32)
+    add_act_kernel<float><<<blocks, 256, 0, stream>>>((const float*)a, lda, M, N, ep, (float*)y, ldy);
+  else if (dtype == LLP_BF16) {
+    const bool vec = N % 8 == 0 && lda % 8 == 0 && ldy % 8 == 0 && aligned(a, 16) && aligned(y, 16) &&
+                     (addend == nullptr || (ldadd % 8 == 0 && aligned(addend, 16)));
+    if (vec) {
+      blocks = (unsigned)imin64(ceil_div(M * (N / 8), 256), (int64_t)kNumSMs * 16);
+      add_act_vec8_kernel<<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)a, lda, M, N, ep, (__nv_bfloat16*)y, ldy);
+    } else {
+      add_act_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)a, lda, M, N, ep, (__nv_bfloat16*)y, ldy);
+    }
+  } else {
+    return LLP_E_BADARG;
+  }
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int llp_weights_prep(int count, const llp_weight_desc* host_descs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(count >= 0 && (count == 0 || host_descs != nullptr));

@@ -893,18 +893,29 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   return LLP_E_SHAPE;
 }
 
-// split count so that (tiles x splits) fills the SMs; every split gets a multiple of BLOCK_K rows
+// Split count over the M (reduction) rows.  Cost model in units of one k-block step of a CTA: a launch takes
+// waves x (k-blocks per split + fill/epilogue) and every split adds one fp32 partial of the whole [N1,N2] result to
+// write and re-read.  The previous rule ("just enough splits to cover the SMs") picked 3 splits for the 66 tiles of the
+// Coauthor-Physics weight gradient (256 x 8415): 198 work units = two waves, the second one a third full.
 void tn_split_plan(int64_t M, int64_t N1, int64_t N2, int* splits, int64_t* k_per_split) {
   using namespace tc;
   int bn = pick_block_n(N2);
-  int64_t tiles = ceil_div(N1, BLOCK_M) * ceil_div(N2, bn);
-  int64_t want = ceil_div((int64_t)kNumSMs, tiles);
-  int64_t kblocks = ceil_div(M, BLOCK_K);
-  int64_t s = want < kblocks ? want : kblocks;
-  if (s < 1) s = 1;
-  int64_t per = ceil_div(kblocks, s) * BLOCK_K;
-  *k_per_split = per;
-  *splits = (int)ceil_div(M, per);
+  const int64_t tiles = ceil_div(N1, BLOCK_M) * ceil_div(N2, bn);
+  const int64_t kblocks = ceil_div(M, BLOCK_K);
+  const double partial_cost = (double)N1 * (double)N2 * 2.7e-6;  // 8 bytes per element at ~5 TB/s over a 0.6 us k-block
+  const double fixed_cost = 10.0;                                 // pipeline fill + 128 x bn fp32 tile store
+  double best = 1e300;
+  int64_t best_per = kblocks;
+  const int64_t smax = kblocks < 64 ? kblocks : 64;
+  for (int64_t s = 1; s <= smax; ++s) {
+    const int64_t per = ceil_div(kblocks, s);
+    const int64_t actual = ceil_div(kblocks, per);
+    const int64_t waves = ceil_div(tiles * actual, (int64_t)kNumSMs);
+    const double cost = (double)waves * ((double)per + fixed_cost) + (double)actual * partial_cost;
+    if (cost < best) { best = cost; best_per = per; }
+  }
+  *k_per_split = best_per * BLOCK_K;
+  *splits = (int)ceil_div(M, *k_per_split);
 }
 
 int gemm_tn_tcgen05(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, const void* B, int64_t ldb, float* D,

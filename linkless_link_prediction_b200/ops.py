@@ -207,6 +207,20 @@ def gate(g: torch.Tensor, y: torch.Tensor, scale: float) -> torch.Tensor:
     return out
 
 
+def add_act(a: torch.Tensor, addend: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, relu: bool = False,
+            dropout_p: float = 0.0, seed: int = 0, offset: int = 0, rng_state=None) -> torch.Tensor:
+    """``dropout(relu(a + addend + bias))`` with the GEMM epilogue's dropout stream (``llp_add_act``)."""
+    lib = N.require_gpu()
+    M, Nn = a.shape
+    out = empty_mat(M, Nn, a.dtype, a.device)
+    ap, lda = N.mat(a)
+    dp, ldadd = N.mat(addend) if addend is not None else (None, 0)
+    op, ldo = N.mat(out)
+    N.check(lib.llp_add_act(N.dtype_id(a.dtype), ap, lda, dp, ldadd, N.ptr(bias), M, Nn, int(relu), float(dropout_p),
+                            int(seed), int(offset), N.ptr(rng_state), op, ldo, N.stream_ptr()), "llp_add_act")
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # graph structure (CSR + transpose + work plan), cached per edge_index tensor
 # --------------------------------------------------------------------------------------------
@@ -365,6 +379,35 @@ def _weights_t(W: torch.Tensor) -> torch.Tensor:
     return cast2d(W.detach(), compute_dtype(), transpose=True)
 
 
+STACK_MIN_IN_FEATURES = 1024  # SAGEConv_updated: stack [W_l ; W_r] into one GEMM when the input is at least this wide
+
+
+def stacked_weights(Wl: torch.Tensor, Wr: torch.Tensor) -> Optional[torch.Tensor]:
+    """bf16 ``[W_l ; W_r]`` (``[2*out, in]``) for layers that apply both weights to the SAME input
+    (sageconv_updated.py:71,76): one GEMM reads ``x`` once instead of twice.  The two halves ARE the per-parameter bf16
+    working copies (``_llp_lowp``) that ``prepare_weights`` refreshes after every optimiser step, so stacking costs
+    nothing per step.  Returns None outside the bf16 mode."""
+    if compute_dtype() != torch.bfloat16 or Wl.shape != Wr.shape or Wl.dtype != torch.float32 or not Wl.is_cuda:
+        return None
+    out, K = Wl.shape
+    S = getattr(Wl, "_llp_stack", None)
+    if S is None or S.shape != (2 * out, K) or S.device != Wl.device:
+        S = empty_mat(2 * out, K, torch.bfloat16, Wl.device)
+        Wl._llp_stack = S
+    fresh = True
+    for W, view in ((Wl, S[:out]), (Wr, S[out:])):
+        c = getattr(W, "_llp_lowp", None)
+        if c is None or c[1].data_ptr() != view.data_ptr() or c[1].shape != view.shape:
+            wt = c[2] if (c is not None and c[2].shape == (K, out)) else empty_mat(K, out, torch.bfloat16, W.device)
+            W._llp_lowp = (-1, view, wt)  # stale on purpose: refilled below
+            fresh = False
+        elif c[0] != W._version:
+            fresh = False
+    if not fresh:
+        prepare_weights([Wl, Wr])
+    return S
+
+
 def prepare_weights(params: Sequence[torch.nn.Parameter]) -> None:
     """(Re)build the bf16 ``[out, in]`` and ``[in, out]`` copies of every 2-D fp32 parameter in one launch and attach
     them to the parameter (``_llp_lowp``).  Called by ``FusedAdam`` after each step; the buffers are allocated once."""
@@ -465,10 +508,22 @@ class SageConvUpdatedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
-        t = gemm_nt(x, _weights(Wl), bias=bl)
-        agg = graph.spmm(t)
-        y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset,
-                    rng_state=rng_state(x.device) if p > 0 else None)
+        S = stacked_weights(Wl, Wr) if x.size(1) >= STACK_MIN_IN_FEATURES else None
+        if S is not None:
+            # wide inputs (Coauthor-Physics: 8415 features): [t | r] = x [W_l ; W_r]^T in ONE tensor-core GEMM (x is read
+            # once: 580 MB), then the aggregate of t and the epilogue over agg + r
+            out_ch = Wl.size(0)
+            bias2 = torch.zeros(2 * out_ch, dtype=torch.float32, device=x.device)
+            bias2[:out_ch].copy_(bl.detach())
+            tr = gemm_nt(x, S, bias=bias2)
+            agg = graph.spmm(tr[:, :out_ch])
+            y = add_act(agg, tr[:, out_ch:], relu=relu, dropout_p=p, seed=seed, offset=offset,
+                        rng_state=rng_state(x.device) if p > 0 else None)
+        else:
+            t = gemm_nt(x, _weights(Wl), bias=bl)
+            agg = graph.spmm(t)
+            y = gemm_nt(x, _weights(Wr), addend=agg, relu=relu, dropout_p=p, seed=seed, offset=offset,
+                        rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
         ctx.graph, ctx.cfg = graph, (p, in_gate, defer_gate)
         ctx.params = (Wl, bl, Wr)

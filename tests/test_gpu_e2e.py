@@ -79,6 +79,61 @@ def test_encoder_gradients_match_oracle(cuda, mode):
             torch.testing.assert_close(b.grad.cpu(), a.grad, msg=lambda m, k=k: f"{k}: {m}", **gtol)
 
 
+def test_wide_input_sageconv_updated_stacked_gemm(cuda, mode):
+    """Coauthor-Physics-shaped first layer (C3): with >= 1024 input features the bf16 path computes lin_l and lin_r as
+    ONE stacked GEMM + aggregate + epilogue pass.  One layer (no relu in between, so no mask flips): forward and all
+    three parameter gradients vs the CPU oracle over two optimiser steps; then the 2-layer model forward.  Odd width
+    (rows padded for TMA) and isolated nodes (the lin_l bias must not reach them)."""
+    seed_all(1)
+    n, f, hdim = 257, 1433, 32
+    ei = O.synthetic_undirected_graph(n - 7, 900, seed=3)  # the last 7 nodes are isolated
+    x = (torch.rand(n, f) < 0.02).float()
+    co = O.SAGEConvUpdated(f, hdim)
+    cd = L.SAGEConv_updated(f, hdim); cd.load_state_dict(co.state_dict()); cd.to(cuda)
+    opt_o = torch.optim.Adam(co.parameters(), lr=0.01)
+    opt_d = L.FusedAdam(cd.parameters(), lr=0.01)
+    w = torch.randn(n, hdim)
+    tol = TOL[mode]
+    for step in range(2):
+        opt_o.zero_grad(); opt_d.zero_grad()
+        if mode == torch.bfloat16:
+            # Adam's first steps move every weight by ~lr whatever the gradient size, so bf16 trajectories drift apart by
+            # sign flips of tiny gradients: compare each step from the DEVICE's current weights (this also proves that
+            # the stacked bf16 copies were refreshed by the optimiser step)
+            co.load_state_dict({k: v.detach().cpu() for k, v in cd.state_dict().items()})
+        ho = co(x, ei)
+        hd = cd(x.to(cuda), ei.to(cuda))
+        torch.testing.assert_close(hd.float().cpu(), ho.detach(), **tol)
+        (ho * w).sum().backward()
+        (hd.float() * w.to(cuda)).sum().backward()
+        for (k, a), (_, b) in zip(co.named_parameters(), cd.named_parameters()):
+            if mode == torch.float32:
+                torch.testing.assert_close(b.grad.cpu(), a.grad, msg=lambda m, k=k: f"step {step} {k}: {m}", rtol=1e-4, atol=1e-5)
+            else:  # bound the error against the size of the whole gradient (elements are sums of +/- terms that cancel)
+                rel = float((b.grad.cpu() - a.grad).norm() / a.grad.norm())
+                assert rel < 1e-2, (step, k, rel)
+        opt_o.step(); opt_d.step()
+    mo = O.SAGE("p", f, hdim, hdim, 2, 0.0, O.SAGEConvUpdated)
+    md = L.SAGE("p", f, hdim, hdim, 2, 0.0, L.SAGEConv_updated); md.load_state_dict(mo.state_dict()); md.to(cuda).eval()
+    with torch.no_grad():
+        hs = md(x.to(cuda), ei.to(cuda))
+        torch.testing.assert_close(hs.float().cpu(), mo.eval()(x, ei), **tol)
+    if mode == torch.bfloat16:
+        S = ops.stacked_weights(cd.lin_l.weight, cd.lin_r.weight)
+        assert S is not None and S.shape == (2 * hdim, f)
+        # the stacked halves are the live bf16 working copies of the two parameters (refreshed by the optimiser step)
+        torch.testing.assert_close(S[:hdim].float(), cd.lin_l.weight.detach().bfloat16().float())
+        torch.testing.assert_close(S[hdim:].float(), cd.lin_r.weight.detach().bfloat16().float())
+        # stacked == unstacked path up to one bf16 rounding of lin_r x
+        saved, ops.STACK_MIN_IN_FEATURES = ops.STACK_MIN_IN_FEATURES, 1 << 30
+        try:
+            with torch.no_grad():
+                hu = md(x.to(cuda), ei.to(cuda))
+        finally:
+            ops.STACK_MIN_IN_FEATURES = saved
+        torch.testing.assert_close(hs.float(), hu.float(), rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("tag", ["teacher_fullbatch", "teacher_minibatch"])
 def test_teacher_epochs_match_reference_golden(cuda, golden, mode, tag):
     g = golden[tag]

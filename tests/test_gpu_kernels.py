@@ -264,6 +264,31 @@ def test_dropout_epilogue_simt_and_tcgen05(cuda):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,Nn", [(300, 256), (77, 40), (5, 9), (0, 8)])
+def test_add_act_equals_gemm_epilogue(cuda, dtype, M, Nn):
+    """llp_add_act == the llp_gemm_nt epilogue (bias + addend + relu + dropout, identical Philox mask) applied to a
+    pre-activation that is not a GEMM output — checked exactly through an identity GEMM, in the vector and scalar paths,
+    for p = 0.5 (1-bit stream) and p = 0.3 (16-bit stream), on row-padded and strided views."""
+    torch.manual_seed(3)
+    wide = torch.randn(max(M, 1), 2 * Nn + 8, device=cuda).to(dtype)
+    a, add = wide[:M, :Nn], wide[:M, Nn:2 * Nn]                       # strided views of one buffer (the [t | r] layout)
+    bias = torch.randn(Nn, device=cuda)
+    eye = torch.eye(Nn, device=cuda).to(dtype)
+    backend = N.GEMM_SIMT
+    for p, relu in ((0.0, False), (0.0, True), (0.5, True), (0.3, True)):
+        y = ops.add_act(a, add, bias, relu=relu, dropout_p=p, seed=11, offset=5)
+        assert y.shape == (M, Nn)
+        if M == 0:
+            continue
+        ref = ops.gemm_nt(a.contiguous(), eye, bias=bias, addend=add.contiguous(), relu=relu, dropout_p=p, seed=11, offset=5,
+                          backend=backend)
+        assert torch.equal(y, ref), (p, relu)
+    if M:
+        y = ops.add_act(a, None, None, relu=True)
+        assert torch.equal(y, torch.relu(a))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_colsum_cast_gate(cuda, dtype):
     g = torch.Generator().manual_seed(1)
     A = torch.randn(3001, 70, generator=g).to(dtype)
