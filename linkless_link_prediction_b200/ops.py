@@ -224,76 +224,203 @@ def add_act(a: torch.Tensor, addend: Optional[torch.Tensor] = None, bias: Option
 # --------------------------------------------------------------------------------------------
 # graph structure (CSR + transpose + work plan), cached per edge_index tensor
 # --------------------------------------------------------------------------------------------
+def _build_csr(val: torch.Tensor, key: torch.Tensor, num_rows: int, want_inv: bool):
+    """CSR of the messages ``val[e] -> key[e]`` grouped by ``key`` (``llp_csr_build``) plus its SpMM work plan
+    (``llp_spmm_plan``).  Returns ``(rowptr, col, perm, inv_deg or None, plan, (hub_list, n_hubs))``."""
+    lib = N.require_gpu()
+    dev = val.device
+    E = int(val.numel())
+    nbytes = lib.llp_csr_build_workspace_bytes(num_rows, E)
+    ws = _ws(nbytes, dev)
+    n_chunks = lib.llp_spmm_num_chunks(E)
+    rowptr = torch.empty(num_rows + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    inv = torch.empty(max(num_rows, 1), dtype=torch.float32, device=dev) if want_inv else None
+    N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, num_rows, rowptr.data_ptr(), col.data_ptr(),
+                              perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
+    plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+    hub_list = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
+    N.check(lib.llp_spmm_plan(rowptr.data_ptr(), num_rows, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),
+                              N.stream_ptr()), "llp_spmm_plan")
+    n_hubs = int(n_hubs.item())  # the one host sync per graph, at build time
+    return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs)
+
+
+def _spmm_launch(csr, num_rows: int, num_edges: int, x: torch.Tensor, src_scale, mean: bool, transpose: bool) -> torch.Tensor:
+    """One ``llp_spmm`` launch over ``csr = (rowptr, col, plan, hubs)``: ``[num_rows, F]`` out of the rows of ``x`` the
+    column indices name; records the bench's event pair when ``SPMM_PROFILE`` is set."""
+    lib = N.require_gpu()
+    rowptr, col, plan, hubs = csr
+    F = x.size(1)
+    out = empty_mat(num_rows, F, x.dtype, x.device)
+    ws = _ws(lib.llp_spmm_workspace_bytes(num_edges, F), x.device)
+    xp, ldx = N.mat(x)
+    op, ldo = N.mat(out)
+    prof = SPMM_PROFILE
+    if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
+        # inside a stream capture the events become event-record NODES (external=True), re-recorded by every replay
+        ext = torch.cuda.is_current_stream_capturing()
+        ev0 = torch.cuda.Event(enable_timing=True, external=ext)
+        ev1 = torch.cuda.Event(enable_timing=True, external=ext)
+        ev0.record()
+    rc = lib.llp_spmm(N.dtype_id(x.dtype), rowptr.data_ptr(), col.data_ptr(), plan.data_ptr(), num_rows, num_edges, xp, ldx, F,
+                      N.ptr(src_scale), int(mean), op, ldo, ws.data_ptr(), hubs[0].data_ptr(), hubs[1], N.stream_ptr())
+    N.check(rc, "llp_spmm")
+    if prof is not None:
+        ev1.record()
+        # algorithmic bytes (SURVEY.md §8d): gather E rows + write N rows + int32 col + rowptr (+ fp32 scale on the transpose)
+        s_elt = x.element_size()
+        nbytes = num_edges * F * s_elt + num_rows * F * s_elt + 4 * num_edges + 4 * (num_rows + 1) + (4 * num_rows if transpose else 0)
+        prof.append((ev0, ev1, nbytes))
+    return out
+
+
 class Graph:
     """Device CSR of the message graph ``edge_index[0] -> edge_index[1]`` and of its transpose.
     Stands in for PyG's per-call gather/scatter bookkeeping (models.py:113 -> SAGEConv.propagate)."""
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int):
-        lib = N.require_gpu()
+        N.require_gpu()
         if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64:
             raise RuntimeError("edge_index must be a LongTensor of shape [2, E]")
         if not edge_index.is_cuda:
             raise RuntimeError("edge_index must be a CUDA tensor (no CPU fallback)")
         ei = edge_index.contiguous()
         self.num_nodes, self.num_edges = int(num_nodes), int(ei.size(1))
-        dev = ei.device
-        E, Nn = self.num_edges, self.num_nodes
-        nbytes = lib.llp_csr_build_workspace_bytes(Nn, E)
-        ws = _ws(nbytes, dev)
-        n_chunks = lib.llp_spmm_num_chunks(E)
-
-        def build(val, key, want_inv):
-            rowptr = torch.empty(Nn + 1, dtype=torch.int32, device=dev)
-            col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-            perm = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-            inv = torch.empty(max(Nn, 1), dtype=torch.float32, device=dev) if want_inv else None
-            N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, Nn, rowptr.data_ptr(), col.data_ptr(),
-                                      perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
-            plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
-            hub_list = torch.empty(n_chunks, dtype=torch.int32, device=dev)
-            n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
-            N.check(lib.llp_spmm_plan(rowptr.data_ptr(), Nn, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),
-                                      N.stream_ptr()), "llp_spmm_plan")
-            n_hubs = int(n_hubs.item())  # the one host sync per graph, at build time
-            return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs)
-
         src, dst = ei[0], ei[1]
         # forward: rows = destinations, cols = sources; inv_deg = 1/max(in-degree, 1)
-        self.rowptr, self.col, self.perm, self.inv_deg, self.plan, self.hubs = build(src, dst, True)
+        self.rowptr, self.col, self.perm, self.inv_deg, self.plan, self.hubs = _build_csr(src, dst, self.num_nodes, True)
         # transpose: rows = sources, cols = destinations
-        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan, self.t_hubs = build(dst, src, False)
+        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan, self.t_hubs = _build_csr(dst, src, self.num_nodes, False)
+
+    @property
+    def rows_out(self) -> int:
+        """Rows the encoder produces on this rank (all nodes here; the local block of a PartitionedGraph)."""
+        return self.num_nodes
 
     def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
         """forward: ``out[d] = mean_{s->d} x[s]``; transpose: ``out[s] = sum_{s->d} x[d] / deg_in(d)``."""
-        lib = N.require_gpu()
-        Nn, E = self.num_nodes, self.num_edges
-        F = x.size(1)
-        out = empty_mat(Nn, F, x.dtype, x.device)
-        ws = _ws(lib.llp_spmm_workspace_bytes(E, F), x.device)
-        xp, ldx = N.mat(x)
-        op, ldo = N.mat(out)
-        prof = SPMM_PROFILE
-        if prof is not None:  # bench.py: CUDA events around the dominant kernel, on the launching stream
-            # inside a stream capture the events become event-record NODES (external=True), re-recorded by every replay
-            ext = torch.cuda.is_current_stream_capturing()
-            ev0 = torch.cuda.Event(enable_timing=True, external=ext)
-            ev1 = torch.cuda.Event(enable_timing=True, external=ext)
-            ev0.record()
         if not transpose:
-            rc = lib.llp_spmm(N.dtype_id(x.dtype), self.rowptr.data_ptr(), self.col.data_ptr(), self.plan.data_ptr(), Nn, E,
-                              xp, ldx, F, None, 1, op, ldo, ws.data_ptr(), self.hubs[0].data_ptr(), self.hubs[1], N.stream_ptr())
-        else:
-            rc = lib.llp_spmm(N.dtype_id(x.dtype), self.t_rowptr.data_ptr(), self.t_col.data_ptr(), self.t_plan.data_ptr(),
-                              Nn, E, xp, ldx, F, self.inv_deg.data_ptr(), 0, op, ldo, ws.data_ptr(), self.t_hubs[0].data_ptr(),
-                              self.t_hubs[1], N.stream_ptr())
-        N.check(rc, "llp_spmm")
-        if prof is not None:
-            ev1.record()
-            # algorithmic bytes (SURVEY.md §8d): gather E rows + write N rows + int32 col + rowptr (+ fp32 scale on the transpose)
-            s_elt = x.element_size()
-            nbytes = E * F * s_elt + Nn * F * s_elt + 4 * E + 4 * (Nn + 1) + (4 * Nn if transpose else 0)
-            prof.append((ev0, ev1, nbytes))
+            return _spmm_launch((self.rowptr, self.col, self.plan, self.hubs), self.num_nodes, self.num_edges, x, None, True,
+                                False)
+        return _spmm_launch((self.t_rowptr, self.t_col, self.t_plan, self.t_hubs), self.num_nodes, self.num_edges, x,
+                            self.inv_deg, False, True)
+
+
+def partition_messages(edge_index: torch.Tensor, num_nodes: int, rank: int, world: int):
+    """Host/device-agnostic arithmetic of the node partition (pure torch; exercised on CPU by the world_size-2 gloo
+    test).  Rank r owns the node block ``[lo, hi) = [r*n_loc, (r+1)*n_loc)``, ``n_loc = ceil(N/W)``.  Returns
+    ``(n_loc, lo, hi, (src, dst - lo) of the messages INTO the block, (src - lo, dst) of the messages OUT of the block,
+    inv_deg[N_padded])`` — both message lists keep the original edge order, so the per-row reduction order matches the
+    unpartitioned CSR."""
+    n_loc = (int(num_nodes) + world - 1) // world
+    lo = int(rank) * n_loc
+    hi = lo + n_loc
+    src, dst = edge_index[0], edge_index[1]
+    deg = torch.zeros(n_loc * world, dtype=torch.int64, device=edge_index.device)
+    deg.scatter_add_(0, dst, torch.ones_like(dst))
+    inv_deg = (1.0 / deg.clamp(min=1).to(torch.float32)).contiguous()
+    own_dst = (dst >= lo) & (dst < hi)
+    own_src = (src >= lo) & (src < hi)
+    into = (src[own_dst].contiguous(), (dst[own_dst] - lo).contiguous())
+    out_of = ((src[own_src] - lo).contiguous(), dst[own_src].contiguous())
+    return n_loc, lo, hi, into, out_of, inv_deg
+
+
+class PartitionedGraph(Graph):
+    """Node-partitioned message graph: rank r of W owns the contiguous node block
+    ``[r*n_loc, (r+1)*n_loc)`` with ``n_loc = ceil(N / W)`` (the last block is padded with isolated nodes), i.e. the rows
+    ``r`` of the aggregation matrix and of its transpose.  ``spmm`` takes this rank's ROWS of the activation matrix,
+    all-gathers the blocks over NCCL (NVSwitch: every rank receives ``(W-1)/W * N * F`` elements) and aggregates its own
+    rows from the gathered matrix — forward and transpose alike, so every output row is still reduced on exactly one
+    rank in CSR order and there is no cross-rank reduction: results equal the single-GPU ``Graph``'s bit for bit, except
+    that rows longer than one 64-edge chunk regroup their fp32 partial sums (the chunk grid follows the local edge array).
+    Everything row-wise around it (lin_l/lin_r GEMMs, relu/dropout, weight gradients over the local rows) runs
+    unchanged on ``n_loc`` rows; weight gradients are partial sums that the optimiser's all-reduce completes."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, rank: int, world: int, group=None):
+        N.require_gpu()
+        if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64 or not edge_index.is_cuda:
+            raise RuntimeError("edge_index must be a CUDA LongTensor of shape [2, E] (no CPU fallback)")
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.num_nodes_global = int(num_nodes)
+        # inv_deg: 1/max(in-degree, 1) of EVERY node — the transpose scales gathered gradient rows by their destination's degree
+        self.n_loc, self.lo, self.hi, (f_src, f_dst), (t_src, t_dst), self.inv_deg = partition_messages(
+            edge_index, num_nodes, self.rank, self.world)
+        self.num_nodes_padded = self.n_loc * world
+        self.num_nodes = self.n_loc                       # rows of the local CSRs
+        self.num_edges, self.t_num_edges = int(f_src.numel()), int(t_dst.numel())
+        self.rowptr, self.col, self.perm, _, self.plan, self.hubs = _build_csr(f_src, f_dst, self.n_loc, False)
+        self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan, self.t_hubs = _build_csr(t_dst, t_src, self.n_loc, False)
+
+    @property
+    def rows_out(self) -> int:
+        return self.n_loc
+
+    def local_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """This rank's block of a full ``[N, F]`` matrix, zero-padded to ``n_loc`` rows."""
+        blk = x[self.lo:min(self.hi, x.size(0))]
+        if blk.size(0) == self.n_loc:
+            return blk.contiguous()
+        out = x.new_zeros((self.n_loc, x.size(1)))
+        out[:blk.size(0)] = blk
         return out
+
+    def gather_rows(self, x_loc: torch.Tensor) -> torch.Tensor:
+        """``[n_loc, F]`` blocks of all ranks -> ``[N_padded, F]`` (NCCL all-gather on the current stream; no autograd)."""
+        import torch.distributed as dist
+        if x_loc.size(0) != self.n_loc:
+            raise RuntimeError(f"expected this rank's {self.n_loc} rows, got {x_loc.size(0)}")
+        F = x_loc.size(1)
+        src = x_loc if x_loc.is_contiguous() else x_loc.contiguous()
+        if (F * src.element_size()) % 16 == 0:
+            full = torch.empty((self.num_nodes_padded, F), dtype=src.dtype, device=src.device)
+            dist.all_gather_into_tensor(full, src, group=self.group)
+            return full
+        # odd widths: gather the row-padded buffers so that the result keeps 16-byte-aligned rows
+        padded = empty_mat(self.n_loc, F, src.dtype, src.device)
+        padded.copy_(src)
+        ld = padded.stride(0)
+        buf = torch.empty((self.num_nodes_padded, ld), dtype=src.dtype, device=src.device)
+        dist.all_gather_into_tensor(buf, padded.as_strided((self.n_loc, ld), (ld, 1)), group=self.group)
+        return buf[:, :F]
+
+    def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        full = self.gather_rows(x)
+        if not transpose:
+            return _spmm_launch((self.rowptr, self.col, self.plan, self.hubs), self.n_loc, self.num_edges, full, None, True,
+                                False)
+        return _spmm_launch((self.t_rowptr, self.t_col, self.t_plan, self.t_hubs), self.n_loc, self.t_num_edges, full,
+                            self.inv_deg, False, True)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """Embedding rows of all ranks for the edge scorer: forward = all-gather of the local blocks, backward = the
+    reduce-scatter (sum) of the per-rank gradients of the gathered matrix back onto the owning rank's rows."""
+
+    @staticmethod
+    def forward(ctx, x_loc, graph):
+        ctx.graph = graph
+        return graph.gather_rows(x_loc)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        import torch.distributed as dist
+        graph = ctx.graph
+        g = g_full if g_full.is_contiguous() else g_full.contiguous()
+        out = torch.empty((graph.n_loc, g.size(1)), dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=graph.group)
+        return out, None
+
+
+def gather_encoder_output(h: torch.Tensor, graph) -> torch.Tensor:
+    """Full embedding matrix the scorers index: identity for a replicated ``Graph``, autograd-aware all-gather for a
+    ``PartitionedGraph`` (rows beyond the real node count are padding)."""
+    if isinstance(graph, PartitionedGraph):
+        return GatherRowsFn.apply(h, graph)
+    return h
 
 
 SPMM_PROFILE = None  # set to a list by bench.py to collect (start_event, end_event, algorithmic_bytes) per SpMM call

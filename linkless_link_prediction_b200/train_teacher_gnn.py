@@ -64,13 +64,15 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     train_edges = torch.cat((edge, neg_edge), dim=-1)
     u, v = train_edges[0].contiguous(), train_edges[1].contiguous()
     # the sort behind the gather backward only needs (u, v): it runs on a side stream under the encoder forward
-    plan = ops.EdgePlan(u, v, data.x.size(0), side_stream=True) if torch.is_grad_enabled() else None
+    graph = None if encoder_name == 'mlp' else (data.adj_t if transductive == "transductive" else data.edge_index)
+    # node-partitioned encoder (ops.PartitionedGraph): data.x holds this rank's rows; the scorer indexes
+    # the all-gathered embedding matrix and its gradient is reduce-scattered back to the owning ranks
+    n_rows = graph.num_nodes_padded if isinstance(graph, ops.PartitionedGraph) else data.x.size(0)
+    plan = ops.EdgePlan(u, v, n_rows, side_stream=True) if torch.is_grad_enabled() else None
     if encoder_name == 'mlp':
         h = model(data.x)
-    elif transductive == "transductive":
-        h = model(data.x, data.adj_t)
     else:
-        h = model(data.x, data.edge_index)
+        h = ops.gather_encoder_output(model(data.x, graph), graph)
     out = predictor.score(h, u, v, plan=plan).reshape(-1)
     loss = ops.bce_loss(out, edge.size(1))
     if loss_weight != 1.0:
@@ -259,6 +261,8 @@ def test_transductive(model, predictor, data, split_edge, evaluator, batch_size,
         h = model(data.x.to("cuda") if getattr(args, "minibatch", False) else data.x)
     else:
         h = model(data.x, data.adj_t)
+        if isinstance(data.adj_t, ops.PartitionedGraph):  # every rank scores its edge shard against all rows
+            h = data.adj_t.gather_rows(h)[:data.adj_t.num_nodes_global]
 
     dev = h.device
     pos_valid_pred = _score_all(predictor, h, split_edge['valid']['edge'].to(dev), batch_size, rank, world)

@@ -59,6 +59,35 @@ def _worker(rank, world, port, ret):
             nlo, nhi = _shard(n_neg, rank, world)
             auc = shims.roc_auc_score_device(pos[lo:hi], neg[nlo:nhi], group=dist.group.WORLD, pairs_fn=_cpu_pairs)
             assert auc == O.roc_auc(pos, neg), (auc, O.roc_auc(pos, neg))
+        # ---- node-partitioned encoder (ops.partition_messages): all-gather + local-row aggregation, forward
+        # and transpose, reproduces the unpartitioned aggregation bit for bit (odd node count: padded last block) ----
+        from linkless_link_prediction_b200.ops import partition_messages
+        n_nodes, feat = 101, 8
+        ei_p = O.synthetic_undirected_graph(n_nodes - 4, 500, seed=2)           # 4 isolated trailing nodes
+        xg = torch.randn(n_nodes, feat, generator=torch.Generator().manual_seed(4))
+        n_loc, lo, hi, (f_src, f_dst), (t_src, t_dst), inv_deg = partition_messages(ei_p, n_nodes, rank, world)
+        assert n_loc == 51 and (lo, hi) == (rank * 51, rank * 51 + 51) and inv_deg.numel() == 102
+        x_loc = torch.zeros(n_loc, feat); x_loc[: max(min(hi, n_nodes) - lo, 0)] = xg[lo:min(hi, n_nodes)]
+        blocks = [torch.empty_like(x_loc) for _ in range(world)]
+        dist.all_gather(blocks, x_loc)
+        x_full = torch.cat(blocks)                                                # [N_padded, F]
+        assert torch.equal(x_full[:n_nodes], xg)
+        # forward rows of this rank: mean over the messages INTO the block
+        rp, col, _ = O.csr_build(torch.stack([f_src, f_dst]), n_loc, "dst")
+        agg_loc = O.spmm_csr(rp, col, x_full, mean=True)
+        rp_g, col_g, _ = O.csr_build(ei_p, n_nodes, "dst")
+        agg_ref = O.spmm_csr(rp_g, col_g, xg, mean=True)
+        assert torch.equal(agg_loc[: min(hi, n_nodes) - lo], agg_ref[lo:min(hi, n_nodes)])
+        # transpose rows of this rank: sum over the messages OUT of the block, scaled by the destination's 1/deg
+        rp_t, col_t, _ = O.csr_build(torch.stack([t_dst, t_src]), n_loc, "dst")
+        gt_loc = O.spmm_csr(rp_t, col_t, x_full, mean=False, src_scale=inv_deg)
+        deg_g = torch.zeros(n_nodes).index_add_(0, ei_p[1], torch.ones(ei_p.size(1)))
+        rp_tg, col_tg, _ = O.csr_build(ei_p, n_nodes, "src")
+        gt_ref = O.spmm_csr(rp_tg, col_tg, xg, mean=False, src_scale=1.0 / deg_g.clamp(min=1))
+        assert torch.equal(gt_loc[: min(hi, n_nodes) - lo], gt_ref[lo:min(hi, n_nodes)])
+        # every message is owned exactly once per direction
+        cnt = torch.tensor([f_src.numel(), t_src.numel()]); dist.all_reduce(cnt)
+        assert cnt.tolist() == [ei_p.size(1), ei_p.size(1)]
         # ---- training step: W ranks on shards of a 2B batch == 1 rank on the whole batch ----
         torch.manual_seed(0)
         n, f, H, B = 120, 16, 16, 101  # odd batch -> ragged shards
