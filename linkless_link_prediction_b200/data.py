@@ -109,3 +109,12 @@ def synthetic_dataset(name: str, seed: int = 0, scale: float = 1.0) -> Tuple[Dat
     adj = split["train"]["edge"].t().contiguous()
     data = Data(x=features(n, dim, density, seed), adj_t=adj, edge_index=adj)
     return data, split
+
+
+def synthetic_full_graph(name: str, seed: int = 0, scale: float = 1.0) -> Data:
+    """The whole (unsplit) synthetic graph of the named shape as a PyG-style ``Data(x, edge_index)`` — the input of the
+    split generators (``splits.do_edge_split`` / ``do_production_edge_split``), standing in for ``get_dataset(...)[0]``
+    (``src/utils.py:30-50``)."""
+    n, pairs, dim, pl, density = SHAPES[name]
+    n, pairs = max(int(n * scale), 16), max(int(pairs * scale), 32)
+    return Data(x=features(n, dim, density, seed), edge_index=undirected_graph(n, pairs, seed, pl))

@@ -31,7 +31,11 @@ def seed_everything(seed: int) -> None:
 class Data:
     """Minimal PyG ``Data`` look-alike: attribute container with ``.to(device)`` moving every tensor."""
 
-    def __init__(self, **kwargs):
+    def __init__(self, x=None, edge_index=None, **kwargs):
+        if x is not None:
+            self.x = x
+        if edge_index is not None:
+            self.edge_index = edge_index
         for k, v in kwargs.items():
             setattr(self, k, v)
 
@@ -50,44 +54,83 @@ class Data:
         return self.x.size(1)
 
 
+def _sample_ids(population: int, k: int, device) -> torch.Tensor:
+    """PyG 2.2.0 ``utils.negative_sampling.sample``: CPython ``random.sample`` on the host."""
+    if population <= k:
+        return torch.arange(population, device=device)
+    return torch.tensor(random.sample(range(population), k), device=device)
+
+
 def negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None, num_neg_samples: Optional[int] = None,
                       method: str = "sparse", force_undirected: bool = False) -> torch.Tensor:
-    """PyG 2.2.0 ``negative_sampling(method='dense')``: the candidate ids come from Python's
-    ``random.sample`` on the host exactly as upstream (bit-exact indices require the CPython
-    MT19937 stream); the N*N-N validity mask and the filtering stay on ``edge_index.device``."""
-    if method != "dense":
-        raise NotImplementedError("the reference only calls method='dense'")
-    if force_undirected:
-        raise NotImplementedError("force_undirected is never set by the reference")
+    """PyG 2.2.0 ``negative_sampling`` for a single (non-bipartite) node set [3P, restated; parity unpinned].
+    The candidate ids come from Python's ``random.sample`` on the host exactly as upstream (bit-exact
+    indices require the CPython MT19937 stream).  ``method='dense'`` (the training loops, train_teacher_gnn.py:50-51)
+    keeps the N*N-N validity mask and the filtering on ``edge_index.device``; ``method='sparse'`` (the split generators,
+    utils.py:70-72 / RandomLinkSplit) filters with ``isin`` on the host.  ``force_undirected`` (production split,
+    generate_production_split.py:47) samples from the strict upper triangle and returns both directions."""
+    if method not in ("dense", "sparse"):
+        raise ValueError(method)
     if num_nodes is None:
         num_nodes = int(edge_index.max()) + 1
-    if num_neg_samples is None:
-        num_neg_samples = edge_index.size(1)
+    if isinstance(num_nodes, (tuple, list)):
+        if num_nodes[0] != num_nodes[1]:
+            raise NotImplementedError("bipartite negative sampling is never used by the reference")
+        num_nodes = int(num_nodes[0])
     dev = edge_index.device
     row, col = edge_index[0].clone(), edge_index[1].clone()
-    keep = row != col
-    row, col = row[keep], col[keep]
-    col[row < col] -= 1
-    idx = row * (num_nodes - 1) + col
-    population = num_nodes * num_nodes - num_nodes
+    # edge_index_to_vector
+    if force_undirected:
+        keep = row < col
+        row, col = row[keep], col[keep]
+        offset = torch.arange(1, num_nodes, device=dev).cumsum(0)[row]
+        idx = row * num_nodes + col - offset
+        population = (num_nodes * (num_nodes + 1)) // 2 - num_nodes
+    else:
+        keep = row != col
+        row, col = row[keep], col[keep]
+        col[row < col] -= 1
+        idx = row * (num_nodes - 1) + col
+        population = num_nodes * num_nodes - num_nodes
     if idx.numel() >= population:
         return edge_index.new_empty((2, 0))
+    if num_neg_samples is None:
+        num_neg_samples = edge_index.size(1)
+    if force_undirected:
+        num_neg_samples = num_neg_samples // 2
     prob = 1.0 - idx.numel() / population
     sample_size = int(1.1 * num_neg_samples / prob)
-    mask = torch.ones(population, dtype=torch.bool, device=dev)
-    mask[idx] = False
     neg_idx = None
-    for _ in range(3):
-        if population <= sample_size:
-            rnd = torch.arange(population, device=dev)
-        else:
-            rnd = torch.tensor(random.sample(range(population), sample_size), device=dev)
-        rnd = rnd[mask[rnd]]
-        neg_idx = rnd if neg_idx is None else torch.cat([neg_idx, rnd])
-        if neg_idx.numel() >= num_neg_samples:
-            neg_idx = neg_idx[:num_neg_samples]
-            break
-        mask[neg_idx] = False
+    if method == "dense":
+        mask = torch.ones(population, dtype=torch.bool, device=dev)
+        mask[idx] = False
+        for _ in range(3):
+            rnd = _sample_ids(population, sample_size, dev)
+            rnd = rnd[mask[rnd]]
+            neg_idx = rnd if neg_idx is None else torch.cat([neg_idx, rnd])
+            if neg_idx.numel() >= num_neg_samples:
+                neg_idx = neg_idx[:num_neg_samples]
+                break
+            mask[neg_idx] = False
+    else:
+        idx_host = idx.cpu()
+        for _ in range(3):
+            rnd = _sample_ids(population, sample_size, "cpu")
+            bad = torch.isin(rnd, idx_host)
+            if neg_idx is not None:
+                bad |= torch.isin(rnd, neg_idx.cpu())
+            rnd = rnd[~bad].to(dev)
+            neg_idx = rnd if neg_idx is None else torch.cat([neg_idx, rnd])
+            if neg_idx.numel() >= num_neg_samples:
+                neg_idx = neg_idx[:num_neg_samples]
+                break
+    # vector_to_edge_index
+    if force_undirected:
+        offset = torch.arange(1, num_nodes, device=dev).cumsum(0)
+        end = torch.arange(num_nodes, num_nodes * num_nodes, num_nodes, device=dev)
+        r = torch.bucketize(neg_idx, end - offset, right=True)
+        c = (offset[r] + neg_idx) % num_nodes
+        return torch.stack([torch.cat([r, c]), torch.cat([c, r])], dim=0)
     r = neg_idx.div(num_nodes - 1, rounding_mode="floor")
     c = neg_idx % (num_nodes - 1)
     c[r <= c] += 1

@@ -359,17 +359,40 @@ def main(argv=None):
     device = torch.device(f'cuda:{args.device}')
     torch.cuda.set_device(device)
 
-    if args.transductive != "transductive":
-        raise NotImplementedError("the production split generator (generate_production_split.py) is a 'next' row "
-                                  "(SURVEY.md N3); call train()/test_production() with a reference-made split instead")
-    if exists("../data/" + args.datasets + "_synthetic.pkl"):
-        data, split_edge = torch.load("../data/" + args.datasets + "_synthetic.pkl", weights_only=False)
+    production = args.transductive != "transductive"
+    if not production:
+        if exists("../data/" + args.datasets + "_synthetic.pkl"):
+            data, split_edge = torch.load("../data/" + args.datasets + "_synthetic.pkl", weights_only=False)
+        else:
+            data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=args.synthetic_scale)
+            if args.datasets != "collab" and exists("../data/" + args.datasets + ".pkl"):
+                # a split cached by the reference (train_teacher_gnn.py:310-314) or by splits.do_edge_split: same dict
+                split_edge = torch.load("../data/" + args.datasets + ".pkl", weights_only=False)
+                data.adj_t = data.edge_index = split_edge['train']['edge'].t().contiguous()
+        input_size = data.x.size(1)
+        args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
+        data.full_adj_t = data.adj_t  # --use_valedges_as_input builds full_adj_t but nothing reads it
+        data = data.to(device)
     else:
-        data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=args.synthetic_scale)
-    input_size = data.x.size(1)
-    args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
-    data.full_adj_t = data.adj_t  # --use_valedges_as_input builds full_adj_t but nothing reads it
-    data = data.to(device)
+        # production setting (train_teacher_gnn.py:344-371): the 6-tuple of generate_production_split.py, loaded from
+        # the reference's cache file when present, else generated here (splits.do_production_edge_split) on the
+        # synthetic stand-in graph (no network: the Planetoid / Coauthor downloads cannot run)
+        pkl = "../data/" + args.datasets + "_production.pkl"
+        if exists(pkl):
+            training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = torch.load(pkl, weights_only=False)
+        else:
+            print("splitting the datasets now...")
+            from .data import synthetic_full_graph
+            from .splits import do_production_edge_split
+            small = args.datasets in ("cora", "citeseer")
+            test_ratio = val_node_ratio = val_ratio = 0.3 if small else 0.1
+            training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = do_production_edge_split(
+                [synthetic_full_graph(args.datasets, seed=0, scale=args.synthetic_scale)], args.datasets, test_ratio,
+                val_node_ratio, val_ratio, 0.1, verbose=True)
+        input_size = training_data.x.size(1)
+        args.metric = 'Hits@20'
+        training_data.to(device); val_data.to(device); inference_data.to(device)
+        data, split_edge = training_data, None
 
     if args.encoder == 'sage':
         conv = SAGEConv_updated if args.datasets == "coauthor-physics" else SAGEConv
@@ -382,9 +405,9 @@ def main(argv=None):
     predictor = LinkPredictor(args.predictor, args.hidden_channels, args.hidden_channels, 1, 2, args.dropout).to(device)
 
     evaluator = Evaluator(name='ogbl-ddi')
-    keys = ['Hits@10', 'Hits@50', 'Hits@100', 'AUC'] if args.datasets == "collab" else \
+    keys = ['Hits@10', 'Hits@50', 'Hits@100', 'AUC'] if (args.datasets == "collab" and not production) else \
         ['Hits@10', 'Hits@20', 'Hits@30', 'Hits@50', 'AUC']
-    loggers = {k: Logger(args.runs, args) for k in keys}
+    loggers = {k: (ProductionLogger if production else Logger)(args.runs, args) for k in keys}
 
     val_max = 0.0
     for run in range(args.runs):
@@ -398,8 +421,12 @@ def main(argv=None):
         for epoch in range(1, 1 + args.epochs):
             loss = train(model, predictor, data, split_edge, optimizer, args.batch_size, args.encoder, args.datasets,
                          args.transductive)
-            results, h = test_transductive(model, predictor, data, split_edge, evaluator, args.batch_size, args.encoder,
-                                           args.datasets, args)
+            if not production:
+                results, h = test_transductive(model, predictor, data, split_edge, evaluator, args.batch_size, args.encoder,
+                                               args.datasets, args)
+            else:
+                results, h = test_production(model, predictor, val_data, inference_data, test_edge_bundle, negative_samples,
+                                             evaluator, args.batch_size, args.encoder, args.datasets)
 
             if results[args.metric][0] > val_max:
                 val_max = results[args.metric][0]
@@ -420,10 +447,16 @@ def main(argv=None):
 
             if epoch % args.log_steps == 0:
                 for key, result in results.items():
-                    valid_hits, test_hits = result
                     print(key)
-                    print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, '
-                          f'Valid: {100 * valid_hits:.2f}%, Test: {100 * test_hits:.2f}%')
+                    if not production:
+                        valid_hits, test_hits = result
+                        print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, '
+                              f'Valid: {100 * valid_hits:.2f}%, Test: {100 * test_hits:.2f}%')
+                    else:
+                        valid_hits, test_hits, old_old, old_new, new_new = result
+                        print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, valid: {100 * valid_hits:.2f}%, '
+                              f'test: {100 * test_hits:.2f}%, old_old: {100 * old_old:.2f}%, old_new: {100 * old_new:.2f}%, '
+                              f'new_new: {100 * new_new:.2f}%')
                 print('---')
 
             if cnt_wait >= args.patience:
@@ -442,9 +475,17 @@ def main(argv=None):
             best_results = []
             for r in loggers[key].results:
                 r = 100 * torch.tensor(r)
-                best_results.append((r[:, 0].max().item(), r[r[:, 0].argmax(), 1].item()))
-            r = torch.tensor(best_results)[:, 1]
-            file.write(f'Test: {r.mean():.4f} ± {r.std():.4f}\n')
+                best = r[:, 0].argmax()
+                best_results.append(tuple(r[best, j].item() for j in range(r.size(1))) if production else
+                                    (r[:, 0].max().item(), r[best, 1].item()))
+            best_result = torch.tensor(best_results)
+            if not production:
+                r = best_result[:, 1]
+                file.write(f'Test: {r.mean():.4f} ± {r.std():.4f}\n')
+            else:
+                names = ('  Final val', '   Final Test', '   Final old_old', '   Final old_new', '   Final new_new')
+                file.write(''.join(f'{nm}: {best_result[:, j].mean():.2f} ± {best_result[:, j].std():.2f}'
+                                   for j, nm in enumerate(names)) + '\n')
 
 
 if __name__ == "__main__":

@@ -493,6 +493,29 @@ def test_transductive(model, predictor, x, adj_t, split_edge, batch_size, encode
     return results, h
 
 
+@torch.no_grad()
+def test_production(model, predictor, val_data, inference_data, test_edge_bundle, negative_samples, batch_size,
+                    encoder_name="sage"):
+    """``train_teacher_gnn.py:157-268``: validation on the training graph, testing on the inference graph (old-old /
+    old-new / new-new buckets against one global negative set); ``results[key] = (valid, test, old_old, old_new,
+    new_new)``; returns the validation-graph embeddings like the reference (``saved_h``)."""
+    model.eval()
+    predictor.eval()
+    h = model(val_data.x) if encoder_name == "mlp" else model(val_data.x, val_data.edge_index)
+    saved_h = h
+    val_edges = val_data.edge_label_index.t()
+    pos_valid = score_edges(predictor, h, val_edges[val_data.edge_label.bool()], batch_size)
+    neg_valid = score_edges(predictor, h, val_edges[(1 - val_data.edge_label).bool()], batch_size)
+    h = model(inference_data.x) if encoder_name == "mlp" else model(inference_data.x, inference_data.edge_index)
+    old_old, old_new, new_new, test_all = (t.t() for t in test_edge_bundle[:4])
+    pos_test, oo, on, nn_ = (score_edges(predictor, h, e, batch_size) for e in (test_all, old_old, old_new, new_new))
+    neg_test = score_edges(predictor, h, negative_samples.t(), batch_size)
+    pairs = [(pos_valid, neg_valid), (pos_test, neg_test), (oo, neg_test), (on, neg_test), (nn_, neg_test)]
+    results = {f"Hits@{K}": tuple(hits_at_k(p, n, K) for p, n in pairs) for K in (10, 20, 30, 50)}
+    results["AUC"] = tuple(roc_auc(p, n) for p, n in pairs)
+    return results, saved_h
+
+
 # --------------------------------------------------------------------------------------
 # O15: student KD step (``main.py:147-236``, full-batch variant)
 # --------------------------------------------------------------------------------------

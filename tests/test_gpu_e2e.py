@@ -182,6 +182,62 @@ def test_student_epochs_match_reference_golden(cuda, golden, mode):
             torch.testing.assert_close(v.cpu(), g["sd1"]["mlp"][k], rtol=1e-3, atol=1e-5)
 
 
+def test_production_setting_matches_oracle(cuda, mode):
+    """Production split (splits.do_production_edge_split) -> train() on the old-node graph ->
+    test_production() over the five (positive, negative) pairs: loss, embeddings, Hits@K and AUC vs the CPU oracle."""
+    from linkless_link_prediction_b200.data import synthetic_full_graph
+    from linkless_link_prediction_b200.splits import do_production_edge_split
+    full = synthetic_full_graph("cora", seed=0, scale=0.25)
+    full.x = full.x[:, :64].contiguous()
+    parts = do_production_edge_split([full], "cora", 0.3, 0.3, 0.3, 0.1)
+    training_data, val_data, inference_data, _, bundle, negs = parts
+    f, H = training_data.x.size(1), 32
+    seed_all(0)
+    mo = O.SAGE("cora", f, H, H, 2, 0.0); po = O.LinkPredictor("mlp", H, H, 1, 2, 0.0)
+    md = L.SAGE("cora", f, H, H, 2, 0.0); md.load_state_dict(mo.state_dict()); md.to(cuda)
+    pd = L.LinkPredictor("mlp", H, H, 1, 2, 0.0); pd.load_state_dict(po.state_dict()); pd.to(cuda)
+    ro, ho = O.test_production(mo, po, val_data, inference_data, bundle, negs, 256)
+    import copy
+    dev_parts = [copy.copy(d).to(cuda) for d in (training_data, val_data, inference_data)]
+    rd, hd = teacher.test_production(md, pd, dev_parts[1], dev_parts[2], bundle, negs, L.Evaluator(), 256, "sage", "cora")
+    torch.testing.assert_close(hd.float().cpu(), ho, **TOL[mode])
+    assert set(rd) == set(ro) and all(len(v) == 5 for v in rd.values())
+    if mode == torch.float32:
+        n_pos = [int(val_data.edge_label.sum()), bundle[3].size(1), bundle[0].size(1), bundle[1].size(1), bundle[2].size(1)]
+        for K in (10, 20, 30, 50):  # at most one positive on the other side of a threshold (scores agree to ~1e-6)
+            for a, b, n in zip(rd[f"Hits@{K}"], ro[f"Hits@{K}"], n_pos):
+                assert abs(a - b) <= 1.0 / max(n, 1) + 1e-12
+        assert rd["AUC"] == pytest.approx(ro["AUC"], abs=2e-3)
+    # one training epoch on the training graph (production branch of train(): positives = its edge_index)
+    opt_o = torch.optim.Adam(list(mo.parameters()) + list(po.parameters()), lr=0.01)
+    opt_d = L.FusedAdam(list(md.parameters()) + list(pd.parameters()), lr=0.01)
+    mo.train(); po.train()
+    pos = training_data.edge_index
+    g = torch.Generator().manual_seed(3)
+    neg = torch.randint(0, training_data.x.size(0), pos.size(), generator=g)
+    lo = O.teacher_step(mo, po, training_data.x, pos, pos, neg, opt_o)
+    md.train(); pd.train()
+    ld = teacher.train_step(md, pd, dev_parts[0], pos.to(cuda), neg.to(cuda), opt_d, "sage", "production").item()
+    assert ld == pytest.approx(lo, rel=1e-5 if mode == torch.float32 else 2e-2)
+
+
+def test_production_driver_runs_end_to_end(cuda, tmp_path, monkeypatch):
+    """`python train_teacher_gnn.py --transductive=production` (scripts/supervised_production.sh): split generation,
+    training epochs, five-way evaluation, result / checkpoint files in the reference's ../ layout."""
+    work = tmp_path / "src"
+    work.mkdir()
+    monkeypatch.chdir(work)
+    teacher.main(["--datasets=cora", "--encoder=sage", "--transductive=production", "--runs=1", "--epochs=2",
+                  "--synthetic_scale=0.2", "--hidden_channels=32", "--batch_size=512", "--precision=fp32"])
+    out = (tmp_path / "results" / "cora_supervised_production.txt").read_text()
+    assert "All runs:" in out and "Final new_new" in out and "AUC" in out
+    ck = torch.load(tmp_path / "saved-models" / "cora-sage_production.pkl", weights_only=False)
+    assert set(ck) == {"gnn", "predictor"} and "convs.0.lin_l.weight" in ck["gnn"]
+    feats = torch.load(tmp_path / "saved-features" / "cora-sage_production.pkl", weights_only=False)
+    assert set(feats) == {"features"}
+    ops.set_compute_dtype(torch.bfloat16)
+
+
 def test_student_minibatch_equals_fullbatch_losses(cuda):
     """train_minibatch encodes only the touched rows; with dropout 0 its loss equals the full-batch step's."""
     ops.set_compute_dtype(torch.float32)

@@ -1,0 +1,126 @@
+"""Split generators: the restated ``do_edge_split`` / ``split_edges`` / ``do_production_edge_split``
+against fixtures produced by the reference's own functions (tests/golden/make_split_golden.py), plus first-principles
+properties of the splits (the third-party torch_geometric pieces are restated: parity unpinned)."""
+import os
+import random
+
+import pytest
+import torch
+
+from linkless_link_prediction_b200 import shims, splits
+from linkless_link_prediction_b200.data import features, undirected_graph
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "split_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+def graph(n, pairs, f, seed):
+    return shims.Data(x=features(n, f, 0.1, seed), edge_index=undirected_graph(n, pairs, seed, True))
+
+
+def pairs_of(e):  # [E,2] or [2,E] -> set of unordered pairs
+    e = e if e.size(-1) == 2 else e.t()
+    return {(min(a, b), max(a, b)) for a, b in e.tolist()}
+
+
+@pytest.mark.parametrize("tag", ["edge_split", "edge_split_fast", "edge_split_seed7"])
+def test_do_edge_split_matches_reference(golden, tag):
+    g = golden[tag]
+    a = dict(g["args"])
+    data = graph(a.pop("n"), a.pop("pairs"), a.pop("f"), a.pop("seed"))
+    before = data.edge_index.clone()
+    split = splits.do_edge_split([data], **a)
+    for part in ("train", "valid", "test"):
+        for kind in ("edge", "edge_neg"):
+            assert torch.equal(split[part][kind], g["split_edge"][part][kind]), (tag, part, kind)
+    assert torch.equal(data.edge_index, before)  # the caller's dataset is left intact
+
+
+def test_split_edges_matches_reference(golden):
+    g = golden["split_edges"]
+    torch.manual_seed(g["seed"])
+    out = splits.split_edges(g["edge_index"], g["val_ratio"], g["test_ratio"])
+    for mine, ref in zip(out, g["out"]):
+        assert torch.equal(mine, ref)
+
+
+def test_production_split_matches_reference(golden):
+    g = golden["production"]
+    a = dict(g["args"])
+    data = graph(a.pop("n"), a.pop("pairs"), a.pop("f"), a.pop("seed"))
+    training_data, val_data, inference_data, full, bundle, negs = splits.do_production_edge_split([data], "synthetic", **a)
+    for mine, ref in ((training_data, g["training_data"]), (val_data, g["val_data"]), (inference_data, g["inference_data"])):
+        for k, v in ref.items():
+            assert torch.equal(getattr(mine, k), v), k
+    for mine, ref in zip(bundle, g["test_edge_bundle"]):
+        assert torch.equal(mine, ref)
+    assert torch.equal(negs, g["negative_samples"])
+    assert full is data
+
+
+def test_edge_split_properties():
+    n = 500
+    data = graph(n, 3000, 4, 9)
+    und = pairs_of(data.edge_index)
+    split = splits.do_edge_split([data])
+    tr, va, te = (pairs_of(split[k]["edge"]) for k in ("train", "valid", "test"))
+    assert tr | va | te == und and not (tr & va) and not (tr & te) and not (va & te)
+    assert len(va) == int(0.05 * len(und)) and len(te) == int(0.1 * len(und))
+    assert split["train"]["edge"].size(0) == 2 * len(tr)                      # training edges are symmetrised
+    assert split["valid"]["edge_neg"].size(0) == len(va) and split["test"]["edge_neg"].size(0) == len(te)
+    for k in ("valid", "test"):                                                  # eval negatives are non-edges, no self loops
+        neg = split[k]["edge_neg"]
+        assert not (pairs_of(neg) & und) and bool((neg[:, 0] != neg[:, 1]).all())
+    # training negatives are drawn against the TRAINING graph only (utils.py:69-72): never a training edge or a self
+    # loop, but they may coincide with held-out validation / test positives — the reference's behaviour
+    neg = split["train"]["edge_neg"]
+    assert not (pairs_of(neg) & tr) and bool((neg[:, 0] != neg[:, 1]).all())
+    assert split["train"]["edge_neg"].size(0) == split["train"]["edge"].size(0)
+    again = splits.do_edge_split([graph(n, 3000, 4, 9)])
+    assert all(torch.equal(split[a][b], again[a][b]) for a in split for b in split[a])  # seeded: reproducible
+
+
+def test_production_split_properties():
+    n = 600
+    data = graph(n, 4000, 4, 5)
+    und = pairs_of(data.edge_index)
+    training_data, val_data, inference_data, _, (oo, on, nn, test_all), negs = splits.do_production_edge_split(
+        [data], "synthetic", 0.1, 0.1, 0.1, 0.1)
+    n_old = training_data.x.size(0)
+    assert n_old == n - round(0.1 * n) and inference_data.x.size(0) == n
+    assert int(training_data.edge_index.max()) < n_old and int(val_data.edge_label_index.max()) < n_old
+    # testing edges never appear in the inference graph; every inference / testing edge is a real edge
+    inf = pairs_of(inference_data.edge_index)
+    test = pairs_of(test_all)
+    assert not (inf & test) and (inf | test) == und
+    assert test_all.size(1) == oo.size(1) + on.size(1) + nn.size(1)
+    # global negatives: both directions of non-edges
+    assert negs.size(1) == 2 * (round(0.1 * data.edge_index.size(1) / 2) // 2)
+    assert not (pairs_of(negs) & und)
+    # validation labels: positives first (label 1), then sampled negatives (label 0)
+    lab = val_data.edge_label
+    n_pos = int(lab.sum())
+    assert bool((lab[:n_pos] == 1).all()) and bool((lab[n_pos:] == 0).all()) and n_pos > 0
+    # the training message graph excludes the validation positives
+    val_pos = pairs_of(val_data.edge_label_index[:, :n_pos])
+    assert not (pairs_of(training_data.edge_index) & val_pos)
+
+
+def test_negative_sampling_variants():
+    ei = undirected_graph(80, 400, 1, False)
+    pos = {tuple(p) for p in ei.t().tolist()}
+    random.seed(5); a = shims.negative_sampling(ei, 80, 500, method="dense")
+    random.seed(5); b = shims.negative_sampling(ei, 80, 500, method="sparse")
+    assert torch.equal(a, b) and a.size(1) == 500              # same candidate stream, same filter
+    assert all((x, y) not in pos and x != y for x, y in a.t().tolist())
+    random.seed(5); c = shims.negative_sampling(ei, 80, 500, force_undirected=True)
+    h = c.size(1) // 2
+    assert h == 250 and torch.equal(c[:, :h], c[:, h:].flip(0)) and bool((c[0, :h] < c[1, :h]).all())
+    assert all((x, y) not in pos for x, y in c.t().tolist())
+    full = torch.combinations(torch.arange(6)).t()
+    full = torch.cat([full, full.flip(0)], 1)
+    assert shims.negative_sampling(full, 6, 10).size(1) == 0   # complete graph: nothing to sample
