@@ -3,7 +3,7 @@
 8415-wide first SAGEConv_updated layer is the GEMM-bound part of the path (tensor roofline), plus the C2 / collab
 student distillation losses.  CUDA-event timing, L2 flushed between iterations.  Development tool.
 
-    python tools/kbench_c3.py [gemm] [layer] [step] [kd]
+    python tools/kbench_c3.py [gemm] [layer] [step] [kd] [student]
 """
 import os
 import sys
@@ -53,7 +53,7 @@ def report(name, us, nbytes=None, flops=None):
 
 
 def main():
-    which = set(sys.argv[1:]) or {"gemm", "layer", "step", "kd"}
+    which = set(sys.argv[1:]) or {"gemm", "layer", "step", "kd", "student"}
     n, F, H = 34493, 8415, 256
     torch.manual_seed(0)
     x32 = (torch.rand(n, F, device=dev) < 0.004).float()
@@ -109,6 +109,27 @@ def main():
         us = timeit(one, iters=8, warm=4)
         report(f"C3 teacher train step (SAGEConv_updated x2 + predictor, B={B})", us, flops=6 * 2 * n * F * H)
         print(f"   => {B / us:.2f} M positive edges/s", flush=True)
+    if "student" in which:
+        # collab student (scripts/LLP_transductive.sh: hidden 1024, 3 layers, K = 36 context nodes, 13,110 anchors per
+        # mini-batch): the predictor's first layer over [B_n*K, 1024] rows is a square, compute-bound GEMM
+        M, Hs = 13110 * 36, 1024
+        A = torch.randn(M, Hs, device=dev).bfloat16()
+        W = (torch.randn(Hs, Hs, device=dev) * 0.03).bfloat16()
+        bias = torch.randn(Hs, device=dev)
+        nb = M * Hs * 2 * 2 + Hs * Hs * 2
+        report(f"predictor lin1 fwd [{M},{Hs}] x [{Hs},{Hs}]^T + b, relu, dropout", timeit(lambda: ops.gemm_nt(A, W, bias=bias, relu=True, dropout_p=0.5, seed=1)),
+               nbytes=nb, flops=2 * M * Hs * Hs)
+        report(f"predictor lin1 dgrad [{M},{Hs}] x [{Hs},{Hs}]", timeit(lambda: ops.gemm_nt(A, W)), nbytes=nb, flops=2 * M * Hs * Hs)
+        G = torch.randn(M, Hs, device=dev).bfloat16()
+        report(f"predictor lin1 wgrad g[{M},{Hs}]^T z[{M},{Hs}]", timeit(lambda: ops.gemm_tn(G, A)), nbytes=nb, flops=2 * M * Hs * Hs)
+        Mm = 235868
+        X = torch.randn(Mm, 128, device=dev).bfloat16()
+        W1 = (torch.randn(Hs, 128, device=dev) * 0.05).bfloat16()
+        report(f"student MLP layer 1 [{Mm},128] -> 1024", timeit(lambda: ops.gemm_nt(X, W1, bias=bias, relu=True, dropout_p=0.5, seed=1)),
+               nbytes=Mm * (128 + Hs) * 2, flops=2 * Mm * 128 * Hs)
+        Hh = torch.randn(Mm, Hs, device=dev).bfloat16()
+        report(f"student MLP layer 2 [{Mm},1024] -> 1024", timeit(lambda: ops.gemm_nt(Hh, W, bias=bias, relu=True, dropout_p=0.5, seed=1)),
+               nbytes=Mm * 2 * Hs * 2, flops=2 * Mm * Hs * Hs)
     if "kd" in which:
         for rows, K, tag in ((2708, 12, "C2 Cora student"), (13110, 36, "collab student minibatch")):
             s = torch.rand(rows, K, device=dev); t = torch.rand(rows, K, device=dev)
