@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (ops.OVERLAP_WGRAD = False)")
     return ap.parse_args()
 
 
@@ -195,6 +196,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     ops.set_compute_dtype(args.precision)
+    if args.no_overlap:
+        ops.OVERLAP_WGRAD = set()
 
     data_cpu, split = build_workload(args)
     config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1))

@@ -6,6 +6,7 @@ All tensors must live on an sm_100 device; nothing here falls back to ATen or th
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
@@ -560,6 +561,45 @@ def prepare_weights(params: Sequence[torch.nn.Parameter]) -> None:
 # --------------------------------------------------------------------------------------------
 # autograd functions
 # --------------------------------------------------------------------------------------------
+# Weight gradients next to the input-gradient chain.  In a layer's backward the weight-gradient kernel is independent of
+# the chain that produces the input gradient; launched on a second stream forked from the current one (joined before
+# the backward function returns, so every tensor it reads outlives it and later main-stream work sees its results) it
+# becomes a parallel branch of the step's CUDA graph.  Measured per site on one B200 (bench.py / tools/kbench_c3.py):
+#   sage_updated  dW_r = g^T x (wide, tensor-bound) next to the transpose SpMM:      C3 step 1289 -> 1252 us   (on)
+#   edge          predictor dW_1 next to the dgrad GEMM + gather-reduce backward:     C3 1252 -> 1246, C4 2.018 -> 2.012 ms (on)
+#   sage          fused dW_l/dW_r/db next to the transpose SpMM + dual GEMM:          C4 2.018 -> 2.042 ms     (OFF: the
+#                 HBM-bound weight gradient and the issue-bound SpMM share the L2 fabric; the SpMM drops from 5.7 to
+#                 4.9 TB/s and loses more than the overlap hides)
+OVERLAP_WGRAD = set(filter(None, os.environ.get("LLP_OVERLAP_WGRAD", "sage_updated,edge").split(",")))
+
+
+class _SideBranch:
+    """``with _SideBranch(device, enabled) as br: <launches>`` runs the launches on the side stream, forked from the
+    current stream at entry; ``br.join()`` makes the current stream wait for them (no-op when disabled)."""
+
+    def __init__(self, device, enabled: bool):
+        self.enabled = bool(enabled)
+        self.device = device
+        self._ctx = None
+
+    def __enter__(self):
+        if self.enabled:
+            self.cur = torch.cuda.current_stream(self.device)
+            self.side = _side_stream(self.device, "wgrad")
+            self.side.wait_stream(self.cur)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+            self._ctx = None
+        return False
+
+    def join(self) -> None:
+        if self.enabled:
+            self.cur.wait_stream(self.side)
 # Gate fusion convention shared by the layer functions below.  ``in_gate`` > 0 says "my input x is the relu/dropout
 # output of the previous fused layer and I apply that layer's backward mask (x > 0 ? g*in_gate : 0) in the epilogue of
 # my input-gradient GEMM"; ``defer_gate`` says "my consumer does that for me, the incoming gradient is already
@@ -617,16 +657,18 @@ class SageConvFn(torch.autograd.Function):
         Pl, Pb, Pr = ctx.params
         g = _own_gate(to_compute(gy), y, p, defer_gate)
         need = ctx.needs_input_grad
-        if need[1]:  # one pass over g, agg and x: dW_l, dW_r and db_l
-            gWl, gWr, gbl = wgrad(g, agg, Pl, x, Pr if need[3] else None, bias=Pb if need[2] else None)
-        else:
-            gWl, gWr, gbl = wgrad(g, x, Pr if need[3] else None, bias=Pb if need[2] else None)
-            gWl, gWr = None, gWl
+        with _SideBranch(g.device, "sage" in OVERLAP_WGRAD and need[0]) as branch:
+            if need[1]:  # one pass over g, agg and x: dW_l, dW_r and db_l
+                gWl, gWr, gbl = wgrad(g, agg, Pl, x, Pr if need[3] else None, bias=Pb if need[2] else None)
+            else:
+                gWl, gWr, gbl = wgrad(g, x, Pr if need[3] else None, bias=Pb if need[2] else None)
+                gWl, gWr = None, gWl
         gx = None
         if ctx.needs_input_grad[0]:
             # A~^T (g W_l) = (A~^T g) W_l : aggregate first, then one dual GEMM writes gx with no add kernel
             t = ctx.graph.spmm(g, transpose=True)
             gx = gemm_nt(t, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
+        branch.join()
         return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
 
 
@@ -662,24 +704,26 @@ class SageConvUpdatedFn(torch.autograd.Function):
         p, in_gate, defer_gate = ctx.cfg
         Pl, Pb, Pr = ctx.params
         g = _own_gate(to_compute(gy), y, p, defer_gate)
-        gt = ctx.graph.spmm(g, transpose=True)
         need = ctx.needs_input_grad
+        with _SideBranch(g.device, "sage_updated" in OVERLAP_WGRAD and need[3]) as branch:   # dW_r = g^T x next to the transpose SpMM
+            gWr = wgrad(g, x, Pr)[0] if need[3] else None
+        gt = ctx.graph.spmm(g, transpose=True)
+        branch.join()
         gWl, _, gbl = wgrad(gt, x, Pl if need[1] else None, bias=Pb if need[2] else None)
-        gWr = wgrad(g, x, Pr)[0] if need[3] else None
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
         return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
 
 
-_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_SIDE_STREAMS: Dict[Tuple[int, str], "torch.cuda.Stream"] = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
+def _side_stream(device, tag: str = "plan") -> "torch.cuda.Stream":
     idx = torch.device(device).index or 0
-    st = _SIDE_STREAMS.get(idx)
+    st = _SIDE_STREAMS.get((idx, tag))
     if st is None:
-        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=device)
+        st = _SIDE_STREAMS[(idx, tag)] = torch.cuda.Stream(device=device)
     return st
 
 
@@ -869,11 +913,13 @@ class EdgeMlpFn(torch.autograd.Function):
         W1p, b1p = ctx.params
         gate_scale = 1.0 / (1.0 - ctx.p)   # relu + dropout backward from the saved y: 1/(1-p) where y > 0
         gy, gw2, gb2 = score_head_bwd(y, w2, prob, dprob, gate_scale, True, need[5], ctx.has_b2 and need[6])
-        gW1, _, gb1 = wgrad(gy, z, W1p if need[3] else None, bias=b1p if (b1p is not None and need[4]) else None)
+        with _SideBranch(gy.device, "edge" in OVERLAP_WGRAD and need[0]) as branch:   # next to the gather-reduce backward
+            gW1, _, gb1 = wgrad(gy, z, W1p if need[3] else None, bias=b1p if (b1p is not None and need[4]) else None)
         gh = None
         if need[0]:
             gz = gemm_nt(gy, _weights_t(W1p))
             gh = hadamard_bwd(h, ctx.plan, gz)
+        branch.join()
         return gh, None, None, gW1, gb1, gw2, gb2, None, None, None
 
 
