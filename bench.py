@@ -176,7 +176,7 @@ def main():
         config.update(nodes=data.x.size(0), messages=data.adj_t.size(1), feat=data.x.size(1))
         res = run_cpu(args, data, split, budget_s=150.0, max_steps=max(args.steps, 1), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": "train_pos_edges_per_sec", "value": res["value"], "unit": "edges/s",
-                "n_gpus": 0, "steps": res["steps"], "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+                "n_gpus": args.gpus, "gpus_used": 0, "steps": res["steps"], "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
