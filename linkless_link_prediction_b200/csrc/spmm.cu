@@ -119,14 +119,37 @@ __device__ __forceinline__ void load_row(const T* __restrict__ x, int64_t ldx, i
   }
 }
 
+// Packed fp32 arithmetic (sm_100: FADD2 / FFMA2, two IEEE round-to-nearest operations per issue slot).  The kernel is
+// issue-bound (profiles/r01_spmm_ncu_full_summary.json: 71 % issue-active, ~25 warp instructions per edge), and the eight
+// additions per 16-byte bf16 vector are its largest instruction group; each lane's result is bit-identical to the scalar
+// FADD / FFMA it replaces.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& a0, float& a1, float b0, float b1, float s) {
+  asm("{\n\t.reg .b64 ra, rb, rs;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\t"
+      "fma.rn.f32x2 ra, rb, rs, ra;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1), "f"(s));
+}
+
 template <typename T, int VE, int NV, bool kScale>
 __device__ __forceinline__ void add_row(RowAcc<VE, NV>& acc, const uint4 (&v)[NV], float scale) {
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     float f[VE];
     unpack_vec<T, VE>(v[k], f);
+    if constexpr (VE % 2 == 0) {
 #pragma unroll
-    for (int i = 0; i < VE; ++i) acc.a[k][i] = kScale ? fmaf(f[i], scale, acc.a[k][i]) : acc.a[k][i] + f[i];
+      for (int i = 0; i < VE; i += 2) {
+        if constexpr (kScale) fma2(acc.a[k][i], acc.a[k][i + 1], f[i], f[i + 1], scale);
+        else add2(acc.a[k][i], acc.a[k][i + 1], f[i], f[i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VE; ++i) acc.a[k][i] = kScale ? fmaf(f[i], scale, acc.a[k][i]) : acc.a[k][i] + f[i];
+    }
   }
 }
 
