@@ -173,9 +173,22 @@ def random_walk(row: torch.Tensor, col: torch.Tensor, start: torch.Tensor, walk_
     return ops.random_walk_with_rand(rowptr, col, start, rand.to(torch.float32))
 
 
+_KS_INDEX: Dict[tuple, torch.Tensor] = {}
+
+
+def _ks_index(Ks: Sequence[int], dev) -> torch.Tensor:
+    """Device tensor of ``K-1`` for every K (cached: building it is a blocking pageable H2D copy)."""
+    key = (tuple(Ks), str(dev))
+    t = _KS_INDEX.get(key)
+    if t is None:
+        t = _KS_INDEX[key] = torch.tensor([k - 1 for k in Ks], dtype=torch.int64, device=dev)
+    return t
+
+
 def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence[int], group=None, topk_fn=None,
                 count_fn=None):
-    """Integer hit counts for every K in ONE pass over the scores: returns ``(counts int64 [len(Ks)], n_pos int64 [1])``.
+    """Integer hit counts for every K in ONE pass over the scores: returns ``(counts int64 [len(Ks)], n_pos int64 [1])``
+    as device tensors (nothing here synchronises with the host on a single rank).
     With ``group`` (a torch.distributed process group) positives and negatives are rank-local shards: each rank
     contributes its top-K_max negatives (all-gather of W*K_max floats), thresholds are taken from the merged
     candidates and the counts are all-reduced — exact and independent of the sharding.
@@ -186,40 +199,46 @@ def hits_counts(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, Ks: Sequence
     kmax = max(Ks)
     cand = topk_fn(y_pred_neg, kmax)
     dev = cand.device
-    n_neg = torch.tensor([y_pred_neg.numel()], dtype=torch.int64, device=dev)
-    n_pos_total = torch.tensor([y_pred_pos.numel()], dtype=torch.int64, device=dev)
+    n_pos_total = torch.full((1,), y_pred_pos.numel(), dtype=torch.int64, device=dev)
+    n_neg_host = y_pred_neg.numel()
     if group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
         gathered = [torch.empty_like(cand) for _ in range(world)]
         dist.all_gather(gathered, cand, group=group)
         cand = topk_fn(torch.cat(gathered), kmax)
+        n_neg = torch.full((1,), n_neg_host, dtype=torch.int64, device=dev)
         dist.all_reduce(n_neg, group=group)
         dist.all_reduce(n_pos_total, group=group)
     # fewer negatives than K  =>  every positive is a hit (ogb: `if len(y_pred_neg) < K: return 1.0`); the top-k
     # list is padded with -inf in that case, which a strict '>' already treats as "always hit" for finite scores.
-    thr = cand[torch.tensor([k - 1 for k in Ks], device=dev)]
+    thr = cand.index_select(0, _ks_index(Ks, dev))
     counts = count_fn(y_pred_pos, thr)
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(counts, group=group)
-    short = n_neg < torch.tensor(list(Ks), dtype=torch.int64, device=dev)
-    return torch.where(short, n_pos_total.expand_as(counts), counts), n_pos_total
+        short = n_neg < (_ks_index(Ks, dev) + 1)
+        return torch.where(short, n_pos_total.expand_as(counts), counts), n_pos_total
+    if n_neg_host < kmax:  # rare: decided on the host (the negative count is a host integer on a single rank)
+        short = torch.tensor([n_neg_host < k for k in Ks], device=dev)
+        counts = torch.where(short, n_pos_total.expand_as(counts), counts)
+    return counts, n_pos_total
 
 
 def roc_auc_score_device(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, group=None, pairs_fn=None) -> float:
     """``sklearn.metrics.roc_auc_score(cat(ones, zeros), cat(pos, neg))`` of train_teacher_gnn.py:147-153,251-266
     without copying the scores to the host: ``llp_auc_pairs`` counts the (positive, negative) pairs ordered correctly
     and the tied pairs as integers; the only floating-point operation is the final division (in double).
-    With ``group`` the scores are rank-local shards: the negatives are all-gathered (ragged shards padded with +inf,
-    which no finite positive exceeds or ties), every rank counts its own positives against all of them and the two
+    With ``group`` the scores are rank-local shards: the negatives are all-gathered (ragged shards travel padded and are
+    trimmed by the gathered sizes), every rank counts its own positives against all of them and the two
     counters are all-reduced — exact and independent of the sharding.  ``pairs_fn`` is injectable for the gloo tests."""
     pairs_fn = pairs_fn or ops.auc_pairs
     dev = y_pred_pos.device
     neg = y_pred_neg.float().reshape(-1)
     pos = y_pred_pos.float().reshape(-1)
-    n = torch.tensor([pos.numel(), neg.numel()], dtype=torch.int64, device=dev)
+    n_host = (pos.numel(), neg.numel())
     if group is not None:
+        n = torch.tensor(n_host, dtype=torch.int64, device=dev)
         import torch.distributed as dist
         world = dist.get_world_size(group)
         sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
@@ -235,7 +254,7 @@ def roc_auc_score_device(y_pred_pos: torch.Tensor, y_pred_neg: torch.Tensor, gro
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(pairs, group=group)
-    n_pos, n_neg = (int(t) for t in n.tolist())
+    n_pos, n_neg = (int(t) for t in n.tolist()) if group is not None else n_host
     if n_pos == 0 or n_neg == 0:
         raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
     less, equal = (int(t) for t in pairs.tolist())
