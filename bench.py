@@ -123,12 +123,12 @@ def build_workload(args, seed=0):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference step on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_runner(data, split, batch, layers):
+def cpu_step_runner(data, split, batch, layers, updated=False):
     from oracle import llp_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     x, adj = data.x, data.adj_t
-    model = O.SAGE("collab", x.size(1), HIDDEN, HIDDEN, layers, DROPOUT)
+    model = O.SAGE("collab", x.size(1), HIDDEN, HIDDEN, layers, DROPOUT, O.SAGEConvUpdated if updated else O.SAGEConv)
     pred = O.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT)
     opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=LR)
     pos = split["train"]["edge"]
@@ -145,7 +145,7 @@ def cpu_step_runner(data, split, batch, layers):
 
 
 def run_cpu(args, data, split, budget_s, max_steps, warmup=1):
-    step = cpu_step_runner(data, split, BATCH, layers_of(args.workload))
+    step = cpu_step_runner(data, split, BATCH, layers_of(args.workload), updated=args.workload == "coauthor-physics")
     for _ in range(warmup):
         step()
     t0, n = time.perf_counter(), 0
@@ -203,7 +203,9 @@ def main():
     config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1))
     data = shims.Data(x=data_cpu.x, adj_t=data_cpu.adj_t).to(dev)
     shims.seed_everything(0)
-    model = L.SAGE(args.workload, data.x.size(1), HIDDEN, HIDDEN, layers_of(args.workload), DROPOUT).to(dev)
+    # the reference picks SAGEConv_updated for coauthor-physics (train_teacher_gnn.py:376-379), PyG SAGEConv otherwise
+    conv = L.SAGEConv_updated if args.workload == "coauthor-physics" else L.SAGEConv
+    model = L.SAGE(args.workload, data.x.size(1), HIDDEN, HIDDEN, layers_of(args.workload), DROPOUT, conv).to(dev)
     predictor = L.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT).to(dev)
     optimizer = L.FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=LR)
     model.train(); predictor.train()
