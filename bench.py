@@ -77,17 +77,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread (one sample every ~2 ms, so
+    even a 40 ms region is covered), falling back to an `nvidia-smi -lms` child process when NVML is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.max_mhz, self.reasons = [], None, set()
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except AttributeError:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001 - a failed sample is just a missing sample
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it lists integers
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if len(ids) > self.index else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._nvml = nv
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:  # noqa: BLE001 - fall back to nvidia-smi
+            self._nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -98,6 +135,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -111,7 +154,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def build_workload(args, seed=0):
