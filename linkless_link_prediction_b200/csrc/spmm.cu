@@ -19,6 +19,8 @@
 // registers; staging rows through shared memory with cp.async.bulk (one TMA op per row) or cp.async/LDGSTS (16 B per
 // lane) was measured too and was no faster (12 warps/SM, issue-bound), so the kernel keeps the gathered rows in
 // registers, holds the budget at <= 64 registers (32 warps/SM) and keeps the per-row epilogue out of line.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace llp {
@@ -256,6 +258,7 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     bool lane_ok[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) lane_ok[k] = col0 + (k * 32 + lane) * VE < F;
+    const bool all_lanes = col0 + kColsPerPass <= F;  // warp-uniform: every lane vector of this pass lies inside the row
     RowAcc<VE, NV> acc;
     acc.zero();
     int r = cr.r0;
@@ -295,6 +298,27 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
         const int o = e - base;                             // position inside the batch
         const int cnt = min(min(U, run_end - e), 32 - o);  // group: same row, same batch
         uint4 v[U][NV];
+        if (sizeof(T) == 2 && cnt == U && all_lanes) {   // (fp32 rows: measured 6 % slower with this path, left as it was)
+          // Full group and every lane inside the row (F == 32 * VE * NV: the widths this path is built for): no per-edge
+          // or per-lane predicate at all — shuffle, one address multiply-add, load; then unpack and packed adds: ~16 warp
+          // instructions per edge instead of ~58 through the guarded code below.  (A cascade of predicate-free groups of
+          // 8 / 4 / 2 / 1 edges for the partial groups was measured too: slower, 234 vs 200 us — code size.)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int src = __shfl_sync(0xffffffffu, my, (o + u) & 31);
+            const char* row = xlane + (uint64_t)((uint32_t)src) * ld_bytes;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[u][k] = load_vec<T, VE>(reinterpret_cast<const T*>(row) + k * 32 * VE);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float sc = 1.0f;
+            if constexpr (kScale) sc = __shfl_sync(0xffffffffu, mys, (o + u) & 31);
+            add_row<T, VE, NV, kScale>(acc, v[u], sc);
+          }
+          e += U;
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int src = __shfl_sync(0xffffffffu, my, (o + u) & 31);
@@ -396,10 +420,12 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
     const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
                       F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
     if (vec8) {
-      if (variant == 0) LLP_SPMM_LAUNCH(VE / 2, 1, 8, 8); else LLP_SPMM_LAUNCH(VE / 2, 1, 8, 6);
+      if (variant == 0) LLP_SPMM_LAUNCH(VE / 2, 1, 8, 8); else if (variant == 3) LLP_SPMM_LAUNCH(VE / 2, 1, 4, 8); else LLP_SPMM_LAUNCH(VE / 2, 1, 8, 6);
     } else if (vec) {
       if (F * (int64_t)sizeof(T) <= 512) {
-        if (variant == 1) LLP_SPMM_LAUNCH(VE, 1, 8, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 1, 8, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 1, 4, 8); else LLP_SPMM_LAUNCH(VE, 1, 8, 8);
+        // default: groups of 4 gathers (with an average degree of ~10 far more groups are full, i.e. take the predicate-free
+        // path, than with groups of 8: 189 / 208 us vs 200 / 226 us forward / transpose at F = 256 bf16 on the C4 graph)
+        if (variant == 1) LLP_SPMM_LAUNCH(VE, 1, 8, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 1, 8, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 1, 8, 8); else LLP_SPMM_LAUNCH(VE, 1, 4, 8);
       } else {
         if (variant == 1) LLP_SPMM_LAUNCH(VE, 2, 4, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 2, 4, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 2, 2, 8); else LLP_SPMM_LAUNCH(VE, 2, 4, 8);
       }
