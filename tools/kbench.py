@@ -49,7 +49,7 @@ def main():
     ei = undirected_graph(n, 1179052, 0, True, unique=False).to(dev)
     g = ops.Graph(ei, n)
     if "spmmsweep" in which:
-        for variant in (0, 3):
+        for variant in (0, 1, 2, 3):  # 0 = default (groups of 4 for 512-byte rows), 3 = groups of 8
             N.load().llp_set_tuning(0, variant)
             for dt, F in ((torch.bfloat16, 256), (torch.bfloat16, 128), (torch.float32, 256)):
                 x = torch.randn(n, F, device=dev).to(dt)
