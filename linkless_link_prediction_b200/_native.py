@@ -136,6 +136,11 @@ def load() -> ctypes.CDLL:
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        # development aid: LLP_TUNING="key=value,key=value" applies llp_set_tuning knobs at load time (A/B runs of
+        # experimental kernel variants through unmodified tests / benchmarks); results never depend on the knobs
+        for item in filter(None, os.environ.get("LLP_TUNING", "").split(",")):
+            k, _, v = item.partition("=")
+            lib.llp_set_tuning(int(k), int(v))
         _lib = lib
     return _lib
 
