@@ -38,6 +38,15 @@ def test_no_cpu_fallback():
     model = L.SAGE("cora", 8, 16, 16, 2, 0.0)
     with pytest.raises(RuntimeError):
         model(torch.zeros(5, 8), torch.zeros(2, 3, dtype=torch.long))
+    # the rows added later in the round fail just as loudly: device AUC, the stand-alone epilogue, the partitioned graph
+    with pytest.raises(RuntimeError):
+        L.ops.auc_pairs(torch.rand(4), torch.rand(5))
+    with pytest.raises(RuntimeError):
+        L.shims.roc_auc_score_device(torch.rand(4), torch.rand(5))
+    with pytest.raises(RuntimeError):
+        L.ops.add_act(torch.zeros(4, 8), relu=True)
+    with pytest.raises(RuntimeError):
+        L.ops.PartitionedGraph(torch.zeros(2, 3, dtype=torch.long), 5, 0, 2)
 
 
 @pytest.mark.parametrize("seed,n,b", [(0, 100, 32), (5, 8976, 65536), (7, 1000, 100), (9, 7, 3)])
