@@ -77,7 +77,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread (one sample every ~2 ms, so
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread (one sample every ~25 ms, so
     even a 40 ms region is covered), falling back to an `nvidia-smi -lms` child process when NVML is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -105,7 +105,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001 - a failed sample is just a missing sample
                 pass
-            time.sleep(0.002)
+            time.sleep(0.025)   # (NVML queries contend with kernel launches: polling every 2 / 10 / 15 ms slowed 2-rank steps by ~20 / 14 / 11 %)
 
     def start(self):
         try:
