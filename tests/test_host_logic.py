@@ -138,3 +138,35 @@ def test_interleaved_loaders_consume_rng_like_reference():
     assert len(ref) == len(got)
     for (a, b), (c, d) in zip(ref, got):
         assert torch.equal(a, c) and torch.equal(b, d)
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_partition_messages_owns_every_message_once(world):
+    """Node partition of the encoder (ops.partition_messages): blocks tile the padded node range, every
+    message is owned exactly once per direction in its original order, the local aggregation of all ranks stacked
+    equals the unpartitioned aggregation bit for bit."""
+    from linkless_link_prediction_b200.ops import partition_messages
+    from oracle import llp_oracle as O
+    n = 103
+    ei = O.synthetic_undirected_graph(n - 5, 700, seed=4)
+    x = torch.randn(n, 6, generator=torch.Generator().manual_seed(1))
+    parts = [partition_messages(ei, n, r, world) for r in range(world)]
+    n_loc = parts[0][0]
+    assert n_loc == -(-n // world) and [p[1] for p in parts] == [r * n_loc for r in range(world)]
+    x_pad = torch.zeros(n_loc * world, 6); x_pad[:n] = x
+    rp, col, _ = O.csr_build(ei, n, "dst")
+    ref = O.spmm_csr(rp, col, x, mean=True)
+    rows = []
+    seen_in = seen_out = 0
+    for n_loc_r, lo, hi, (f_src, f_dst), (t_src, t_dst), inv_deg in parts:
+        assert f_dst.numel() == 0 or (int(f_dst.min()) >= 0 and int(f_dst.max()) < n_loc)
+        assert t_src.numel() == 0 or int(t_src.max()) < n_loc
+        own = (ei[1] >= lo) & (ei[1] < hi)
+        assert torch.equal(f_src, ei[0][own]) and torch.equal(f_dst + lo, ei[1][own])      # original order kept
+        seen_in += f_src.numel(); seen_out += t_src.numel()
+        rp_l, col_l, _ = O.csr_build(torch.stack([f_src, f_dst]), n_loc, "dst")
+        rows.append(O.spmm_csr(rp_l, col_l, x_pad, mean=True))
+        deg = torch.zeros(n_loc * world).index_add_(0, ei[1], torch.ones(ei.size(1)))
+        assert torch.equal(inv_deg, 1.0 / deg.clamp(min=1))
+    assert seen_in == ei.size(1) and seen_out == ei.size(1)
+    assert torch.equal(torch.cat(rows)[:n], ref)
