@@ -87,22 +87,32 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
-        self.sm, self.max_mhz, self.reasons = [], None, set()
+        self.sm, self.max_mhz, self.reasons, self.reason_samples = [], None, set(), 0
         self._stop = threading.Event()
         self._thread = None
         self._nvml = None
 
+    def _reasons(self, nv, handle):
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+        except AttributeError:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+        for name, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+        self.reason_samples += 1
+
     def _nvml_loop(self, nv, handle):
+        # every NVML query contends with kernel launches (see the sleep below), so the throttle-reason query is issued
+        # with the first sample and whenever the SM clock is below its maximum; a clock AT its maximum is not throttled
+        first = True
         while not self._stop.is_set():
             try:
-                self.sm.append(int(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
-                except AttributeError:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
-                for name, bit in self.BITS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                mhz = int(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                self.sm.append(mhz)
+                if first or (self.max_mhz and mhz < 0.98 * self.max_mhz):
+                    self._reasons(nv, handle)
+                first = False
             except Exception:  # noqa: BLE001 - a failed sample is just a missing sample
                 pass
             time.sleep(0.025)   # (NVML queries contend with kernel launches: polling every 2 / 10 / 15 ms slowed 2-rank steps by ~20 / 14 / 11 %)
@@ -118,6 +128,7 @@ class ClockSampler:
             handle = nv.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
             self._nvml = nv
+            self._handle = handle
             self._thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
             self._thread.start()
             return
@@ -138,9 +149,13 @@ class ClockSampler:
         if self._nvml is not None:
             self._stop.set()
             self._thread.join(timeout=1.0)
+            try:  # one more reason sample right at the end of the region (sticky reasons such as sw_power_cap)
+                self._reasons(self._nvml, self._handle)
+            except Exception:  # noqa: BLE001
+                pass
             sm = sorted(self.sm)
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                    "samples": len(sm), "source": "nvml"}
+                    "samples": len(sm), "reason_samples": self.reason_samples, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
