@@ -288,6 +288,200 @@ def negative_sampling_dense(edge_index: Tensor, num_nodes: int, num_neg_samples:
 
 
 # --------------------------------------------------------------------------------------
+# N3: torch_geometric 2.2.0 pieces behind the split generators [3P, restated; parity unpinned].
+# Written independently of the product's ``splits.py`` / ``shims.py`` (numpy set arithmetic instead of masks and
+# ``isin`` on tensors) so that ``tests/golden/make_split_golden.py`` can run the REFERENCE'S split functions over THESE
+# and the product has to reproduce the result index for index: two implementations have to agree, not one with itself.
+# --------------------------------------------------------------------------------------
+def _linearise(edge_index: Tensor, n: int, undirected: bool) -> Tuple[np.ndarray, int]:
+    r, c = edge_index[0].numpy().astype(np.int64), edge_index[1].numpy().astype(np.int64)
+    if undirected:      # strict upper triangle, rows packed one after another: id = r*n + c - (1 + 2 + ... + (r+1))
+        keep = r < c
+        r, c = r[keep], c[keep]
+        return r * n + c - (r + 1) * (r + 2) // 2, n * (n + 1) // 2 - n
+    keep = r != c       # all ordered pairs without the diagonal: the column index skips the diagonal entry
+    r, c = r[keep], c[keep]
+    return r * (n - 1) + c - (r < c), n * n - n
+
+
+def _delinearise(idx: np.ndarray, n: int, undirected: bool) -> Tensor:
+    if undirected:
+        tri = np.cumsum(np.arange(1, n))                      # tri[r] = 1 + ... + (r+1)
+        row_end = np.arange(n, n * n, n) - tri               # first id that belongs to a later row
+        r = np.searchsorted(row_end, idx, side="right")
+        c = (tri[r] + idx) % n
+        return torch.from_numpy(np.stack([np.concatenate([r, c]), np.concatenate([c, r])]))
+    r, c = idx // (n - 1), idx % (n - 1)
+    c = c + (r <= c)
+    return torch.from_numpy(np.stack([r, c]))
+
+
+def negative_sampling(edge_index: Tensor, num_nodes=None, num_neg_samples: Optional[int] = None, method: str = "sparse",
+                      force_undirected: bool = False) -> Tensor:
+    """PyG 2.2.0 ``utils.negative_sampling`` (one node set).  Up to three rounds of ``random.sample`` candidates (CPython
+    stream), each filtered against the existing edges and the negatives kept so far; 'dense' and 'sparse' only differ
+    upstream in HOW they filter (bool mask vs ``isin``), not in what survives."""
+    if isinstance(num_nodes, (tuple, list)):
+        num_nodes = num_nodes[0]
+    n = int(edge_index.max()) + 1 if num_nodes is None else int(num_nodes)
+    taken, population = _linearise(edge_index, n, force_undirected)
+    if taken.size >= population:
+        return edge_index.new_empty((2, 0))
+    want = edge_index.size(1) if num_neg_samples is None else int(num_neg_samples)
+    if force_undirected:
+        want //= 2
+    k = int(1.1 * want / (1.0 - taken.size / population))
+    forbidden = set(taken.tolist())
+    kept: List[int] = []
+    for _ in range(3):
+        cand = list(range(population)) if population <= k else random.sample(range(population), k)
+        # upstream filters a round against the edges and the negatives of EARLIER rounds only: duplicates inside one
+        # round cannot occur (sampling without replacement)
+        kept.extend(v for v in cand if v not in forbidden)
+        if len(kept) >= want:
+            kept = kept[:want]
+            break
+        forbidden.update(kept)
+    return _delinearise(np.asarray(kept, dtype=np.int64), n, force_undirected)
+
+
+class GraphData:
+    """Attribute bag standing in for ``torch_geometric.data.Data`` in the split generators."""
+
+    def __init__(self, x=None, edge_index=None, **kw):
+        if x is not None:
+            self.x = x
+        if edge_index is not None:
+            self.edge_index = edge_index
+        self.__dict__.update(kw)
+
+    @property
+    def num_nodes(self):
+        return self.x.size(0)
+
+    def to(self, device):
+        for k, v in list(self.__dict__.items()):
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device))
+        return self
+
+
+def add_self_loops(edge_index: Tensor, *_, num_nodes: Optional[int] = None):
+    n = int(edge_index.max()) + 1 if num_nodes is None else num_nodes
+    loops = torch.arange(n, dtype=edge_index.dtype)
+    return torch.cat([edge_index, torch.stack([loops, loops])], dim=1), None
+
+
+def subgraph(subset: Tensor, edge_index: Tensor, edge_attr=None, relabel_nodes: bool = False, num_nodes=None):
+    mask = subset if subset.dtype == torch.bool else torch.zeros(int(num_nodes or edge_index.max() + 1), dtype=torch.bool).index_fill_(0, subset, True)
+    keep = mask[edge_index[0]] & mask[edge_index[1]]
+    ei = edge_index[:, keep]
+    if relabel_nodes:
+        new_id = torch.cumsum(mask.long(), 0) - 1      # rank of every kept node among the kept nodes
+        ei = new_id[ei]
+    return ei, None
+
+
+def train_test_split_edges(data, val_ratio: float = 0.05, test_ratio: float = 0.1):
+    """PyG 2.2.0 ``utils.train_test_split_edges``: RNG order = one ``randperm`` over the undirected pairs, one over the
+    non-edges of the strict upper triangle (enumerated in row-major order)."""
+    n = data.num_nodes
+    r, c = data.edge_index
+    data.edge_index = None
+    up = r < c
+    r, c = r[up], c[up]
+    n_v, n_t = int(math.floor(val_ratio * r.numel())), int(math.floor(test_ratio * r.numel()))
+    order = torch.randperm(r.numel())
+    r, c = r[order], c[order]
+    data.val_pos_edge_index = torch.stack([r[:n_v], c[:n_v]])
+    data.test_pos_edge_index = torch.stack([r[n_v:n_v + n_t], c[n_v:n_v + n_t]])
+    tr = torch.stack([r[n_v + n_t:], c[n_v + n_t:]])
+    both = torch.cat([tr, tr.flip(0)], dim=1)                               # to_undirected: both directions,
+    key = np.unique(both[0].numpy() * n + both[1].numpy())                  # sorted by (row, col), duplicates dropped
+    data.train_pos_edge_index = torch.from_numpy(np.stack([key // n, key % n]))
+    free = np.triu(np.ones((n, n), dtype=bool), k=1)
+    free[r.numpy(), c.numpy()] = False
+    fr, fc = np.nonzero(free)                                                # row-major, like Tensor.nonzero()
+    pick = torch.randperm(fr.size)[:n_v + n_t].numpy()
+    fr, fc = torch.from_numpy(fr[pick]), torch.from_numpy(fc[pick])
+    free[fr.numpy(), fc.numpy()] = False
+    data.train_neg_adj_mask = torch.from_numpy(free)
+    data.val_neg_edge_index = torch.stack([fr[:n_v], fc[:n_v]])
+    data.test_neg_edge_index = torch.stack([fr[n_v:n_v + n_t], fc[n_v:n_v + n_t]])
+    return data
+
+
+class RandomNodeSplit:
+    """PyG 2.2.0 ``transforms.RandomNodeSplit`` with the default ``split='train_rest'``."""
+
+    def __init__(self, split="train_rest", num_splits=1, num_train_per_class=20, num_val=500, num_test=1000, key="y"):
+        assert split == "train_rest" and num_splits == 1
+        self.num_val, self.num_test = num_val, num_test
+
+    def __call__(self, data):
+        import copy
+        out = copy.copy(data)
+        n = data.num_nodes
+        nv = round(n * self.num_val) if isinstance(self.num_val, float) else self.num_val
+        nt = round(n * self.num_test) if isinstance(self.num_test, float) else self.num_test
+        order = torch.randperm(n)
+        role = torch.zeros(n, dtype=torch.int64)          # 0 train, 1 val, 2 test
+        role[order[:nv]] = 1
+        role[order[nv:nv + nt]] = 2
+        out.train_mask, out.val_mask, out.test_mask = role == 0, role == 1, role == 2
+        return out
+
+
+class RandomLinkSplit:
+    """PyG 2.2.0 ``transforms.RandomLinkSplit`` for one homogeneous graph, defaults as the reference leaves them."""
+
+    def __init__(self, num_val=0.1, num_test=0.2, is_undirected=False, key="edge_label", split_labels=False,
+                 add_negative_train_samples=True, neg_sampling_ratio=1.0, disjoint_train_ratio=0.0):
+        assert not split_labels and not disjoint_train_ratio and key == "edge_label"
+        self.num_val, self.num_test, self.is_undirected = num_val, num_test, is_undirected
+        self.neg_train, self.ratio = add_negative_train_samples, neg_sampling_ratio
+
+    def __call__(self, data):
+        import copy
+        ei = data.edge_index
+        if self.is_undirected:
+            ids = torch.nonzero(ei[0] <= ei[1]).view(-1)
+            ids = ids[torch.randperm(ids.numel())]
+        else:
+            ids = torch.randperm(ei.size(1))
+        nv = int(self.num_val * ids.numel()) if isinstance(self.num_val, float) else self.num_val
+        nt = int(self.num_test * ids.numel()) if isinstance(self.num_test, float) else self.num_test
+        ntr = ids.numel() - nv - nt
+        assert ntr > 0
+        parts = {"train": ids[:ntr], "val": ids[ntr:ntr + nv], "test": ids[ntr + nv:]}
+        message = {"train": ids[:ntr], "val": ids[:ntr], "test": ids[:ntr + nv]}   # edges each split may look at
+        n_neg = {"train": int(ntr * self.ratio) if self.neg_train else 0, "val": int(nv * self.ratio), "test": int(nt * self.ratio)}
+        total = sum(n_neg.values())
+        neg = negative_sampling(ei, (data.num_nodes, data.num_nodes), num_neg_samples=total, method="sparse")
+        if neg.size(1) < total:
+            scale = neg.size(1) / total
+            n_neg["train"], n_neg["val"] = int(n_neg["train"] * scale), int(n_neg["val"] * scale)
+            n_neg["test"] = neg.size(1) - n_neg["train"] - n_neg["val"]
+        # the negative columns are dealt out val first, then test, then train
+        start = {"val": 0, "test": n_neg["val"], "train": n_neg["val"] + n_neg["test"]}
+        end = {"val": n_neg["val"], "test": n_neg["val"] + n_neg["test"], "train": neg.size(1)}
+        outs = []
+        for name in ("train", "val", "test"):
+            d = copy.copy(data)
+            m = ei[:, message[name]]
+            d.edge_index = torch.cat([m, m.flip(0)], dim=1) if self.is_undirected else m
+            pos = ei[:, parts[name]]
+            mine = neg[:, start[name]:end[name]]
+            label = torch.ones(pos.size(1))
+            if mine.numel() > 0:
+                label = torch.cat([label, torch.zeros(mine.size(1))])
+                pos = torch.cat([pos, mine], dim=1)
+            d.edge_label, d.edge_label_index = label, pos
+            outs.append(d)
+        return tuple(outs)
+
+
+# --------------------------------------------------------------------------------------
 # O9: random walks (torch_cluster 1.6.0, uniform, coalesced=False) [3P]
 # --------------------------------------------------------------------------------------
 def walk_rowptr(row: Tensor, num_nodes: int) -> Tensor:

@@ -6,9 +6,10 @@ Run here (needs ``/root/reference``; the tests only read the committed ``split_g
 
 ``src/utils.py:62-105`` (``do_edge_split``) and ``src/generate_production_split.py:14-95`` (``split_edges``,
 ``do_production_edge_split``) are imported unmodified; the torch_geometric symbols they call are stubbed with the
-restatements in ``linkless_link_prediction_b200/splits.py`` / ``shims.py`` (torch_geometric itself is not installed: the
-third-party half stays "parity unpinned").  The fixture therefore pins the reference-owned glue — which edges go where,
-in which order the RNG streams are consumed, the container layout — not PyG's internals.
+ORACLE's restatements (``oracle/llp_oracle.py``, section N3 — written independently of the product's ``splits.py`` /
+``shims.py``; torch_geometric itself is not installed, so that half stays "parity unpinned").  The fixture pins the
+reference-owned glue — which edges go where, in which order the RNG streams are consumed, the container layout — and the
+product, which re-implements glue AND third-party pieces, has to reproduce it index for index (``tests/test_splits.py``).
 """
 import os
 import sys
@@ -23,8 +24,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
 from make_golden import _Stub  # noqa: E402
-from linkless_link_prediction_b200 import shims, splits  # noqa: E402
-from linkless_link_prediction_b200.data import features, undirected_graph  # noqa: E402
+from linkless_link_prediction_b200.data import features, undirected_graph  # noqa: E402  (synthetic inputs only)
+from oracle import llp_oracle as O  # noqa: E402
 
 
 def install_stubs():
@@ -37,19 +38,19 @@ def install_stubs():
             parent, child = n.rsplit(".", 1)
             setattr(mods[parent], child, m)
     u, t, d = mods["torch_geometric.utils"], mods["torch_geometric.transforms"], mods["torch_geometric.data"]
-    u.negative_sampling = shims.negative_sampling
-    u.add_self_loops = splits.add_self_loops
-    u.train_test_split_edges = splits.train_test_split_edges
-    u.subgraph = splits.subgraph
-    t.RandomLinkSplit = splits.RandomLinkSplit
-    t.RandomNodeSplit = splits.RandomNodeSplit
-    d.Data = shims.Data
+    u.negative_sampling = O.negative_sampling
+    u.add_self_loops = O.add_self_loops
+    u.train_test_split_edges = O.train_test_split_edges
+    u.subgraph = O.subgraph
+    t.RandomLinkSplit = O.RandomLinkSplit
+    t.RandomNodeSplit = O.RandomNodeSplit
+    d.Data = O.GraphData
     d.Dataset = list
 
 
 def graph(n, pairs, f, seed):
     ei = undirected_graph(n, pairs, seed, True)
-    return shims.Data(x=features(n, f, 0.1, seed), edge_index=ei)
+    return O.GraphData(x=features(n, f, 0.1, seed), edge_index=ei)
 
 
 def pack_data(d):

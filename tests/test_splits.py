@@ -124,3 +124,31 @@ def test_negative_sampling_variants():
     full = torch.combinations(torch.arange(6)).t()
     full = torch.cat([full, full.flip(0)], 1)
     assert shims.negative_sampling(full, 6, 10).size(1) == 0   # complete graph: nothing to sample
+
+
+def test_third_party_pieces_agree_with_the_independent_oracle_restatement():
+    """Product (masks / isin on tensors) vs oracle (numpy set arithmetic): same RNG consumption, same indices."""
+    from oracle import llp_oracle as O
+    ei = undirected_graph(90, 500, 2, True)
+    for kw in ({}, {"method": "dense"}, {"force_undirected": True}, {"num_neg_samples": 7000}):  # 7000: needs > 1 round
+        random.seed(11); a = shims.negative_sampling(ei, 90, **({"num_neg_samples": 300} | kw))
+        random.seed(11); b = O.negative_sampling(ei, 90, **({"num_neg_samples": 300} | kw))
+        assert torch.equal(a, b), kw
+    d1, d2 = graph(90, 500, 4, 2), O.GraphData(x=features(90, 4, 0.1, 2), edge_index=undirected_graph(90, 500, 2, True))
+    torch.manual_seed(5); s1 = splits.train_test_split_edges(d1, 0.1, 0.2)
+    torch.manual_seed(5); s2 = O.train_test_split_edges(d2, 0.1, 0.2)
+    for k in ("train_pos_edge_index", "val_pos_edge_index", "test_pos_edge_index", "val_neg_edge_index", "test_neg_edge_index",
+              "train_neg_adj_mask"):
+        assert torch.equal(getattr(s1, k), getattr(s2, k)), k
+    d1, d2 = graph(90, 500, 4, 2), O.GraphData(x=features(90, 4, 0.1, 2), edge_index=undirected_graph(90, 500, 2, True))
+    torch.manual_seed(6); n1 = splits.RandomNodeSplit(num_val=0.0, num_test=0.2)(d1)
+    torch.manual_seed(6); n2 = O.RandomNodeSplit(num_val=0.0, num_test=0.2)(d2)
+    assert torch.equal(n1.train_mask, n2.train_mask) and torch.equal(n1.test_mask, n2.test_mask)
+    random.seed(7); torch.manual_seed(7); l1 = splits.RandomLinkSplit(0.0, 0.2, is_undirected=True)(d1)
+    random.seed(7); torch.manual_seed(7); l2 = O.RandomLinkSplit(0.0, 0.2, is_undirected=True)(d2)
+    for a, b in zip(l1, l2):
+        assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.edge_label, b.edge_label) \
+            and torch.equal(a.edge_label_index, b.edge_label_index)
+    sub1 = splits.subgraph(n1.train_mask, ei, relabel_nodes=True)[0]
+    sub2 = O.subgraph(n2.train_mask, ei, relabel_nodes=True)[0]
+    assert torch.equal(sub1, sub2)
