@@ -50,7 +50,9 @@ const char* llp_error_string(int code);
 int llp_device_supported(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t llp_launch_count(void);
-/* development knob (benchmark sweeps only; results never depend on it): key 0 = SpMM occupancy/register variant */
+/* development knob for benchmark sweeps: selects between kernel variants that compute the SAME result (key 0 = SpMM
+ * occupancy/register variant, 10/12/14/16-20 = GEMM pipeline variants, 15 = instrumentation).  The work-skipping
+ * experiment keys (1, 2, 11, 13) are compiled only into -DLLP_EXPERIMENT builds; the shipped library ignores them. */
 void llp_set_tuning(int key, int value);
 /* development aid: copy n (<= 4096) int64 of the instrumentation scratch to the host (synchronises the device) */
 int llp_debug_read(int64_t* host_out, int n);

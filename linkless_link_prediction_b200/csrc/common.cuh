@@ -35,6 +35,19 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 
 constexpr int kNumSMs = 148;  // B200
 
+// Function attributes (opt-in shared memory) are per DEVICE: a process that drives several GPUs must set them on each.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  uint64_t bit = 0;
+  bool need() {
+    int d = 0;
+    cudaGetDevice(&d);
+    bit = 1ull << (d & 63);
+    return (mask.load(std::memory_order_acquire) & bit) == 0;
+  }
+  void done() { mask.fetch_or(bit, std::memory_order_release); }
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 static inline int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }

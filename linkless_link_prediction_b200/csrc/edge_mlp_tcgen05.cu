@@ -306,10 +306,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
 template <int BLOCK_N>
 static int launch(const CUtensorMap& map_w, Params& p, cudaStream_t stream) {
   auto kern = edge_mlp_kernel<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    configured = true;
+    configured.done();
   }
   const int num_kb = p.K / kBK;
   const int b_bytes = num_kb * BLOCK_N * 128;

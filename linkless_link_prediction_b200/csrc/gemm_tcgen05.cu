@@ -522,10 +522,10 @@ constexpr int kResBSmemMax = 226 * 1024;
 template <int BLOCK_N, typename TO>
 static int launch_resb(const Maps& maps, const TcParams& p, int num_kb, cudaStream_t stream) {
   auto kern = gemm_nt_resb_kernel<BLOCK_N, TO>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBSmemMax));
-    configured = true;
+    configured.done();
   }
   const int b_bytes = num_kb * BLOCK_N * 128;
   int stages = (kResBSmemMax - 1024 - 512 - b_bytes) / (BLOCK_M * 128);
@@ -781,10 +781,10 @@ gemm_nt_pair_kernel(const __grid_constant__ Maps maps, const TcParams p, const i
 template <typename TO>
 static int launch_pair(const Maps& maps, const TcParams& p, int num_kb, cudaStream_t stream) {
   auto kern = gemm_nt_pair_kernel<TO>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResBSmemMax));
-    configured = true;
+    configured.done();
   }
   const int b_bytes = num_kb * kPairHalfBytes;
   int stages = (kResBSmemMax - 1024 - 512 - b_bytes) / kPairHalfBytes;
@@ -804,10 +804,10 @@ template <int BLOCK_N, bool kTN, typename TO>
 static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
   using Cfg = Config<BLOCK_N>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, kTN, TO>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   int64_t m_tiles = ceil_div(p.M, BLOCK_M), n_tiles = ceil_div(p.N, BLOCK_N);
   int64_t tiles = m_tiles * n_tiles * p.splits;
@@ -854,7 +854,9 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr;
   p.dbg = g_tuning[15] ? debug_buffer() : nullptr;
-  if (g_tuning[11]) p.splits = -1;  // experiment knob read by the pair kernel only
+#ifdef LLP_EXPERIMENT
+  if (g_tuning[11]) p.splits = -1;  // experiment knob read by the pair kernel only (no MMAs: pure load pipeline)
+#endif
   {
     const size_t so = a.out_dtype == LLP_BF16 ? 2 : 4;
     auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * so) % 16 == 0; };

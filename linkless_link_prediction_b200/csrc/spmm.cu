@@ -270,7 +270,9 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     auto fetch_idx = [&](int b) {
       const int i = b + lane;
       int v = (i < n_edges) ? __ldg(col + i) : 0;
+#ifdef LLP_EXPERIMENT
       if (fake_seq_n > 0) v = i % fake_seq_n;
+#endif
       return v;
     };
     int my = fetch_idx(base), my_next = fetch_idx(base + 32);
@@ -398,8 +400,17 @@ spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 }
 
 int g_spmm_variant = 0;  // 0 = 8 blocks/SM (<= 64 registers): fastest for the row-run kernel (tools/kbench.py spmmsweep)
+// Result-changing experiment knobs exist only in -DLLP_EXPERIMENT builds (make EXTRA=-DLLP_EXPERIMENT); the shipped
+// library cannot skip work: llp_set_tuning ignores keys 1, 2, 11 and 13.
+#ifdef LLP_EXPERIMENT
 int g_spmm_chunk_div = 1;  // experiment: process only the first n_chunks/div chunks
 int g_spmm_fake_seq = 0;   // experiment: gather row (edge id mod N) instead of col[e]
+#define LLP_SPMM_CHUNKS(n) ((n) / g_spmm_chunk_div)
+#define LLP_SPMM_FAKE(N) (g_spmm_fake_seq ? (int)(N) : 0)
+#else
+#define LLP_SPMM_CHUNKS(n) (n)
+#define LLP_SPMM_FAKE(N) 0
+#endif
 
 template <typename T, bool kScale>
 static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t* first_row, int64_t N, int64_t E,
@@ -415,7 +426,7 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
   if (E > 0) {
 #define LLP_SPMM_LAUNCH(VE_, NV_, U_, MB_) \
-  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, n_chunks / g_spmm_chunk_div, x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, g_spmm_fake_seq ? (int)N : 0, (int)N, (int)ceil_div(N, n_chunks), (int)E)
+  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, LLP_SPMM_FAKE(N), (int)N, (int)ceil_div(N, n_chunks), (int)E)
     const int variant = g_spmm_variant;  // occupancy/register trade-off (llp_set_tuning(0, v)): 0 = 8 blocks/SM (<=64 regs)
     const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
                       F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
@@ -449,10 +460,15 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
 using namespace llp;
 
 extern "C" void llp_set_tuning(int key, int value) {
+#ifndef LLP_EXPERIMENT
+  if (key == 1 || key == 2 || key == 11 || key == 13) return;  // work-skipping experiments: not compiled into this build
+#endif
   if (key >= 0 && key < 32) g_tuning[key] = value;
   if (key == 0) g_spmm_variant = value;
+#ifdef LLP_EXPERIMENT
   if (key == 1) g_spmm_chunk_div = value < 1 ? 1 : value;
   if (key == 2) g_spmm_fake_seq = value;
+#endif
 }
 
 extern "C" int64_t llp_spmm_num_chunks(int64_t E) { return E <= 0 ? 1 : ceil_div(E, kEPW); }

@@ -314,8 +314,13 @@ static void plan(int64_t M, int64_t N1, int64_t n2a, int64_t n2b, Params* p, int
   int stages = (kSmemBudget - 2048) / stage_bytes;
   p->stages = stages > 12 ? 12 : stages;
   if (g_tuning[10] > 0 && g_tuning[10] < p->stages) p->stages = g_tuning[10];
+#ifdef LLP_EXPERIMENT   // work-skipping experiments exist only in -DLLP_EXPERIMENT builds
   p->debug_skip_mma = g_tuning[11];
   p->debug_wide_box = g_tuning[13];
+#else
+  p->debug_skip_mma = 0;
+  p->debug_wide_box = 0;
+#endif
   p->strided = g_tuning[14];
   p->debug_times = g_tuning[15] ? debug_buffer() : nullptr;
   const int cols = 64 * (p->slabs_a + p->slabs_b);
@@ -362,11 +367,11 @@ int wgrad_tcgen05(int64_t M, int64_t N1, const void* G, int64_t ldg, int64_t n2a
   p.partial = ws;
   p.partial_bias = dbias != nullptr ? ws + (size_t)p.splits * (size_t)N1 * ncols : nullptr;
   const int smem = p.stages * (2 + p.slabs_a + p.slabs_b) * kSlab + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     LLP_CUDA(cudaFuncSetAttribute(wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    configured = true;
+    configured.done();
   }
   const unsigned grid = (unsigned)(ceil_div(N1, kTileN1) * p.splits);
   if (kBK == 64) wgrad_kernel<64><<<grid, kThreads, smem, stream>>>(maps, p);

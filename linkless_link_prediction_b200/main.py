@@ -21,7 +21,8 @@ from .models import MLP, LinkPredictor
 from .optim import FusedAdam
 from .shims import Evaluator, negative_sampling, random_walk, seed_everything
 from . import shims
-from .train_teacher_gnn import _dist, _shard, optimizer_tail, test_production, test_transductive
+from .train_teacher_gnn import (_dist, _shard, finish_distributed, init_device, load_production, load_transductive,
+                                optimizer_tail, test_production, test_transductive)
 
 
 def cosine_loss(s, t):
@@ -53,6 +54,9 @@ def _kd_losses(predictor, teacher_predictor, h, t_h, samples, args):
     """LLP_D and LLP_R for the anchors in ``samples[:,0]`` against the contexts ``samples[:,1:]`` (main.py:183-203).
     ``predictor(h[a].repeat(K), h[ctx])`` becomes one fused edge-scoring call over the (anchor, context) pairs."""
     K = samples.size(1) - 1
+    if samples.size(0) == 0:   # empty anchor shard (fewer anchors than ranks): contributes nothing
+        zero = torch.zeros((), dtype=torch.float32, device=h.device)
+        return zero, zero
     anchor = samples[:, :1].expand(-1, K).contiguous()
     ctx = samples[:, 1:].contiguous()
     s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
@@ -110,18 +114,24 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
         nlo, nhi = _shard(neg_edge.size(1), rank, world)
         edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
         train_edges = torch.cat((edge, neg_edge), dim=-1)
-        out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
-        label_loss = ops.bce_loss(out, edge.size(1))
+        edge_share = 1.0   # this rank's share of the global batch times W: rank means average to the global mean
         if world > 1:
-            label_loss = label_loss * (train_edges.size(1) * world / float(2 * n_global))
+            edge_share = train_edges.size(1) * world / float(2 * n_global)
+        if train_edges.size(1) > 0:
+            out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+            label_loss = ops.bce_loss(out, edge.size(1)) * edge_share
+        else:   # empty shard: zero loss that still reaches backward / the gradient all-reduce through h
+            out = None
+            label_loss = h.float().sum() * 0.0
 
         loss = args.True_label * label_loss
         if args.KD_RM:  # baselines, weight 0 by default; the reference evaluates them regardless
+            # mean over the node batch: every rank evaluates the whole (replicated) batch, so no re-weighting is needed
             loss = loss + args.KD_RM * cosine_loss(h[node_perm], t_h[node_perm])
-        if args.KD_LM:
+        if args.KD_LM and out is not None:
             with torch.no_grad():
                 t_out = teacher_predictor.score(t_h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
-            loss = loss + args.KD_LM * F.mse_loss(out, t_out)
+            loss = loss + args.KD_LM * F.mse_loss(out, t_out) * edge_share   # a mean over this rank's edge shard
         if args.LLP_D or args.LLP_R:
             loss = loss + args.LLP_D * llp_d_loss + args.LLP_R * llp_r_loss
 
@@ -248,26 +258,30 @@ def main(argv=None):
     ops.set_compute_dtype(args.precision)
     os.makedirs("../results", exist_ok=True)
     Logger_file = "../results/" + args.datasets + "_KD_" + args.transductive + ".txt"
-    with open(Logger_file, "a") as file:
-        file.write(str(args) + "\n")
-        if args.KD_RM != 0:
-            file.write("Logit-matching\n")
-        elif args.KD_LM != 0:
-            file.write("Representation-matching\n")
-        elif args.LLP_D != 0 or args.LLP_R != 0:
-            file.write("LLP (Relational Distillation)\n")
-    if not torch.cuda.is_available():
-        raise RuntimeError("this implementation has no CPU path: an sm_100 (B200) GPU is required")
-    device = torch.device(f'cuda:{args.device}')
-    torch.cuda.set_device(device)
-    if args.transductive != "transductive":
-        raise NotImplementedError("production split generation is a 'next' row (SURVEY.md N3)")
+    if int(os.environ.get("RANK", "0")) == 0:
+        with open(Logger_file, "a") as file:
+            file.write(str(args) + "\n")
+            if args.KD_RM != 0:
+                file.write("Logit-matching\n")
+            elif args.KD_LM != 0:
+                file.write("Representation-matching\n")
+            elif args.LLP_D != 0 or args.LLP_R != 0:
+                file.write("LLP (Relational Distillation)\n")
+    device, rank, world = init_device(args)
 
-    data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=args.synthetic_scale)
-    input_size = data.x.size(1)
-    args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
-    data = data.to(device)
-    args.node_batch_size = int(data.x.size()[0] / (split_edge['train']['edge'].size()[0] / args.link_batch_size))
+    production = args.transductive != "transductive"
+    if not production:
+        # the SAME loader as the teacher driver: a split cached next to the data is the one the teacher's saved features
+        # and predictor were trained on, so the student's valid/test edges can never be teacher training edges
+        data, split_edge = load_transductive(args, device)
+        input_size = data.x.size(1)
+        args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
+        args.node_batch_size = int(data.x.size()[0] / (split_edge['train']['edge'].size()[0] / args.link_batch_size))
+    else:   # main.py:337-348
+        training_data, val_data, inference_data, test_edge_bundle, negative_samples = load_production(args, device)
+        input_size = training_data.x.size(1)
+        args.metric = 'Hits@20'
+        args.node_batch_size = int(training_data.x.size()[0] / (training_data.edge_index.size(1) / args.link_batch_size))
 
     model = MLP(args.num_layers, input_size, args.hidden_channels, args.hidden_channels, args.dropout).to(device)
     predictor = LinkPredictor(args.predictor, args.hidden_channels, args.hidden_channels, 1, args.num_layers,
@@ -282,9 +296,9 @@ def main(argv=None):
         para.requires_grad = False
 
     evaluator = Evaluator(name='ogbl-ddi')
-    keys = ['Hits@10', 'Hits@50', 'Hits@100', 'AUC'] if args.datasets == "collab" else \
+    keys = ['Hits@10', 'Hits@50', 'Hits@100', 'AUC'] if (args.datasets == "collab" and not production) else \
         ['Hits@10', 'Hits@20', 'Hits@30', 'Hits@50', 'AUC']
-    loggers = {k: Logger(args.runs, args) for k in keys}
+    loggers = {k: (ProductionLogger if production else Logger)(args.runs, args) for k in keys}
 
     for run in range(args.runs):
         seed_everything(run + 1)
@@ -293,10 +307,15 @@ def main(argv=None):
         optimizer = FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=args.lr)
         cnt_wait, best_val = 0, 0.0
         for epoch in range(1, 1 + args.epochs):
-            step_fn = train_minibatch if args.minibatch else train
-            loss = step_fn(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device)
-            results, h = test_transductive(model, predictor, data, split_edge, evaluator, args.link_batch_size, 'mlp',
-                                           args.datasets, args)
+            if not production:
+                step_fn = train_minibatch if args.minibatch else train
+                loss = step_fn(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device)
+                results, h = test_transductive(model, predictor, data, split_edge, evaluator, args.link_batch_size, 'mlp',
+                                               args.datasets, args)
+            else:   # main.py:419-423
+                loss = train(model, predictor, t_h, teacher_predictor, training_data, None, optimizer, args, device)
+                results, h = test_production(model, predictor, val_data, inference_data, test_edge_bundle, negative_samples,
+                                             evaluator, args.link_batch_size, 'mlp', args.datasets)
             if results[args.metric][0] >= best_val:
                 best_val, cnt_wait = results[args.metric][0], 0
             else:
@@ -305,10 +324,16 @@ def main(argv=None):
                 loggers[key].add_result(run, result)
             if epoch % args.log_steps == 0:
                 for key, result in results.items():
-                    valid_hits, test_hits = result
                     print(key)
-                    print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, '
-                          f'Valid: {100 * valid_hits:.2f}%, Test: {100 * test_hits:.2f}%')
+                    if not production:
+                        valid_hits, test_hits = result
+                        print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, '
+                              f'Valid: {100 * valid_hits:.2f}%, Test: {100 * test_hits:.2f}%')
+                    else:
+                        valid_hits, test_hits, old_old, old_new, new_new = result
+                        print(f'Run: {run + 1:02d}, Epoch: {epoch:02d}, Loss: {loss:.4f}, valid: {100 * valid_hits:.2f}%, '
+                              f'test: {100 * test_hits:.2f}%, old_old: {100 * old_old:.2f}%, old_new: {100 * old_new:.2f}%, '
+                              f'new_new: {100 * new_new:.2f}%')
                 print('---')
             if cnt_wait >= args.patience:
                 break
@@ -316,6 +341,11 @@ def main(argv=None):
             print(key)
             loggers[key].print_statistics(run)
 
+    if world > 1:
+        optimizer = None
+        finish_distributed()
+    if rank != 0:
+        return
     with open(Logger_file, "a") as file:
         file.write('All runs:\n')
         for key in loggers.keys():
@@ -325,9 +355,17 @@ def main(argv=None):
             best_results = []
             for r in loggers[key].results:
                 r = 100 * torch.tensor(r)
-                best_results.append((r[:, 0].max().item(), r[r[:, 0].argmax(), 1].item()))
-            r = torch.tensor(best_results)[:, 1]
-            file.write(f'Test: {r.mean():.4f} ± {r.std():.4f}\n')
+                best = r[:, 0].argmax()
+                best_results.append(tuple(r[best, j].item() for j in range(r.size(1))) if production else
+                                    (r[:, 0].max().item(), r[best, 1].item()))
+            best_result = torch.tensor(best_results)
+            if not production:
+                r = best_result[:, 1]
+                file.write(f'Test: {r.mean():.4f} ± {r.std():.4f}\n')
+            else:   # main.py:488-511
+                names = ('  Final val', '   Final Test', '   Final old_old', '   Final old_new', '   Final new_new')
+                file.write(''.join(f'{nm}: {best_result[:, j].mean():.2f} ± {best_result[:, j].std():.2f}'
+                                   for j, nm in enumerate(names)) + '\n')
 
 
 if __name__ == "__main__":

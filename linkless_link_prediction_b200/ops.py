@@ -83,8 +83,8 @@ def to_compute(x: torch.Tensor, cache: bool = False) -> torch.Tensor:
         hit = _FEATURE_CACHE.get(key)
         if hit is not None and hit[0]() is x:
             return hit[1]
-        if len(_FEATURE_CACHE) > 8:
-            _FEATURE_CACHE.clear()
+        while len(_FEATURE_CACHE) >= 8:   # evict the oldest entry only; users that baked a pointer into a CUDA graph
+            _FEATURE_CACHE.pop(next(iter(_FEATURE_CACHE)))   # (CapturedTrainStep) hold their own strong reference
         out = cast2d(x if x.dim() == 2 else x.reshape(-1, x.size(-1)), dt)
         _FEATURE_CACHE[key] = (weakref.ref(x), out)
         return out
@@ -436,8 +436,8 @@ def graph_of(edge_index: torch.Tensor, num_nodes: int) -> Graph:
     hit = _GRAPH_CACHE.get(key)
     if hit is not None and hit[0]() is edge_index:
         return hit[1]
-    if len(_GRAPH_CACHE) > 16:
-        _GRAPH_CACHE.clear()
+    while len(_GRAPH_CACHE) >= 16:   # oldest first; captured steps keep their Graph alive themselves
+        _GRAPH_CACHE.pop(next(iter(_GRAPH_CACHE)))
     g = Graph(edge_index, num_nodes)
     _GRAPH_CACHE[key] = (weakref.ref(edge_index), g)
     return g

@@ -37,10 +37,9 @@ def _dist():
 
 
 def _shard(n: int, rank: int, world: int):
-    """Contiguous shard [lo, hi) of n items for this rank."""
-    per = (n + world - 1) // world
-    lo = min(rank * per, n)
-    return lo, min(lo + per, n)
+    """Contiguous, balanced shard [lo, hi) of n items for this rank: sizes differ by at most one, so a
+    short tail batch leaves a rank empty only when n < world."""
+    return n * rank // world, n * (rank + 1) // world
 
 
 def optimizer_tail(model, predictor, optimizer) -> None:
@@ -129,6 +128,16 @@ class CapturedTrainStep:
         finally:
             ops.SPMM_PROFILE = saved_profile
         self.launches_per_replay = N.launch_count() - n0
+        # The graph baked raw pointers of the cached CSR / work plan and of the converted feature matrix into its
+        # nodes: hold strong references so that cache eviction (ops._GRAPH_CACHE / _FEATURE_CACHE) can never free them
+        # under a live graph.  Both calls are cache hits that return the very objects the capture used.
+        self._pinned = [ops.to_compute(self.data.x, cache=True)]
+        adj = None if self.encoder_name == 'mlp' else (
+            self.data.adj_t if self.transductive == "transductive" else self.data.edge_index)
+        if isinstance(adj, torch.Tensor):
+            self._pinned.append(ops.graph_of(adj, self.data.x.size(0)))
+        elif adj is not None:
+            self._pinned.append(adj)
 
     def __call__(self, edge, neg_edge):
         if not (self.model.training and self.predictor.training):
@@ -193,6 +202,13 @@ def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_nam
             edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
             # mean over the global batch = average over ranks of (local mean * local share * W)
             weight = (edge.size(1) + neg_edge.size(1)) * world / float(n_global + perm.size(0))
+        if edge.size(1) + neg_edge.size(1) == 0:
+            # an empty shard (tail batch smaller than the world size): contribute zero gradients, but still join the
+            # gradient all-reduce inside the optimiser tail so the other ranks are not left waiting
+            optimizer.zero_grad()
+            optimizer_tail(model, predictor, optimizer)
+            total_examples += n_global
+            continue
         step = None
         if USE_CUDA_GRAPH and isinstance(optimizer, FusedAdam):
             key = (id(model), id(predictor), id(data), tuple(edge.shape), tuple(neg_edge.shape), encoder_name,
@@ -335,6 +351,82 @@ def test_production(model, predictor, val_data, inference_data, test_edge_bundle
     return results, saved_h
 
 
+def init_device(args):
+    """Device of this process.  Single process: ``cuda:{args.device}`` as the reference (train_teacher_gnn.py:302).
+    Under ``torchrun`` (WORLD_SIZE > 1): ``cuda:{LOCAL_RANK}`` and an NCCL process group, so that ``train`` / ``test_*``
+    shard their edge batches (``_dist``) — without it W launched processes would all run the whole job on GPU 0."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("this implementation has no CPU path: an sm_100 (B200) GPU is required")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        device = torch.device(f'cuda:{int(os.environ.get("LOCAL_RANK", "0"))}')
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+    else:
+        device = torch.device(f'cuda:{args.device}')
+        torch.cuda.set_device(device)
+    return device, rank, world
+
+
+def finish_distributed() -> None:
+    """Tear the process group down after every captured CUDA graph (which holds the in-graph gradient all-reduce) has
+    been released and the device is idle."""
+    import gc
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def is_main_process() -> bool:
+    """Rank 0 writes checkpoints / result files; the other ranks of a ``torchrun`` job only compute."""
+    return _dist()[0] == 0
+
+
+def load_transductive(args, device):
+    """``(data, split_edge)`` of the transductive setting, shared by the teacher and the student driver so both see the
+    SAME split (train_teacher_gnn.py:305-344, main.py:290-334): a cached synthetic dataset, else the synthetic stand-in
+    graph of the named shape with — when present — the split the reference (or ``splits.do_edge_split``) cached as
+    ``../data/<ds>.pkl``."""
+    root = args.dataset_dir if getattr(args, "dataset_dir", None) else "../data"
+    if exists(os.path.join(root, args.datasets + "_synthetic.pkl")):
+        data, split_edge = torch.load(os.path.join(root, args.datasets + "_synthetic.pkl"), weights_only=False)
+    else:
+        data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=getattr(args, "synthetic_scale", 1.0))
+        if args.datasets != "collab" and exists(os.path.join(root, args.datasets + ".pkl")):
+            split_edge = torch.load(os.path.join(root, args.datasets + ".pkl"), weights_only=False)
+            data.adj_t = data.edge_index = split_edge['train']['edge'].t().contiguous()
+    data.full_adj_t = data.adj_t  # --use_valedges_as_input builds full_adj_t but nothing reads it (SURVEY.md Q10)
+    return data.to(device), split_edge
+
+
+def load_production(args, device):
+    """The production 6-tuple of generate_production_split.py (train_teacher_gnn.py:344-371, main.py:337-348): loaded
+    from the reference's cache file when present, else generated (``splits.do_production_edge_split``) on the synthetic
+    stand-in graph — there is no network for the Planetoid / Coauthor downloads.  Returns
+    ``(training_data, val_data, inference_data, test_edge_bundle, negative_samples)`` on ``device``."""
+    root = args.dataset_dir if getattr(args, "dataset_dir", None) else "../data"
+    pkl = os.path.join(root, args.datasets + "_production.pkl")
+    if exists(pkl):
+        training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = torch.load(pkl, weights_only=False)
+    else:
+        print("splitting the datasets now...")
+        from .data import synthetic_full_graph
+        from .splits import do_production_edge_split
+        small = args.datasets in ("cora", "citeseer")
+        test_ratio = val_node_ratio = val_ratio = 0.3 if small else 0.1
+        training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = do_production_edge_split(
+            [synthetic_full_graph(args.datasets, seed=0, scale=getattr(args, "synthetic_scale", 1.0))], args.datasets,
+            test_ratio, val_node_ratio, val_ratio, 0.1, verbose=True)
+    training_data.to(device); val_data.to(device); inference_data.to(device)
+    return training_data, val_data, inference_data, test_edge_bundle, negative_samples
+
+
 def build_parser():
     parser = argparse.ArgumentParser(description='OGBL-DDI (GNN)')
     parser.add_argument('--device', type=int, default=0)
@@ -371,48 +463,22 @@ def main(argv=None):
 
     os.makedirs("../results", exist_ok=True)
     Logger_file = "../results/" + args.datasets + "_supervised_" + args.transductive + ".txt"
-    with open(Logger_file, "a") as file:
-        file.write(str(args))
-        file.write(args.encoder + " as the encoder\n")
+    if int(os.environ.get("RANK", "0")) == 0:
+        with open(Logger_file, "a") as file:
+            file.write(str(args))
+            file.write(args.encoder + " as the encoder\n")
 
-    if not torch.cuda.is_available():
-        raise RuntimeError("this implementation has no CPU path: an sm_100 (B200) GPU is required")
-    device = torch.device(f'cuda:{args.device}')
-    torch.cuda.set_device(device)
+    device, rank, world = init_device(args)
 
     production = args.transductive != "transductive"
     if not production:
-        if exists("../data/" + args.datasets + "_synthetic.pkl"):
-            data, split_edge = torch.load("../data/" + args.datasets + "_synthetic.pkl", weights_only=False)
-        else:
-            data, split_edge = synthetic_dataset(args.datasets, seed=0, scale=args.synthetic_scale)
-            if args.datasets != "collab" and exists("../data/" + args.datasets + ".pkl"):
-                # a split cached by the reference (train_teacher_gnn.py:310-314) or by splits.do_edge_split: same dict
-                split_edge = torch.load("../data/" + args.datasets + ".pkl", weights_only=False)
-                data.adj_t = data.edge_index = split_edge['train']['edge'].t().contiguous()
+        data, split_edge = load_transductive(args, device)
         input_size = data.x.size(1)
         args.metric = 'Hits@50' if args.datasets == "collab" else 'Hits@20'
-        data.full_adj_t = data.adj_t  # --use_valedges_as_input builds full_adj_t but nothing reads it
-        data = data.to(device)
     else:
-        # production setting (train_teacher_gnn.py:344-371): the 6-tuple of generate_production_split.py, loaded from
-        # the reference's cache file when present, else generated here (splits.do_production_edge_split) on the
-        # synthetic stand-in graph (no network: the Planetoid / Coauthor downloads cannot run)
-        pkl = "../data/" + args.datasets + "_production.pkl"
-        if exists(pkl):
-            training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = torch.load(pkl, weights_only=False)
-        else:
-            print("splitting the datasets now...")
-            from .data import synthetic_full_graph
-            from .splits import do_production_edge_split
-            small = args.datasets in ("cora", "citeseer")
-            test_ratio = val_node_ratio = val_ratio = 0.3 if small else 0.1
-            training_data, val_data, inference_data, _, test_edge_bundle, negative_samples = do_production_edge_split(
-                [synthetic_full_graph(args.datasets, seed=0, scale=args.synthetic_scale)], args.datasets, test_ratio,
-                val_node_ratio, val_ratio, 0.1, verbose=True)
+        training_data, val_data, inference_data, test_edge_bundle, negative_samples = load_production(args, device)
         input_size = training_data.x.size(1)
         args.metric = 'Hits@20'
-        training_data.to(device); val_data.to(device); inference_data.to(device)
         data, split_edge = training_data, None
 
     if args.encoder == 'sage':
@@ -451,7 +517,7 @@ def main(argv=None):
 
             if results[args.metric][0] > val_max:
                 val_max = results[args.metric][0]
-                if args.encoder != 'mlp':
+                if args.encoder != 'mlp' and rank == 0:
                     os.makedirs("../saved-features", exist_ok=True)
                     os.makedirs("../saved-models", exist_ok=True)
                     tag = args.datasets + "-" + args.encoder + "_" + args.transductive + ".pkl"
@@ -487,6 +553,11 @@ def main(argv=None):
             print(key)
             loggers[key].print_statistics(run)
 
+    if world > 1:
+        optimizer = None   # drops the captured steps (and with them the in-graph all-reduce) before the teardown
+        finish_distributed()
+    if rank != 0:
+        return
     with open(Logger_file, "a") as file:
         file.write('All runs:\n')
         for key in loggers.keys():

@@ -750,6 +750,36 @@ def student_step(model, predictor, t_h, teacher_predictor, x, samples, pos_edge,
     return loss.item()
 
 
+def student_train_epoch(model, predictor, t_h, teacher_predictor, x, adj_t, pos_train_edge, optimizer, args,
+                        dataset: str = "cora") -> float:
+    """One epoch of the full-batch student loop in the reference's RNG order (``main.py:147-236``): node loader created
+    first (:167), link loader per epoch (:168); per step ``next(node_loader)`` (:171), encoder forward (:173), context
+    sampling (:180: ``torch.rand`` per walk, then the CPU ``randint``), negative edges (:205-209), losses, clip x2, Adam.
+    Returns ``total_loss / total_examples`` (:232-236)."""
+    row, col = adj_t
+    edge_index = torch.stack([col, row], dim=0)
+    model.train()
+    predictor.train()
+    total_loss = total_examples = 0
+    node_loader = iter(DataLoader(range(x.size(0)), args.node_batch_size, shuffle=True))
+    for link_perm in DataLoader(range(pos_train_edge.size(0)), args.link_batch_size, shuffle=True):
+        node_perm = next(node_loader)
+        edge = pos_train_edge[link_perm].t()
+        pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, x, args.rw_step, args.ps_method, args.ns_rate,
+                                                   args.hops)
+        samples = torch.cat((pos_sample, neg_sample), 1)
+        if dataset != "collab":
+            neg_edge = negative_sampling_dense(edge_index, x.size(0), link_perm.size(0))
+        else:
+            neg_edge = torch.randint(0, x.size(0), [edge.size(0), edge.size(1)], dtype=torch.long)
+        loss = student_step(model, predictor, t_h, teacher_predictor, x, samples, edge, neg_edge, node_perm, optimizer,
+                            True_label=args.True_label, LLP_D=args.LLP_D, LLP_R=args.LLP_R, KD_RM=args.KD_RM,
+                            KD_LM=args.KD_LM, margin=args.margin)
+        total_loss += loss * edge.size(1)
+        total_examples += edge.size(1)
+    return total_loss / total_examples
+
+
 # --------------------------------------------------------------------------------------
 # Synthetic graphs of the BASELINE.json shapes (SURVEY §8d) — shared by tests and bench
 # --------------------------------------------------------------------------------------

@@ -67,24 +67,11 @@ def test_student_step_matches_reference(golden):
     t_pred = O.LinkPredictor("mlp", H, H, 1, 2, 0.0); t_pred.load_state_dict(g["teacher_pred_sd"])
     opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=g["lr"])
     random.seed(g["seed_train"]); np.random.seed(g["seed_train"]); torch.manual_seed(g["seed_train"])
-    from torch.utils.data import DataLoader
-    row, col = split["train"]["edge"].t()
-    edge_index = torch.stack([col, row], 0)
-    pos = split["train"]["edge"]
-    losses = []
-    for _ in range(2):
-        tot = n = 0
-        node_loader = iter(DataLoader(range(x.size(0)), a["node_batch_size"], shuffle=True))
-        for link_perm in DataLoader(range(pos.size(0)), a["link_batch_size"], shuffle=True):
-            node_perm = next(node_loader)
-            ps, ns = O.neighbor_samplers(row, col, node_perm, x, a["rw_step"], a["ps_method"], a["ns_rate"], a["hops"])
-            samples = torch.cat((ps, ns), 1)
-            edge = pos[link_perm].t()
-            neg = O.negative_sampling_dense(edge_index, x.size(0), link_perm.size(0))
-            l = O.student_step(model, pred, t_h, t_pred, x, samples, edge, neg, node_perm, opt,
-                               a["True_label"], a["LLP_D"], a["LLP_R"], a["KD_RM"], a["KD_LM"], a["margin"])
-            tot += l * edge.size(1); n += edge.size(1)
-        losses.append(tot / n)
+    # the oracle's epoch loop (main.py:147-236 in the reference's RNG order) against the reference's own train()
+    args = type("A", (), dict(a))()
+    adj_t = split["train"]["edge"].t()
+    losses = [O.student_train_epoch(model, pred, t_h, t_pred, x, adj_t, split["train"]["edge"], opt, args, "cora")
+              for _ in range(2)]
     np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
 
 

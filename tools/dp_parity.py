@@ -62,14 +62,12 @@ def main():
         print(json.dumps({"world": world, "loss_dp": loss_dp, "loss_1rank_bigbatch": loss_1, "max_param_diff": diff,
                           "param_scale": scale, "hits_unsharded": res_1, "hits_sharded": res_1_sharded,
                           "hits_dp_model": res_dp, "ok": bool(ok)}))
-    # CUDA graphs that captured the gradient all-reduce are still alive: release them and leave without NCCL teardown
-    # (destroying the communicator under a live graph can block forever)
+    # CUDA graphs that captured the gradient all-reduce are still alive: release them first, then a regular teardown
     for o in (opt, opt1):
         o.__dict__.pop("_llp_captured_steps", None)
-    torch.cuda.synchronize()
-    dist.barrier()
-    sys.stdout.flush()
-    os._exit(0 if ok else 1)
+    del opt, opt1
+    teacher.finish_distributed()
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

@@ -204,10 +204,8 @@ def main():
     res["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(res))
-    torch.cuda.synchronize()
-    dist.barrier()
-    sys.stdout.flush()
-    os._exit(0 if ok else 1)
+    teacher.finish_distributed()   # graphs were released by their owners (step.graph = None / optimizers out of scope)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
