@@ -40,9 +40,11 @@ extern "C" {
 #define LLP_E_DEVICE (-4)    /* current device is not sm_100                           */
 #define LLP_E_SHAPE (-5)     /* shape not supported by the selected backend            */
 
-#define LLP_GEMM_AUTO 0    /* bf16 -> tcgen05, f32 -> SIMT fp32                         */
-#define LLP_GEMM_SIMT 1    /* CUDA-core FFMA, fp32 accumulate (the fp32-parity path)    */
-#define LLP_GEMM_TCGEN05 2 /* tcgen05.mma + TMA + TMEM (bf16 operands, fp32 accumulate) */
+#define LLP_GEMM_AUTO 0    /* bf16 -> tcgen05 kind::f16, f32 -> tcgen05 3xTF32 (SIMT only when TMA cannot address an operand) */
+#define LLP_GEMM_SIMT 1    /* CUDA-core FFMA, fp32 accumulate                            */
+#define LLP_GEMM_TCGEN05 2 /* tcgen05.mma + TMA + TMEM (bf16 operands, fp32 accumulate)  */
+#define LLP_GEMM_TF32X3 3  /* tcgen05.mma kind::tf32, 3-term split accumulation of fp32 operands (fp32-grade results:
+                              the reference's GEMMs are true fp32, src/models.py:48,143,146) */
 
 int llp_version(void);
 const char* llp_error_string(int code);
@@ -226,6 +228,13 @@ int llp_kd_d(const float* s, const float* t, int64_t rows, int64_t K, float T, f
              void* workspace, void* stream);
 int llp_kd_r(const float* s, const float* t, int64_t rows, int64_t K, float margin, float* loss, float* ds,
              void* workspace, void* stream);
+
+/* LLP_D and LLP_R of the same score rows in one pass (main.py:188,190-203 read the same s_r / t_r):
+ * losses[0] = LLP_D, losses[1] = LLP_R (the arithmetic and reduction tree of llp_kd_d / llp_kd_r), losses[2] = w_d*LLP_D + w_r*LLP_R,
+ * ds = d losses[2] / d s (or NULL).  1 < K <= 1024. */
+size_t llp_kd_fused_workspace_bytes(int64_t rows);
+int llp_kd_fused(const float* s, const float* t, int64_t rows, int64_t K, float T, float margin, float w_d, float w_r,
+                 float* losses /*[3]*/, float* ds, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Hits@K.  Replaces ogb Evaluator._eval_hits = torch.topk on CPU tensors + compare + sum

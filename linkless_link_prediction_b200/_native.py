@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libllp_b200.so")
 
 LLP_F32, LLP_BF16 = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TF32X3 = 0, 1, 2, 3
 
 
 class GemmNtArgs(ctypes.Structure):
@@ -107,6 +107,9 @@ PROTOTYPES = {
     "llp_bce": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_kd_d": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_kd_r": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "llp_kd_fused_workspace_bytes": (c_size_t, [c_int64]),
+    "llp_kd_fused": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                             c_void_p, c_void_p]),
     "llp_topk_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_topk_desc": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "llp_count_greater": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),

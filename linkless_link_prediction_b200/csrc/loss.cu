@@ -129,6 +129,103 @@ __global__ void kd_r_kernel(const float* __restrict__ s, const float* __restrict
   if (lane == 0) row_loss[r] = loss;
 }
 
+// LLP_D and LLP_R of the same score rows in ONE pass (main.py:188 and :190-203 read the same s_r / t_r): the row is
+// staged in shared memory once, one warp computes the softmax/KL term, the C(K,2) margin-rank term and the gradient of
+// w_d * LLP_D + w_r * LLP_R.  Per-term arithmetic is the same as kd_d_kernel / kd_r_kernel (same operation order).
+__global__ void kd_fused_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t rows, int K, float invT,
+                                float margin, float dsd_scale, float dsr_scale, float* __restrict__ row_loss_d,
+                                float* __restrict__ row_loss_r, float* __restrict__ ds) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  float* ss = sm + (size_t)w * 2 * K;
+  float* ts = ss + K;
+  if (r < rows) {
+    for (int j = lane; j < K; j += 32) {
+      ss[j] = s[r * K + j];
+      ts[j] = t[r * K + j];
+    }
+  }
+  __syncwarp();
+  if (r >= rows) return;
+  // ---- LLP_D: KL(softmax(t/T) || softmax(s/T)) ----
+  float ms = -INFINITY, mt = -INFINITY;
+  for (int j = lane; j < K; j += 32) {
+    ms = fmaxf(ms, ss[j] * invT);
+    mt = fmaxf(mt, ts[j] * invT);
+  }
+  ms = warp_max(ms);
+  mt = warp_max(mt);
+  float zs = 0.0f, zt = 0.0f;
+  for (int j = lane; j < K; j += 32) {
+    zs += expf(ss[j] * invT - ms);
+    zt += expf(ts[j] * invT - mt);
+  }
+  zs = warp_sum(zs);
+  zt = warp_sum(zt);
+  const float lzs = logf(zs), lzt = logf(zt);
+  float acc_d = 0.0f, acc_r = 0.0f;
+  for (int i = lane; i < K; i += 32) {
+    const float si = ss[i], ti = ts[i];
+    const float ls = si * invT - ms - lzs;
+    const float lt = ti * invT - mt - lzt;
+    const float yt = expf(lt);
+    acc_d += yt > 0.0f ? yt * (lt - ls) : 0.0f;
+    const float gd = (expf(ls) - yt) * dsd_scale;
+    // ---- LLP_R: every partner j of score i ----
+    float g = 0.0f;
+    for (int j = 0; j < K; ++j) {
+      if (j == i) continue;
+      const float sj = ss[j], tj = ts[j];
+      const float sa = i < j ? si : sj, sb = i < j ? sj : si;
+      const float ta = i < j ? ti : tj, tb = i < j ? tj : ti;
+      const float y = ta > tb + margin ? 1.0f : (ta < tb - margin ? -1.0f : 0.0f);
+      const float term = -y * (sa - sb) + margin;
+      if (term >= 0.0f) {
+        if (i < j) { acc_r += term; g -= y; } else { g += y; }
+      }
+    }
+    if (ds != nullptr) ds[r * K + i] = gd + g * dsr_scale;
+  }
+  acc_d = warp_sum(acc_d);
+  acc_r = warp_sum(acc_r);
+  if (lane == 0) { row_loss_d[r] = acc_d; row_loss_r[r] = acc_r; }
+}
+
+// out[0] = scale_a * sum(a), out[1] = scale_b * sum(b), out[2] = w_a * out[0] + w_b * out[1]: two deterministic sums in
+// the launches of one (same fixed-order tree as sum_f32)
+__global__ void sum2_stage1_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* __restrict__ partial) {
+  __shared__ double red[kSumThreads];
+  const float* in = blockIdx.y == 0 ? a : b;
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kSumThreads + threadIdx.x; i < n; i += (int64_t)kSumBlocks * kSumThreads)
+    acc += (double)in[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = kSumThreads / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.y * kSumBlocks + blockIdx.x] = red[0];
+}
+__global__ void sum2_stage2_kernel(const double* __restrict__ partial, float scale_a, float scale_b, float w_a, float w_b,
+                                   float* __restrict__ out) {
+  __shared__ double red[2][kSumBlocks];
+  red[0][threadIdx.x] = partial[threadIdx.x];
+  red[1][threadIdx.x] = partial[kSumBlocks + threadIdx.x];
+  __syncthreads();
+  for (int st = kSumBlocks / 2; st > 0; st >>= 1) {
+    if (threadIdx.x < st) { red[0][threadIdx.x] += red[0][threadIdx.x + st]; red[1][threadIdx.x] += red[1][threadIdx.x + st]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float la = (float)(red[0][0] * (double)scale_a), lb = (float)(red[1][0] * (double)scale_b);
+    out[0] = la;
+    out[1] = lb;
+    out[2] = w_a * la + w_b * lb;
+  }
+}
+
 }  // namespace llp
 
 using namespace llp;
@@ -177,4 +274,29 @@ extern "C" int llp_kd_r(const float* s, const float* t, int64_t rows, int64_t K,
   kd_r_kernel<<<(unsigned)ceil_div(rows, warps), warps * 32, smem, stream>>>(s, t, rows, (int)K, margin, scale, row_loss, ds);
   LLP_LAUNCH_OK();
   return sum_f32(row_loss, rows, scale, loss, workspace, stream);
+}
+
+extern "C" size_t llp_kd_fused_workspace_bytes(int64_t rows) { return kSumWsBytes + 2 * (size_t)(rows > 0 ? rows : 1) * sizeof(float); }
+
+extern "C" int llp_kd_fused(const float* s, const float* t, int64_t rows, int64_t K, float T, float margin, float w_d,
+                            float w_r, float* losses, float* ds, void* workspace, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(s && t && losses && workspace && rows > 0 && K > 1 && T > 0.0f);
+  if (K > kMaxRankK) return LLP_E_SHAPE;
+  if (int rc = check_device()) return rc;
+  float* row_d = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kSumWsBytes);
+  float* row_r = row_d + rows;
+  const double pairs = (double)rows * (double)K * (double)(K - 1) / 2.0;
+  const float r_scale = (float)(1.0 / pairs);
+  const int warps = 4;
+  const size_t smem = (size_t)warps * 2 * K * sizeof(float);
+  kd_fused_kernel<<<(unsigned)ceil_div(rows, warps), warps * 32, smem, stream>>>(
+      s, t, rows, (int)K, 1.0f / T, margin, w_d * T / (float)rows, w_r * r_scale, row_d, row_r, ds);
+  LLP_LAUNCH_OK();
+  double* partial = reinterpret_cast<double*>(workspace);   // 2 x 256 doubles = 4 KiB of the 8 KiB reduction scratch
+  sum2_stage1_kernel<<<dim3(kSumBlocks, 2), kSumThreads, 0, stream>>>(row_d, row_r, rows, partial);
+  LLP_LAUNCH_OK();
+  sum2_stage2_kernel<<<1, kSumBlocks, 0, stream>>>(partial, T * T / (float)rows, r_scale, w_d, w_r, losses);
+  LLP_LAUNCH_OK();
+  return 0;
 }

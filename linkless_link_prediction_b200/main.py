@@ -21,8 +21,10 @@ from .models import MLP, LinkPredictor
 from .optim import FusedAdam
 from .shims import Evaluator, negative_sampling, random_walk, seed_everything
 from . import shims
-from .train_teacher_gnn import (_dist, _shard, finish_distributed, init_device, load_production, load_transductive,
-                                optimizer_tail, test_production, test_transductive)
+from . import train_teacher_gnn as _teacher
+from .train_teacher_gnn import (CapturedStep, _captured_step_for, _dist, _shard, finish_distributed,
+                                init_device, load_production, load_transductive, optimizer_tail, test_production,
+                                test_transductive)
 
 
 def cosine_loss(s, t):
@@ -50,22 +52,72 @@ def neighbor_samplers(row, col, sample, x, step, ps_method, ns_rate, hops):
     return pos_batch.to(batch.device), neg_batch.to(batch.device)
 
 
-def _kd_losses(predictor, teacher_predictor, h, t_h, samples, args):
-    """LLP_D and LLP_R for the anchors in ``samples[:,0]`` against the contexts ``samples[:,1:]`` (main.py:183-203).
-    ``predictor(h[a].repeat(K), h[ctx])`` becomes one fused edge-scoring call over the (anchor, context) pairs."""
+def _kd_losses(predictor, teacher_predictor, h, t_h, samples, args, weight=1.0):
+    """``weight * (LLP_D * llp_d + LLP_R * llp_r)`` for the anchors in ``samples[:,0]`` against the contexts
+    ``samples[:,1:]`` (main.py:183-203), plus the two unweighted values.  ``predictor(h[a].repeat(K), h[ctx])`` becomes
+    one fused edge-scoring call over the (anchor, context) pairs and the two losses one pass over the score rows."""
     K = samples.size(1) - 1
     if samples.size(0) == 0:   # empty anchor shard (fewer anchors than ranks): contributes nothing
         zero = torch.zeros((), dtype=torch.float32, device=h.device)
-        return zero, zero
+        return zero, zero, zero
     anchor = samples[:, :1].expand(-1, K).contiguous()
     ctx = samples[:, 1:].contiguous()
     s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
     with torch.no_grad():
         # the teacher predictor is never put in eval() by the reference (SURVEY.md Q4): dropout stays active
         t_r = teacher_predictor.score(t_h, anchor, ctx).reshape(samples.size(0), K)
-    llp_d = kl_loss(s_r, t_r, 1)
-    llp_r = ops.rank_loss(s_r, t_r, args.margin)
-    return llp_d, llp_r
+    return ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * weight, args.LLP_R * weight)
+
+
+def student_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge, samples=None, node_perm=None,
+                 kd_weight=1.0, edge_share=1.0):
+    """One optimisation step of the full-batch student loop (main.py:169-230) on explicit device tensors: ``edge`` /
+    ``neg_edge`` ``[2, B]`` (this rank's shard), ``samples`` ``[B_n, 1+K]`` = anchor | walk contexts | random contexts (or
+    None when ``LLP_D == LLP_R == 0``), ``node_perm`` (only read when ``KD_RM`` != 0).  ``kd_weight`` / ``edge_share``
+    are this rank's share of the global anchor / edge batch times W (1 on a single GPU).  A pure function of device
+    tensors: ``StudentCapturedStep`` replays it as one CUDA graph.  Returns the (device) loss."""
+    optimizer.zero_grad()
+    ops.advance_rng(x.device)
+    h = model(x)
+    kd_total = None
+    if samples is not None:
+        kd_total, _, _ = _kd_losses(predictor, teacher_predictor, h, t_h, samples, args, kd_weight)
+    train_edges = torch.cat((edge, neg_edge), dim=-1)
+    if train_edges.size(1) > 0:
+        out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+        label_loss = ops.bce_loss(out, edge.size(1))
+        if edge_share != 1.0:
+            label_loss = label_loss * edge_share
+    else:   # empty shard: zero loss that still reaches backward / the gradient all-reduce through h
+        out = None
+        label_loss = h.float().sum() * 0.0
+    loss = args.True_label * label_loss
+    if args.KD_RM:  # baselines, weight 0 by default; the reference evaluates them regardless (SURVEY.md Q8)
+        # a mean over the node batch: every rank evaluates the whole (replicated) batch, so no re-weighting is needed
+        loss = loss + args.KD_RM * cosine_loss(h[node_perm], t_h[node_perm])
+    if args.KD_LM and out is not None:
+        with torch.no_grad():
+            t_out = teacher_predictor.score(t_h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+        loss = loss + args.KD_LM * F.mse_loss(out, t_out) * edge_share   # a mean over this rank's edge shard
+    if kd_total is not None:
+        loss = loss + kd_total
+    loss.backward()
+    optimizer_tail(model, predictor, optimizer)
+    return loss.detach()
+
+
+class StudentCapturedStep(CapturedStep):
+    """``student_step`` for fixed batch shapes as one CUDA-graph replay: ``step(edge, neg_edge, samples[, node_perm])``.
+    Sampling (walks, random contexts, negative edges — host / torch RNG in the reference's order) stays outside the graph;
+    everything from the encoder forward to Adam is inside."""
+
+    def __init__(self, model, predictor, t_h, teacher_predictor, data, optimizer, args, kd_weight=1.0, edge_share=1.0,
+                 eager_steps=2, profile=False):
+        def fn(edge, neg_edge, samples=None, node_perm=None):
+            return student_step(model, predictor, t_h, teacher_predictor, data.x, optimizer, args, edge, neg_edge, samples,
+                                node_perm, kd_weight, edge_share)
+
+        super().__init__(fn, (model, predictor), eager_steps, profile, lambda: [ops.to_compute(data.x, cache=True), t_h])
 
 
 def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device):
@@ -86,22 +138,18 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
     total_examples = 0
     node_loader = shuffled_batches(data.x.size(0), args.node_batch_size * world)
     for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size * world):
-        optimizer.zero_grad()
-        ops.advance_rng(dev)
         node_perm = next(node_loader).to(dev)
-        h = model(data.x)
         edge = pos_train_edge[link_perm.to(dev)].t()
 
-        llp_d_loss = llp_r_loss = None
+        samples, kd_weight = None, 1.0
         if args.LLP_R or args.LLP_D:
             pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, data.x, args.rw_step, args.ps_method,
                                                        args.ns_rate, args.hops)
             samples = torch.cat((pos_sample, neg_sample), 1)
             a_lo, a_hi = _shard(samples.size(0), rank, world)
-            llp_d_loss, llp_r_loss = _kd_losses(predictor, teacher_predictor, h, t_h, samples[a_lo:a_hi], args)
-            if world > 1:  # both are means over anchors: weight the shard by its share
-                w = (a_hi - a_lo) * world / float(samples.size(0))
-                llp_d_loss, llp_r_loss = llp_d_loss * w, llp_r_loss * w
+            if world > 1:  # both terms are means over anchors: weight the shard by its share
+                kd_weight = (a_hi - a_lo) * world / float(samples.size(0))
+            samples = samples[a_lo:a_hi].contiguous()
 
         if args.datasets != "collab":
             neg_edge = negative_sampling(edge_index, num_nodes=data.x.size(0), num_neg_samples=link_perm.size(0),
@@ -112,33 +160,28 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
         n_global = edge.size(1)
         lo, hi = _shard(n_global, rank, world)
         nlo, nhi = _shard(neg_edge.size(1), rank, world)
-        edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
-        train_edges = torch.cat((edge, neg_edge), dim=-1)
-        edge_share = 1.0   # this rank's share of the global batch times W: rank means average to the global mean
-        if world > 1:
-            edge_share = train_edges.size(1) * world / float(2 * n_global)
-        if train_edges.size(1) > 0:
-            out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
-            label_loss = ops.bce_loss(out, edge.size(1)) * edge_share
-        else:   # empty shard: zero loss that still reaches backward / the gradient all-reduce through h
-            out = None
-            label_loss = h.float().sum() * 0.0
+        edge, neg_edge = edge[:, lo:hi].contiguous(), neg_edge[:, nlo:nhi].contiguous()
+        # this rank's share of the global batch times W: rank means average to the global mean
+        edge_share = (edge.size(1) + neg_edge.size(1)) * world / float(2 * n_global) if world > 1 else 1.0
 
-        loss = args.True_label * label_loss
-        if args.KD_RM:  # baselines, weight 0 by default; the reference evaluates them regardless
-            # mean over the node batch: every rank evaluates the whole (replicated) batch, so no re-weighting is needed
-            loss = loss + args.KD_RM * cosine_loss(h[node_perm], t_h[node_perm])
-        if args.KD_LM and out is not None:
-            with torch.no_grad():
-                t_out = teacher_predictor.score(t_h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
-            loss = loss + args.KD_LM * F.mse_loss(out, t_out) * edge_share   # a mean over this rank's edge shard
-        if args.LLP_D or args.LLP_R:
-            loss = loss + args.LLP_D * llp_d_loss + args.LLP_R * llp_r_loss
+        tensors = [edge, neg_edge] + ([samples] if samples is not None else []) + \
+                  ([node_perm] if (args.KD_RM and samples is not None) else [])
+        step = None
+        capturable = edge.size(1) + neg_edge.size(1) > 0 and (samples is None or samples.size(0) > 0) and \
+            (samples is not None or not args.KD_RM)
+        if _teacher.USE_CUDA_GRAPH and isinstance(optimizer, FusedAdam) and capturable:
+            key = ("student", id(model), id(predictor), id(data), id(t_h), tuple(tuple(t.shape) for t in tensors),
+                   float(kd_weight), float(edge_share), ops.compute_dtype(),
+                   tuple(float(getattr(args, k)) for k in ("True_label", "KD_RM", "KD_LM", "LLP_D", "LLP_R", "margin")))
+            step = _captured_step_for(optimizer, key, lambda: StudentCapturedStep(
+                model, predictor, t_h, teacher_predictor, data, optimizer, args, kd_weight, edge_share))
+        if step is not None:
+            loss = step(*tensors)
+        else:
+            loss = student_step(model, predictor, t_h, teacher_predictor, data.x, optimizer, args, edge, neg_edge, samples,
+                                node_perm, kd_weight, edge_share)
 
-        loss.backward()
-        optimizer_tail(model, predictor, optimizer)
-
-        total_loss += loss.detach() * n_global
+        total_loss += loss * n_global
         total_examples += n_global
 
     if world > 1:
@@ -148,10 +191,64 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
     return total_loss.item() / total_examples
 
 
+def student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge, samples,
+                           kd_weight=1.0, edge_share=1.0):
+    """One step of the feature-minibatch student loop (main.py:75-139) on explicit device tensors: only the rows the step
+    touches — ``[samples.flatten(), src, dst]`` (:93-101) — go through the encoder; the scorers index that compact
+    embedding matrix by position.  ``x`` stays resident in HBM (the reference keeps it on the host and copies the rows
+    every step, :95-96), so the row gather is a device gather.  Capturable (``StudentCapturedStep``)."""
+    optimizer.zero_grad()
+    dev = x.device
+    ops.advance_rng(dev)
+    train_edges = torch.cat((edge, neg_edge), dim=-1)
+    src, dst = train_edges[0], train_edges[1]
+    this_target = torch.cat((samples.reshape(-1), src, dst), 0)
+    h = model(x[this_target])  # rows of the touched nodes only
+    n_s = samples.numel()
+    K = samples.size(1) - 1
+    if samples.size(0) > 0:
+        local = torch.arange(n_s, device=dev).reshape(samples.shape)   # positions inside h of every sample
+        anchor = local[:, :1].expand(-1, K).contiguous()
+        ctx = local[:, 1:].contiguous()
+        s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
+        with torch.no_grad():
+            t_r = teacher_predictor.score(t_h, samples[:, :1].expand(-1, K).contiguous(),
+                                          samples[:, 1:].contiguous()).reshape(samples.size(0), K)
+        kd_total, _, _ = ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * kd_weight, args.LLP_R * kd_weight)
+    else:
+        kd_total = h.float().sum() * 0.0
+    if src.numel() > 0:
+        src_pos = torch.arange(n_s, n_s + src.numel(), device=dev)
+        dst_pos = src_pos + src.numel()
+        out = predictor.score(h, src_pos, dst_pos).reshape(-1)
+        label_loss = ops.bce_loss(out, edge.size(1))
+        if edge_share != 1.0:
+            label_loss = label_loss * edge_share
+    else:
+        label_loss = h.float().sum() * 0.0
+    loss = args.True_label * label_loss + kd_total   # no KD_RM / KD_LM terms in this variant (main.py:129-130)
+    loss.backward()
+    optimizer_tail(model, predictor, optimizer)
+    return loss.detach()
+
+
+class StudentMinibatchCapturedStep(CapturedStep):
+    """``student_minibatch_step`` for fixed batch shapes as one CUDA-graph replay: ``step(edge, neg_edge, samples)``."""
+
+    def __init__(self, model, predictor, t_h, teacher_predictor, x, optimizer, args, kd_weight=1.0, edge_share=1.0,
+                 eager_steps=2, profile=False):
+        def fn(edge, neg_edge, samples):
+            return student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge,
+                                          samples, kd_weight, edge_share)
+
+        super().__init__(fn, (model, predictor), eager_steps, profile, lambda: [x, t_h])
+
+
 def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer, args, device):
     """Feature-minibatch variant (main.py:52-144): only the rows a step touches are encoded.  On a 180 GB B200 the
     features stay resident in HBM (the reference keeps them on the host and copies rows every step, :95-96;
-    SURVEY.md N4), so the per-step gather is a device gather."""
+    SURVEY.md N4), so the per-step gather is a device gather.  Under ``torchrun`` the anchors and the edge batch of a
+    (global) step are sharded across the ranks exactly as in ``train``."""
     if args.transductive == "transductive":
         pos_train_edge = split_edge['train']['edge'].to(device)
         row, col = data.adj_t
@@ -161,17 +258,17 @@ def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, 
     row, col = row.to(device), col.to(device)
     edge_index = torch.stack([col, row], dim=0)
     x = data.x.to(device)
+    t_h = t_h.to(device)
     if not (args.LLP_D or args.LLP_R):
         raise NameError("name 'loss' is not defined")  # what the reference raises for this flag combination (:129-132)
+    rank, world = _dist()
 
     model.train()
     predictor.train()
     total_loss = torch.zeros((), dtype=torch.float32, device=device)
     total_examples = 0
-    node_loader = shuffled_batches(x.size(0), args.node_batch_size)
-    for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size):
-        optimizer.zero_grad()
-        ops.advance_rng(device)
+    node_loader = shuffled_batches(x.size(0), args.node_batch_size * world)
+    for link_perm in shuffled_batches(pos_train_edge.size(0), args.link_batch_size * world):
         node_perm = next(node_loader).to(device)
         edge = pos_train_edge[link_perm.to(device)].t()
         if args.datasets != "collab":
@@ -179,36 +276,40 @@ def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, 
                                          method='dense')
         else:
             neg_edge = torch.randint(0, x.size()[0], [edge.size(0), edge.size(1)], dtype=torch.long).to(device)
-        train_edges = torch.cat((edge, neg_edge), dim=-1)
-        src, dst = train_edges[0], train_edges[1]
 
         pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, x, args.rw_step, args.ps_method, args.ns_rate,
                                                    args.hops)
         samples = torch.cat((pos_sample, neg_sample), 1)
-        this_target = torch.cat((samples.reshape(-1), src, dst), 0)
-        h = model(x[this_target])  # rows of the touched nodes only
-        n_s = samples.numel()
-        # positions inside h of every sample / edge endpoint
-        local = torch.arange(n_s, device=device).reshape(samples.shape)
-        K = samples.size(1) - 1
-        anchor = local[:, :1].expand(-1, K).contiguous()
-        ctx = local[:, 1:].contiguous()
-        s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
-        with torch.no_grad():
-            t_r = teacher_predictor.score(t_h.to(device), samples[:, :1].expand(-1, K).contiguous(),
-                                          samples[:, 1:].contiguous()).reshape(samples.size(0), K)
-        llp_d_loss = kl_loss(s_r, t_r, 1)
-        llp_r_loss = ops.rank_loss(s_r, t_r, args.margin)
+        n_global = edge.size(1)
+        kd_weight = edge_share = 1.0
+        if world > 1:
+            a_lo, a_hi = _shard(samples.size(0), rank, world)
+            kd_weight = (a_hi - a_lo) * world / float(samples.size(0))
+            samples = samples[a_lo:a_hi]
+            lo, hi = _shard(n_global, rank, world)
+            nlo, nhi = _shard(neg_edge.size(1), rank, world)
+            edge, neg_edge = edge[:, lo:hi], neg_edge[:, nlo:nhi]
+            edge_share = (edge.size(1) + neg_edge.size(1)) * world / float(2 * n_global)
+        edge, neg_edge, samples = edge.contiguous(), neg_edge.contiguous(), samples.contiguous()
 
-        src_pos = torch.arange(n_s, n_s + src.numel(), device=device)
-        dst_pos = src_pos + src.numel()
-        out = predictor.score(h, src_pos, dst_pos).reshape(-1)
-        label_loss = ops.bce_loss(out, edge.size(1))
-        loss = args.True_label * label_loss + args.LLP_D * llp_d_loss + args.LLP_R * llp_r_loss
-        loss.backward()
-        optimizer_tail(model, predictor, optimizer)
-        total_loss += loss.detach() * edge.size(1)
-        total_examples += edge.size(1)
+        step = None
+        if _teacher.USE_CUDA_GRAPH and isinstance(optimizer, FusedAdam) and samples.size(0) > 0 and edge.size(1) + neg_edge.size(1) > 0:
+            key = ("student_mb", id(model), id(predictor), id(data), id(t_h), tuple(edge.shape), tuple(neg_edge.shape),
+                   tuple(samples.shape), float(kd_weight), float(edge_share), ops.compute_dtype(),
+                   tuple(float(getattr(args, k)) for k in ("True_label", "LLP_D", "LLP_R", "margin")))
+            step = _captured_step_for(optimizer, key, lambda: StudentMinibatchCapturedStep(
+                model, predictor, t_h, teacher_predictor, x, optimizer, args, kd_weight, edge_share))
+        if step is not None:
+            loss = step(edge, neg_edge, samples)
+        else:
+            loss = student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge,
+                                          samples, kd_weight, edge_share)
+        total_loss += loss * n_global
+        total_examples += n_global
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(total_loss)
+        total_loss /= world
     return total_loss.item() / total_examples
 
 

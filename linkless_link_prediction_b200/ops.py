@@ -91,6 +91,28 @@ def to_compute(x: torch.Tensor, cache: bool = False) -> torch.Tensor:
     return cast2d(x if x.dim() == 2 else x.reshape(-1, x.size(-1)), dt)
 
 
+GEMM_PROFILE = None  # set to a list by bench.py to collect (start_event, end_event, flops, bytes) per dense-layer launch
+
+
+class _GemmTimer:
+    """CUDA events around one dense-layer launch on the launching stream (event-record NODES inside a stream capture,
+    re-recorded by every replay) — bench.py's roofline of the GEMM-bound workloads."""
+
+    def __init__(self, flops: float, nbytes: float):
+        self.on = GEMM_PROFILE is not None
+        if self.on:
+            ext = torch.cuda.is_current_stream_capturing()
+            self.ev0 = torch.cuda.Event(enable_timing=True, external=ext)
+            self.ev1 = torch.cuda.Event(enable_timing=True, external=ext)
+            self.work = (flops, nbytes)
+            self.ev0.record()
+
+    def stop(self):
+        if self.on:
+            self.ev1.record()
+            GEMM_PROFILE.append((self.ev0, self.ev1) + self.work)
+
+
 def gemm_nt(A1, B1, A2=None, B2=None, bias=None, addend=None, gate=None, gate_scale=1.0, relu=False, dropout_p=0.0,
             seed=0, offset=0, out_dtype=None, backend=N.GEMM_AUTO, rng_state=None) -> torch.Tensor:
     """D = epi(A1 @ B1.T [+ A2 @ B2.T]) — F.linear and the fused lin_l+lin_r of SAGEConv
@@ -117,7 +139,10 @@ def gemm_nt(A1, B1, A2=None, B2=None, bias=None, addend=None, gate=None, gate_sc
     a.gate_scale, a.dropout_p, a.seed, a.offset = float(gate_scale), float(dropout_p), int(seed), int(offset)
     a.rng_state = N.ptr(rng_state)
     a.D, a.ldd = N.mat(D)
+    Kt = K1 + (A2.shape[1] if A2 is not None else 0)
+    timer = _GemmTimer(2.0 * M * Nn * Kt, (M * Kt + Nn * Kt) * A1.element_size() + M * Nn * D.element_size())
     N.check(lib.llp_gemm_nt(ctypes.byref(a), N.stream_ptr()), "llp_gemm_nt")
+    timer.stop()
     return D
 
 
@@ -178,8 +203,10 @@ def wgrad(g: torch.Tensor, a: torch.Tensor, Wa, b: Optional[torch.Tensor] = None
     gp, ldg = N.mat(g)
     ap, lda = N.mat(a)
     bp, ldb = N.mat(b) if n2b else (None, 0)
+    timer = _GemmTimer(2.0 * M * N1 * (n2a + n2b), M * (N1 + n2a + n2b) * g.element_size() + 4.0 * N1 * (n2a + n2b))
     N.check(lib.llp_wgrad(N.dtype_id(g.dtype), backend, M, N1, gp, ldg, n2a, ap, lda, dWa.data_ptr(), n2a, n2b, bp, ldb,
                           N.ptr(dWb), n2b, N.ptr(db), int(direct), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_wgrad")
+    timer.stop()
     if direct:
         return None, None, None
     return dWa, dWb, db
@@ -967,6 +994,43 @@ def kl_loss(s: torch.Tensor, t: torch.Tensor, T: float) -> torch.Tensor:
 def rank_loss(s: torch.Tensor, t: torch.Tensor, margin: float) -> torch.Tensor:
     """LLP_R: main.py:190-203 (all C(K,2) pairs, 3-valued teacher sign, MarginRankingLoss(margin))."""
     return _LossFn.apply("kd_r", s.float(), t.detach().float(), margin, None)
+
+
+class _KdFusedFn(torch.autograd.Function):
+    """LLP_D and LLP_R of the same score rows in one pass (``llp_kd_fused``): returns ``(w_d*LLP_D + w_r*LLP_R, LLP_D,
+    LLP_R)``; only the first output carries a gradient (w.r.t. the student scores)."""
+
+    @staticmethod
+    def forward(ctx, s, t, T, margin, w_d, w_r):
+        lib = N.require_gpu()
+        s = s.contiguous()
+        rows, K = s.shape
+        losses = torch.empty(3, dtype=torch.float32, device=s.device)
+        ds = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+        nbytes = lib.llp_kd_fused_workspace_bytes(rows)
+        ws = _ws(nbytes, s.device)
+        N.check(lib.llp_kd_fused(s.data_ptr(), t.contiguous().data_ptr(), rows, K, float(T), float(margin), float(w_d),
+                                 float(w_r), losses.data_ptr(), N.ptr(ds), ws.data_ptr(), N.stream_ptr()), "llp_kd_fused")
+        ctx.save_for_backward(ds)
+        total, d, r = losses[2], losses[0], losses[1]
+        ctx.mark_non_differentiable(d, r)
+        return total, d, r
+
+    @staticmethod
+    def backward(ctx, g_total, _gd, _gr):
+        (ds,) = ctx.saved_tensors
+        return (ds * g_total if ds is not None else None), None, None, None, None, None
+
+
+def kd_losses(s: torch.Tensor, t: torch.Tensor, T: float, margin: float, w_d: float = 1.0, w_r: float = 1.0):
+    """``(w_d * kl_loss(s, t, T) + w_r * rank_loss(s, t, margin), kl_loss, rank_loss)`` from ONE pass over the
+    ``[B_n, K]`` score rows (main.py:188 and :190-203 read the same ``s_r`` / ``t_r``); the two individual values equal
+    ``kl_loss`` / ``rank_loss`` (same arithmetic and reduction tree).  Rows of a single context (K == 1) have no pairs: falls back to the
+    separate kernels there."""
+    if s.size(1) < 2:
+        d = kl_loss(s, t, T)
+        return w_d * d, d.detach(), torch.zeros_like(d)
+    return _KdFusedFn.apply(s.float(), t.detach().float(), T, margin, w_d, w_r)
 
 
 # --------------------------------------------------------------------------------------------

@@ -87,74 +87,99 @@ USE_CUDA_GRAPH = True   # replay whole training steps as one CUDA graph once the
 _EAGER_STEPS_BEFORE_CAPTURE = 2
 
 
-class CapturedTrainStep:
-    """``train_step`` for a fixed batch shape as ONE CUDA-graph replay (zero_grad, encoder forward/backward, scoring,
-    BCE, gradient all-reduce, clip, Adam: ~65 launches whose host enqueue time otherwise exceeds their GPU time).
+class CapturedStep:
+    """A training step over fixed tensor shapes as ONE CUDA-graph replay.
 
-    The first ``_EAGER_STEPS_BEFORE_CAPTURE`` calls run eagerly (they are real optimisation steps and double as the
-    warm-up a capture needs: CSR/plan built, feature cast cached).  The next call captures the step on a side stream and
-    every call from then on copies the batch into static buffers and replays.  Everything that varies between steps
-    lives on the device: the dropout stream (``ops.advance_rng``) and Adam's bias-correction step counter
-    (``llp_clip_adam(device_step=...)``), so replays are ordinary, distinct optimisation steps.  The returned loss is a
-    static tensor that the next replay overwrites."""
+    ``fn(*tensors)`` must be a pure function of its device-tensor arguments and of device-resident state (parameters,
+    optimiser moments, the dropout stream ``ops.advance_rng`` and Adam's step counter ``llp_clip_adam(device_step=...)``
+    all live on the device), returning the loss tensor.  The first ``eager_steps`` calls run eagerly (they are real
+    optimisation steps and double as the warm-up a capture needs: CSR / plans built, feature casts cached); the next call
+    captures ``fn`` on static copies of its arguments and every later call copies the new batch into those buffers and
+    replays.  The returned loss is a static tensor that the next replay overwrites."""
+
+    def __init__(self, fn, modules=(), eager_steps=2, profile_spmm=False, pin=None):
+        self.fn, self.modules = fn, tuple(modules)
+        self.eager_left = int(eager_steps)
+        self.graph = None
+        self.static = None
+        self.loss = None
+        self.launches_per_replay = 0
+        self.replays = 0
+        self.profile_spmm = bool(profile_spmm)  # bench.py: event-record nodes around every SpMM / dense-layer launch
+        self.spmm_events = []
+        self.gemm_events = []
+        self._pin = pin
+        self._pinned = []
+
+    def _capture(self, tensors):
+        from . import _native as N
+        self.static = [t.clone() for t in tensors]
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = N.launch_count()
+        saved_profile = (ops.SPMM_PROFILE, ops.GEMM_PROFILE)
+        if self.profile_spmm:
+            ops.SPMM_PROFILE = self.spmm_events = []
+            ops.GEMM_PROFILE = self.gemm_events = []
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self.fn(*self.static)
+        finally:
+            ops.SPMM_PROFILE, ops.GEMM_PROFILE = saved_profile
+        self.launches_per_replay = N.launch_count() - n0
+        # The graph baked raw pointers of cached buffers (CSR / work plan, converted feature matrix) into its nodes: hold
+        # strong references so that cache eviction (ops._GRAPH_CACHE / _FEATURE_CACHE) can never free them under a live
+        # graph.  ``pin()`` returns the very objects the capture used (cache hits).
+        self._pinned = list(self._pin()) if self._pin is not None else []
+
+    def __call__(self, *tensors):
+        if not all(m.training for m in self.modules):
+            raise RuntimeError("a captured step replays a training-mode step: call model.train() first")
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            return self.fn(*tensors)
+        if self.graph is None:
+            self._capture(tensors)
+        else:
+            for st, t in zip(self.static, tensors):
+                if st.shape != t.shape:
+                    raise RuntimeError("captured step: batch shape changed; build a new instance per shape")
+                st.copy_(t, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.loss
+
+
+class CapturedTrainStep(CapturedStep):
+    """``train_step`` for a fixed batch shape as ONE CUDA-graph replay (zero_grad, encoder forward/backward, scoring,
+    BCE, gradient all-reduce, clip, Adam: ~55 launches whose host enqueue time otherwise exceeds their GPU time).
+    ``step(edge, neg_edge)`` -> loss."""
 
     def __init__(self, model, predictor, data, optimizer, encoder_name='sage', transductive='transductive',
                  loss_weight=1.0, eager_steps=_EAGER_STEPS_BEFORE_CAPTURE, profile_spmm=False):
         self.model, self.predictor, self.data, self.optimizer = model, predictor, data, optimizer
         self.encoder_name, self.transductive, self.loss_weight = encoder_name, transductive, loss_weight
-        self.eager_left = int(eager_steps)
-        self.graph = None
-        self.edge = self.neg = self.loss = None
-        self.launches_per_replay = 0
-        self.replays = 0
-        self.profile_spmm = bool(profile_spmm)  # bench.py: event-record nodes around every SpMM launch of the graph
-        self.spmm_events = []
 
-    def _eager(self, edge, neg_edge):
-        return train_step(self.model, self.predictor, self.data, edge, neg_edge, self.optimizer, self.encoder_name,
-                          self.transductive, self.loss_weight)
+        def fn(edge, neg_edge):
+            return train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name, transductive, loss_weight)
 
-    def _capture(self, edge, neg_edge):
-        from . import _native as N
-        self.edge, self.neg = edge.clone(), neg_edge.clone()
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = N.launch_count()
-        saved_profile = ops.SPMM_PROFILE
-        if self.profile_spmm:
-            ops.SPMM_PROFILE = self.spmm_events = []
-        try:
-            with torch.cuda.graph(self.graph):
-                self.loss = self._eager(self.edge, self.neg)
-        finally:
-            ops.SPMM_PROFILE = saved_profile
-        self.launches_per_replay = N.launch_count() - n0
-        # The graph baked raw pointers of the cached CSR / work plan and of the converted feature matrix into its
-        # nodes: hold strong references so that cache eviction (ops._GRAPH_CACHE / _FEATURE_CACHE) can never free them
-        # under a live graph.  Both calls are cache hits that return the very objects the capture used.
-        self._pinned = [ops.to_compute(self.data.x, cache=True)]
-        adj = None if self.encoder_name == 'mlp' else (
-            self.data.adj_t if self.transductive == "transductive" else self.data.edge_index)
-        if isinstance(adj, torch.Tensor):
-            self._pinned.append(ops.graph_of(adj, self.data.x.size(0)))
-        elif adj is not None:
-            self._pinned.append(adj)
+        def pin():
+            keep = [ops.to_compute(data.x, cache=True)]
+            adj = None if encoder_name == 'mlp' else (data.adj_t if transductive == "transductive" else data.edge_index)
+            if isinstance(adj, torch.Tensor):
+                keep.append(ops.graph_of(adj, data.x.size(0)))
+            elif adj is not None:
+                keep.append(adj)
+            return keep
 
-    def __call__(self, edge, neg_edge):
-        if not (self.model.training and self.predictor.training):
-            raise RuntimeError("CapturedTrainStep replays a training-mode step: call model.train() first")
-        if self.eager_left > 0:
-            self.eager_left -= 1
-            return self._eager(edge, neg_edge)
-        if self.graph is None:
-            self._capture(edge, neg_edge)
-        else:
-            if edge.shape != self.edge.shape or neg_edge.shape != self.neg.shape:
-                raise RuntimeError("CapturedTrainStep: batch shape changed; build a new instance per shape")
-            self.edge.copy_(edge, non_blocking=True)
-            self.neg.copy_(neg_edge, non_blocking=True)
-        self.graph.replay()
-        self.replays += 1
-        return self.loss
+        super().__init__(fn, (model, predictor), eager_steps, profile_spmm, pin)
+
+    @property
+    def edge(self):
+        return self.static[0] if self.static else None
+
+    @property
+    def neg(self):
+        return self.static[1] if self.static else None
 
 
 def _captured_step_for(optimizer, key, make):

@@ -114,7 +114,7 @@ def _ref_gemm(A1, B1, A2, B2, bias, addend, relu, gate, gate_scale):
     return D.float()
 
 
-@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05, N.GEMM_TF32X3], ids=["simt", "tcgen05", "tf32x3"])
 @pytest.mark.parametrize("M,Nn,K1,K2", [(1, 8, 8, 0), (127, 64, 64, 0), (128, 256, 256, 256), (300, 200, 100, 36),
                                         (1000, 256, 1433, 0), (5000, 256, 128, 128), (129, 16, 520, 0), (2048, 1, 256, 0)])
 def test_gemm_nt(cuda, backend, M, Nn, K1, K2):
@@ -173,7 +173,7 @@ def test_gemm_nt_resident_weights(cuda, M, Nn, K1, K2):
     torch.testing.assert_close(outs[0][0].cpu(), ref, rtol=1e-3, atol=1e-3 * math.sqrt(K1 + K2))
 
 
-@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05, N.GEMM_TF32X3], ids=["simt", "tcgen05", "tf32x3"])
 @pytest.mark.parametrize("M,N1,N2", [(64, 8, 8), (1000, 256, 256), (5000, 256, 1433), (333, 200, 36), (20000, 256, 512),
                                      (100, 1, 256)])
 def test_gemm_tn(cuda, backend, M, N1, N2):
@@ -188,7 +188,7 @@ def test_gemm_tn(cuda, backend, M, N1, N2):
     torch.testing.assert_close(D, ref, **tol)
 
 
-@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05], ids=["simt_fp32", "tcgen05_bf16"])
+@pytest.mark.parametrize("backend", [N.GEMM_SIMT, N.GEMM_TCGEN05, N.GEMM_TF32X3], ids=["simt_fp32", "tcgen05_bf16", "tf32x3_fp32"])
 @pytest.mark.parametrize("M,N1,n2a,n2b,bias", [(1, 8, 8, 0, True), (77, 64, 128, 128, True), (1000, 256, 256, 256, True),
                                               (5000, 256, 128, 128, False), (4099, 200, 136, 72, True),
                                               (30000, 256, 256, 0, True), (3000, 384, 64, 256, True),
@@ -235,6 +235,33 @@ def test_wgrad_fused(cuda, backend, M, N1, n2a, n2b, bias):
     assert torch.equal(again, dWa)
 
 
+@pytest.mark.parametrize("M,Nn,K", [(4096, 256, 512), (1000, 200, 1433), (20000, 256, 8415)])
+def test_tf32x3_is_fp32_grade(cuda, M, Nn, K):
+    """The fp32-parity mode runs its GEMMs on the tensor cores as 3xTF32 split accumulation (tcgen05.mma.kind::tf32).
+    Against an fp64 reference its error must be of the size of a true-fp32 FFMA GEMM's (the CUDA-core kernel, i.e. what
+    the reference's cuBLAS SGEMM delivers), NOT of a single TF32 product (~1e-3 relative): bounded by 2x the fp32
+    kernel's error + 1e-6 of the result scale, NT and TN."""
+    g = torch.Generator().manual_seed(K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(Nn, K, generator=g)
+    Ad, Bd = ops.cast2d(A.to(cuda), torch.float32), ops.cast2d(B.to(cuda), torch.float32)
+    ref = (A.double() @ B.double().t())
+    scale = float(ref.abs().max())
+    e_tf = float((ops.gemm_nt(Ad, Bd, backend=N.GEMM_TF32X3).cpu().double() - ref).abs().max())
+    e_fp = float((ops.gemm_nt(Ad, Bd, backend=N.GEMM_SIMT).cpu().double() - ref).abs().max())
+    assert e_tf <= 2.0 * e_fp + 1e-6 * scale, (e_tf, e_fp, scale)
+    assert e_tf <= 2e-6 * scale * math.sqrt(K / 512), (e_tf, scale)
+    auto = ops.gemm_nt(Ad, Bd)                      # AUTO picks the tensor-core path for fp32 operands
+    assert torch.equal(auto, ops.gemm_nt(Ad, Bd, backend=N.GEMM_TF32X3))
+    if M <= 4096:   # weight-gradient orientation on the same operands: [K, M]^T-style product reduced over M rows
+        G = torch.randn(M, Nn, generator=g)
+        Gd = ops.cast2d(G.to(cuda), torch.float32)
+        ref_t = G.double().t() @ A.double()
+        s_t = float(ref_t.abs().max())
+        e_tf = float((ops.gemm_tn(Gd, Ad, backend=N.GEMM_TF32X3).cpu().double() - ref_t).abs().max())
+        e_fp = float((ops.gemm_tn(Gd, Ad, backend=N.GEMM_SIMT).cpu().double() - ref_t).abs().max())
+        assert e_tf <= 2.0 * e_fp + 1e-6 * s_t, (e_tf, e_fp, s_t)
+
+
 def test_tcgen05_matches_simt_on_identical_bf16_inputs(cuda):
     g = torch.Generator().manual_seed(0)
     A, B = torch.randn(777, 320, generator=g).bfloat16().to(cuda), torch.randn(256, 320, generator=g).bfloat16().to(cuda)
@@ -246,7 +273,7 @@ def test_tcgen05_matches_simt_on_identical_bf16_inputs(cuda):
 def test_dropout_epilogue_simt_and_tcgen05(cuda):
     A = torch.ones(4096, 64, device=cuda)
     W = torch.eye(64, device=cuda)
-    for backend, dt in ((N.GEMM_SIMT, torch.float32), (N.GEMM_TCGEN05, torch.bfloat16)):
+    for backend, dt in ((N.GEMM_SIMT, torch.float32), (N.GEMM_TCGEN05, torch.bfloat16), (N.GEMM_TF32X3, torch.float32)):
         y1 = ops.gemm_nt(A.to(dt), W.to(dt), relu=True, dropout_p=0.5, seed=123, offset=7, backend=backend).float()
         y2 = ops.gemm_nt(A.to(dt), W.to(dt), relu=True, dropout_p=0.5, seed=123, offset=7, backend=backend).float()
         y3 = ops.gemm_nt(A.to(dt), W.to(dt), relu=True, dropout_p=0.5, seed=124, offset=7, backend=backend).float()
@@ -385,6 +412,32 @@ def test_llp_r_value_and_grad(cuda, rows, K, margin):
     lo.backward()
     torch.testing.assert_close(sd.grad.cpu(), so.grad, rtol=1e-4, atol=1e-8)
     assert torch.count_nonzero(sd.grad[0]) == 0
+
+
+@pytest.mark.parametrize("rows,K,margin,wd,wr", [(64, 12, 0.1, 1.0, 1.0), (500, 36, 0.01, 0.5, 2.0), (3, 100, 0.2, 1.0, 0.0),
+                                                  (2708, 12, 0.1, 1.0, 1.0), (10, 2, 0.05, 0.0, 1.0)])
+def test_llp_fused_equals_separate_kernels(cuda, rows, K, margin, wd, wr):
+    """LLP_D and LLP_R in one pass over the score rows (llp_kd_fused): both loss values equal to the separate
+    kernels' (same arithmetic, same reduction tree), the combined gradient equal to wd * dLLP_D + wr * dLLP_R, and both against the oracle."""
+    g = torch.Generator().manual_seed(rows + K)
+    s = torch.sigmoid(torch.randn(rows, K, generator=g))
+    t = torch.sigmoid(torch.randn(rows, K, generator=g))
+    t[:, : K // 3] = t[:, :1]   # teacher ties: the constant-margin pairs of SURVEY.md Q6
+    sd = s.to(cuda).requires_grad_(True)
+    total, d, r = ops.kd_losses(sd, t.to(cuda), 1.0, margin, wd, wr)
+    total.backward()
+    s2 = s.to(cuda).requires_grad_(True)
+    d2, r2 = ops.kl_loss(s2, t.to(cuda), 1.0), ops.rank_loss(s2, t.to(cuda), margin)
+    (wd * d2 + wr * r2).backward()
+    torch.testing.assert_close(d, d2.detach(), rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(r, r2.detach(), rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(total.detach(), wd * d2.detach() + wr * r2.detach(), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(sd.grad, s2.grad, rtol=1e-5, atol=1e-8)
+    so = s.clone().requires_grad_(True)
+    lo = wd * O.kl_loss(so, t, 1.0) + wr * O.llp_r_loss(so, t, margin)
+    lo.backward()
+    torch.testing.assert_close(total.detach().cpu(), lo.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(sd.grad.cpu(), so.grad, rtol=1e-4, atol=1e-7)
 
 
 def test_golden_losses_from_reference(cuda, golden):

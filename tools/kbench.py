@@ -105,6 +105,35 @@ def main():
             us = timeit(lambda: ops.wgrad(G, A, Wa, B, Wb if n2b else None, bias=bp))
             report(f"wgrad fused M={M} {N1}x({n2a}+{n2b})+bias {tag}", us, nbytes=M * (N1 + n2a + n2b) * 2,
                    flops=2 * M * N1 * (n2a + n2b))
+    if "tf32" in which:
+        # fp32-parity mode: 3xTF32 tensor-core GEMMs (gemm_tf32.cu) vs the CUDA-core fp32 kernels, C4 layer shapes
+        H = 256
+        tf_peak = PEAK["bf16_tflops"] / 2.0   # dense TF32 runs at half the bf16 tensor rate; 3 MMAs per product => / 3 of that
+        for M, K1, K2, kw, tag in ((n, 128, 128, dict(relu=True, dropout_p=0.5, seed=1), "L1 fwd relu+drop"),
+                                   (n, 256, 256, dict(relu=True, dropout_p=0.5, seed=1), "L2 fwd relu+drop"),
+                                   (n, 256, 256, dict(), "L3 fwd / dgrad"),
+                                   (131072, 256, 0, dict(relu=True, dropout_p=0.5, seed=1), "pred fwd relu+drop"),
+                                   (34493, 8415, 0, dict(), "C3 layer 1 (N=256)")):
+            A1 = torch.randn(M, K1, device=dev); B1 = torch.randn(H, K1, device=dev)
+            A2 = torch.randn(M, K2, device=dev) if K2 else None
+            B2 = torch.randn(H, K2, device=dev) if K2 else None
+            bias = torch.randn(H, device=dev)
+            A1, B1 = ops.cast2d(A1, torch.float32), ops.cast2d(B1, torch.float32)
+            fl = 2 * M * H * (K1 + K2)
+            nb = M * (K1 + K2) * 4 + M * H * 4
+            for bname, be in (("tf32x3", N.GEMM_TF32X3), ("simt", N.GEMM_SIMT)):
+                us = timeit(lambda: ops.gemm_nt(A1, B1, A2, B2, bias=bias, backend=be, **kw), iters=5)
+                t = fl / us / 1e6
+                print(f"gemm_nt fp32 [{bname}] M={M} K={K1}+{K2} {tag:22s} {us:9.1f} us  {t:7.1f} fp32-TFLOP/s "
+                      f"({100 * 3 * t / tf_peak:5.1f}% of the TF32 tensor peak counting 3 MMAs)  {nb / us / 1e3:7.0f} GB/s", flush=True)
+        for M, N1, N2 in ((n, 256, 256), (n, 256, 128), (131072, 256, 256)):
+            A = torch.randn(M, N1, device=dev); B = torch.randn(M, N2, device=dev)
+            fl = 2 * M * N1 * N2
+            for bname, be in (("tf32x3", N.GEMM_TF32X3), ("simt", N.GEMM_SIMT)):
+                us = timeit(lambda: ops.gemm_tn(A, B, backend=be), iters=5)
+                t = fl / us / 1e6
+                print(f"gemm_tn fp32 [{bname}] M={M} {N1}x{N2} {us:9.1f} us  {t:7.1f} fp32-TFLOP/s "
+                      f"({100 * 3 * t / tf_peak:5.1f}% of the TF32 tensor peak counting 3 MMAs)", flush=True)
     if "gemmexp" in which:
         import ctypes
         lib = N.load()
