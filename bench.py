@@ -1,18 +1,28 @@
 #!/usr/bin/env python
 """Headline benchmark of the LLP hot path (BASELINE.json: "edges/sec: SAGE+LinkPredictor train & Hits@K eval scoring").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload collab]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload collab] [--precision bf16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is ONE training step of the ogbl-collab-shaped teacher (BASELINE.json configs[3]: 235,868 nodes,
-2,358,104 messages, 128-d features, SAGE 128->256->256->256 + LinkPredictor(256,256,1,2), dropout 0.5, B = 65,536
-positive edges + 65,536 negatives per rank): full-graph encoder forward+backward, fused edge scoring, BCE,
-(all-reduce at N>1), clip + Adam.  ``value`` = positive edges consumed per second over all ranks with inputs resident
-in HBM; ``e2e`` = the same through the public ``train_step`` with the step's edge batch coming from pinned host memory
-and the loss read back every step.  One eval pass (encoder forward + 4 scoring sets + Hits@{10,50,100}) is timed
-separately and reported under ``eval``.  The CPU arm (``--impl reference`` and the ``cpu_baseline`` object) times the
-pure-torch CPU oracle of the same step on the host cores: the reference itself cannot run here (its torch_geometric /
-torch_scatter / torch_cluster / ogb dependencies are absent).
+Default workload (`collab`, BASELINE.json configs[3], the configuration the metric's "1/2/4/8 B200" is quoted on): a
+"step" is ONE training step of the ogbl-collab-shaped teacher — 235,868 nodes, 2,358,104 messages, 128-d features, SAGE
+128->256->256->256 + LinkPredictor(256,256,1,2), dropout 0.5, B = 65,536 positive edges + 65,536 negatives per rank:
+full-graph encoder forward+backward, fused edge scoring, BCE, (all-reduce at N>1), clip + Adam.  ``value`` = positive
+edges consumed per second over all ranks with inputs resident in HBM; ``e2e`` = the same through the public step with
+the step's edge batch coming from pinned host memory and the loss read back every step.  One eval pass (encoder forward
++ 4 scoring sets + Hits@{10,50,100}) is timed separately and reported under ``eval``.  The default bf16 line also carries
+an ``"fp32"`` object: the same measurement in the fp32-parity mode (3xTF32 tensor-core GEMMs), run inside the same
+invocation.
+
+Other workloads (``--workload``): ``powerlaw-10m`` (configs[4], ``--scale``), ``coauthor-physics`` (configs[2] teacher),
+``cora`` (configs[0] on the GPU) and the LLP student steps ``cora-student`` (configs[1]: MLP student, LLP_D = LLP_R =
+True_label = 1), ``physics-student`` (configs[2] student, scripts/LLP_production.sh) and ``collab-student``
+(scripts/LLP_transductive.sh: H = 1024, 3 layers, K = 36, --minibatch): context sampling + two predictor passes + fused
+LLP_D/LLP_R + BCE + tail per step.
+
+The CPU arm (``--impl reference`` and the ``cpu_baseline`` object) times the pure-torch CPU oracle of the same step on
+the host cores: the reference itself cannot run here (its torch_geometric / torch_scatter / torch_cluster / ogb
+dependencies are absent).
 """
 import argparse
 import json
@@ -27,23 +37,34 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HIDDEN, LAYERS, BATCH, DROPOUT, LR = 256, 3, 65536, 0.5, 0.005   # LAYERS is per workload: see layers_of()
+HIDDEN, BATCH, DROPOUT, LR = 256, 65536, 0.5, 0.005
 
-
-def layers_of(workload):
-    """collab: SAGE 128->256->256->256 (scripts/supervised_transductive.sh); the synthetic power-law config
-    (BASELINE.json configs[4]) is 256->256->256."""
-    return 3 if workload == "collab" else 2
+TEACHER = {
+    # workload: (dataset shape, SAGE layers, BASELINE.json config)
+    "collab": ("collab", 3, "configs[3]"),
+    "powerlaw-10m": ("powerlaw-10m", 2, "configs[4]"),
+    "coauthor-physics": ("coauthor-physics", 2, "configs[2] (teacher)"),
+    "cora": ("cora", 2, "configs[0]"),
+}
+STUDENT = {
+    # workload: dataset shape, student hidden / layers, dropout, (rw_step, hops, ns_rate), margin, (True_label, LLP_D, LLP_R),
+    #           feature-minibatch loop, BASELINE.json config / reference script
+    "cora-student": dict(ds="cora", H=256, L=2, p=0.5, ctx=(3, 2, 1), margin=0.1, w=(1.0, 1.0, 1.0), minibatch=False,
+                         cfg="configs[1] (LLP_D = LLP_R = True_label = 1; sampling defaults of main.py:264-266)"),
+    "physics-student": dict(ds="coauthor-physics", H=256, L=2, p=0.0, ctx=(2, 2, 4), margin=0.2, w=(0.1, 10.0, 0.01),
+                            minibatch=False, cfg="configs[2] (student; scripts/LLP_production.sh:5, transductive-shaped graph)"),
+    "collab-student": dict(ds="collab", H=1024, L=3, p=0.0, ctx=(3, 3, 3), margin=0.01, w=(1.0, 1.0, 0.0), minibatch=True,
+                           cfg="collab student of scripts/LLP_transductive.sh:8 (H=1024, 3 layers, K=36, --minibatch)"),
+}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch (mean of one step's five launches) from the committed
-# `ncu --set full` capture of this same command (tools/ncu_summary.py); algorithmic bytes per launch are 1.2 GB, the rest
-# are L2 hits.  Only meaningful for the collab workload the capture was taken on.
+# `ncu --set full` capture of this same command (tools/ncu_summary.py).  Only meaningful for the collab bf16 workload.
 SPMM_TRAFFIC_SOURCE = "profiles/r01_spmm_ncu_full_summary.json"
 
 
-def spmm_traffic(workload):
+def spmm_traffic(workload, precision):
     path = os.path.join(ROOT, SPMM_TRAFFIC_SOURCE)
-    if workload != "collab" or not os.path.exists(path):
+    if workload != "collab" or precision != "bf16" or not os.path.exists(path):
         return None
     try:
         t = [l["traffic_bytes"] for l in json.load(open(path))["launches"] if "spmm_kernel" in l["kernel"] and "traffic_bytes" in l]
@@ -52,19 +73,26 @@ def spmm_traffic(workload):
         return None
 
 
-
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="collab")
+    ap.add_argument("--workload", default="collab", choices=sorted(TEACHER) + sorted(STUDENT))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debugging only)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement the default bf16 run appends")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (ops.OVERLAP_WGRAD = False)")
+    ap.add_argument("--clock-sampler", default="auto", choices=["auto", "thread", "proc", "none"],
+                    help="where the SM-clock samples of the timed region come from: an NVML thread of rank 0 (thread), a "
+                         "separate nvidia-smi process (proc: nothing runs inside the rank processes), or none; auto = "
+                         "thread on one GPU, proc on several")
+    ap.add_argument("--profile-dense", action="store_true", help="teacher workloads: also time the dense-layer launches "
+                    "(event nodes in the graph); always on for the fp32 measurement and the student workloads")
+    ap.add_argument("--allow-tuning", action="store_true", help="run although LLP_TUNING is set (recorded in the line)")
     return ap.parse_args()
 
 
@@ -72,25 +100,35 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return p["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return p, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread (one sample every ~25 ms, so
-    even a 40 ms region is covered), falling back to an `nvidia-smi -lms` child process when NVML is unavailable."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    ``thread``: NVML from a thread of this process, one sample every ~25 ms (so even a 40 ms region is covered).
+    ``proc``:   an `nvidia-smi -lms 20` CHILD process — no sampling code runs inside the rank process; used for multi-rank
+                runs, where NVML calls from a Python thread of rank 0 compete with that rank's enqueue loop (GIL) and,
+                through the per-step all-reduce, slow every rank down."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     # nvmlClocksEventReason* bits
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, mode="thread"):
+        self.index, self.mode, self.rows, self.proc = index, mode, [], None
         self.sm, self.max_mhz, self.reasons, self.reason_samples = [], None, set(), 0
         self._stop = threading.Event()
         self._thread = None
         self._nvml = None
+
+    def _phys_index(self):
+        # NVML / nvidia-smi enumerate physical devices: map through CUDA_VISIBLE_DEVICES when it lists integers
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        return int(ids[self.index]) if len(ids) > self.index else self.index
 
     def _reasons(self, nv, handle):
         try:
@@ -103,8 +141,8 @@ class ClockSampler:
         self.reason_samples += 1
 
     def _nvml_loop(self, nv, handle):
-        # every NVML query contends with kernel launches (see the sleep below), so the throttle-reason query is issued
-        # with the first sample and whenever the SM clock is below its maximum; a clock AT its maximum is not throttled
+        # the throttle-reason query is issued with the first sample and whenever the SM clock is below its maximum; a
+        # clock AT its maximum is not throttled
         first = True
         while not self._stop.is_set():
             try:
@@ -115,29 +153,30 @@ class ClockSampler:
                 first = False
             except Exception:  # noqa: BLE001 - a failed sample is just a missing sample
                 pass
-            time.sleep(0.025)   # (NVML queries contend with kernel launches: polling every 2 / 10 / 15 ms slowed 2-rank steps by ~20 / 14 / 11 %)
+            time.sleep(0.025)
 
     def start(self):
-        try:
-            import pynvml as nv
-            nv.nvmlInit()
-            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it lists integers
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            ids = [v for v in vis.split(",") if v.strip().isdigit()]
-            phys = int(ids[self.index]) if len(ids) > self.index else self.index
-            handle = nv.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
-            self._nvml = nv
-            self._handle = handle
-            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
-            self._thread.start()
+        if self.mode == "none":
             return
-        except Exception:  # noqa: BLE001 - fall back to nvidia-smi
-            self._nvml = None
+        if self.mode == "thread":
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                handle = nv.nvmlDeviceGetHandleByIndex(self._phys_index())
+                self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+                self._nvml = nv
+                self._handle = handle
+                self._thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self._thread.start()
+                return
+            except Exception:  # noqa: BLE001 - fall back to nvidia-smi
+                self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", str(self._phys_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.3)   # let the child attach before the timed region starts
+            self._skip = len(self.rows)
         except OSError:
             self.proc = None
 
@@ -146,6 +185,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.mode == "none":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "none (--clock-sampler none)"}
         if self._nvml is not None:
             self._stop.set()
             self._thread.join(timeout=1.0)
@@ -155,55 +196,116 @@ class ClockSampler:
                 pass
             sm = sorted(self.sm)
             return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                    "samples": len(sm), "reason_samples": self.reason_samples, "source": "nvml"}
+                    "samples": len(sm), "reason_samples": self.reason_samples, "source": "nvml thread"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        rows = self.rows[getattr(self, "_skip", 0):] or self.rows[-1:]
+        sm = sorted(int(r[1]) for r in rows if len(r) > 2 and r[1].isdigit())
         mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi child process"}
 
 
 def build_workload(args, seed=0):
     from linkless_link_prediction_b200.data import synthetic_dataset
-    data, split = synthetic_dataset(args.workload, seed=seed, scale=args.scale)
-    return data, split
+    ds = TEACHER[args.workload][0] if args.workload in TEACHER else STUDENT[args.workload]["ds"]
+    return synthetic_dataset(ds, seed=seed, scale=args.scale)
+
+
+def student_args(cfg, n_nodes, n_train):
+    """The argparse namespace main.train / train_minibatch read (main.py:240-269), filled from the workload table."""
+    rw, hops, ns = cfg["ctx"]
+    tl, d, r = cfg["w"]
+    node_bs = max(int(n_nodes / max(n_train / BATCH, 1.0)), 1)   # main.py:335
+    return type("A", (), dict(transductive="transductive", link_batch_size=BATCH, node_batch_size=min(node_bs, n_nodes),
+                              True_label=tl, LLP_D=d, LLP_R=r, KD_RM=0.0, KD_LM=0.0, margin=cfg["margin"], rw_step=rw,
+                              ps_method="nb", ns_rate=ns, hops=hops, datasets=cfg["ds"], minibatch=cfg["minibatch"]))()
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of the reference step on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_runner(data, split, batch, layers, updated=False):
+def cpu_step_runner(args, data, split):
     from oracle import llp_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     x, adj = data.x, data.adj_t
-    model = O.SAGE("collab", x.size(1), HIDDEN, HIDDEN, layers, DROPOUT, O.SAGEConvUpdated if updated else O.SAGEConv)
-    pred = O.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT)
-    opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=LR)
     pos = split["train"]["edge"]
-    model.train(); pred.train()
     g = torch.Generator().manual_seed(1)
+    if args.workload in TEACHER:
+        ds, layers, _ = TEACHER[args.workload]
+        batch = min(BATCH, pos.size(0))
+        model = O.SAGE(ds, x.size(1), HIDDEN, HIDDEN, layers, DROPOUT, O.SAGEConvUpdated if ds == "coauthor-physics" else O.SAGEConv)
+        pred = O.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT)
+        opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=LR)
+        model.train(); pred.train()
 
-    def step():
+        def step():
+            perm = torch.randint(0, pos.size(0), (batch,), generator=g)
+            edge = pos[perm].t()
+            neg = torch.randint(0, x.size(0), edge.size(), dtype=torch.long, generator=g)
+            return O.teacher_step(model, pred, x, adj, edge, neg, opt)
+
+        return step, batch, "pure-torch CPU oracle (index_select + index_add_ mean, fp32 nn.Linear)"
+    cfg = STUDENT[args.workload]
+    a = student_args(cfg, x.size(0), pos.size(0))
+    batch = min(BATCH, pos.size(0))
+    model = O.MLP(cfg["L"], x.size(1), cfg["H"], cfg["H"], cfg["p"])
+    pred = O.LinkPredictor("mlp", cfg["H"], cfg["H"], 1, cfg["L"], cfg["p"])
+    t_pred = O.LinkPredictor("mlp", 256, 256, 1, 2, cfg["p"])
+    for q in t_pred.parameters():
+        q.requires_grad = False
+    t_h = torch.randn(x.size(0), 256, generator=g) * 0.3
+    opt = torch.optim.Adam(list(model.parameters()) + list(pred.parameters()), lr=LR)
+    model.train(); pred.train()
+    row, col = adj
+
+    def draw():
         perm = torch.randint(0, pos.size(0), (batch,), generator=g)
         edge = pos[perm].t()
         neg = torch.randint(0, x.size(0), edge.size(), dtype=torch.long, generator=g)
-        return O.teacher_step(model, pred, x, adj, edge, neg, opt)
+        node_perm = torch.randperm(x.size(0), generator=g)[:a.node_batch_size]
+        ps, ns = O.neighbor_samplers(row, col, node_perm, x, a.rw_step, a.ps_method, a.ns_rate, a.hops)
+        return edge, neg, node_perm, torch.cat((ps, ns), 1)
 
-    return step
+    if not cfg["minibatch"]:   # full-batch loop (main.py:147-236): needs student hidden == 256 (SURVEY.md Q8)
+        def step():
+            edge, neg, node_perm, samples = draw()
+            return O.student_step(model, pred, t_h, t_pred, x, samples, edge, neg, node_perm, opt, a.True_label, a.LLP_D,
+                                  a.LLP_R, 0.0, 0.0, a.margin)
+    else:                      # feature-minibatch loop (main.py:52-144): encode only the touched rows
+        def step():
+            edge, neg, node_perm, samples = draw()
+            opt.zero_grad()
+            te = torch.cat((edge, neg), dim=-1)
+            target = torch.cat((samples.reshape(-1), te[0], te[1]), 0)
+            h = model(x[target])
+            n_s, K = samples.numel(), samples.size(1) - 1
+            hs = h[:n_s].reshape(samples.size(0), K + 1, -1)
+            s_r = pred(hs[:, :1].repeat(1, K, 1), hs[:, 1:]).reshape(samples.size(0), K)
+            t_r = t_pred(t_h[samples[:, :1]].repeat(1, K, 1), t_h[samples[:, 1:]]).reshape(samples.size(0), K)
+            out = pred(h[n_s:n_s + te.size(1)], h[n_s + te.size(1):]).squeeze()
+            label = torch.cat((torch.ones(edge.size(1)), torch.zeros(neg.size(1))))
+            loss = a.True_label * O.bce_loss(out, label) + a.LLP_D * O.kl_loss(s_r, t_r, 1) + a.LLP_R * O.llp_r_loss(s_r, t_r, a.margin)
+            loss.backward()
+            O.clip_grad_norm(list(model.parameters()), 1.0)
+            O.clip_grad_norm(list(pred.parameters()), 1.0)
+            opt.step()
+            return loss.item()
+
+    return step, batch, "pure-torch CPU oracle of the student step (random walks, 3-D predictor inputs, kl_loss, C(K,2) rank loss)"
 
 
 def run_cpu(args, data, split, budget_s, max_steps, warmup=1):
-    step = cpu_step_runner(data, split, BATCH, layers_of(args.workload), updated=args.workload == "coauthor-physics")
+    step, batch, what = cpu_step_runner(args, data, split)
     for _ in range(warmup):
         step()
     t0, n = time.perf_counter(), 0
@@ -211,21 +313,281 @@ def run_cpu(args, data, split, budget_s, max_steps, warmup=1):
         step()
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": BATCH * n / dt, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} full training steps (B={BATCH}) of the same {args.workload}-shaped workload after {warmup} warm-up, "
-                      f"pure-torch CPU oracle (index_select + index_add_ mean, fp32 nn.Linear)", "steps": n,
-            "ms_per_step": 1e3 * dt / n}
+    return {"value": batch * n / dt, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} full training steps (B={batch}) of the same {args.workload} workload after {warmup} warm-up, {what}",
+            "steps": n, "ms_per_step": 1e3 * dt / n}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Harness:
+    """Process-wide state of one bench invocation (device, ranks, timing helpers)."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dev = torch.device(f"cuda:{self.local_rank}")
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def sampler(self):
+        mode = self.args.clock_sampler
+        if mode == "auto":
+            mode = "thread" if self.world == 1 else "proc"
+        return ClockSampler(self.local_rank, mode)
+
+
+def make_teacher(hz, precision, data_cpu, split):
+    import linkless_link_prediction_b200 as L
+    from linkless_link_prediction_b200 import ops, shims
+    from linkless_link_prediction_b200 import train_teacher_gnn as teacher
+    args, dev = hz.args, hz.dev
+    ds, layers, _ = TEACHER[args.workload]
+    ops.set_compute_dtype(precision)
+    data = shims.Data(x=data_cpu.x, adj_t=data_cpu.adj_t).to(dev)
+    shims.seed_everything(0)
+    # the reference picks SAGEConv_updated for coauthor-physics (train_teacher_gnn.py:376-379), PyG SAGEConv otherwise
+    conv = L.SAGEConv_updated if ds == "coauthor-physics" else L.SAGEConv
+    model = L.SAGE(ds, data.x.size(1), HIDDEN, HIDDEN, layers, DROPOUT, conv).to(dev)
+    predictor = L.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT).to(dev)
+    optimizer = L.FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=LR)
+    model.train(); predictor.train()
+    pos_dev = split["train"]["edge"].to(dev)
+    n_nodes = data.x.size(0)
+    batch = min(BATCH, pos_dev.size(0))
+    shims.seed_everything(1234 + hz.rank)  # every rank trains on its own shard of the global batch
+    # The step is replayed as ONE CUDA graph: the first two warm-up steps run eagerly, the third captures.  Event-record
+    # nodes around every SpMM / dense-layer launch of the graph give those kernels' durations on the stream they run on.
+    step = teacher.CapturedTrainStep(model, predictor, data, optimizer, eager_steps=min(2, max(args.warmup - 1, 1)),
+                                     profile_spmm=True if (args.profile_dense or precision == "fp32") else "spmm")
+
+    def resident():
+        perm = torch.randint(0, pos_dev.size(0), (batch,), device=dev)
+        edge = pos_dev[perm].t()
+        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)  # collab branch, train_teacher_gnn.py:53
+        return step(edge, neg)
+
+    host_batches = [split["train"]["edge"][torch.randint(0, pos_dev.size(0), (batch,))].t().contiguous().pin_memory()
+                    for _ in range(8)]
+
+    def e2e(i):
+        edge = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
+        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)
+        return step(edge, neg).item()  # 4-byte D2H + sync every step, like the reference's loss.item() (:70)
+
+    def evaluate():
+        ev_args = type("A", (), {"minibatch": False, "compute_auc": False})()
+        return teacher.test_transductive(model, predictor, data, split, L.Evaluator(), BATCH, "sage", ds, ev_args)[0]
+
+    h2d = host_batches[0].numel() * host_batches[0].element_size()
+    keep = (model, predictor, optimizer, data)
+    return dict(step=step, resident=resident, e2e=e2e, evaluate=evaluate, batch=batch, h2d=h2d, keep=keep, modules=(model, predictor),
+                kernel="spmm_kernel (+fix-up), SAGE mean aggregation fwd + transpose-bwd", bound="hbm")
+
+
+def make_student(hz, precision, data_cpu, split):
+    import linkless_link_prediction_b200 as L
+    from linkless_link_prediction_b200 import main as student
+    from linkless_link_prediction_b200 import ops, shims
+    args, dev = hz.args, hz.dev
+    cfg = STUDENT[args.workload]
+    ops.set_compute_dtype(precision)
+    data = shims.Data(x=data_cpu.x, adj_t=data_cpu.adj_t).to(dev)
+    n_nodes = data.x.size(0)
+    pos_dev = split["train"]["edge"].to(dev)
+    a = student_args(cfg, n_nodes, pos_dev.size(0))
+    batch = min(BATCH, pos_dev.size(0))
+    shims.seed_everything(0)
+    model = L.MLP(cfg["L"], data.x.size(1), cfg["H"], cfg["H"], cfg["p"]).to(dev)
+    predictor = L.LinkPredictor("mlp", cfg["H"], cfg["H"], 1, cfg["L"], cfg["p"]).to(dev)
+    t_pred = L.LinkPredictor("mlp", 256, 256, 1, 2, cfg["p"]).to(dev)   # frozen teacher predictor, hard-coded shape (main.py:358)
+    for q in t_pred.parameters():
+        q.requires_grad = False
+    t_pred.train()  # never put in eval() by the reference (SURVEY.md Q4)
+    t_h = ops.to_compute(torch.randn(n_nodes, 256, generator=torch.Generator().manual_seed(3)).to(dev) * 0.3)
+    optimizer = L.FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=LR)
+    model.train(); predictor.train()
+    row, col = data.adj_t
+    edge_index = torch.stack([col, row], dim=0)
+    shims.seed_everything(1234 + hz.rank)
+    eager = min(2, max(args.warmup - 1, 1))
+    if cfg["minibatch"]:
+        step = student.StudentMinibatchCapturedStep(model, predictor, t_h, t_pred, data.x, optimizer, a, eager_steps=eager, profile="gemm")
+    else:
+        step = student.StudentCapturedStep(model, predictor, t_h, t_pred, data, optimizer, a, eager_steps=eager, profile="gemm")
+
+    def sample_and_step(edge):
+        node_perm = torch.randperm(n_nodes, device=dev)[:a.node_batch_size]
+        # context sampling exactly as main.py:33-50: walks on the device, the random contexts with the CPU generator
+        ps, ns = student.neighbor_samplers(row, col, node_perm, data.x, a.rw_step, a.ps_method, a.ns_rate, a.hops)
+        samples = torch.cat((ps, ns), 1)
+        if cfg["ds"] != "collab":   # main.py:205-207: PyG dense negative sampling (host python RNG + device mask)
+            neg = shims.negative_sampling(edge_index, num_nodes=n_nodes, num_neg_samples=edge.size(1), method="dense")
+        else:
+            neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)
+        return step(edge, neg, samples)
+
+    def resident():
+        perm = torch.randint(0, pos_dev.size(0), (batch,), device=dev)
+        return sample_and_step(pos_dev[perm].t().contiguous())
+
+    host_batches = [split["train"]["edge"][torch.randint(0, pos_dev.size(0), (batch,))].t().contiguous().pin_memory()
+                    for _ in range(8)]
+
+    def e2e(i):
+        return sample_and_step(host_batches[i % len(host_batches)].to(dev, non_blocking=True)).item()
+
+    h2d = host_batches[0].numel() * host_batches[0].element_size()
+    keep = (model, predictor, t_pred, t_h, optimizer, data)
+    return dict(step=step, resident=resident, e2e=e2e, evaluate=None, batch=batch, h2d=h2d, keep=keep, modules=(model, predictor),
+                kernel="dense layers (MLP encoder + predictor GEMMs, forward / input-gradient / weight-gradient)", bound="tensor",
+                extra={"anchors_per_step": int(a.node_batch_size), "contexts_per_anchor": int(a.rw_step * a.hops * (1 + a.ns_rate)),
+                       "loss_weights": {"True_label": a.True_label, "LLP_D": a.LLP_D, "LLP_R": a.LLP_R},
+                       "student": f"MLP {cfg['L']} x {cfg['H']}", "loop": "train_minibatch" if cfg["minibatch"] else "train"})
+
+
+def measure(hz, precision, data_cpu, split, steps, warmup):
+    """One full measurement (resident value, end-to-end, kernel roofline, eval) in one precision mode."""
+    from linkless_link_prediction_b200 import _native as N
+    args, dev, world = hz.args, hz.dev, hz.world
+    w = (make_teacher if args.workload in TEACHER else make_student)(hz, precision, data_cpu, split)
+    step, batch = w["step"], w["batch"]
+    pk, peak_src = peaks()
+
+    # ---- (1) device-resident timing: value ------------------------------------------------------
+    for _ in range(warmup):
+        w["resident"]()
+    hz.barrier()
+    sampler = hz.sampler()
+    if hz.rank == 0:
+        sampler.start()
+    hz.barrier()
+    launches0, replays0 = N.launch_count(), step.replays
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_host0 = time.perf_counter()
+    for _ in range(steps):
+        w["resident"]()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # CPU time to enqueue one step (no sync inside)
+    e1.record()
+    hz.barrier()
+    launches = (N.launch_count() - launches0) + (step.replays - replays0) * step.launches_per_replay
+    clocks = sampler.stop() if hz.rank == 0 else None
+    ms = hz.max_over_ranks(e0.elapsed_time(e1))
+    value = batch * world * steps / (ms / 1e3)
+
+    # kernel durations: the event nodes hold the LAST timed step's launches now; then `steps` more replays, read one by one
+    spmm, gemm = step.spmm_events, step.gemm_events
+    spmm_ms = gemm_ms = 0.0
+    for _ in range(steps if (spmm or gemm) else 0):
+        w["resident"]()
+        torch.cuda.synchronize()
+        spmm_ms += sum(a.elapsed_time(b) for a, b, _ in spmm)
+        gemm_ms += sum(a.elapsed_time(b) for a, b, _, _ in gemm)
+    spmm_bytes = sum(nb for _, _, nb in spmm)
+    gemm_flops = sum(f for _, _, f, _ in gemm)
+    gemm_bytes = sum(nb for _, _, _, nb in gemm)
+    step_ms = ms / steps
+    dense = {"launches_per_step": len(gemm), "flops_per_step": gemm_flops, "bytes_per_step": gemm_bytes,
+             "ms_per_step": gemm_ms / steps if gemm else None,
+             "tflops": gemm_flops * steps / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None,
+             "share_of_step": (gemm_ms / steps) / step_ms if gemm_ms > 0 else None}
+    if w["bound"] == "hbm":
+        achieved = spmm_bytes * steps / (spmm_ms / 1e3) / 1e9 if spmm_ms > 0 else None
+        roofline = {"bound": "hbm", "kernel": w["kernel"], "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": peak_src,
+                    "unit": "GB/s", "frac": (achieved / pk["hbm_gbs"]) if achieved else None,
+                    "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+                    "traffic": spmm_traffic(args.workload, precision), "traffic_source": SPMM_TRAFFIC_SOURCE,
+                    "launches_timed": len(spmm) * steps, "share_of_step": (spmm_ms / steps) / step_ms if spmm_ms > 0 else None,
+                    "algorithmic_bytes_per_launch": spmm_bytes / max(len(spmm), 1), "algorithmic_bytes_per_step": spmm_bytes,
+                    "dense_layers": dense,
+                    "timing": "event-record nodes around each SpMM / dense-layer launch inside the step's CUDA graph, on the "
+                              "capture stream; `steps` replays read one by one after the timed region"}
+    else:
+        # tensor-bound workloads: the dense layers against the measured cuBLAS bf16 rate sustained inside a long step;
+        # fp32 mode runs 3 TF32 MMAs (each at half the bf16 rate) per product: its tensor peak is a sixth
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / (1.0 if precision == "bf16" else 6.0)
+        roofline = {"bound": "tensor", "kernel": w["kernel"], "achieved": dense["tflops"], "peak": peak,
+                    "peak_source": peak_src + (" bf16 sustained" if precision == "bf16" else " bf16 sustained / 6 (3xTF32)"),
+                    "unit": "TFLOP/s", "frac": (dense["tflops"] / peak) if dense["tflops"] else None, "traffic": None,
+                    "launches_timed": len(gemm) * steps, "share_of_step": dense["share_of_step"],
+                    "flops_per_step": gemm_flops, "bytes_per_step": gemm_bytes,
+                    "timing": "event-record nodes around each dense-layer launch inside the step's CUDA graph"}
+
+    # ---- (2) end-to-end through the public step with host inputs: e2e ---------------------------
+    for i in range(warmup):
+        w["e2e"](i)
+    hz.barrier()
+    e0.record()
+    last = None
+    for i in range(steps):
+        last = w["e2e"](i)
+    e1.record()
+    hz.barrier()
+    ms_e2e = hz.max_over_ranks(e0.elapsed_time(e1))
+    e2e = batch * world * steps / (ms_e2e / 1e3)
+
+    out = {"value": value, "ms_per_step": step_ms, "host_enqueue_ms_per_step": host_enqueue_ms, "dtype": precision,
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": e2e, "unit": "edges/s", "h2d_bytes_per_step": w["h2d"], "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / steps, "last_loss": last},
+           "roofline": roofline, "batch": batch, "extra": w.get("extra")}
+
+    # ---- (3) eval pass: encoder forward + scoring of valid/test pos/neg + Hits@K ----------------
+    if w["evaluate"] is not None:
+        n_scored = sum(split[k][j].size(0) for k in ("valid", "test") for j in ("edge", "edge_neg"))
+        w["evaluate"]()
+        hz.barrier()
+        e0.record()
+        results = w["evaluate"]()
+        e1.record()
+        hz.barrier()
+        ms_eval = hz.max_over_ranks(e0.elapsed_time(e1))
+        for m in w["modules"]:
+            m.train()
+        out["eval"] = {"scored_edges_per_sec": n_scored * 1e3 / ms_eval, "ms": ms_eval, "scored_edges": n_scored,
+                       "hits": {k: v for k, v in results.items()}}
+    # release the captured graph (it holds the in-graph gradient all-reduce) and everything it pinned
+    step.graph = None
+    step.static = None
+    step.spmm_events, step.gemm_events, step._pinned = [], [], []
+    torch.cuda.synchronize()
+    return out
 
 
 def main():
     args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    which = "configs[3]" if args.workload == "collab" else ("configs[4], scaled by %g" % args.scale if args.workload == "powerlaw-10m" else "shape table in data.py")
-    config = {"workload": f"{args.workload}-shaped teacher train step (BASELINE.json {which})", "nodes": None,
-              "messages": None, "feat": None, "hidden": HIDDEN, "layers": layers_of(args.workload), "batch_pos_edges_per_gpu": BATCH,
-              "dropout": DROPOUT, "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2"}
+    hz = Harness(args)
+    rank, world = hz.rank, hz.world
+    teacher_wl = args.workload in TEACHER
+    which = TEACHER[args.workload][2] if teacher_wl else STUDENT[args.workload]["cfg"]
+    if args.workload == "powerlaw-10m":
+        which += ", scaled by %g" % args.scale
+    kind = "teacher train step" if teacher_wl else "LLP student train step"
+    config = {"workload": f"{args.workload}: {kind} (BASELINE.json {which})", "nodes": None, "messages": None, "feat": None,
+              "hidden": HIDDEN if teacher_wl else STUDENT[args.workload]["H"],
+              "layers": TEACHER[args.workload][1] if teacher_wl else STUDENT[args.workload]["L"],
+              "batch_pos_edges_per_gpu": BATCH, "dropout": DROPOUT if teacher_wl else STUDENT[args.workload]["p"],
+              "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2"}
+    tuning = os.environ.get("LLP_TUNING", "")
+    if tuning and not args.allow_tuning:
+        raise SystemExit(f"bench.py refuses to run with LLP_TUNING={tuning!r} set (kernel-variant knobs change what is "
+                         "measured); unset it or pass --allow-tuning to have it recorded in the output line")
 
     if args.impl == "reference":
         if rank != 0:
@@ -233,6 +595,7 @@ def main():
         data, split = build_workload(args)
         config.update(nodes=data.x.size(0), messages=data.adj_t.size(1), feat=data.x.size(1))
         res = run_cpu(args, data, split, budget_s=150.0, max_steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        config["batch_pos_edges_per_gpu"] = min(BATCH, split["train"]["edge"].size(0))
         line = {"impl": "reference", "metric": "train_pos_edges_per_sec", "value": res["value"], "unit": "edges/s",
                 "n_gpus": args.gpus, "gpus_used": 0, "steps": res["steps"], "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -242,175 +605,61 @@ def main():
         print(json.dumps(line))
         return
 
-    import linkless_link_prediction_b200 as L
     from linkless_link_prediction_b200 import _native as N
-    from linkless_link_prediction_b200 import ops, shims
+    from linkless_link_prediction_b200 import ops
     from linkless_link_prediction_b200 import train_teacher_gnn as teacher
 
-    dev = torch.device(f"cuda:{local_rank}")
-    torch.cuda.set_device(dev)
+    torch.cuda.set_device(hz.dev)
     N.require_gpu()
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    ops.set_compute_dtype(args.precision)
+        dist.init_process_group("nccl", device_id=hz.dev)
     if args.no_overlap:
         ops.OVERLAP_WGRAD = set()
 
     data_cpu, split = build_workload(args)
-    config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1))
-    data = shims.Data(x=data_cpu.x, adj_t=data_cpu.adj_t).to(dev)
-    shims.seed_everything(0)
-    # the reference picks SAGEConv_updated for coauthor-physics (train_teacher_gnn.py:376-379), PyG SAGEConv otherwise
-    conv = L.SAGEConv_updated if args.workload == "coauthor-physics" else L.SAGEConv
-    model = L.SAGE(args.workload, data.x.size(1), HIDDEN, HIDDEN, layers_of(args.workload), DROPOUT, conv).to(dev)
-    predictor = L.LinkPredictor("mlp", HIDDEN, HIDDEN, 1, 2, DROPOUT).to(dev)
-    optimizer = L.FusedAdam(list(model.parameters()) + list(predictor.parameters()), lr=LR)
-    model.train(); predictor.train()
-    pos_dev = split["train"]["edge"].to(dev)
-    n_nodes = data.x.size(0)
-    shims.seed_everything(1234 + rank)  # every rank trains on its own shard of the global batch
-    total = args.warmup + args.steps
+    config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1),
+                  batch_pos_edges_per_gpu=min(BATCH, split["train"]["edge"].size(0)))
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    main_res = measure(hz, args.precision, data_cpu, split, args.steps, args.warmup)
+    fp32_res = None
+    if args.precision == "bf16" and not args.no_fp32 and args.workload == "collab":
+        # the reference's arithmetic is fp32: the same workload in the fp32-parity mode, same invocation
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        fp32_res = measure(hz, "fp32", data_cpu, split, max(args.steps // 2, 5), args.warmup)
+        ops.set_compute_dtype(torch.bfloat16)
 
-    def max_over_ranks(ms):
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return ms
-
-    # ---- (1) device-resident timing: value ------------------------------------------------------
-    # The step is replayed as ONE CUDA graph (teacher.CapturedTrainStep): the first two warm-up steps run eagerly, the
-    # third captures.  Event-record nodes around every SpMM launch of the graph give the dominant kernel's duration on
-    # the stream it runs on.
-    step = teacher.CapturedTrainStep(model, predictor, data, optimizer, eager_steps=min(2, max(args.warmup - 1, 1)),
-                                     profile_spmm=True)
-
-    def step_resident():
-        perm = torch.randint(0, pos_dev.size(0), (BATCH,), device=dev)
-        edge = pos_dev[perm].t()
-        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)  # collab branch, train_teacher_gnn.py:53
-        return step(edge, neg)
-
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0, replays0 = N.launch_count(), step.replays
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t_host0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_resident()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # CPU time to enqueue one step (no sync inside)
-    e1.record()
-    barrier()
-    launches = (N.launch_count() - launches0) + (step.replays - replays0) * step.launches_per_replay
-    clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    value = BATCH * world * args.steps / (ms / 1e3)
-    peak, peak_src = peaks()
-    # SpMM durations: the event nodes hold the LAST timed step's launches now; then `steps` more replays, read one by one
-    prof = step.spmm_events
-    spmm_bytes_step = sum(nb for _, _, nb in prof)
-    last_step_ms = sum(a.elapsed_time(b) for a, b, _ in prof) if prof else 0.0
-    spmm_ms = 0.0
-    for _ in range(args.steps if prof else 0):
-        step_resident()
-        torch.cuda.synchronize()
-        spmm_ms += sum(a.elapsed_time(b) for a, b, _ in prof)
-    spmm_launches = len(prof) * args.steps
-    spmm_bytes = spmm_bytes_step * args.steps
-    achieved = spmm_bytes / (spmm_ms / 1e3) / 1e9 if spmm_ms > 0 else None
-    achieved_last = spmm_bytes_step / (last_step_ms / 1e3) / 1e9 if last_step_ms > 0 else None
-    spmm_share = (spmm_ms / args.steps) / (ms / args.steps) if ms and args.steps else None
-
-    # ---- (2) end-to-end through the public step with host inputs: e2e ---------------------------
-    host_batches = [split["train"]["edge"][torch.randint(0, pos_dev.size(0), (BATCH,))].t().contiguous().pin_memory()
-                    for _ in range(min(total, 8))]
-    h2d = host_batches[0].numel() * host_batches[0].element_size()
-
-    def step_e2e(i):
-        edge = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
-        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)
-        loss = step(edge, neg)
-        return loss.item()  # 4-byte D2H + sync every step, like the reference's loss.item() (train_teacher_gnn.py:70)
-
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    e0.record()
-    last = None
-    for i in range(args.steps):
-        last = step_e2e(i)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e = BATCH * world * args.steps / (ms_e2e / 1e3)
-
-    # ---- (3) eval pass: encoder forward + scoring of valid/test pos/neg + Hits@K ----------------
-    ev_args = type("A", (), {"minibatch": False, "compute_auc": False})()
-    n_scored = sum(split[k][j].size(0) for k in ("valid", "test") for j in ("edge", "edge_neg"))
-    teacher.test_transductive(model, predictor, data, split, L.Evaluator(), BATCH, "sage", args.workload, ev_args)
-    barrier()
-    e0.record()
-    results, _ = teacher.test_transductive(model, predictor, data, split, L.Evaluator(), BATCH, "sage", args.workload, ev_args)
-    e1.record()
-    barrier()
-    ms_eval = max_over_ranks(e0.elapsed_time(e1))
-    model.train(); predictor.train()
-
-    def finish():
-        """Leave without NCCL teardown: a CUDA graph that captured the gradient all-reduce is still alive, and
-        destroying the communicator under it can block forever.  Everything has been synchronised by now."""
-        if world > 1:
-            import torch.distributed as dist
-            step.graph = None
-            torch.cuda.synchronize()
-            dist.barrier()
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
-
+    if world > 1:
+        import gc
+        gc.collect()
+        teacher.finish_distributed()   # graphs are released (measure() drops them): a regular NCCL teardown
     if rank != 0:
-        finish()
         return
 
     line = {
-        "metric": "train_pos_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_enqueue_ms,
+        "metric": "train_pos_edges_per_sec", "value": main_res["value"], "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "host_enqueue_ms_per_step": main_res["host_enqueue_ms_per_step"],
         "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps, "last_loss": last},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "spmm_kernel (+fix-up), SAGE mean aggregation fwd + transpose-bwd",
-                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-                     "traffic": spmm_traffic(args.workload), "traffic_source": SPMM_TRAFFIC_SOURCE,
-                     "launches_timed": spmm_launches, "share_of_step": spmm_share,
-                     "algorithmic_bytes_per_launch": spmm_bytes_step / max(len(prof), 1),
-                     "algorithmic_bytes_per_step": spmm_bytes_step,
-                     "achieved_last_timed_step": achieved_last,
-                     "timing": "event-record nodes around each SpMM launch inside the step's CUDA graph, on the capture "
-                               "stream; `steps` replays read one by one after the timed region (+ the last timed step)"},
-        "eval": {"scored_edges_per_sec": n_scored * 1e3 / ms_eval, "ms": ms_eval, "scored_edges": n_scored,
-                 "hits": {k: v for k, v in results.items()}},
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config, "clocks": main_res["clocks"],
+        "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"],
     }
+    if main_res.get("extra"):
+        line["config"].update(main_res["extra"])
+    if "eval" in main_res:
+        line["eval"] = main_res["eval"]
+    if fp32_res is not None:
+        line["fp32"] = {k: fp32_res[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "clocks") if k in fp32_res}
+        line["fp32"].update(unit="edges/s", steps=max(args.steps // 2, 5), gemm="tcgen05.mma kind::tf32, 3-term split + chunked "
+                            "promotion (csrc/gemm_tf32.cu)", ratio_to_bf16_step=fp32_res["ms_per_step"] / main_res["ms_per_step"])
+        if "eval" in fp32_res:
+            line["fp32"]["eval"] = fp32_res["eval"]
+    if tuning:
+        line["llp_tuning"] = tuning
     if world == 1 and not args.no_cpu_baseline:
         res = run_cpu(args, data_cpu, split, budget_s=args.cpu_baseline_seconds, max_steps=3, warmup=1)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
-    finish()
 
 
 if __name__ == "__main__":

@@ -74,7 +74,7 @@ PROTOTYPES = {
     "llp_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                         c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+                         c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),
     "llp_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "llp_gemm_tn": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
@@ -115,6 +115,7 @@ PROTOTYPES = {
     "llp_count_greater": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "llp_auc_workspace_bytes": (c_size_t, [c_int64]),
     "llp_auc_pairs": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "llp_py_random_sample": (c_int, [c_void_p, c_uint64, c_int64, c_void_p]),
     "llp_random_walk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_rng_advance": (c_int, [c_void_p, c_void_p]),
     "llp_clip_adam_workspace_bytes": (c_size_t, [c_int]),

@@ -226,10 +226,10 @@ __global__ void colreduce_final_kernel(const float* __restrict__ partial, int sp
   const int lane = threadIdx.x & 31;
   const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (n >= N) return;
-  float s = 0.0f;
-  for (int i = lane; i < splits; i += 32) s += partial[(int64_t)i * N + n];
+  double s = 0.0;   // up to 2048 signed partials per column: double keeps the bias gradient at fp32-oracle accuracy
+  for (int i = lane; i < splits; i += 32) s += (double)partial[(int64_t)i * N + n];
   s = warp_sum(s);
-  if (lane == 0) out[n] = accumulate ? out[n] + s : s;
+  if (lane == 0) out[n] = accumulate ? out[n] + (float)s : (float)s;
 }
 
 constexpr int kColreduceSplits = 2048;

@@ -48,6 +48,7 @@ extern "C" int llp_gemm_nt(const llp_gemm_nt_args* a, void* stream_) {
               (!dual || (tma_ok(a->A2, a->lda2) && tma_ok(a->B2, a->ldb2)));
     bool ok32 = a->dtype == LLP_F32 && a->out_dtype == LLP_F32 && tf32_operand_ok(a->A1, a->lda1) &&
                 tf32_operand_ok(a->B1, a->ldb1) && (!dual || (tf32_operand_ok(a->A2, a->lda2) && tf32_operand_ok(a->B2, a->ldb2)));
+    if (g_tuning[21]) ok32 = false;   // A/B knob: fp32 operands on the CUDA cores (same result up to fp32 round-off)
     backend = ok ? LLP_GEMM_TCGEN05 : (ok32 ? LLP_GEMM_TF32X3 : LLP_GEMM_SIMT);
   }
   if (backend == LLP_GEMM_TCGEN05) return gemm_nt_tcgen05(*a, stream);
@@ -77,7 +78,7 @@ extern "C" int llp_gemm_tn(int dtype, int backend, int64_t M, int64_t N1, int64_
   if (int rc = check_device()) return rc;
   if (backend == LLP_GEMM_AUTO) {
     backend = (dtype == LLP_BF16 && tma_ok(A, lda) && tma_ok(B, ldb)) ? LLP_GEMM_TCGEN05 : LLP_GEMM_SIMT;
-    if (dtype == LLP_F32 && tf32_operand_ok(A, lda) && tf32_operand_ok(B, ldb)) backend = LLP_GEMM_TF32X3;
+    if (dtype == LLP_F32 && tf32_operand_ok(A, lda) && tf32_operand_ok(B, ldb) && !g_tuning[21]) backend = LLP_GEMM_TF32X3;
   }
   if (backend == LLP_GEMM_TCGEN05) {
     if (dtype != LLP_BF16) return LLP_E_SHAPE;
@@ -131,7 +132,8 @@ extern "C" int llp_wgrad(int dtype, int backend, int64_t M, int64_t N1, const vo
   // separate launches: fp32-parity mode (3xTF32 tensor-core GEMMs; CUDA cores only for operands TMA cannot address or when
   // LLP_GEMM_SIMT was asked for explicitly) and shapes the fused bf16 kernel does not take (N2 > 256)
   const bool tc = dtype == LLP_BF16 && tma_ok(G, ldg);
-  const bool tf = dtype == LLP_F32 && tf32_operand_ok(G, ldg) && !(backend == LLP_GEMM_SIMT && !auto_backend);
+  const bool tf = dtype == LLP_F32 && tf32_operand_ok(G, ldg) && !(backend == LLP_GEMM_SIMT && !auto_backend) &&
+                  !(auto_backend && g_tuning[21]);
   auto one = [&](const void* X, int64_t ldx, int64_t n2, float* dW, int64_t ldw) -> int {
     if (tc && tma_ok(X, ldx)) return gemm_tn_tcgen05(M, N1, n2, G, ldg, X, ldx, dW, ldw, accumulate, ws, stream);
     if (tf && tf32_operand_ok(X, ldx)) return gemm_tn_tf32(M, N1, n2, G, ldg, X, ldx, dW, ldw, accumulate, ws, stream);

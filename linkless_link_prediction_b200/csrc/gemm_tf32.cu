@@ -43,7 +43,7 @@ constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant (warps 4.
 constexpr int kConvWarps = 4;      // operand splitters (warps 12..15)
 constexpr int kThreads = 512;      // warpgroup 0: TMA + MMA (+2 spare warps), 1-2: epilogue, 3: splitters
 constexpr int kAccStages = 2;
-constexpr int kChunkKB = 4;        // k-blocks (of 32) per accumulator chain: 128 reduction elements = 48 MMAs
+constexpr int kChunkKBDefault = 4;  // k-blocks (of 32) per accumulator chain: 128 reduction elements = 48 MMAs (llp_set_tuning(23, n))
 constexpr int kSlabBytes = BLOCK_K * 128;  // MN-major: one TMA box of 32 columns x 32 reduction rows
 
 template <int BLOCK_N>
@@ -69,17 +69,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool mn_maj
   return (1u << 4) | (2u << 7) | (2u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// Round to the nearest TF32 value (ties away from zero, like cvt.rna.tf32.f32) with two integer ALU operations: add half
+// a TF32 ulp to the bit pattern and clear the 13 low bits.  The conversion instruction itself runs on the 16-lane
+// conversion pipe; at 24,576 conversions per 32-wide k-block it would take as long as the k-block's MMAs.
+__device__ __forceinline__ uint32_t rna_tf32_bits(uint32_t b) { return (b + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  const float h = rna_tf32(x);
-  // x - h is exact; a non-finite x keeps its value in the high part only (inf - inf would poison the product with NaN)
-  const float l = (fabsf(h) <= 3.4028234664e38f) ? rna_tf32(x - h) : 0.0f;
-  hi = __float_as_uint(h);
-  lo = __float_as_uint(l);
+  hi = rna_tf32_bits(__float_as_uint(x));
+  // x - hi is exact; a non-finite x keeps its value in the high part only (inf - inf would poison the product with NaN)
+  const float l = x - __uint_as_float(hi);
+  lo = (hi & 0x7f800000u) == 0x7f800000u ? 0u : rna_tf32_bits(__float_as_uint(l));
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <uint32_t kRegs>
@@ -114,6 +112,7 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
   const int64_t num_tiles = m_tiles * n_tiles * p.splits;
   const int kb1 = kTN ? 0 : (int)((p.K1 + BLOCK_K - 1) / BLOCK_K);
   const int kb2 = kTN ? 0 : (int)((p.K2 + BLOCK_K - 1) / BLOCK_K);
+  const int kChunkKB = p.chunk_kb;
   auto tile_kblocks = [&](int64_t tile) -> int {   // k-blocks of one output tile (TN: of its split of the M rows)
     if constexpr (kTN) {
       const int64_t split = tile / (m_tiles * n_tiles);
@@ -204,14 +203,20 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
             if (elect_one_sync()) {
               const uint32_t a_hi = a_lo0 + (uint32_t)stage * ((uint32_t)Cfg::kStageBytes >> 4);
               const uint32_t b_hi = b_lo0 + (uint32_t)stage * ((uint32_t)Cfg::kStageBytes >> 4);
+              // The eight cross-term MMAs of the k-block first, then its four hi x hi MMAs: every MMA's sum is TRUNCATED into
+              // the accumulator, and the error of a truncation scales with the accumulator's magnitude — cross terms are
+              // 2^-11 of the main terms, so while only they have been added (the first k-block of a chain) truncation
+              // costs nothing, and the main terms hit the accumulator in as few steps as possible.
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K_TF32; ++k) {
                 const uint64_t ah = desc_from(a_hi + k * kStep, kHi), bh = desc_from(b_hi + k * kStep, kHi);
                 const uint64_t al = desc_from(a_hi + kLoOff + k * kStep, kHi), bl = desc_from(b_hi + kLoOff + k * kStep, kHi);
-                umma_tf32(tmem_d, al, bh, idesc, (uint32_t)((kb > kb0) | (k != 0)));   // small terms first
+                umma_tf32(tmem_d, al, bh, idesc, (uint32_t)((kb > kb0) | (k != 0)));
                 umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                umma_tf32(tmem_d, ah, bh, idesc, 1u);
               }
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K_TF32; ++k)
+                umma_tf32(tmem_d, desc_from(a_hi + k * kStep, kHi), desc_from(b_hi + k * kStep, kHi), idesc, 1u);
               umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs retire
             }
             __syncwarp();
@@ -419,6 +424,7 @@ int gemm_nt_tf32(const llp_gemm_nt_args& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr; p.dbg = nullptr;
+  p.chunk_kb = g_tuning[23] > 0 ? g_tuning[23] : kChunkKBDefault;
   auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * 4) % 16 == 0; };
   auto ok32 = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 32) && (ld * 4) % 32 == 0; };
   p.ep_flags = (a.bias != nullptr && aligned(a.bias, 16) ? kVecBias : 0) | (ok(a.addend, a.ldadd) ? kVecAddend : 0) |
@@ -443,6 +449,7 @@ int gemm_tn_tf32(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, 
   tn_plan(M, N1, N2, &p.splits, &p.k_per_split);
   p.ep = EpilogueParams{};
   p.D = nullptr; p.ldd = 0; p.partial = ws; p.dbg = nullptr;
+  p.chunk_kb = g_tuning[23] > 0 ? g_tuning[23] : kChunkKBDefault;
   int rc;
   if (bn == 256) rc = launch<256, true>(maps, p, stream);
   else if (bn == 128) rc = launch<128, true>(maps, p, stream);

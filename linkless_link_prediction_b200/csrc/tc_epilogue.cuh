@@ -19,6 +19,7 @@ struct TcParams {
   int ep_flags;          // kVec*: which epilogue operands may be accessed with 128-bit vectors
   void* D; int64_t ldd;
   float* partial;        // TN: [splits][M][N] fp32
+  int chunk_kb;          // 3xTF32 kernels: k-blocks per accumulator chain (chunked promotion)
   long long* dbg;        // instrumentation (llp_set_tuning(15, 1)): per CTA {issue loop ns, operand wait ns, accumulator wait ns}
 };
 

@@ -41,12 +41,13 @@ def neighbor_samplers(row, col, sample, x, step, ps_method, ns_rate, hops):
     """Context nodes of each anchor: ``step`` uniform walks of ``hops`` ('nb') or one walk of ``step*hops`` ('rw')
     plus ``step*hops*ns_rate`` uniformly random nodes drawn with the CPU generator (main.py:47)."""
     batch = sample
+    n = x.size(0)   # every node id is < n: spares torch_cluster's three blocking max() reductions per walk
     if ps_method == 'rw':
-        pos_batch = random_walk(row, col, batch, walk_length=step * hops, coalesced=False)
+        pos_batch = random_walk(row, col, batch, walk_length=step * hops, coalesced=False, num_nodes=n)
     elif ps_method == 'nb':
         pos_batch = None
         for _ in range(step):
-            w = random_walk(row, col, batch, walk_length=hops, coalesced=False)
+            w = random_walk(row, col, batch, walk_length=hops, coalesced=False, num_nodes=n)
             pos_batch = w if pos_batch is None else torch.cat((pos_batch, w[:, 1:]), 1)
     neg_batch = torch.randint(0, x.size(0), (batch.numel(), step * hops * ns_rate), dtype=torch.long)
     return pos_batch.to(batch.device), neg_batch.to(batch.device)

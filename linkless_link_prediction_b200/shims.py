@@ -54,11 +54,55 @@ class Data:
         return self.x.size(1)
 
 
+def py_random_sample(population: int, k: int) -> torch.Tensor:
+    """``torch.tensor(random.sample(range(population), k))`` — same values, same advance of Python's global ``random``
+    state — through the C++ restatement of CPython's algorithm in ``libllp_b200.so`` (``llp_py_random_sample``; host code,
+    works without a GPU).  The Python loop costs ~0.4 us per draw: 4-30 ms per training step at 10^4-10^5 candidates."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _native as N
+    version, internal, gauss = random.getstate()
+    state = np.array(internal, dtype=np.uint32)
+    out = torch.empty(k, dtype=torch.int64)
+    N.check(N.load().llp_py_random_sample(state.ctypes.data_as(ctypes.c_void_p), int(population), int(k), out.data_ptr()),
+            "llp_py_random_sample")
+    random.setstate((version, tuple(int(v) for v in state), gauss))
+    return out
+
+
 def _sample_ids(population: int, k: int, device) -> torch.Tensor:
     """PyG 2.2.0 ``utils.negative_sampling.sample``: CPython ``random.sample`` on the host."""
     if population <= k:
         return torch.arange(population, device=device)
-    return torch.tensor(random.sample(range(population), k), device=device)
+    return py_random_sample(population, k).to(device)
+
+
+_EDGE_ID_CACHE: Dict[tuple, tuple] = {}
+
+
+def _sorted_edge_ids(edge_index: torch.Tensor, idx: torch.Tensor, num_nodes: int, force_undirected: bool) -> torch.Tensor:
+    """Sorted linearised ids of the existing edges, kept per (edge_index tensor, version): the training loops pass the
+    same graph every step."""
+    import weakref
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), bool(force_undirected))
+    hit = _EDGE_ID_CACHE.get(key)
+    if hit is not None and hit[0]() is edge_index:
+        return hit[1]
+    while len(_EDGE_ID_CACHE) >= 8:
+        _EDGE_ID_CACHE.pop(next(iter(_EDGE_ID_CACHE)))
+    srt = torch.sort(idx).values
+    _EDGE_ID_CACHE[key] = (weakref.ref(edge_index), srt)
+    return srt
+
+
+def _not_in_sorted(values: torch.Tensor, sorted_ids: torch.Tensor) -> torch.Tensor:
+    """``~isin(values, sorted_ids)`` by binary search — what indexing PyG's N*N - N boolean mask answers, without the mask."""
+    if sorted_ids.numel() == 0:
+        return torch.ones_like(values, dtype=torch.bool)
+    pos = torch.searchsorted(sorted_ids, values).clamp_(max=sorted_ids.numel() - 1)
+    return sorted_ids[pos] != values
 
 
 def negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None, num_neg_samples: Optional[int] = None,
@@ -102,16 +146,20 @@ def negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None,
     sample_size = int(1.1 * num_neg_samples / prob)
     neg_idx = None
     if method == "dense":
-        mask = torch.ones(population, dtype=torch.bool, device=dev)
-        mask[idx] = False
+        # PyG builds a boolean mask over the whole N*N - N population (1.2 GB per step at the Coauthor-Physics size) and
+        # indexes it with the candidates; membership in the SORTED edge ids answers the same question (same candidates
+        # kept, same order), on the device, without the mask
+        taken = _sorted_edge_ids(edge_index, idx, num_nodes, force_undirected)
         for _ in range(3):
             rnd = _sample_ids(population, sample_size, dev)
-            rnd = rnd[mask[rnd]]
+            keep = _not_in_sorted(rnd, taken)
+            if neg_idx is not None:   # upstream: mask[neg_idx] = False after an incomplete round
+                keep &= _not_in_sorted(rnd, torch.sort(neg_idx).values)
+            rnd = rnd[keep]
             neg_idx = rnd if neg_idx is None else torch.cat([neg_idx, rnd])
             if neg_idx.numel() >= num_neg_samples:
                 neg_idx = neg_idx[:num_neg_samples]
                 break
-            mask[neg_idx] = False
     else:
         idx_host = idx.cpu()
         for _ in range(3):
@@ -156,21 +204,43 @@ def random_walk(row: torch.Tensor, col: torch.Tensor, start: torch.Tensor, walk_
     if p != 1 or q != 1 or return_edge_indices:
         raise NotImplementedError("only uniform walks returning node sequences are used by the reference")
     dev = start.device
-    if num_nodes is None:
+    if num_nodes is None:   # upstream's default: three blocking reductions; pass num_nodes to stay asynchronous
         num_nodes = max(int(row.max()), int(col.max()), int(start.max())) + 1
     if coalesced:
         perm = torch.argsort(row * num_nodes + col)
         row, col = row[perm], col[perm]
-    deg = row.new_zeros(num_nodes)
-    deg.scatter_add_(0, row, torch.ones_like(row))
-    rowptr = row.new_zeros(num_nodes + 1)
-    torch.cumsum(deg, 0, out=rowptr[1:])
+        rowptr = _walk_rowptr(row, num_nodes, cache=False)
+    else:
+        rowptr = _walk_rowptr(row, num_nodes, cache=True)
     if rand is None:
         if _RAND_ON_HOST:
             rand = torch.rand(start.size(0), walk_length).to(dev)
         else:
             rand = torch.rand(start.size(0), walk_length, device=dev)
     return ops.random_walk_with_rand(rowptr, col, start, rand.to(torch.float32))
+
+
+_ROWPTR_CACHE: Dict[tuple, tuple] = {}
+
+
+def _walk_rowptr(row: torch.Tensor, num_nodes: int, cache: bool) -> torch.Tensor:
+    """``rowptr = cumsum(bincount(row))`` of torch_cluster's walk.  The training loops walk the same
+    graph every step (three walks per step): kept per (row tensor, version, num_nodes)."""
+    import weakref
+    key = (row.data_ptr(), int(row.numel()), row._version, int(num_nodes))
+    if cache:
+        hit = _ROWPTR_CACHE.get(key)
+        if hit is not None and hit[0]() is row:
+            return hit[1]
+    deg = row.new_zeros(num_nodes)
+    deg.scatter_add_(0, row, torch.ones_like(row))
+    rowptr = row.new_zeros(num_nodes + 1)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    if cache:
+        while len(_ROWPTR_CACHE) >= 8:
+            _ROWPTR_CACHE.pop(next(iter(_ROWPTR_CACHE)))
+        _ROWPTR_CACHE[key] = (weakref.ref(row), rowptr)
+    return rowptr
 
 
 _KS_INDEX: Dict[tuple, torch.Tensor] = {}

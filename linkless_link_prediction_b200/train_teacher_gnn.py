@@ -106,6 +106,7 @@ class CapturedStep:
         self.launches_per_replay = 0
         self.replays = 0
         self.profile_spmm = bool(profile_spmm)  # bench.py: event-record nodes around every SpMM / dense-layer launch
+        self.profile_what = profile_spmm
         self.spmm_events = []
         self.gemm_events = []
         self._pin = pin
@@ -117,9 +118,11 @@ class CapturedStep:
         self.graph = torch.cuda.CUDAGraph()
         n0 = N.launch_count()
         saved_profile = (ops.SPMM_PROFILE, ops.GEMM_PROFILE)
-        if self.profile_spmm:
-            ops.SPMM_PROFILE = self.spmm_events = []
-            ops.GEMM_PROFILE = self.gemm_events = []
+        if self.profile_spmm:   # True: both kernel families; "spmm" / "gemm": only that one (each pair of event-record
+            if self.profile_what in (True, "spmm"):   # nodes costs a few microseconds of the replayed step)
+                ops.SPMM_PROFILE = self.spmm_events = []
+            if self.profile_what in (True, "gemm"):
+                ops.GEMM_PROFILE = self.gemm_events = []
         try:
             with torch.cuda.graph(self.graph):
                 self.loss = self.fn(*self.static)

@@ -170,3 +170,47 @@ def test_partition_messages_owns_every_message_once(world):
         assert torch.equal(inv_deg, 1.0 / deg.clamp(min=1))
     assert seen_in == ei.size(1) and seen_out == ei.size(1)
     assert torch.equal(torch.cat(rows)[:n], ref)
+
+
+def test_py_random_sample_is_bit_exact_with_cpython():
+    """`llp_py_random_sample` (C++ restatement of CPython's `random.sample(range(n), k)`: MT19937, getrandbits,
+    _randbelow rejection, pool vs set selection) returns the same indices AND leaves Python's global generator in the
+    same state — the candidate stream of PyG's negative_sampling (train_teacher_gnn.py:50-51) stays bit-exact."""
+    import random
+
+    from linkless_link_prediction_b200 import shims
+    cases = [(7_330_556, 9_873), (10, 10), (25, 6), (30, 5), (100, 3), (1_189_732_556, 72_089), (1 << 33, 1000),
+             ((1 << 40) + 12345, 257), (4 ** 7 + 21, 4 ** 6), (4 ** 7 + 22, 4 ** 6), (2, 1), (65, 64), (1000, 999)]
+    for seed, (n, k) in enumerate(cases):
+        random.seed(seed)
+        ref = random.sample(range(n), k)
+        after_ref = random.random()
+        random.seed(seed)
+        got = shims.py_random_sample(n, k).tolist()
+        after_got = random.random()
+        assert got == ref, (n, k)
+        assert after_got == after_ref, (n, k)
+    # consecutive draws continue one stream
+    random.seed(99)
+    a = [random.sample(range(5000), 40) for _ in range(30)]
+    random.seed(99)
+    b = [shims.py_random_sample(5000, 40).tolist() for _ in range(30)]
+    assert a == b
+
+
+def test_negative_sampling_dense_equals_mask_formulation():
+    """The sorted-id membership test that replaced PyG's N*N - N boolean mask keeps exactly the candidates the mask keeps
+    (same order), including the second round after an incomplete first one."""
+    import random
+
+    import torch
+
+    from linkless_link_prediction_b200 import shims
+    from oracle import llp_oracle as O
+    for n, pairs, want, seed in ((60, 200, 150, 3), (40, 700, 600, 4), (300, 2000, 1000, 5)):
+        ei = O.synthetic_undirected_graph(n, pairs, seed=seed)
+        random.seed(seed)
+        ref = O.negative_sampling_dense(ei, n, want)
+        random.seed(seed)
+        got = shims.negative_sampling(ei, num_nodes=n, num_neg_samples=want, method="dense")
+        assert torch.equal(got, ref), (n, pairs, want)
