@@ -11,11 +11,13 @@
 // Accumulator precision.  The tensor core adds every MMA's products into the fp32 TMEM accumulator with TRUNCATION
 // (measured on B200, tests/test_gpu_kernels.py::test_tf32x3_is_fp32_grade: with one accumulator chain per tile the error
 // grows linearly in K — 4e-6 / 1.3e-5 / 6e-5 of the result scale at K = 512 / 1433 / 8415 against 1e-6 / 1.5e-6 / 4e-6 for
-// round-to-nearest FFMA).  So the chain is cut: the MMA warp accumulates CHUNKS of 128 reduction elements (48 MMAs) from
-// zero, alternating between the two TMEM accumulator stages, and the epilogue warps add each finished chunk into fp32
-// REGISTER accumulators with round-to-nearest adds on the CUDA cores (the "promotion" DeepGEMM uses for FP8 on Hopper).
-// Truncation errors of different chunks are independent in sign, the result is fp32-grade for every K, and the TMEM
-// drain of chunk i overlaps the MMAs of chunk i+1.
+// round-to-nearest FFMA).  So the chain is cut: the MMA warp accumulates ONE 32-wide k-block (8 cross-term MMAs, then 4
+// hi x hi MMAs) from zero, alternating between the two TMEM accumulator stages, and the epilogue warps add each finished
+// chunk into fp32 REGISTER accumulators with round-to-nearest adds on the CUDA cores (the "promotion" DeepGEMM uses for
+// FP8 on Hopper); the TMEM drain of chunk i overlaps the MMAs of chunk i+1.  Measured on one C4 training step against an
+// fp64 oracle (tools/fp32_accuracy.py, profiles/r02_fp32_accuracy.txt): embeddings 2.7e-7 (CUDA-core fp32 kernels
+// 3.9e-7), every parameter gradient at or below the CUDA-core kernels' error; chains of 2 / 4 k-blocks are 7 % / 10 %
+// faster and 2-5x / 5-50x less accurate (llp_set_tuning(23, n)).
 //
 // Pipeline per CTA (persistent, warp-specialised; 512 threads = 4 warpgroups, registers re-balanced with setmaxnreg):
 //   warp 0        TMA producer: raw fp32 tiles of both operands -> shared memory ring (cp.async.bulk.tensor, SW128)
@@ -43,7 +45,7 @@ constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant (warps 4.
 constexpr int kConvWarps = 4;      // operand splitters (warps 12..15)
 constexpr int kThreads = 512;      // warpgroup 0: TMA + MMA (+2 spare warps), 1-2: epilogue, 3: splitters
 constexpr int kAccStages = 2;
-constexpr int kChunkKBDefault = 4;  // k-blocks (of 32) per accumulator chain: 128 reduction elements = 48 MMAs (llp_set_tuning(23, n))
+constexpr int kChunkKBDefault = 1;  // k-blocks (of 32) per accumulator chain (llp_set_tuning(23, n) for A/B runs)
 constexpr int kSlabBytes = BLOCK_K * 128;  // MN-major: one TMA box of 32 columns x 32 reduction rows
 
 template <int BLOCK_N>

@@ -50,6 +50,8 @@ def neighbor_samplers(row, col, sample, x, step, ps_method, ns_rate, hops):
             w = random_walk(row, col, batch, walk_length=hops, coalesced=False, num_nodes=n)
             pos_batch = w if pos_batch is None else torch.cat((pos_batch, w[:, 1:]), 1)
     neg_batch = torch.randint(0, x.size(0), (batch.numel(), step * hops * ns_rate), dtype=torch.long)
+    if batch.is_cuda:   # pinned + asynchronous: a pageable copy would block the host until the stream's earlier work (the
+        neg_batch = neg_batch.pin_memory().to(batch.device, non_blocking=True)   # whole previous step) has finished
     return pos_batch.to(batch.device), neg_batch.to(batch.device)
 
 
@@ -276,7 +278,8 @@ def train_minibatch(model, predictor, t_h, teacher_predictor, data, split_edge, 
             neg_edge = negative_sampling(edge_index, num_nodes=x.size(0), num_neg_samples=link_perm.size(0),
                                          method='dense')
         else:
-            neg_edge = torch.randint(0, x.size()[0], [edge.size(0), edge.size(1)], dtype=torch.long).to(device)
+            neg_edge = torch.randint(0, x.size()[0], [edge.size(0), edge.size(1)], dtype=torch.long).pin_memory().to(
+                device, non_blocking=True)   # CPU generator as the reference (main.py:83-84); asynchronous copy
 
         pos_sample, neg_sample = neighbor_samplers(row, col, node_perm, x, args.rw_step, args.ps_method, args.ns_rate,
                                                    args.hops)

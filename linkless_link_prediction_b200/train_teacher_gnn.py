@@ -258,6 +258,23 @@ def train(model, predictor, data, split_edge, optimizer, batch_size, encoder_nam
     return total_loss.item() / total_examples
 
 
+# Evaluation edges are sharded across the ranks only when there is enough of them to pay for the exchange (per pair: an
+# all-gather of the per-rank top-K candidates + two all-reduces): scoring the 306 k evaluation edges of ogbl-collab takes
+# ~60 us on one B200, less than one small collective, and sharding them made the pass SLOWER with every added GPU
+# (1.66 -> 2.2 ms from 1 to 8 GPUs, SCALE_r01).  Below the threshold every rank scores all lists (replicated, identical
+# results, no collective); BASELINE.json configs[4] (10^6 positives against 10^6 negatives) is far above it.
+EVAL_SHARD_MIN_EDGES = 1 << 20
+
+
+def _eval_sharding(n_edges: int):
+    """(rank, world) the evaluation pass shards its edge lists over: the process group's, or (0, 1) when the lists are
+    too small for the exchange to pay."""
+    rank, world = _dist()
+    if world > 1 and n_edges < EVAL_SHARD_MIN_EDGES:
+        return 0, 1
+    return rank, world
+
+
 _EDGE_CACHE = {}
 
 
@@ -292,9 +309,8 @@ def _score_all(predictor, h, edges, batch_size, rank=0, world=1):
     return preds[0] if len(preds) == 1 else torch.cat(preds, dim=0)
 
 
-def _hits(pairs, Ks, world):
-    """pairs: list of (pos_scores, neg_scores) -> per pair, list of Hits@K floats for every K (ONE host read-back for
-    all pairs: the reference's evaluator syncs per K and per pair)."""
+def _hits_device(pairs, Ks, world) -> torch.Tensor:
+    """pairs: list of (pos_scores, neg_scores) -> device tensor ``[len(pairs), len(Ks)]`` of Hits@K (float64)."""
     group = None
     if world > 1:
         import torch.distributed as dist
@@ -303,7 +319,13 @@ def _hits(pairs, Ks, world):
     for pos, neg in pairs:
         counts, n_pos = hits_counts(pos, neg, Ks, group=group)
         rows.append(counts.double() / n_pos.double())
-    return torch.stack(rows).tolist()
+    return torch.stack(rows)
+
+
+def _hits(pairs, Ks, world):
+    """Per pair, the list of Hits@K floats for every K (ONE host read-back for all pairs: the reference's evaluator syncs
+    per K and per pair)."""
+    return _hits_device(pairs, Ks, world).tolist()
 
 
 def _auc(pos: torch.Tensor, neg: torch.Tensor, world: int = 1) -> float:
@@ -316,29 +338,97 @@ def _auc(pos: torch.Tensor, neg: torch.Tensor, world: int = 1) -> float:
     return roc_auc_score_device(pos, neg, group=group)
 
 
-@torch.no_grad()
-def test_transductive(model, predictor, data, split_edge, evaluator, batch_size, encoder_name, dataset, args):
-    model.eval()
-    predictor.eval()
-    rank, world = _dist()
-
+def _transductive_scores(model, predictor, data, split_edge, batch_size, encoder_name, args, rank, world):
+    """Device part of ``test_transductive`` up to the four score vectors (:81-116)."""
     if encoder_name == 'mlp':
         h = model(data.x.to("cuda") if getattr(args, "minibatch", False) else data.x)
     else:
         h = model(data.x, data.adj_t)
         if isinstance(data.adj_t, ops.PartitionedGraph):  # every rank scores its edge shard against all rows
             h = data.adj_t.gather_rows(h)[:data.adj_t.num_nodes_global]
-
     dev = h.device
     pos_valid_pred = _score_all(predictor, h, _edges_on(split_edge['valid']['edge'], dev), batch_size, rank, world)
     neg_valid_pred = _score_all(predictor, h, _edges_on(split_edge['valid']['edge_neg'], dev), batch_size, rank, world)
     pos_test_pred = _score_all(predictor, h, _edges_on(split_edge['test']['edge'], dev), batch_size, rank, world)
     neg_test_pred = _score_all(predictor, h, _edges_on(split_edge['test']['edge_neg'], dev), batch_size, rank, world)
+    return h, pos_valid_pred, neg_valid_pred, pos_test_pred, neg_test_pred
 
+
+class _CapturedEval:
+    """The whole unsharded evaluation pass of ``test_transductive`` — encoder forward, the four scoring loops, Hits@K for
+    every K and the ROC-AUC pair counts — as ONE CUDA-graph replay (~40 launches; eager, their host enqueue time is
+    a quarter of the pass).  Parameters are read from their live buffers, so each replay evaluates the current model;
+    the first call runs eagerly (cache warm-up), the second captures.  ``h`` is a static tensor the next replay
+    overwrites (the drivers copy it when they checkpoint)."""
+
+    def __init__(self, model, predictor, data, split_edge, batch_size, encoder_name, Ks, compute_auc, args):
+        self.refs = (model, predictor, data, split_edge)
+        self.cfg = (batch_size, encoder_name, tuple(Ks), bool(compute_auc), args)
+        self.graph = None
+        self.eager_left = 1
+        self.out = None
+
+    def _pass(self):
+        model, predictor, data, split_edge = self.refs
+        batch_size, encoder_name, Ks, compute_auc, args = self.cfg
+        h, pv, nv, pt, nt = _transductive_scores(model, predictor, data, split_edge, batch_size, encoder_name, args, 0, 1)
+        hits = _hits_device([(pv, nv), (pt, nt)], list(Ks), 1)
+        pairs = torch.stack([ops.auc_pairs(pv, nv), ops.auc_pairs(pt, nt)]) if compute_auc else None
+        return h, hits, pairs, (pv.numel(), nv.numel(), pt.numel(), nt.numel())
+
+    def __call__(self):
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            return self._pass()
+        if self.graph is None:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._pass()
+        self.graph.replay()
+        return self.out
+
+
+_EVAL_GRAPHS = {}
+
+
+def _captured_eval_for(model, predictor, data, split_edge, batch_size, encoder_name, Ks, compute_auc, args):
+    key = (id(model), id(predictor), id(data), id(split_edge), int(batch_size), encoder_name, tuple(Ks), bool(compute_auc),
+           ops.compute_dtype(), bool(getattr(args, "minibatch", False)))
+    ev = _EVAL_GRAPHS.get(key)
+    if ev is None or ev.refs[0] is not model or ev.refs[2] is not data or ev.refs[3] is not split_edge:
+        while len(_EVAL_GRAPHS) >= 4:
+            _EVAL_GRAPHS.pop(next(iter(_EVAL_GRAPHS)))
+        ev = _EVAL_GRAPHS[key] = _CapturedEval(model, predictor, data, split_edge, batch_size, encoder_name, Ks, compute_auc, args)
+    return ev
+
+
+@torch.no_grad()
+def test_transductive(model, predictor, data, split_edge, evaluator, batch_size, encoder_name, dataset, args):
+    model.eval()
+    predictor.eval()
+    rank, world = _eval_sharding(sum(split_edge[k][j].size(0) for k in ('valid', 'test') for j in ('edge', 'edge_neg')))
     Ks = [10, 20, 30, 50] if dataset != "collab" else [10, 50, 100]
+    compute_auc = getattr(args, "compute_auc", True)
+
+    if USE_CUDA_GRAPH and world == 1 and not isinstance(getattr(data, "adj_t", None), ops.PartitionedGraph) \
+            and data.x.is_cuda and not getattr(args, "minibatch", False):
+        # unsharded pass: one graph replay + one host read-back
+        h, hits, pairs, (n_pv, n_nv, n_pt, n_nt) = _captured_eval_for(model, predictor, data, split_edge, batch_size,
+                                                                      encoder_name, Ks, compute_auc, args)()
+        valid_hits, test_hits = hits.tolist()
+        results = {f'Hits@{K}': (valid_hits[i], test_hits[i]) for i, K in enumerate(Ks)}
+        if compute_auc:
+            if min(n_pv, n_nv, n_pt, n_nt) == 0:
+                raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+            (lv, ev), (lt, et) = pairs.tolist()
+            results['AUC'] = ((2 * lv + ev) / (2.0 * n_pv * n_nv), (2 * lt + et) / (2.0 * n_pt * n_nt))
+        return results, h
+
+    h, pos_valid_pred, neg_valid_pred, pos_test_pred, neg_test_pred = _transductive_scores(
+        model, predictor, data, split_edge, batch_size, encoder_name, args, rank, world)
     (valid_hits, test_hits) = _hits([(pos_valid_pred, neg_valid_pred), (pos_test_pred, neg_test_pred)], Ks, world)
     results = {f'Hits@{K}': (valid_hits[i], test_hits[i]) for i, K in enumerate(Ks)}
-    if getattr(args, "compute_auc", True):
+    if compute_auc:
         results['AUC'] = (_auc(pos_valid_pred, neg_valid_pred, world), _auc(pos_test_pred, neg_test_pred, world))
     return results, h
 
@@ -348,7 +438,8 @@ def test_production(model, predictor, val_data, inference_data, test_edge_bundle
                     batch_size, encoder_name, dataset):
     model.eval()
     predictor.eval()
-    rank, world = _dist()
+    rank, world = _eval_sharding(int(val_data.edge_label_index.size(1)) + sum(int(t.size(1)) for t in test_edge_bundle[:4])
+                                 + int(negative_samples.size(1)))
 
     h = model(val_data.x) if encoder_name == 'mlp' else model(val_data.x, val_data.edge_index)
     saved_h = h

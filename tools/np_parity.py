@@ -195,6 +195,7 @@ def main():
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
+    teacher.EVAL_SHARD_MIN_EDGES = 0   # exercise the sharded Hits@K / AUC exchange even on these small edge lists
     res = {"world": world, "fp32": parity(rank, world, dev, torch.float32), "bf16": parity(rank, world, dev, torch.bfloat16)}
     ok = res["fp32"]["ok"] and res["bf16"]["ok"]
     if "--time" in sys.argv:
