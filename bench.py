@@ -215,10 +215,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi child process"}
 
 
-def build_workload(args, seed=0):
+def build_workload(args, seed=0, rank=0, world=1):
+    """(data, split) of the workload's synthetic graph.  Multi-rank runs build it ONCE (rank 0) and share it through a file
+    in /dev/shm that the other ranks map: the 10M-node / 200M-message graph of configs[4] takes minutes of host time and
+    ~25 GB of host memory to generate — times 8 ranks it would not fit the box."""
     from linkless_link_prediction_b200.data import synthetic_dataset
     ds = TEACHER[args.workload][0] if args.workload in TEACHER else STUDENT[args.workload]["ds"]
-    return synthetic_dataset(ds, seed=seed, scale=args.scale)
+    gen_dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}" if (ds == "powerlaw-10m" and args.impl == "ours") else "cpu"
+    if world == 1:
+        return synthetic_dataset(ds, seed=seed, scale=args.scale, device=gen_dev)
+    import torch.distributed as dist
+    path = f"/dev/shm/llp_bench_{ds}_{args.scale:g}_{seed}_{os.environ.get('MASTER_PORT', '0')}.pt"
+    if rank == 0:
+        data, split = synthetic_dataset(ds, seed=seed, scale=args.scale, device=gen_dev)
+        torch.save({"x": data.x, "adj_t": data.adj_t, "split": split}, path)
+    dist.barrier()
+    if rank != 0:
+        from linkless_link_prediction_b200 import shims
+        blob = torch.load(path, mmap=True, weights_only=False)
+        data, split = shims.Data(x=blob["x"], adj_t=blob["adj_t"], edge_index=blob["adj_t"]), blob["split"]
+    dist.barrier()
+    if rank == 0:
+        os.remove(path)   # the mappings of the other ranks stay valid until they drop them
+    return data, split
 
 
 def student_args(cfg, n_nodes, n_train):
@@ -620,7 +639,7 @@ def main():
     if args.no_overlap:
         ops.OVERLAP_WGRAD = set()
 
-    data_cpu, split = build_workload(args)
+    data_cpu, split = build_workload(args, rank=rank, world=world)
     config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1),
                   batch_pos_edges_per_gpu=min(BATCH, split["train"]["edge"].size(0)))
 

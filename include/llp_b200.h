@@ -77,8 +77,7 @@ int llp_csr_build(const int64_t* edge_val, const int64_t* edge_key, int64_t num_
 int64_t llp_spmm_num_chunks(int64_t num_edges);
 int llp_spmm_plan(const int32_t* rowptr, int64_t num_nodes, int64_t num_edges,
                   int32_t* chunk_first_row /*[num_chunks+1]*/, int32_t* hub_list /*[num_chunks] out*/,
-                  int32_t* num_hubs /*[2] device out: rows longer than the split threshold; those of them with more than 32
-                                      chunk partials (combined by the separate fix-up kernel)*/, void* stream);
+                  int32_t* num_hubs /*[1] device out: rows longer than the split threshold*/, void* stream);
 size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 
 /* CSR gather-reduce SpMM: out[r,:] = (mean ? 1/max(deg r,1) : 1) * sum_{e in row r} scale[col e] * x[col e,:]
@@ -89,11 +88,7 @@ size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
              int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
              const float* src_scale, int mean, void* out, int64_t ldo, void* workspace,
-             const int32_t* hub_list, int64_t num_hubs, int64_t num_big_hubs /* host copies of llp_spmm_plan's num_hubs[0..1] */,
-             int32_t* hub_counters /* NULL, or int32[llp_spmm_num_chunks] that is ZERO before the first launch and belongs to
-                                      this CSR: split rows of <= 32 partials are then combined inside the main kernel (the
-                                      kernel leaves the counters zero again; one launch at a time per CSR) */,
-             void* stream);
+             const int32_t* hub_list, int64_t num_hubs /* from llp_spmm_plan (host copy of *num_hubs) */, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Dense layers.  Replaces cuBLAS SGEMM behind F.linear (sageconv_updated.py:71,76; PyG

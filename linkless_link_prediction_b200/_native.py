@@ -74,7 +74,7 @@ PROTOTYPES = {
     "llp_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                         c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+                         c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),
     "llp_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "llp_gemm_tn": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

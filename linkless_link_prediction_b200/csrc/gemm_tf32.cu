@@ -39,24 +39,27 @@ namespace tf {
 using namespace tc;
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;        // fp32 elements = 128 bytes = one swizzle row
 constexpr int UMMA_K_TF32 = 8;     // 32 bytes of K per tcgen05.mma.kind::tf32
+// k-block length kBK (template parameter): 32 fp32 = one 128-byte swizzle row (K-major SWIZZLE_128B), or 16 fp32 = 64-byte
+// rows (SWIZZLE_64B): half the bytes per stage, so twice the stages fit (the hi AND lo copy of both operands live in
+// shared memory: 96 KB per 32-wide stage at N = 256 leaves room for two stages only, which leaves the TMA round trip and
+// the split pass exposed; 16-wide stages are 48 KB: four of them).  MN-major (TN) tiles keep 128-byte rows either way.
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant (warps 4..11)
 constexpr int kConvWarps = 4;      // operand splitters (warps 12..15)
 constexpr int kThreads = 512;      // warpgroup 0: TMA + MMA (+2 spare warps), 1-2: epilogue, 3: splitters
 constexpr int kAccStages = 2;
-constexpr int kChunkKBDefault = 1;  // k-blocks (of 32) per accumulator chain (llp_set_tuning(23, n) for A/B runs)
-constexpr int kSlabBytes = BLOCK_K * 128;  // MN-major: one TMA box of 32 columns x 32 reduction rows
+constexpr int kChainK = 32;        // reduction elements per accumulator chain by default (llp_set_tuning(23, k-blocks) for A/B runs)
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kBK>
 struct Config {
-  static constexpr int kABytes = BLOCK_M * 128;
-  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kABytes = BLOCK_M * kBK * 4;
+  static constexpr int kBBytes = BLOCK_N * kBK * 4;
   static constexpr int kHiBytes = kABytes + kBBytes;      // what TMA lands per stage (and the x_hi operands after the split)
   static constexpr int kStageBytes = 2 * kHiBytes;        // + the x_lo twins
-  static constexpr int kStages = (BLOCK_N == 256) ? 2 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
+  static constexpr int kSlabBytes = kBK * 128;            // MN-major: one TMA box of 32 columns x kBK reduction rows
   static constexpr int kTmemCols = kAccStages * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -91,12 +94,16 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 // sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout"): 128-byte rows, the
 // swizzle pattern repeats every 4 rows, so SBO = 512 B.
 __host__ __device__ constexpr uint32_t desc_hi_sw128_base32(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (1u << 29); }
+// K-major operands with 64-byte rows: SWIZZLE_64B (layout type 4), 8 rows = 512 B per group
+__host__ __device__ constexpr uint32_t desc_hi_sw64(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (4u << 29); }
 
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool kTN>
+template <int BLOCK_N, bool kTN, int kBK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
-  using Cfg = Config<BLOCK_N>;
+  using Cfg = Config<BLOCK_N, kBK>;
+  constexpr int BLOCK_K = kBK;
+  constexpr int kSlabBytes = Cfg::kSlabBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // stage s: [A_hi | B_hi | A_lo | B_lo]
@@ -185,7 +192,7 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
       // K-major SW128: LBO 16 B, SBO = 8 rows (1024 B), one UMMA_K step = 32 B inside the swizzle row.
       // MN-major SW128 with 32-byte atoms: LBO = distance between the 32-column slabs, SBO = 4 reduction rows (512 B),
       // one UMMA_K step = 8 reduction rows = 1024 B.
-      constexpr uint32_t kHi = kTN ? desc_hi_sw128_base32(512) : desc_hi_sw128(1024);
+      constexpr uint32_t kHi = kTN ? desc_hi_sw128_base32(512) : (kBK == 32 ? desc_hi_sw128(1024) : desc_hi_sw64(512));
       constexpr uint32_t kStep = (kTN ? UMMA_K_TF32 * 128 : UMMA_K_TF32 * 4) >> 4;
       constexpr uint32_t kLoOff = (uint32_t)Cfg::kHiBytes >> 4;   // x_lo twin of an operand
       const uint32_t a_lo0 = desc_lo(smem_u32(smem), kTN ? kSlabBytes : 16);
@@ -344,7 +351,7 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
 
 // 2-D fp32 row-major [rows, cols] with leading dimension ld; box = {box_cols (inner, 32 floats = 128 B), box_rows}
 static int make_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-                        bool atom32 = false) {
+                        CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return LLP_E_DEVICE;
   if (!aligned(base, 16) || (ld * 4) % 16 != 0) return LLP_E_ALIGN;
@@ -353,15 +360,14 @@ static int make_map_f32(CUtensorMap* map, const void* base, int64_t rows, int64_
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : LLP_E_BADARG;
 }
 
-template <int BLOCK_N, bool kTN>
+template <int BLOCK_N, bool kTN, int kBK>
 static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
-  using Cfg = Config<BLOCK_N>;
-  auto kern = gemm_tf32x3_kernel<BLOCK_N, kTN>;
+  using Cfg = Config<BLOCK_N, kBK>;
+  auto kern = gemm_tf32x3_kernel<BLOCK_N, kTN, kBK>;
   static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
   if (configured.need()) {
     LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -375,12 +381,32 @@ static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
 }
 
 static int pick_block_n(int64_t N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+// k-block length: 32 (two 96 KB stages at N = 256; SWIZZLE_128B) unless llp_set_tuning(24, 16) asks for the 16-wide ring
+// (four 48 KB stages; SWIZZLE_64B).  Measured equal (436 vs 440 us at M = 235,868, K = 512): with the hi AND lo copies of
+// both operands in shared memory the kernel is bound by shared-memory bandwidth — per 32-wide k-block the 12 MMAs read
+// 144 KB of operands, the split pass moves another 144 KB and TMA writes 48 KB, i.e. ~2,600 cycles at 128 B/clk against
+// 1,536 cycles of tensor time — not by the depth of the ring.
+static int pick_block_k() { return g_tuning[24] == 16 ? 16 : 32; }
+static int chain_kblocks(int bk) { return g_tuning[23] > 0 ? g_tuning[23] : kChainK / bk; }
+
+template <bool kTN>
+static int dispatch(int bn, int bk, const Maps& maps, const TcParams& p, cudaStream_t stream) {
+  if (bk == 32) {
+    if (bn == 256) return launch<256, kTN, 32>(maps, p, stream);
+    if (bn == 128) return launch<128, kTN, 32>(maps, p, stream);
+    return launch<64, kTN, 32>(maps, p, stream);
+  }
+  if (bn == 256) return launch<256, kTN, 16>(maps, p, stream);
+  if (bn == 128) return launch<128, kTN, 16>(maps, p, stream);
+  return launch<64, kTN, 16>(maps, p, stream);
+}
 
 // Split count over the reduction rows of the TN product (same cost model as the bf16 kernel's tn_split_plan: waves x
 // (k-blocks per split + fill) + one fp32 partial of the result per split), with this kernel's 32-row k-blocks.
 static void tn_plan(int64_t M, int64_t N1, int64_t N2, int* splits, int64_t* k_per_split) {
   const int bn = pick_block_n(N2);
   const int64_t tiles = ceil_div(N1, BLOCK_M) * ceil_div(N2, bn);
+  constexpr int BLOCK_K = 32;   // planning granularity (a multiple of both k-block lengths)
   const int64_t kblocks = ceil_div(M, BLOCK_K);
   const double partial_cost = (double)N1 * (double)N2 * 2.0e-6;
   const double fixed_cost = 8.0;
@@ -413,50 +439,45 @@ int gemm_nt_tf32(const llp_gemm_nt_args& a, cudaStream_t stream) {
   using namespace tf;
   if (a.dtype != LLP_F32 || a.out_dtype != LLP_F32) return LLP_E_SHAPE;
   const bool dual = a.A2 != nullptr && a.K2 > 0;
-  const int bn = pick_block_n(a.N);
+  const int bn = pick_block_n(a.N), bk = pick_block_k();
+  const CUtensorMapSwizzle sw = bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   Maps maps;
   memset(&maps, 0, sizeof(maps));
-  if (int rc = make_map_f32(&maps.a1, a.A1, a.M, a.K1, a.lda1, BLOCK_K, BLOCK_M)) return rc;
-  if (int rc = make_map_f32(&maps.b1, a.B1, a.N, a.K1, a.ldb1, BLOCK_K, bn)) return rc;
+  if (int rc = make_map_f32(&maps.a1, a.A1, a.M, a.K1, a.lda1, bk, BLOCK_M, sw)) return rc;
+  if (int rc = make_map_f32(&maps.b1, a.B1, a.N, a.K1, a.ldb1, bk, bn, sw)) return rc;
   if (dual) {
-    if (int rc = make_map_f32(&maps.a2, a.A2, a.M, a.K2, a.lda2, BLOCK_K, BLOCK_M)) return rc;
-    if (int rc = make_map_f32(&maps.b2, a.B2, a.N, a.K2, a.ldb2, BLOCK_K, bn)) return rc;
+    if (int rc = make_map_f32(&maps.a2, a.A2, a.M, a.K2, a.lda2, bk, BLOCK_M, sw)) return rc;
+    if (int rc = make_map_f32(&maps.b2, a.B2, a.N, a.K2, a.ldb2, bk, bn, sw)) return rc;
   }
   TcParams p{};
   p.M = a.M; p.N = a.N; p.K1 = a.K1; p.K2 = dual ? a.K2 : 0; p.splits = 1; p.k_per_split = 0;
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr; p.dbg = nullptr;
-  p.chunk_kb = g_tuning[23] > 0 ? g_tuning[23] : kChunkKBDefault;
+  p.chunk_kb = chain_kblocks(bk);
   auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * 4) % 16 == 0; };
   auto ok32 = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 32) && (ld * 4) % 32 == 0; };
   p.ep_flags = (a.bias != nullptr && aligned(a.bias, 16) ? kVecBias : 0) | (ok(a.addend, a.ldadd) ? kVecAddend : 0) |
                (ok(a.gate, a.ldgate) ? kVecGate : 0) | (ok(a.D, a.ldd) ? kVecOut : 0) |
                (ok32(a.addend, a.ldadd) ? kVec32Addend : 0) | (ok32(a.gate, a.ldgate) ? kVec32Gate : 0) |
                (ok32(a.D, a.ldd) ? kVec32Out : 0);
-  if (bn == 256) return launch<256, false>(maps, p, stream);
-  if (bn == 128) return launch<128, false>(maps, p, stream);
-  return launch<64, false>(maps, p, stream);
+  return dispatch<false>(bn, bk, maps, p, stream);
 }
 
 int gemm_tn_tf32(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, const void* B, int64_t ldb, float* D,
                  int64_t ldd, int accumulate, float* ws, cudaStream_t stream) {
   using namespace tf;
-  const int bn = pick_block_n(N2);
+  const int bn = pick_block_n(N2), bk = pick_block_k();
   Maps maps;
   memset(&maps, 0, sizeof(maps));
-  if (int rc = make_map_f32(&maps.a1, A, M, N1, lda, 32, BLOCK_K, true)) return rc;
-  if (int rc = make_map_f32(&maps.b1, B, M, N2, ldb, 32, BLOCK_K, true)) return rc;
+  if (int rc = make_map_f32(&maps.a1, A, M, N1, lda, 32, bk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_map_f32(&maps.b1, B, M, N2, ldb, 32, bk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
   TcParams p{};
   p.M = N1; p.N = N2; p.K1 = M; p.K2 = 0;
   tn_plan(M, N1, N2, &p.splits, &p.k_per_split);
   p.ep = EpilogueParams{};
   p.D = nullptr; p.ldd = 0; p.partial = ws; p.dbg = nullptr;
-  p.chunk_kb = g_tuning[23] > 0 ? g_tuning[23] : kChunkKBDefault;
-  int rc;
-  if (bn == 256) rc = launch<256, true>(maps, p, stream);
-  else if (bn == 128) rc = launch<128, true>(maps, p, stream);
-  else rc = launch<64, true>(maps, p, stream);
-  if (rc) return rc;
+  p.chunk_kb = chain_kblocks(bk);
+  if (int rc = dispatch<true>(bn, bk, maps, p, stream)) return rc;
   return splitk_reduce(ws, p.splits, N1, N2, D, ldd, accumulate, stream);
 }
 

@@ -28,9 +28,6 @@ namespace llp {
 constexpr int kEPW = 64;    // nominal edges per warp-chunk (32 and 128 were measured: slower on the C4 graph)
 constexpr int kHub = 64;    // rows with more edges than this are split along the chunk grid (>= kEPW; 128 and 256 measured: longer warp tails)
 constexpr int kSpmmThreads = 128;
-constexpr int kMergeParts = 32;  // hub rows of up to this many chunk partials are combined INSIDE the main kernel by the
-                                 // warp that finishes the row's last partial (fixed chunk order: deterministic); longer
-                                 // rows (power-law giants: thousands of partials) go to the parallel fix-up kernel
 
 // Hub list: chunk c is appended when it is the FIRST continuation chunk of a row longer than kHub (that row started in
 // chunk c-1).  One entry per hub row; the order of the list does not matter (every hub is combined independently).
@@ -41,10 +38,7 @@ __global__ void spmm_hub_list_kernel(const int32_t* __restrict__ rowptr, const i
   const int r0 = first_row[c];
   if (r0 == 0) return;
   const int ps = rowptr[r0 - 1], pe = rowptr[r0];
-  if (pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1) {
-    hub_list[atomicAdd(num_hubs, 1)] = (int32_t)c;
-    if ((pe - 1) / kEPW - ps / kEPW + 1 > kMergeParts) atomicAdd(num_hubs + 1, 1);   // needs the fix-up kernel
-  }
+  if (pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1) hub_list[atomicAdd(num_hubs, 1)] = (int32_t)c;
 }
 
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N, int64_t n_chunks,
@@ -166,57 +160,6 @@ __device__ __forceinline__ void add_row(RowAcc<VE, NV>& acc, const uint4 (&v)[NV
 // reciprocal multiply for bf16 outputs).  The slice of a longer (hub) row goes to this chunk's fp32 partial slot
 // (0: the row started in an earlier chunk, 1: it starts here).
 template <typename T, int VE, int NV>
-__device__ __forceinline__ void merge_hub(T* __restrict__ out, int64_t ldo, int F, int r, int col0, int lane, int mean, int deg,
-                                       int c_first, int n_part, const float* partial) {
-  // the row's partials in chunk order: slot 1 of its first chunk, slot 0 of every continuation chunk
-  float s[NV][VE];
-#pragma unroll
-  for (int k = 0; k < NV; ++k)
-#pragma unroll
-    for (int i = 0; i < VE; ++i) s[k][i] = 0.0f;
-  for (int q = 0; q < n_part; ++q) {
-    const float* part = partial + ((int64_t)(c_first + q) * 2 + (q == 0 ? 1 : 0)) * F;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int col = col0 + (k * 32 + lane) * VE;
-      if (col < F) {
-#pragma unroll
-        for (int i = 0; i < VE; ++i) s[k][i] += __ldcg(part + col + i);   // written by other SMs in this launch: L2, not L1
-      }
-    }
-  }
-  const float d = mean ? (float)deg : 1.0f;
-  T* row = out + (int64_t)r * ldo;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int col = col0 + (k * 32 + lane) * VE;
-    if (col >= F) continue;
-    float f[VE];
-#pragma unroll
-    for (int i = 0; i < VE; ++i) f[i] = __fdiv_rn(s[k][i], d);
-    store_vec<T, VE>(row + col, f);
-  }
-}
-
-// In-kernel combine of a split row (single column pass only): every chunk that published a partial of the row arrives on
-// the row's counter; the warp that arrives LAST adds all partials in chunk order — the order is fixed whoever that is, so
-// the result is deterministic and equal to the fix-up kernel's — and resets the counter for the next launch.
-template <typename T, int VE, int NV>
-__device__ __noinline__ void hub_arrive(T* __restrict__ out, int64_t ldo, int F, int r, int lane, int mean, int rs, int re,
-                                        const float* partial, int* __restrict__ hub_counter) {
-  const int c_first = rs / kEPW;
-  const int n_part = (re - 1) / kEPW - c_first + 1;
-  if (n_part > kMergeParts) return;   // a giant: the fix-up kernel takes it
-  int last = 0;
-  if (lane == 0) last = atomicAdd(hub_counter + c_first, 1) == n_part - 1;
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  if (lane == 0) hub_counter[c_first] = 0;
-  __threadfence();
-  merge_hub<T, VE, NV>(out, ldo, F, r, 0, lane, mean, re - rs, c_first, n_part, partial);
-}
-
-template <typename T, int VE, int NV>
 __device__ __forceinline__ void close_row(const RowAcc<VE, NV>& acc, T* __restrict__ out, int64_t ldo, int F, int r, int col0,
                                        int lane, int mean, int rs, int re, int cb, int c, float* __restrict__ partial) {
   const int deg = re - rs;
@@ -287,7 +230,7 @@ __global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
 spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ first_row,
             int n_chunks, const T* __restrict__ x, int ldx, int F, const float* __restrict__ src_scale, int mean,
             T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int zero_rows_per_warp,
-            int n_edges, int* __restrict__ hub_counter) {
+            int n_edges) {
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (c >= n_chunks) return;
@@ -309,7 +252,6 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
   const int cb = c * kEPW;
   constexpr int kColsPerPass = 32 * VE * NV;
   const uint32_t ld_bytes = (uint32_t)ldx * (uint32_t)sizeof(T);
-  int last_r = 0, last_rs = 0, last_re = 0;
 
   for (int col0 = 0; col0 < F; col0 += kColsPerPass) {
     const char* xlane = reinterpret_cast<const char*>(x + col0 + lane * VE);
@@ -400,22 +342,6 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     }
     // the last open row: complete (it ends exactly at ee) or a hub slice
     close_row<T, VE, NV>(acc, out, ldo, F, r, col0, lane, mean, row_start, row_end, cb, c, partial);
-    last_r = r; last_rs = row_start; last_re = row_end;
-  }
-  if (hub_counter != nullptr) {
-    // Tail (the host enables it for single-pass widths only): announce the split-row slices this chunk published — the
-    // continuation of a row that started in an earlier chunk and / or a split row that starts here — and combine a row
-    // when this was its last slice.  Outside the streaming loops on purpose (no register pressure there), and only the
-    // few warps that did publish a slice pay for the fence (a MEMBAR waits for ALL of the warp's earlier stores: with
-    // every warp fencing, the kernel measured 8 % slower).
-    const bool cont = cr.row_start < cb;
-    const bool starts_hub = last_re - last_rs > kHub && last_rs >= cb;
-    if (cont || starts_hub) {
-      __threadfence();
-      __syncwarp();
-      if (cont) hub_arrive<T, VE, NV>(out, ldo, F, cr.r0, lane, mean, cr.row_start, rowptr[cr.r0 + 1], partial, hub_counter);
-      if (starts_hub) hub_arrive<T, VE, NV>(out, ldo, F, last_r, lane, mean, last_rs, last_re, partial, hub_counter);
-    }
   }
 }
 
@@ -427,14 +353,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
                   const int32_t* __restrict__ hub_list, int F, int mean, T* __restrict__ out, int64_t ldo,
-                  const float* __restrict__ partial, int merged) {
+                  const float* __restrict__ partial) {
   __shared__ float red[8][kFixTile];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = hub_list[blockIdx.x];
   const int rp = first_row[c] - 1;
   const int ps = rowptr[rp], pe = rowptr[rp + 1];
   const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
-  if (merged && n_part <= kMergeParts) return;  // combined inside the main kernel
   const float divisor = mean ? (float)(pe - ps) : 1.0f;
   auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
   for (int f0 = 0; f0 < F; f0 += kFixTile) {
@@ -490,8 +415,7 @@ int g_spmm_fake_seq = 0;   // experiment: gather row (edge id mod N) instead of 
 template <typename T, bool kScale>
 static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t* first_row, int64_t N, int64_t E,
                        const void* x_, int64_t ldx, int64_t F, const float* src_scale, int mean, void* out_,
-                       int64_t ldo, void* ws, const int32_t* hub_list, int num_hubs, int num_big_hubs, int32_t* hub_counter,
-                       cudaStream_t stream) {
+                       int64_t ldo, void* ws, const int32_t* hub_list, int num_hubs, cudaStream_t stream) {
   const T* x = reinterpret_cast<const T*>(x_);
   T* out = reinterpret_cast<T*>(out_);
   float* partial = reinterpret_cast<float*>(ws);
@@ -500,14 +424,9 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   const bool vec = aligned(x, 16) && aligned(out, 16) && (ldx * sizeof(T)) % 16 == 0 && (ldo * sizeof(T)) % 16 == 0 &&
                    F % VE == 0;
   const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
-  // in-kernel combine of short hub rows: needs the persistent zeroed counters and a single column pass
-  const int64_t cols_per_pass = vec ? (F * (int64_t)sizeof(T) <= 512 ? 32 * VE : 64 * VE) : 128;
-  const bool vec8_ = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
-                     F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
-  int32_t* merge_counter = (hub_counter != nullptr && g_tuning[22] == 0 && (vec8_ || F <= cols_per_pass)) ? hub_counter : nullptr;
   if (E > 0) {
 #define LLP_SPMM_LAUNCH(VE_, NV_, U_, MB_) \
-  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, LLP_SPMM_FAKE(N), (int)N, (int)ceil_div(N, n_chunks), (int)E, merge_counter)
+  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, LLP_SPMM_FAKE(N), (int)N, (int)ceil_div(N, n_chunks), (int)E)
     const int variant = g_spmm_variant;  // occupancy/register trade-off (llp_set_tuning(0, v)): 0 = 8 blocks/SM (<=64 regs)
     const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
                       F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
@@ -527,9 +446,8 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
 #undef LLP_SPMM_LAUNCH
     LLP_LAUNCH_OK();
   }
-  if (E > 0 && num_hubs > 0 && (merge_counter == nullptr || num_big_hubs > 0)) {
-    spmm_fixup_kernel<T><<<(unsigned)num_hubs, 256, 0, stream>>>(rowptr, first_row, hub_list, (int)F, mean, out, ldo, partial,
-                                                                  merge_counter != nullptr);
+  if (E > 0 && num_hubs > 0) {
+    spmm_fixup_kernel<T><<<(unsigned)num_hubs, 256, 0, stream>>>(rowptr, first_row, hub_list, (int)F, mean, out, ldo, partial);
     LLP_LAUNCH_OK();
   } else if (E == 0) {
     LLP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(T), 0, (size_t)F * sizeof(T), (size_t)N, stream));
@@ -563,7 +481,7 @@ extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_
   int64_t n_chunks = llp_spmm_num_chunks(E);
   spmm_plan_kernel<<<(unsigned)ceil_div(n_chunks + 1, 256), 256, 0, stream>>>(rowptr, N, n_chunks, chunk_first_row);
   LLP_LAUNCH_OK();
-  LLP_CUDA(cudaMemsetAsync(num_hubs, 0, 2 * sizeof(int32_t), stream));
+  LLP_CUDA(cudaMemsetAsync(num_hubs, 0, sizeof(int32_t), stream));
   if (n_chunks > 1) {
     spmm_hub_list_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(rowptr, chunk_first_row, n_chunks, hub_list, num_hubs);
     LLP_LAUNCH_OK();
@@ -577,19 +495,17 @@ extern "C" size_t llp_spmm_workspace_bytes(int64_t E, int64_t F) {
 
 extern "C" int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
                         int64_t N, int64_t E, const void* x, int64_t ldx, int64_t F, const float* src_scale, int mean,
-                        void* out, int64_t ldo, void* workspace, const int32_t* hub_list, int64_t num_hubs, int64_t num_big_hubs,
-                        int32_t* hub_counters, void* stream_) {
+                        void* out, int64_t ldo, void* workspace, const int32_t* hub_list, int64_t num_hubs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0 && F > 0 && ldx >= F && ldo >= F);
-  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (num_hubs == 0 || hub_list) &&
-                num_big_hubs >= 0 && num_big_hubs <= num_hubs);
+  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (num_hubs == 0 || hub_list));
   LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && F < (1 << 24) && ldx * 4 < (int64_t)UINT32_MAX);
   if (int rc = check_device()) return rc;
   if (N == 0) return 0;
 #define LLP_SPMM(T)                                                                                                     \
   return src_scale != nullptr                                                                                           \
-             ? spmm_launch<T, true>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, (int)num_big_hubs, hub_counters, stream)  \
-             : spmm_launch<T, false>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, (int)num_big_hubs, hub_counters, stream)
+             ? spmm_launch<T, true>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)  \
+             : spmm_launch<T, false>(rowptr, col, chunk_first_row, N, E, x, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)
   if (dtype == LLP_F32) { LLP_SPMM(float); }
   if (dtype == LLP_BF16) { LLP_SPMM(__nv_bfloat16); }
 #undef LLP_SPMM

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .sageconv import SAGEConv, _SageBase
@@ -22,6 +23,14 @@ def _linear(x, lin: nn.Linear, relu: bool, p: float, in_gate: float = 0.0, defer
 FUSE_EDGE_MLP = True  # LinkPredictor.score: gather + lin1 + head as one tcgen05 kernel when the shapes allow it
 
 
+def _append_norm(norms: nn.ModuleList, norm_type: str, width: int) -> None:
+    """The norm layer the reference appends next to a hidden layer (models.py:27-37,90-100)."""
+    if norm_type == "batch":
+        norms.append(nn.BatchNorm1d(width))
+    elif norm_type == "layer":
+        norms.append(nn.LayerNorm(width))
+
+
 def _gate_scale(p: float) -> float:
     """Backward factor of relu + dropout(p) taken from the saved output: 1/(1-p) where the output is positive."""
     return 1.0 / (1.0 - p)
@@ -30,8 +39,6 @@ def _gate_scale(p: float) -> float:
 class MLP(nn.Module):
     def __init__(self, num_layers, input_dim, hidden_dim, output_dim, dropout_ratio, norm_type="none"):
         super().__init__()
-        if norm_type != "none":
-            raise NotImplementedError("norm layers are never enabled by the reference drivers")
         self.num_layers, self.norm_type = num_layers, norm_type
         self.dropout = nn.Dropout(dropout_ratio)
         self.layers, self.norms = nn.ModuleList(), nn.ModuleList()
@@ -39,8 +46,10 @@ class MLP(nn.Module):
             self.layers.append(nn.Linear(input_dim, output_dim))
         else:
             self.layers.append(nn.Linear(input_dim, hidden_dim))
+            _append_norm(self.norms, norm_type, hidden_dim)
             for _ in range(num_layers - 2):
                 self.layers.append(nn.Linear(hidden_dim, hidden_dim))
+                _append_norm(self.norms, norm_type, hidden_dim)
             self.layers.append(nn.Linear(hidden_dim, output_dim))
 
     def reset_parameters(self):
@@ -50,6 +59,14 @@ class MLP(nn.Module):
     def forward(self, feats):
         h = ops.to_compute(feats, cache=True)
         p = float(self.dropout.p) if self.training else 0.0
+        if self.norm_type != "none":
+            # models.py:48-53 with a norm layer between the linear layer and relu: the GEMM runs bare and the norm / relu /
+            # dropout go through torch (the reference drivers never enable norms, so this branch is off the measured path)
+            for l, layer in enumerate(self.layers):
+                h = _linear(h, layer, relu=False, p=0.0)
+                if l != self.num_layers - 1:
+                    h = self.dropout(F.relu(self.norms[l](h.float()))).to(ops.compute_dtype()).contiguous()
+            return h
         for l, layer in enumerate(self.layers):
             last = l == self.num_layers - 1
             # every hidden activation is consumed by the next layer, which applies its relu/dropout mask in backward
@@ -62,12 +79,12 @@ class SAGE(nn.Module):
     def __init__(self, data_name, in_channels, hidden_channels, out_channels, num_layers, dropout, conv_layer=SAGEConv,
                  norm_type="none"):
         super().__init__()
-        if norm_type != "none":
-            raise NotImplementedError("norm layers are never enabled by the reference drivers")
         self.convs, self.norms, self.norm_type = nn.ModuleList(), nn.ModuleList(), norm_type
+        _append_norm(self.norms, norm_type, hidden_channels)
         self.convs.append(conv_layer(in_channels, hidden_channels))
         for _ in range(num_layers - 2):
             self.convs.append(conv_layer(hidden_channels, hidden_channels))
+            _append_norm(self.norms, norm_type, hidden_channels)
         self.convs.append(conv_layer(hidden_channels, out_channels))
         self.dropout = dropout
 
@@ -80,12 +97,23 @@ class SAGE(nn.Module):
         x = ops.to_compute(x, cache=True)
         p = float(self.dropout) if self.training else 0.0
         n = len(self.convs)
+        deferred = False   # did the previous layer leave its relu/dropout backward mask to this one?
         for l, conv in enumerate(self.convs):
             if not isinstance(conv, _SageBase):
                 raise RuntimeError("SAGE expects the SAGEConv / SAGEConv_updated layers of this package")
             last = l == n - 1
-            x = conv(x, graph, _relu=not last, _dropout=0.0 if last else self.dropout,
-                     _in_gate=_gate_scale(p) if l > 0 else 0.0, _defer_gate=not last)
+            fused = self.norm_type == "none" and not conv.normalize
+            if fused:   # relu + dropout inside the layer's GEMM epilogue, their backward mask in the next layer's
+                x = conv(x, graph, _relu=not last, _dropout=0.0 if last else self.dropout,
+                         _in_gate=_gate_scale(p) if deferred else 0.0, _defer_gate=not last)
+                deferred = not last
+            else:       # a norm layer (models.py:113-116) or L2 normalisation (sageconv_updated.py:78-79) sits between the
+                x = conv(x, graph, _in_gate=_gate_scale(p) if deferred else 0.0)   # layer and relu: those go through torch
+                deferred = False
+                if not last:
+                    if self.norm_type != "none":
+                        x = self.norms[l](x.float())
+                    x = F.dropout(F.relu(x), p=self.dropout, training=self.training).to(ops.compute_dtype()).contiguous()
         return x
 
 

@@ -269,13 +269,11 @@ def _build_csr(val: torch.Tensor, key: torch.Tensor, num_rows: int, want_inv: bo
                               perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
     plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
     hub_list = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
-    n_hubs = torch.zeros(2, dtype=torch.int32, device=dev)
+    n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
     N.check(lib.llp_spmm_plan(rowptr.data_ptr(), num_rows, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),
                               N.stream_ptr()), "llp_spmm_plan")
-    n_hubs, n_big = (int(v) for v in n_hubs.tolist())  # the one host sync per graph, at build time
-    # per-CSR arrival counters of the in-kernel hub combine: zero now, and every launch leaves them zero again
-    counters = torch.zeros(max(n_chunks, 1), dtype=torch.int32, device=dev)
-    return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs, n_big, counters)
+    n_hubs = int(n_hubs.item())  # the one host sync per graph, at build time
+    return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs)
 
 
 def _spmm_launch(csr, num_rows: int, num_edges: int, x: torch.Tensor, src_scale, mean: bool, transpose: bool) -> torch.Tensor:
@@ -296,8 +294,7 @@ def _spmm_launch(csr, num_rows: int, num_edges: int, x: torch.Tensor, src_scale,
         ev1 = torch.cuda.Event(enable_timing=True, external=ext)
         ev0.record()
     rc = lib.llp_spmm(N.dtype_id(x.dtype), rowptr.data_ptr(), col.data_ptr(), plan.data_ptr(), num_rows, num_edges, xp, ldx, F,
-                      N.ptr(src_scale), int(mean), op, ldo, ws.data_ptr(), hubs[0].data_ptr(), hubs[1], hubs[2],
-                      hubs[3].data_ptr(), N.stream_ptr())
+                      N.ptr(src_scale), int(mean), op, ldo, ws.data_ptr(), hubs[0].data_ptr(), hubs[1], N.stream_ptr())
     N.check(rc, "llp_spmm")
     if prof is not None:
         ev1.record()

@@ -21,9 +21,8 @@ class _SageBase(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, normalize: bool = False, root_weight: bool = True,
                  bias: bool = True, **kwargs):
         super().__init__()
-        if normalize or not root_weight or not bias:
-            raise NotImplementedError("only the configuration the reference drivers use is built: "
-                                      "normalize=False, root_weight=True, bias=True")
+        if not root_weight or not bias:
+            raise NotImplementedError("only root_weight=True, bias=True (what the reference drivers use) is built")
         self.in_channels, self.out_channels = in_channels, out_channels
         self.normalize, self.root_weight = normalize, root_weight
         self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
@@ -43,6 +42,17 @@ class _SageBase(nn.Module):
         x = ops.to_compute(x, cache=True)
         p = float(_dropout) if self.training else 0.0
         seed, offset = ops._dropout_seed() if p > 0 else (0, 0)
+        if self.normalize:
+            # sageconv_updated.py:78-79 (and PyG SAGEConv): L2-normalise the layer output; relu / dropout asked for by the
+            # caller then run after the normalisation through torch (never enabled by the reference drivers)
+            out = type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, False, 0.0, 0, 0,
+                                       float(_in_gate), False)
+            out = torch.nn.functional.normalize(out.float(), p=2.0, dim=-1)
+            if _relu:
+                out = torch.relu(out)
+            if _dropout > 0:
+                out = torch.nn.functional.dropout(out, p=float(_dropout), training=self.training)
+            return out.to(ops.compute_dtype()).contiguous()
         return type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, bool(_relu), p, seed,
                                     offset, float(_in_gate), bool(_defer_gate))
 

@@ -407,3 +407,67 @@ def test_fused_edge_scorer_equals_unfused(cuda, p, n, f, H, m):
         z = hf[u.cpu()] * hf[v.cpu()]
         ref = torch.sigmoid(torch.relu(z @ w1.t() + b1) @ w2.t() + b2).reshape(-1)
         torch.testing.assert_close(ea.cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("norm_type", ["batch", "layer"])
+def test_norm_layers_and_l2_normalize_match_torch_formula(cuda, mode, norm_type):
+    """The surface options the reference drivers never enable but its classes accept: ``norm_type`` of MLP / SAGE
+    (models.py:27-37,48-53,90-100,113-116) and ``SAGEConv_updated(normalize=True)`` (sageconv_updated.py:78-79): forward
+    and parameter gradients against the same formulas written with plain torch + the oracle's aggregation on the CPU."""
+    import torch.nn.functional as F
+    seed_all(0)
+    n, f, H = 300, 24, 32
+    ei = O.synthetic_undirected_graph(n, 1200, seed=2)
+    x = torch.randn(n, f)
+    tol = TOL[mode] if mode == torch.float32 else dict(rtol=5e-2, atol=5e-2)
+
+    def check(dev_model, ref_forward, dev_inputs):
+        dev_model.train()
+        ref_params = [p.detach().cpu().clone().requires_grad_(True) for p in dev_model.parameters()]
+        out_ref = ref_forward(ref_params)
+        w = torch.randn(out_ref.shape)
+        (out_ref * w).sum().backward()
+        out = dev_model(*dev_inputs)
+        (out.float() * w.to(cuda)).sum().backward()
+        torch.testing.assert_close(out.float().cpu(), out_ref.detach(), **tol)
+        # the bias in front of a batch norm has an analytically ZERO gradient (the norm removes the mean): errors are
+        # bounded against the larger of the tensor's own norm and 1e-3 of the largest gradient norm of the model
+        scale = max(float(q.grad.norm()) for q in ref_params)
+        for p, q in zip(dev_model.parameters(), ref_params):
+            err = float((p.grad.cpu() - q.grad).norm()) / max(float(q.grad.norm()), 1e-3 * scale)
+            assert err < (1e-4 if mode == torch.float32 else 1.5e-1), err
+
+    norm = (lambda h, wgt, b: F.batch_norm(h, None, None, wgt, b, True)) if norm_type == "batch" else \
+        (lambda h, wgt, b: F.layer_norm(h, (H,), wgt, b))
+    # MLP 3 layers, dropout 0: linear -> norm -> relu, twice, then linear
+    mlp = L.MLP(3, f, H, 16, 0.0, norm_type).to(cuda)
+    names = [k for k, _ in mlp.named_parameters()]
+
+    def mlp_ref(ps):
+        P = dict(zip(names, ps))
+        h = x
+        for l in range(3):
+            h = F.linear(h, P[f"layers.{l}.weight"], P[f"layers.{l}.bias"])
+            if l != 2:
+                h = torch.relu(norm(h, P[f"norms.{l}.weight"], P[f"norms.{l}.bias"]))
+        return h
+
+    check(mlp, mlp_ref, (x.to(cuda),))
+    # SAGE 3 layers with norms, the last conv with L2 normalisation
+    sage = L.SAGE("t", f, H, H, 3, 0.0, L.SAGEConv_updated, norm_type).to(cuda)
+    sage.convs[2].normalize = True
+    snames = [k for k, _ in sage.named_parameters()]
+
+    def sage_ref(ps):
+        P = dict(zip(snames, ps))
+        h = x
+        for l in range(3):
+            t = F.linear(h, P[f"convs.{l}.lin_l.weight"], P[f"convs.{l}.lin_l.bias"])
+            h = O.mean_aggregate(t, ei, n) + F.linear(h, P[f"convs.{l}.lin_r.weight"])
+            if l == 2:
+                h = F.normalize(h, p=2.0, dim=-1)
+            else:
+                h = torch.relu(norm(h, P[f"norms.{l}.weight"], P[f"norms.{l}.bias"]))
+        return h
+
+    check(sage, sage_ref, (x.to(cuda), ei.to(cuda)))

@@ -65,34 +65,6 @@ def test_spmm_forward_and_transpose(cuda, dtype, n, e, f, hub):
     torch.testing.assert_close(gx, xo.grad, **(FP32 if dtype == torch.float32 else dict(rtol=2e-2, atol=6e-2)))
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_spmm_in_kernel_hub_combine_equals_fixup_kernel(cuda, dtype):
-    """Split rows of up to 32 chunk partials are combined inside the main kernel by whichever warp publishes the row's
-    last partial; the order of the additions is fixed (chunk order), so the result must equal the separate fix-up
-    kernel's bit for bit, run after run, forward and transpose, with short hubs (merged), giant hubs (fix-up kernel) and
-    both in one graph — and the self-resetting arrival counters must be zero again after every launch."""
-    n, f = 3000, 256
-    ei = rand_graph(n, 60000, 7, hub=1500)          # one row of ~1500 edges: 24 partials -> merged in the kernel
-    big = torch.stack([torch.randint(0, n, (5000,), generator=torch.Generator().manual_seed(8)), torch.full((5000,), 17)])
-    med = torch.stack([torch.full((1000,), 5), torch.randint(0, n, (1000,), generator=torch.Generator().manual_seed(10))])
-    ei = torch.cat([ei, big, big.flip(0), med], dim=1)   # node 17: ~5000 edges in both directions -> 79 partials: fix-up
-    #                                                      kernel; node 5: 1000 out-edges -> a merged row of the transpose
-    g = ops.Graph(ei.to(cuda), n)
-    assert g.hubs[1] > g.hubs[2] >= 1 and g.t_hubs[1] > g.t_hubs[2] >= 1   # merged hubs AND big hubs present
-    x = ops.cast2d(torch.randn(n, f, generator=torch.Generator().manual_seed(9)).to(cuda), dtype)
-    lib = N.load()
-    outs = {}
-    for knob in (0, 1):
-        lib.llp_set_tuning(22, knob)   # 1 = combine every split row in the fix-up kernel (the round-1 path)
-        try:
-            outs[knob] = [(g.spmm(x), g.spmm(x, transpose=True)) for _ in range(3)]
-        finally:
-            lib.llp_set_tuning(22, 0)
-    for a, b in outs[0] + outs[1]:
-        assert torch.equal(a, outs[1][0][0]) and torch.equal(b, outs[1][0][1])
-    assert int(g.hubs[3].abs().sum()) == 0 and int(g.t_hubs[3].abs().sum()) == 0
-
-
 def test_spmm_fp32_is_bit_exact_in_edge_order(cuda):
     # no hub rows: the kernel sums each row in CSR (= original edge) order like index_add_ on the CPU
     ei = rand_graph(400, 3000, 5)
