@@ -73,10 +73,13 @@ int llp_csr_build(const int64_t* edge_val, const int64_t* edge_key, int64_t num_
                   float* inv_deg /*[N] 1/max(deg,1) or NULL*/, void* workspace, size_t workspace_bytes,
                   void* stream);
 
-/* Edge-balanced work plan for llp_spmm: chunk c owns rows [first_row[c], first_row[c+1]). */
+/* Edge-balanced work plan for llp_spmm: chunk c owns rows [first_row[c], first_row[c+1]).  The plan buffer holds
+ * llp_spmm_plan_ints(num_edges) int32 (32-byte aligned): the first-row table [num_chunks+1], then one 32-byte
+ * descriptor per chunk (its edge range and first rows, so the kernel starts without chasing the tables). */
 int64_t llp_spmm_num_chunks(int64_t num_edges);
+int64_t llp_spmm_plan_ints(int64_t num_edges);
 int llp_spmm_plan(const int32_t* rowptr, int64_t num_nodes, int64_t num_edges,
-                  int32_t* chunk_first_row /*[num_chunks+1]*/, int32_t* hub_list /*[num_chunks] out*/,
+                  int32_t* chunk_first_row /*[llp_spmm_plan_ints(num_edges)]*/, int32_t* hub_list /*[num_chunks] out*/,
                   int32_t* num_hubs /*[1] device out: rows longer than the split threshold*/, void* stream);
 size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "llp_csr_build": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "llp_spmm_num_chunks": (c_int64, [c_int64]),
+    "llp_spmm_plan_ints": (c_int64, [c_int64]),
     "llp_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,

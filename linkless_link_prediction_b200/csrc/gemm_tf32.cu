@@ -45,8 +45,8 @@ constexpr int UMMA_K_TF32 = 8;     // 32 bytes of K per tcgen05.mma.kind::tf32
 // shared memory: 96 KB per 32-wide stage at N = 256 leaves room for two stages only, which leaves the TMA round trip and
 // the split pass exposed; 16-wide stages are 48 KB: four of them).  MN-major (TN) tiles keep 128-byte rows either way.
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant (warps 4..11)
-constexpr int kConvWarps = 4;      // operand splitters (warps 12..15)
-constexpr int kThreads = 512;      // warpgroup 0: TMA + MMA (+2 spare warps), 1-2: epilogue, 3: splitters
+constexpr int kConvWarps = 6;      // operand splitters (warps 12..15 and the two spare warps 2, 3 of warpgroup 0)
+constexpr int kThreads = 512;      // warpgroup 0: TMA, MMA, 2 splitters; 1-2: epilogue; 3: 4 splitters
 constexpr int kAccStages = 2;
 constexpr int kChainK = 32;        // reduction elements per accumulator chain by default (llp_set_tuning(23, k-blocks) for A/B runs)
 
@@ -78,11 +78,20 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool mn_maj
 // a TF32 ulp to the bit pattern and clear the 13 low bits.  The conversion instruction itself runs on the 16-lane
 // conversion pipe; at 24,576 conversions per 32-wide k-block it would take as long as the k-block's MMAs.
 __device__ __forceinline__ uint32_t rna_tf32_bits(uint32_t b) { return (b + 0x1000u) & 0xffffe000u; }
+// kTruncHi (experiment, llp_set_tuning(25, 1)): leave the landed tile as the high operand — the tensor core then uses its
+// upper 19 bits, i.e. x_hi = trunc_tf32(x) — and only write x_lo = x - trunc_tf32(x): 48 KB less shared-memory traffic per
+// 32-wide k-block at N = 256 (the kernel is shared-memory-bandwidth bound), |x_lo| up to 2^-10 |x| instead of 2^-11 |x|.
+__device__ __forceinline__ uint32_t lo_of_trunc(float x) {
+  const float l = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return (l == l) ? __float_as_uint(l) : 0u;
+}
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = rna_tf32_bits(__float_as_uint(x));
-  // x - hi is exact; a non-finite x keeps its value in the high part only (inf - inf would poison the product with NaN)
+  // x - hi is exact (at most 13 significant bits) and is stored as it is: the tensor core reads the upper 19 bits of an
+  // operand word, i.e. truncates the low part to TF32 — an error of 2^-22 of x, the size of the dropped lo x lo term.
+  // A non-finite x keeps its value in the high part only (inf - inf would poison the product with NaN).
   const float l = x - __uint_as_float(hi);
-  lo = (hi & 0x7f800000u) == 0x7f800000u ? 0u : rna_tf32_bits(__float_as_uint(l));
+  lo = (l == l) ? __float_as_uint(l) : 0u;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <uint32_t kRegs>
@@ -151,10 +160,51 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // Operand split, shared by the six splitter warps (ct = 0 .. 191): the measured limiter of the first version was this
+  // pass on four warps (~2,500 cycles per 32-wide k-block against 1,536 cycles of tensor time; ncu: tensor pipe 42 %).
+  auto split_loop = [&](int ct) {
+    constexpr int kVecs = Cfg::kHiBytes / 16;
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int num_kb = tile_kblocks(tile);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        uint4* hi = reinterpret_cast<uint4*>(smem + stage * Cfg::kStageBytes);
+        uint4* lo = reinterpret_cast<uint4*>(smem + stage * Cfg::kStageBytes + Cfg::kHiBytes);
+        if (p.trunc_hi) {
+#pragma unroll 4
+          for (int i = ct; i < kVecs; i += 32 * kConvWarps) {
+            const uint4 v = hi[i];
+            lo[i] = make_uint4(lo_of_trunc(__uint_as_float(v.x)), lo_of_trunc(__uint_as_float(v.y)),
+                               lo_of_trunc(__uint_as_float(v.z)), lo_of_trunc(__uint_as_float(v.w)));
+          }
+        } else {
+#pragma unroll 4
+          for (int i = ct; i < kVecs; i += 32 * kConvWarps) {
+            const uint4 v = hi[i];
+            uint4 h, l;
+            split_tf32(__uint_as_float(v.x), h.x, l.x);
+            split_tf32(__uint_as_float(v.y), h.y, l.y);
+            split_tf32(__uint_as_float(v.z), h.z, l.z);
+            split_tf32(__uint_as_float(v.w), h.w, l.w);
+            hi[i] = h;
+            lo[i] = l;
+          }
+        }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&conv_bar[stage]));
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  };
+
   const int wg = warp >> 2;
   if (wg == 0) {
     setmaxnreg_dec<56>();
-    if (warp == 0) {
+    if (warp >= 2) {
+      split_loop(128 + threadIdx.x - 64);   // warps 2, 3: splitter threads 128 .. 191
+    } else if (warp == 0) {
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -240,32 +290,7 @@ gemm_tf32x3_kernel(const __grid_constant__ Maps maps, const TcParams p) {
   } else if (wg == 3) {
     // ===================== splitters: x -> (x_hi in place, x_lo twin) =====================
     setmaxnreg_dec<56>();
-    const int ct = threadIdx.x - 32 * 12;   // 0 .. 32 * kConvWarps - 1
-    constexpr int kVecs = Cfg::kHiBytes / 16;
-    int stage = 0; uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int num_kb = tile_kblocks(tile);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        uint4* hi = reinterpret_cast<uint4*>(smem + stage * Cfg::kStageBytes);
-        uint4* lo = reinterpret_cast<uint4*>(smem + stage * Cfg::kStageBytes + Cfg::kHiBytes);
-#pragma unroll 4
-        for (int i = ct; i < kVecs; i += 32 * kConvWarps) {
-          const uint4 v = hi[i];
-          uint4 h, l;
-          split_tf32(__uint_as_float(v.x), h.x, l.x);
-          split_tf32(__uint_as_float(v.y), h.y, l.y);
-          split_tf32(__uint_as_float(v.z), h.z, l.z);
-          split_tf32(__uint_as_float(v.w), h.w, l.w);
-          hi[i] = h;
-          lo[i] = l;
-        }
-        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&conv_bar[stage]));
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      }
-    }
+    split_loop(threadIdx.x - 32 * 12);
   } else {
     // ===================== chunk promotion + epilogue: TMEM -> register accumulators -> global =====================
     setmaxnreg_inc<200>();
@@ -454,6 +479,7 @@ int gemm_nt_tf32(const llp_gemm_nt_args& a, cudaStream_t stream) {
   p.ep = EpilogueParams{a.bias, a.addend, a.ldadd, a.gate, a.ldgate, a.gate_scale, a.relu, a.dropout_p, a.seed, a.offset, a.rng_state};
   p.D = a.D; p.ldd = a.ldd; p.partial = nullptr; p.dbg = nullptr;
   p.chunk_kb = chain_kblocks(bk);
+  p.trunc_hi = g_tuning[25];
   auto ok = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 16) && (ld * 4) % 16 == 0; };
   auto ok32 = [&](const void* ptr, int64_t ld) { return ptr != nullptr && aligned(ptr, 32) && (ld * 4) % 32 == 0; };
   p.ep_flags = (a.bias != nullptr && aligned(a.bias, 16) ? kVecBias : 0) | (ok(a.addend, a.ldadd) ? kVecAddend : 0) |
@@ -477,6 +503,7 @@ int gemm_tn_tf32(int64_t M, int64_t N1, int64_t N2, const void* A, int64_t lda, 
   p.ep = EpilogueParams{};
   p.D = nullptr; p.ldd = 0; p.partial = ws; p.dbg = nullptr;
   p.chunk_kb = chain_kblocks(bk);
+  p.trunc_hi = g_tuning[25];
   if (int rc = dispatch<true>(bn, bk, maps, p, stream)) return rc;
   return splitk_reduce(ws, p.splits, N1, N2, D, ldd, accumulate, stream);
 }

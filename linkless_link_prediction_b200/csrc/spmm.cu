@@ -13,7 +13,7 @@
 //   * rows longer than kHub are split along the chunk grid: every chunk writes an fp32 partial for its
 //     slice and the fix-up pass adds the partials in chunk order -> a power-law hub cannot serialise a
 //     warp and the result has no atomics (deterministic);
-//   * rows without edges are zero-filled by the fix-up pass.
+//   * rows without edges are zero-filled by the fix-up pass (extra blocks of the same launch).
 // Design notes from the round-1 measurements (profiles/r01_spmm_*): the first version spent 76 instructions per edge
 // (inlined IEEE divisions + store code in the streaming loop, I-cache misses) and ran at 8 warps/SM because of 158
 // registers; staging rows through shared memory with cp.async.bulk (one TMA op per row) or cp.async/LDGSTS (16 B per
@@ -155,6 +155,28 @@ __device__ __forceinline__ void add_row(RowAcc<VE, NV>& acc, const uint4 (&v)[NV
   }
 }
 
+// add_row for the streaming kernel: the bf16 -> fp32 unpack is an `asm volatile`, which keeps it next to its additions.
+// Left to the compiler, the unpack of all U gathered rows is hoisted in front of the accumulation (32 extra live
+// registers for U = 4: spills under the 64-register cap the kernel's occupancy needs).
+template <typename T, int VE, int NV, bool kScale>
+__device__ __forceinline__ void add_row_pinned(RowAcc<VE, NV>& acc, const uint4 (&v)[NV], float scale) {
+  if constexpr (sizeof(T) == 2 && VE % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int i = 0; i < VE / 2; ++i) {
+        float lo, hi;
+        asm volatile("shl.b32 %0, %2, 16;\n\tand.b32 %1, %2, 0xffff0000;" : "=f"(lo), "=f"(hi) : "r"(w[i]));
+        if constexpr (kScale) fma2(acc.a[k][2 * i], acc.a[k][2 * i + 1], lo, hi, scale);
+        else add2(acc.a[k][2 * i], acc.a[k][2 * i + 1], lo, hi);
+      }
+    }
+  } else {
+    add_row<T, VE, NV, kScale>(acc, v, scale);
+  }
+}
+
 // A row [rs, re) is done for this chunk.  Rows of up to kHub edges were streamed whole and go to `out` (mean: divided
 // by the degree — an exact IEEE division in fp32 so the result is bit-identical to scatter-mean's true_divide, a
 // reciprocal multiply for bf16 outputs).  The slice of a longer (hub) row goes to this chunk's fp32 partial slot
@@ -177,7 +199,8 @@ __device__ __forceinline__ void close_row(const RowAcc<VE, NV>& acc, T* __restri
   }
   T* row = out + (int64_t)r * ldo;
   const float d = mean ? (float)deg : 1.0f;
-  const float inv = 1.0f / d;
+  float inv = 1.0f;   // bf16 outputs: reciprocal multiply (rcp.approx: 1 ulp of fp32, far below the bf16 rounding that follows)
+  if (sizeof(T) == 2) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(d));
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int col = col0 + (k * 32 + lane) * VE;
@@ -221,6 +244,26 @@ __device__ __forceinline__ ChunkRange chunk_range(const int32_t* __restrict__ ro
   return cr;
 }
 
+// Chunk descriptors for the streaming kernel, written once per graph by llp_spmm_plan: what chunk_range() derives
+// through a chain of three dependent loads (first_row -> rowptr -> rowptr) plus the first two row ends, as two 16-byte
+// vectors per chunk {r0, eb, ee, row_start} {row_end, row_end_next, -, -}.  A warp lives for ~16 gather round trips; the
+// descriptor takes four dependent round trips out of the front of every one of them.
+__global__ void spmm_desc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row, int64_t N,
+                                 int64_t n_chunks, int4* __restrict__ desc) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const ChunkRange cr = chunk_range(rowptr, first_row, (int)c);
+  int4 d0 = make_int4(cr.r0, cr.eb, cr.ee, cr.row_start), d1 = make_int4(0, 0, 0, 0);
+  if (cr.ee > cr.eb) {
+    d1.x = rowptr[cr.r0 + 1];
+    d1.y = rowptr[min((int64_t)cr.r0 + 2, N)];
+  }
+  desc[2 * c] = d0;
+  desc[2 * c + 1] = d1;
+}
+// descriptors start at the first 32-byte boundary behind the [n_chunks + 1] first-row table
+__host__ __device__ inline int64_t spmm_desc_offset_ints(int64_t n_chunks) { return (n_chunks + 1 + 7) / 8 * 8; }
+
 // Row-run traversal: the warp walks its edge range row by row; inside a row, edges are consumed in groups of up to U
 // whose gathers are all issued before the first one is used.  Every branch is warp-uniform and there is no per-edge
 // boundary test: a group never crosses a row end (or the 32-wide index batch held in registers), so the inner body is
@@ -229,24 +272,10 @@ template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks>
 __global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
 spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ first_row,
             int n_chunks, const T* __restrict__ x, int ldx, int F, const float* __restrict__ src_scale, int mean,
-            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int zero_rows_per_warp,
-            int n_edges) {
+            T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int fake_seq_n, int n_rows, int n_edges) {
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
   if (c >= n_chunks) return;
-  // Rows without edges get zeros.  They are spread over the warps by row index (not by edge ownership), so a long run
-  // of isolated nodes cannot pile up on one warp.
-  for (int rb = c * zero_rows_per_warp; rb < min(n_rows, (c + 1) * zero_rows_per_warp); rb += 32) {
-    const int rr = rb + lane;
-    const bool empty = rr < min(n_rows, (c + 1) * zero_rows_per_warp) && rowptr[rr + 1] == rowptr[rr];
-    unsigned m = __ballot_sync(0xffffffffu, empty);
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      T* row = out + (int64_t)(rb + j) * ldo;
-      for (int f = lane; f < F; f += 32) row[f] = from_f32<T>(0.0f);
-    }
-  }
   const ChunkRange cr = chunk_range(rowptr, first_row, c);
   if (cr.ee <= cr.eb) return;
   const int cb = c * kEPW;
@@ -345,57 +374,219 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
   }
 }
 
-// Fix-up: one block per hub row adds the row's fp32 partials.  Warp w sums the partials w, w+8, ... (8 x 16 bytes in
-// flight per lane), the eight warp sums are combined in warp order through shared memory: a fixed association, so the
-// result is deterministic, and a 12k-edge hub (200 partials) costs a few microseconds instead of one long serial chain.
+// Streaming variant for rows that are exactly one pass of the warp (F == 32 * VE * NV: 128 / 256 / 512 bf16, 64 / 128 /
+// 256 fp32 — every width the C3-C5 encoders aggregate).  Same chunk plan, same per-row summation order, same split-row
+// partials as spmm_kernel (bit-identical results); what changes is that the LOAD groups are decoupled from the rows.
+// spmm_kernel never lets a group of U gathers cross a row end, so at an average degree of ~10 a third of the groups are
+// partial: fewer loads in flight and the ~58-instruction guarded path.  Here the warp walks its edge range in U-aligned
+// groups of exactly U gathers whatever rows they belong to (the 32-wide index batches are 32-aligned and U divides 32, so
+// a group never straddles a batch either): shuffle, one multiply-add for the address, load — no predicate.  The first
+// and last group of a chunk may hold edges of the neighbouring chunks (real edges, so the loads are safe; they are not
+// accumulated).  A group that lies inside one row and inside the chunk's range — the common case — is then U unguarded
+// adds; any other group is walked in row pieces: each finished row is closed at ONE out-of-line site, each piece is a
+// fall-through chain of adds entered at its first edge and left at its last (one warp-uniform test per edge).  The next
+// row end is fetched one row ahead so that closing a row never waits on memory.
+// (ncu, C4 F = 256 bf16: 41 -> STREAM_INSTR warp instructions per edge.)
+#define LLP_STREAM_ADD(k_)                                                    \
+  {                                                                           \
+    float sc = 1.0f;                                                          \
+    if constexpr (kScale) sc = __shfl_sync(0xffffffffu, mys, o + (k_));       \
+    add_row_pinned<T, VE, NV, kScale>(acc, v[k_], sc);                        \
+  }
+template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks>
+__global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
+spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int4* __restrict__ desc,
+                   int n_chunks, const T* __restrict__ x, int ldx, int F, const float* __restrict__ src_scale, int mean,
+                   T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int n_rows, int n_edges) {
+  static_assert(U == 2 || U == 4 || U == 8, "load groups of 2, 4 or 8 (a group must not straddle a 32-wide index batch)");
+  const int lane = threadIdx.x & 31;
+  const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (c >= n_chunks) return;
+  const int4 d0 = __ldg(desc + 2 * c), d1 = __ldg(desc + 2 * c + 1);
+  struct { int r0, eb, ee, row_start; } cr = {d0.x, d0.y, d0.z, d0.w};
+  if (cr.ee <= cr.eb) return;
+  const uint32_t ld_bytes = (uint32_t)ldx * (uint32_t)sizeof(T);
+  const char* xlane = reinterpret_cast<const char*>(x + lane * VE);
+  RowAcc<VE, NV> acc;
+  acc.zero();
+  int r = cr.r0;
+  int row_start = cr.row_start;
+  int row_end = d1.x;
+  int row_end_next = d1.y;
+  int e = cr.eb & ~(U - 1);
+  int u = cr.eb - e;                         // first edge of the group to accumulate: > 0 only in the chunk's first group
+  // the 32-wide index batch holding edge e is the 32-aligned one (e is U-aligned, U divides 32): lane i has col[(e & ~31) + i]
+  auto fetch_idx = [&](int b) {
+    const int i = b + lane;
+    return (i < n_edges) ? __ldg(col + i) : 0;
+  };
+  int my = fetch_idx(e & ~31), my_next = fetch_idx((e & ~31) + 32);
+  float mys = 1.0f, mys_next = 1.0f;
+  if constexpr (kScale) { mys = __ldg(src_scale + my); mys_next = __ldg(src_scale + my_next); }
+  const int ee = cr.ee;
+  while (e < ee) {
+    const int o = e & 31;
+    uint4 v[U][NV];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int src = __shfl_sync(0xffffffffu, my, o + k);
+      const char* row = xlane + (uint64_t)((uint32_t)src) * ld_bytes;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[k][j] = load_vec<T, VE>(reinterpret_cast<const T*>(row) + j * 32 * VE);
+    }
+    if (u == 0 && min(row_end, ee) - e >= U) {   // the whole group continues the open row: no test per edge
+#pragma unroll
+      for (int k = 0; k < U; ++k) LLP_STREAM_ADD(k)
+    } else {
+      const int u_end = min(U, ee - e);      // < U only in the chunk's last group
+      while (u < u_end) {                    // one trip per row piece inside the group; every test is warp-uniform
+        while (e + u == row_end) {           // edge e + u opens a new row: close the finished one, skip empty rows
+          if (row_end > row_start) {
+            close_row<T, VE, NV>(acc, out, ldo, F, r, 0, lane, mean, row_start, row_end, c * kEPW, c, partial);
+            acc.zero();
+          }
+          ++r;
+          row_start = row_end;
+          row_end = row_end_next;
+          row_end_next = rowptr[min(r + 2, n_rows)];
+        }
+        const int stop = min(u_end, row_end - e);   // > u
+        switch (u) {                         // enter at the piece's first edge, leave after its last
+          case 0: LLP_STREAM_ADD(0) if (stop == 1) break;  // fall through
+          case 1: LLP_STREAM_ADD(1) if (U == 2 || stop == 2) break;
+          case 2: if constexpr (U > 2) { LLP_STREAM_ADD(2) } if (stop == 3) break;
+          case 3: if constexpr (U > 2) { LLP_STREAM_ADD(3) } if (U == 4 || stop == 4) break;
+          case 4: if constexpr (U > 4) { LLP_STREAM_ADD(4) } if (stop == 5) break;
+          case 5: if constexpr (U > 4) { LLP_STREAM_ADD(5) } if (stop == 6) break;
+          case 6: if constexpr (U > 4) { LLP_STREAM_ADD(6) } if (stop == 7) break;
+          case 7: if constexpr (U > 4) { LLP_STREAM_ADD(7) } break;
+        }
+        u = stop;
+      }
+      u = 0;
+    }
+    e += U;
+    if ((e & 31) == 0) {   // next index batch (already in registers), prefetch the one after
+      my = my_next;
+      my_next = fetch_idx(e + 32);
+      if constexpr (kScale) { mys = mys_next; mys_next = __ldg(src_scale + my_next); }
+    }
+  }
+  close_row<T, VE, NV>(acc, out, ldo, F, r, 0, lane, mean, row_start, row_end, c * kEPW, c, partial);
+}
+#undef LLP_STREAM_ADD
+
+// Fix-up: adds the fp32 partials of every hub row.  A block takes eight hubs.  Most hubs are barely longer than a chunk
+// (C4: 2,870 rows above 64 edges, 1,850 of them below 128), so a warp first combines its own hub alone when it has at
+// most eight partials: eight independent 16-byte loads per lane and pass, added in chunk order.  Longer hubs are then
+// taken one after the other by the whole block: warp w sums the partials w, w+8, ... (8 x 16 bytes in flight per lane),
+// the eight warp sums are combined in warp order through shared memory — the same association as the single-warp path
+// for up to eight partials, so the result does not depend on which path a hub takes; deterministic, and a 12k-edge hub
+// (200 partials) costs a few microseconds instead of one long serial chain.
 constexpr int kFixTile = 1024;  // floats per column tile (8 warps x 4 KB of shared memory)
+constexpr int kFixHubsPerBlock = 8;
+constexpr int kFixZeroRows = 2048;   // rows scanned per zero-fill block
 template <typename T>
 __global__ void __launch_bounds__(256)
 spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
-                  const int32_t* __restrict__ hub_list, int F, int mean, T* __restrict__ out, int64_t ldo,
-                  const float* __restrict__ partial) {
+                  const int32_t* __restrict__ hub_list, int num_hubs, int hub_blocks, int n_rows, int F, int mean,
+                  T* __restrict__ out, int64_t ldo, const float* __restrict__ partial) {
   __shared__ float red[8][kFixTile];
+  __shared__ int big[kFixHubsPerBlock];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = hub_list[blockIdx.x];
-  const int rp = first_row[c] - 1;
-  const int ps = rowptr[rp], pe = rowptr[rp + 1];
-  const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
-  const float divisor = mean ? (float)(pe - ps) : 1.0f;
-  auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
-  for (int f0 = 0; f0 < F; f0 += kFixTile) {
-    const int fw = min(kFixTile, F - f0);
-    if (F % 4 == 0) {  // 128-bit loads: a 256-float row is two passes of the warp
-      for (int f = lane * 4; f < fw; f += 128) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int k = w;
-        for (; k + 56 < n_part; k += 64) {
+  if ((int)blockIdx.x >= hub_blocks) {
+    // the blocks behind the hub blocks zero-fill the rows without edges (kFixZeroRows rows per block, one row per lane
+    // and pass; the warp then writes each empty row together): the main kernels only ever write rows that own edges
+    const int base = ((int)blockIdx.x - hub_blocks) * kFixZeroRows + w * (kFixZeroRows / 8);
+#pragma unroll 1
+    for (int rb = base; rb < min(n_rows, base + kFixZeroRows / 8); rb += 32) {
+      const int rr = rb + lane;
+      const bool empty = rr < min(n_rows, base + kFixZeroRows / 8) && rowptr[rr + 1] == rowptr[rr];
+      unsigned m = __ballot_sync(0xffffffffu, empty);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        T* row = out + (int64_t)(rb + j) * ldo;
+        for (int f = lane; f < F; f += 32) row[f] = from_f32<T>(0.0f);
+      }
+    }
+    return;
+  }
+  {
+    const int h = blockIdx.x * kFixHubsPerBlock + w;
+    bool is_big = false;
+    if (h < num_hubs) {
+      const int c = hub_list[h];
+      const int rp = first_row[c] - 1;
+      const int ps = rowptr[rp], pe = rowptr[rp + 1];
+      const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
+      if (n_part <= 8 && F % 4 == 0) {
+        const float divisor = mean ? (float)(pe - ps) : 1.0f;
+        const float* p0 = partial + ((int64_t)(c - 1) * 2 + 1) * F;   // partial k >= 1 lies at p0 + (2k - 1) * F
+        for (int f = lane * 4; f < F; f += 128) {
           float4 t[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(part_ptr(k + 8 * i) + f0 + f));
+          for (int k = 0; k < 8; ++k)
+            t[k] = k < n_part ? __ldg(reinterpret_cast<const float4*>(p0 + (k == 0 ? 0 : (int64_t)(2 * k - 1) * F) + f))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 acc = t[0];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+          for (int k = 1; k < 8; ++k) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+          float r[4] = {__fdiv_rn(acc.x, divisor), __fdiv_rn(acc.y, divisor), __fdiv_rn(acc.z, divisor), __fdiv_rn(acc.w, divisor)};
+          T* dst = out + (int64_t)rp * ldo + f;
+          if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+          else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
         }
-        for (; k < n_part; k += 8) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(part_ptr(k) + f0 + f));
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-        *reinterpret_cast<float4*>(&red[w][f]) = acc;
-      }
-    } else {
-      for (int f = lane; f < fw; f += 32) {
-        float acc = 0.0f;
-        for (int k = w; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
-        red[w][f] = acc;
+      } else {
+        is_big = true;
       }
     }
-    __syncthreads();
-    for (int f = threadIdx.x; f < fw; f += 256) {
-      float acc = red[0][f];
+    if (lane == 0) big[w] = is_big;
+  }
+  __syncthreads();
+  for (int j = 0; j < kFixHubsPerBlock; ++j) {
+    if (!big[j]) continue;   // block-uniform
+    const int c = hub_list[blockIdx.x * kFixHubsPerBlock + j];
+    const int rp = first_row[c] - 1;
+    const int ps = rowptr[rp], pe = rowptr[rp + 1];
+    const int n_part = (pe - 1) / kEPW - c + 2;
+    const float divisor = mean ? (float)(pe - ps) : 1.0f;
+    auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
+    for (int f0 = 0; f0 < F; f0 += kFixTile) {
+      const int fw = min(kFixTile, F - f0);
+      if (F % 4 == 0) {  // 128-bit loads: a 256-float row is two passes of the warp
+        for (int f = lane * 4; f < fw; f += 128) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          int k = w;
+          for (; k + 56 < n_part; k += 64) {
+            float4 t[8];
 #pragma unroll
-      for (int i = 1; i < 8; ++i) acc += red[i][f];
-      out[(int64_t)rp * ldo + f0 + f] = from_f32<T>(__fdiv_rn(acc, divisor));
+            for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(part_ptr(k + 8 * i) + f0 + f));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+          }
+          for (; k < n_part; k += 8) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(part_ptr(k) + f0 + f));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          *reinterpret_cast<float4*>(&red[w][f]) = acc;
+        }
+      } else {
+        for (int f = lane; f < fw; f += 32) {
+          float acc = 0.0f;
+          for (int k = w; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
+          red[w][f] = acc;
+        }
+      }
+      __syncthreads();
+      for (int f = threadIdx.x; f < fw; f += 256) {
+        float acc = red[0][f];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) acc += red[i][f];
+        out[(int64_t)rp * ldo + f0 + f] = from_f32<T>(__fdiv_rn(acc, divisor));
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -420,13 +611,22 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   T* out = reinterpret_cast<T*>(out_);
   float* partial = reinterpret_cast<float*>(ws);
   const int n_chunks = (int)llp_spmm_num_chunks(E);
+  const int4* desc = reinterpret_cast<const int4*>(first_row + spmm_desc_offset_ints(n_chunks));
   constexpr int VE = Vec16<T>::n;
   const bool vec = aligned(x, 16) && aligned(out, 16) && (ldx * sizeof(T)) % 16 == 0 && (ldo * sizeof(T)) % 16 == 0 &&
                    F % VE == 0;
   const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
   if (E > 0) {
+    // rows of exactly one warp pass go to the streaming kernel (llp_set_tuning(3, 1): always the row-run kernel; A/B knob,
+    // the two are bit-identical)
+    const int stream_mode = LLP_SPMM_FAKE(N) != 0 ? 1 : g_tuning[3];   // 0: rows of one 16-byte (or 8-byte) vector per lane; 1: never; 2: every full-width row
 #define LLP_SPMM_LAUNCH(VE_, NV_, U_, MB_) \
-  spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, LLP_SPMM_FAKE(N), (int)N, (int)ceil_div(N, n_chunks), (int)E)
+  do { \
+    if (stream_mode != 1 && F == 32 * (VE_) * (NV_) && ((NV_) == 1 || stream_mode == 2)) \
+      spmm_stream_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, desc, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, (int)N, (int)E); \
+    else \
+      spmm_kernel<T, VE_, NV_, U_, kScale, MB_><<<blocks, kSpmmThreads, 0, stream>>>(rowptr, col, first_row, LLP_SPMM_CHUNKS(n_chunks), x, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, LLP_SPMM_FAKE(N), (int)N, (int)E); \
+  } while (0)
     const int variant = g_spmm_variant;  // occupancy/register trade-off (llp_set_tuning(0, v)): 0 = 8 blocks/SM (<=64 regs)
     const bool vec8 = aligned(x, 8) && aligned(out, 8) && (ldx * sizeof(T)) % 8 == 0 && (ldo * sizeof(T)) % 8 == 0 &&
                       F % (VE / 2) == 0 && F * (int64_t)sizeof(T) <= 256;
@@ -436,7 +636,8 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
       if (F * (int64_t)sizeof(T) <= 512) {
         // default: groups of 4 gathers (with an average degree of ~10 far more groups are full, i.e. take the predicate-free
         // path, than with groups of 8: 189 / 208 us vs 200 / 226 us forward / transpose at F = 256 bf16 on the C4 graph)
-        if (variant == 1) LLP_SPMM_LAUNCH(VE, 1, 8, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 1, 8, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 1, 8, 8); else LLP_SPMM_LAUNCH(VE, 1, 4, 8);
+        if (variant == 1) LLP_SPMM_LAUNCH(VE, 1, 8, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 1, 8, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 1, 8, 8);
+        else if (variant == 4) LLP_SPMM_LAUNCH(VE, 1, 2, 10); else if (variant == 5) LLP_SPMM_LAUNCH(VE, 1, 4, 10); else if (variant == 6) LLP_SPMM_LAUNCH(VE, 1, 2, 12); else LLP_SPMM_LAUNCH(VE, 1, 4, 8);
       } else {
         if (variant == 1) LLP_SPMM_LAUNCH(VE, 2, 4, 6); else if (variant == 2) LLP_SPMM_LAUNCH(VE, 2, 4, 5); else if (variant == 3) LLP_SPMM_LAUNCH(VE, 2, 2, 8); else LLP_SPMM_LAUNCH(VE, 2, 4, 8);
       }
@@ -446,10 +647,13 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
 #undef LLP_SPMM_LAUNCH
     LLP_LAUNCH_OK();
   }
-  if (E > 0 && num_hubs > 0) {
-    spmm_fixup_kernel<T><<<(unsigned)num_hubs, 256, 0, stream>>>(rowptr, first_row, hub_list, (int)F, mean, out, ldo, partial);
+  if (E > 0) {   // hub rows: add the partials; rows without edges: zeros (the main kernel writes neither)
+    const int hub_blocks = (int)ceil_div(num_hubs, kFixHubsPerBlock);
+    const unsigned fix_blocks = (unsigned)(hub_blocks + ceil_div(N, kFixZeroRows));
+    spmm_fixup_kernel<T><<<fix_blocks, 256, 0, stream>>>(rowptr, first_row, hub_list, num_hubs, hub_blocks, (int)N, (int)F, mean,
+                                                        out, ldo, partial);
     LLP_LAUNCH_OK();
-  } else if (E == 0) {
+  } else {
     LLP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(T), 0, (size_t)F * sizeof(T), (size_t)N, stream));
   }
   return 0;
@@ -473,6 +677,11 @@ extern "C" void llp_set_tuning(int key, int value) {
 
 extern "C" int64_t llp_spmm_num_chunks(int64_t E) { return E <= 0 ? 1 : ceil_div(E, kEPW); }
 
+extern "C" int64_t llp_spmm_plan_ints(int64_t E) {
+  const int64_t n_chunks = llp_spmm_num_chunks(E);
+  return spmm_desc_offset_ints(n_chunks) + 8 * n_chunks;
+}
+
 extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_t* chunk_first_row, int32_t* hub_list,
                              int32_t* num_hubs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -480,6 +689,9 @@ extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_
   if (int rc = check_device()) return rc;
   int64_t n_chunks = llp_spmm_num_chunks(E);
   spmm_plan_kernel<<<(unsigned)ceil_div(n_chunks + 1, 256), 256, 0, stream>>>(rowptr, N, n_chunks, chunk_first_row);
+  LLP_LAUNCH_OK();
+  spmm_desc_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(
+      rowptr, chunk_first_row, N, n_chunks, reinterpret_cast<int4*>(chunk_first_row + spmm_desc_offset_ints(n_chunks)));
   LLP_LAUNCH_OK();
   LLP_CUDA(cudaMemsetAsync(num_hubs, 0, sizeof(int32_t), stream));
   if (n_chunks > 1) {

@@ -20,6 +20,7 @@ struct TcParams {
   void* D; int64_t ldd;
   float* partial;        // TN: [splits][M][N] fp32
   int chunk_kb;          // 3xTF32 kernels: k-blocks per accumulator chain (chunked promotion)
+  int trunc_hi;          // 3xTF32 kernels: experiment, see gemm_tf32.cu
   long long* dbg;        // instrumentation (llp_set_tuning(15, 1)): per CTA {issue loop ns, operand wait ns, accumulator wait ns}
 };
 

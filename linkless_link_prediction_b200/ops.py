@@ -267,7 +267,7 @@ def _build_csr(val: torch.Tensor, key: torch.Tensor, num_rows: int, want_inv: bo
     inv = torch.empty(max(num_rows, 1), dtype=torch.float32, device=dev) if want_inv else None
     N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, num_rows, rowptr.data_ptr(), col.data_ptr(),
                               perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
-    plan = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+    plan = torch.empty(lib.llp_spmm_plan_ints(E), dtype=torch.int32, device=dev)   # torch allocations are 512-byte aligned
     hub_list = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
     n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
     N.check(lib.llp_spmm_plan(rowptr.data_ptr(), num_rows, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),

@@ -431,10 +431,10 @@ def test_norm_layers_and_l2_normalize_match_torch_formula(cuda, mode, norm_type)
         (out.float() * w.to(cuda)).sum().backward()
         torch.testing.assert_close(out.float().cpu(), out_ref.detach(), **tol)
         # the bias in front of a batch norm has an analytically ZERO gradient (the norm removes the mean): errors are
-        # bounded against the larger of the tensor's own norm and 1e-3 of the largest gradient norm of the model
+        # bounded against the larger of the tensor's own norm and 1e-3 (bf16: 2e-2) of the largest gradient norm of the model
         scale = max(float(q.grad.norm()) for q in ref_params)
         for p, q in zip(dev_model.parameters(), ref_params):
-            err = float((p.grad.cpu() - q.grad).norm()) / max(float(q.grad.norm()), 1e-3 * scale)
+            err = float((p.grad.cpu() - q.grad).norm()) / max(float(q.grad.norm()), (1e-3 if mode == torch.float32 else 2e-2) * scale)
             assert err < (1e-4 if mode == torch.float32 else 1.5e-1), err
 
     norm = (lambda h, wgt, b: F.batch_norm(h, None, None, wgt, b, True)) if norm_type == "batch" else \
@@ -471,3 +471,24 @@ def test_norm_layers_and_l2_normalize_match_torch_formula(cuda, mode, norm_type)
         return h
 
     check(sage, sage_ref, (x.to(cuda), ei.to(cuda)))
+
+
+@pytest.mark.parametrize("setting", ["transductive", "production"])
+def test_teacher_then_student_drivers_run_end_to_end(cuda, tmp_path, monkeypatch, setting):
+    """scripts/supervised_*.sh followed by scripts/LLP_*.sh: the teacher driver writes ../saved-models and
+    ../saved-features, the student driver (main.py) loads them through the reference's file names, trains with
+    LLP_D + LLP_R + True_label on the SAME split (one shared loader) and writes its result file — both settings."""
+    work = tmp_path / "src"
+    work.mkdir()
+    monkeypatch.chdir(work)
+    common = ["--datasets=cora", "--encoder=sage", f"--transductive={setting}", "--runs=1", "--epochs=2",
+              "--synthetic_scale=0.2", "--precision=fp32"]
+    teacher.main(common + ["--hidden_channels=256", "--batch_size=512"])   # the student hard-codes a 256-wide teacher predictor
+    assert (tmp_path / "saved-models" / f"cora-sage_{setting}.pkl").exists()
+    student.main(common + ["--hidden_channels=256", "--link_batch_size=512", "--LLP_D=1", "--LLP_R=1", "--True_label=1",
+                           "--dropout=0.0", "--rw_step=2", "--hops=2", "--ns_rate=1"])
+    out = (tmp_path / "results" / f"cora_KD_{setting}.txt").read_text()
+    assert "LLP (Relational Distillation)" in out and "All runs:" in out and "AUC" in out
+    if setting == "production":
+        assert "Final new_new" in out
+    ops.set_compute_dtype(torch.bfloat16)

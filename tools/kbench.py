@@ -58,6 +58,23 @@ def main():
                 report(f"variant {variant}: spmm fwd {dt} F={F}", timeit(lambda: g.spmm(x)), nbytes=nb)
                 report(f"variant {variant}: spmm bwd {dt} F={F}", timeit(lambda: g.spmm(x, transpose=True)), nbytes=nb)
         N.load().llp_set_tuning(0, 0)
+    if "spmmab" in which:   # row-run kernel (llp_set_tuning(3, 1)) vs streaming kernel (3, 0), per occupancy / group variant
+        lib = N.load()
+        for dt, F in ((torch.bfloat16, 256), (torch.bfloat16, 128), (torch.float32, 256), (torch.float32, 128)):
+            x = torch.randn(n, F, device=dev).to(dt)
+            s = x.element_size()
+            nb = E * F * s + n * F * s + 4 * E + 4 * (n + 1)
+            lib.llp_set_tuning(3, 1); lib.llp_set_tuning(0, 0)
+            ref_f, ref_b = g.spmm(x), g.spmm(x, transpose=True)
+            for stream, pf in ((1, 0), (2, 0)):
+                for variant in (0, 4, 5, 6):
+                    lib.llp_set_tuning(3, stream); lib.llp_set_tuning(0, variant); lib.llp_set_tuning(4, 1 if pf else 0)
+                    same = bool(torch.equal(g.spmm(x), ref_f) and torch.equal(g.spmm(x, transpose=True), ref_b))
+                    tag = f"{ {1: 'row-run', 2: 'stream '}[stream]}{' +L2 prefetch' if pf else ''} variant {variant} {str(dt)[6:]} F={F} same={same}"
+                    report(f"{tag} fwd", timeit(lambda: g.spmm(x)), nbytes=nb)
+                    report(f"{tag} bwd", timeit(lambda: g.spmm(x, transpose=True)), nbytes=nb + 4 * n)
+        lib.llp_set_tuning(4, 0)
+        lib.llp_set_tuning(3, 0); lib.llp_set_tuning(0, 0)
     if "spmmexp" in which:
         N.load().llp_set_tuning(0, 0)
         x = torch.randn(n, 256, device=dev).bfloat16()

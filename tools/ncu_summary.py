@@ -32,6 +32,12 @@ KEEP = [
     "launch__block_size",
     "launch__shared_mem_per_block_dynamic",
     "sm__cycles_elapsed.max",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "sm__inst_executed_pipe_lsu.sum",
+    "l1tex__t_sector_hit_rate.pct",
 ]
 
 
