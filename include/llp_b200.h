@@ -79,8 +79,12 @@ int llp_csr_build(const int64_t* edge_val, const int64_t* edge_key, int64_t num_
 int64_t llp_spmm_num_chunks(int64_t num_edges);
 int64_t llp_spmm_plan_ints(int64_t num_edges);
 int llp_spmm_plan(const int32_t* rowptr, int64_t num_nodes, int64_t num_edges,
-                  int32_t* chunk_first_row /*[llp_spmm_plan_ints(num_edges)]*/, int32_t* hub_list /*[num_chunks] out*/,
-                  int32_t* num_hubs /*[1] device out: rows longer than the split threshold*/, void* stream);
+                  int32_t* chunk_first_row /*[llp_spmm_plan_ints(num_edges)]*/,
+                  int32_t* hub_list /*[4*(num_chunks+1)] out, 16-byte aligned: hub table = header {n_small, n_big, index of
+                                       the first big record, -} + one record {chunk, row, begin, end} per split row; small
+                                       hubs fill records 1.., big ones the last records downwards.  A compacted copy
+                                       (header, small records, big records; header[2] = n_small + n_big) works as well */,
+                  int32_t* num_hubs /*[1] device out: rows longer than the split threshold (small + big)*/, void* stream);
 size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 
 /* CSR gather-reduce SpMM: out[r,:] = (mean ? 1/max(deg r,1) : 1) * sum_{e in row r} scale[col e] * x[col e,:]
@@ -91,7 +95,8 @@ size_t llp_spmm_workspace_bytes(int64_t num_edges, int64_t feat);
 int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
              int64_t num_rows, int64_t num_edges, const void* x, int64_t ldx, int64_t feat,
              const float* src_scale, int mean, void* out, int64_t ldo, void* workspace,
-             const int32_t* hub_list, int64_t num_hubs /* from llp_spmm_plan (host copy of *num_hubs) */, void* stream);
+             const int32_t* hub_list /* the hub table of llp_spmm_plan */, int64_t num_hubs /* host copy of *num_hubs */,
+             void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Dense layers.  Replaces cuBLAS SGEMM behind F.linear (sageconv_updated.py:71,76; PyG

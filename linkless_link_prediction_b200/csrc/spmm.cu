@@ -29,16 +29,27 @@ constexpr int kEPW = 64;    // nominal edges per warp-chunk (32 and 128 were mea
 constexpr int kHub = 64;    // rows with more edges than this are split along the chunk grid (>= kEPW; 128 and 256 measured: longer warp tails)
 constexpr int kSpmmThreads = 128;
 
-// Hub list: chunk c is appended when it is the FIRST continuation chunk of a row longer than kHub (that row started in
-// chunk c-1).  One entry per hub row; the order of the list does not matter (every hub is combined independently).
+// Hub table: one record {c, row, row begin, row end} per row longer than kHub, appended by the FIRST continuation chunk
+// c of that row (the row started in chunk c-1).  Record 0 is the header {n_small, n_big, index of big hub 0, -}: hubs of
+// at most kFixWarpParts partials ("small": one warp of the fix-up kernel combines them) fill the records from 1 upwards,
+// longer ones ("big": one block each) from the last record downwards.  The order inside either group does not matter
+// (every hub is combined independently of the others).
+constexpr int kFixWarpParts = 8;
 __global__ void spmm_hub_list_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
-                                     int64_t n_chunks, int32_t* __restrict__ hub_list, int32_t* __restrict__ num_hubs) {
+                                     int64_t n_chunks, int4* __restrict__ hub_tbl, int32_t* __restrict__ num_hubs) {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x + 1;
   if (c >= n_chunks) return;
   const int r0 = first_row[c];
   if (r0 == 0) return;
   const int ps = rowptr[r0 - 1], pe = rowptr[r0];
-  if (pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1) hub_list[atomicAdd(num_hubs, 1)] = (int32_t)c;
+  if (pe > c * kEPW && pe - ps > kHub && ps / kEPW == c - 1) {
+    const int n_part = (pe - 1) / kEPW - (int)c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
+    int32_t* hdr = reinterpret_cast<int32_t*>(hub_tbl);
+    const int4 rec = make_int4((int)c, r0 - 1, ps, pe);
+    if (n_part <= kFixWarpParts) hub_tbl[1 + atomicAdd(hdr + 0, 1)] = rec;
+    else hub_tbl[n_chunks - atomicAdd(hdr + 1, 1)] = rec;
+    atomicAdd(num_hubs, 1);
+  }
 }
 
 __global__ void spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t N, int64_t n_chunks,
@@ -249,9 +260,10 @@ __device__ __forceinline__ ChunkRange chunk_range(const int32_t* __restrict__ ro
 // vectors per chunk {r0, eb, ee, row_start} {row_end, row_end_next, -, -}.  A warp lives for ~16 gather round trips; the
 // descriptor takes four dependent round trips out of the front of every one of them.
 __global__ void spmm_desc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row, int64_t N,
-                                 int64_t n_chunks, int4* __restrict__ desc) {
+                                 int64_t n_chunks, int4* __restrict__ desc, int4* __restrict__ hub_tbl) {
   const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= n_chunks) return;
+  if (c == 0) hub_tbl[0] = make_int4(0, 0, (int)n_chunks, 0);   // header of the hub table (spmm_hub_list_kernel)
   const ChunkRange cr = chunk_range(rowptr, first_row, (int)c);
   int4 d0 = make_int4(cr.r0, cr.eb, cr.ee, cr.row_start), d1 = make_int4(0, 0, 0, 0);
   if (cr.ee > cr.eb) {
@@ -421,8 +433,10 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     return (i < n_edges) ? __ldg(col + i) : 0;
   };
   int my = fetch_idx(e & ~31), my_next = fetch_idx((e & ~31) + 32);
-  float mys = 1.0f, mys_next = 1.0f;
-  if constexpr (kScale) { mys = __ldg(src_scale + my); mys_next = __ldg(src_scale + my_next); }
+  // the scale of the CURRENT batch is requested when the batch becomes current (its indices are in registers by then)
+  // and first read behind the batch's first gathers; requesting it for the NEXT batch would wait on that batch's indices
+  float mys = 1.0f;
+  if constexpr (kScale) mys = __ldg(src_scale + my);
   const int ee = cr.ee;
   while (e < ee) {
     const int o = e & 31;
@@ -468,124 +482,131 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     e += U;
     if ((e & 31) == 0) {   // next index batch (already in registers), prefetch the one after
       my = my_next;
+      if constexpr (kScale) mys = __ldg(src_scale + my);
       my_next = fetch_idx(e + 32);
-      if constexpr (kScale) { mys = mys_next; mys_next = __ldg(src_scale + my_next); }
     }
   }
   close_row<T, VE, NV>(acc, out, ldo, F, r, 0, lane, mean, row_start, row_end, c * kEPW, c, partial);
 }
 #undef LLP_STREAM_ADD
 
-// Fix-up: adds the fp32 partials of every hub row.  A block takes eight hubs.  Most hubs are barely longer than a chunk
-// (C4: 2,870 rows above 64 edges, 1,850 of them below 128), so a warp first combines its own hub alone when it has at
-// most eight partials: eight independent 16-byte loads per lane and pass, added in chunk order.  Longer hubs are then
-// taken one after the other by the whole block: warp w sums the partials w, w+8, ... (8 x 16 bytes in flight per lane),
-// the eight warp sums are combined in warp order through shared memory — the same association as the single-warp path
-// for up to eight partials, so the result does not depend on which path a hub takes; deterministic, and a 12k-edge hub
-// (200 partials) costs a few microseconds instead of one long serial chain.
-constexpr int kFixTile = 1024;  // floats per column tile (8 warps x 4 KB of shared memory)
+// Fix-up: adds the fp32 partials of every hub row and zero-fills the rows without edges.  Most hubs are barely longer
+// than a chunk (C4: 2,870 rows above 64 edges, 1,850 of them below 128): a hub of at most kFixWarpParts partials is
+// combined by ONE warp — eight independent 16-byte loads per lane and pass, added in chunk order — eight such hubs per
+// block.  A longer hub is cut into slices of 128 columns and each (hub, slice) is taken by a whole block, before the small
+// hubs (the longest hub is the critical path of the launch: every other SM idles behind it): warp w sums the partials
+// w, w+8, ... (8 x 16 bytes in flight per lane) and the eight warp sums are combined in warp order through shared memory — for up to eight partials the same association as the
+// single-warp path, so a result never depends on the path; deterministic, and a 12k-edge hub (200 partials) costs a few
+// microseconds instead of one long serial chain.  The hub records carry the row and its bounds (no table chasing).
 constexpr int kFixHubsPerBlock = 8;
 constexpr int kFixZeroRows = 2048;   // rows scanned per zero-fill block
 template <typename T>
 __global__ void __launch_bounds__(256)
-spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ first_row,
-                  const int32_t* __restrict__ hub_list, int num_hubs, int hub_blocks, int n_rows, int F, int mean,
-                  T* __restrict__ out, int64_t ldo, const float* __restrict__ partial) {
-  __shared__ float red[8][kFixTile];
-  __shared__ int big[kFixHubsPerBlock];
+spmm_fixup_kernel(const int32_t* __restrict__ rowptr, const int4* __restrict__ hub_tbl, int hub_blocks, int n_rows, int F,
+                  int mean, T* __restrict__ out, int64_t ldo, const float* __restrict__ partial) {
+  __shared__ float red[8][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if ((int)blockIdx.x >= hub_blocks) {
     // the blocks behind the hub blocks zero-fill the rows without edges (kFixZeroRows rows per block, one row per lane
     // and pass; the warp then writes each empty row together): the main kernels only ever write rows that own edges
     const int base = ((int)blockIdx.x - hub_blocks) * kFixZeroRows + w * (kFixZeroRows / 8);
-#pragma unroll 1
-    for (int rb = base; rb < min(n_rows, base + kFixZeroRows / 8); rb += 32) {
-      const int rr = rb + lane;
-      const bool empty = rr < min(n_rows, base + kFixZeroRows / 8) && rowptr[rr + 1] == rowptr[rr];
-      unsigned m = __ballot_sync(0xffffffffu, empty);
+    const int lim = min(n_rows, base + kFixZeroRows / 8);
+    bool empty[kFixZeroRows / 8 / 32];
+#pragma unroll
+    for (int i = 0; i < kFixZeroRows / 8 / 32; ++i) {   // all loads first: one round trip for the warp's 256 rows
+      const int rr = base + i * 32 + lane;
+      empty[i] = rr < lim && rowptr[rr + 1] == rowptr[rr];
+    }
+#pragma unroll
+    for (int i = 0; i < kFixZeroRows / 8 / 32; ++i) {
+      unsigned m = __ballot_sync(0xffffffffu, empty[i]);
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        T* row = out + (int64_t)(rb + j) * ldo;
+        T* row = out + (int64_t)(base + i * 32 + j) * ldo;
         for (int f = lane; f < F; f += 32) row[f] = from_f32<T>(0.0f);
       }
     }
     return;
   }
-  {
-    const int h = blockIdx.x * kFixHubsPerBlock + w;
-    bool is_big = false;
-    if (h < num_hubs) {
-      const int c = hub_list[h];
-      const int rp = first_row[c] - 1;
-      const int ps = rowptr[rp], pe = rowptr[rp + 1];
-      const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
-      if (n_part <= 8 && F % 4 == 0) {
-        const float divisor = mean ? (float)(pe - ps) : 1.0f;
-        const float* p0 = partial + ((int64_t)(c - 1) * 2 + 1) * F;   // partial k >= 1 lies at p0 + (2k - 1) * F
-        for (int f = lane * 4; f < F; f += 128) {
-          float4 t[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            t[k] = k < n_part ? __ldg(reinterpret_cast<const float4*>(p0 + (k == 0 ? 0 : (int64_t)(2 * k - 1) * F) + f))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 acc = t[0];
-#pragma unroll
-          for (int k = 1; k < 8; ++k) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
-          float r[4] = {__fdiv_rn(acc.x, divisor), __fdiv_rn(acc.y, divisor), __fdiv_rn(acc.z, divisor), __fdiv_rn(acc.w, divisor)};
-          T* dst = out + (int64_t)rp * ldo + f;
-          if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-          else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
-        }
-      } else {
-        is_big = true;
-      }
-    }
-    if (lane == 0) big[w] = is_big;
-  }
-  __syncthreads();
-  for (int j = 0; j < kFixHubsPerBlock; ++j) {
-    if (!big[j]) continue;   // block-uniform
-    const int c = hub_list[blockIdx.x * kFixHubsPerBlock + j];
-    const int rp = first_row[c] - 1;
-    const int ps = rowptr[rp], pe = rowptr[rp + 1];
+  const int4 hdr = hub_tbl[0];
+  const int n_small = hdr.x, n_big = hdr.y, big0 = hdr.z;
+  // Big hubs first (they are the critical path of the launch): one work item = (hub, slice of 128 columns); block b takes
+  // the items b, b + hub_blocks, ...  Lane l owns columns 4l..4l+3 of the slice (one 16-byte vector when F % 4 == 0,
+  // else the four columns l, l+32, l+64, l+96).
+  const bool vec = F % 4 == 0;
+  const int n_slices = (F + 127) / 128;
+  for (int item = blockIdx.x; item < n_big * n_slices; item += hub_blocks) {   // block-uniform
+    const int4 rec = hub_tbl[big0 - item / n_slices];
+    const int f0 = (item % n_slices) * 128;
+    const int c = rec.x, rp = rec.y, ps = rec.z, pe = rec.w;
     const int n_part = (pe - 1) / kEPW - c + 2;
     const float divisor = mean ? (float)(pe - ps) : 1.0f;
-    auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F; };
-    for (int f0 = 0; f0 < F; f0 += kFixTile) {
-      const int fw = min(kFixTile, F - f0);
-      if (F % 4 == 0) {  // 128-bit loads: a 256-float row is two passes of the warp
-        for (int f = lane * 4; f < fw; f += 128) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          int k = w;
-          for (; k + 56 < n_part; k += 64) {
-            float4 t[8];
+    auto part_ptr = [&](int k) { return partial + (k == 0 ? ((int64_t)(c - 1) * 2 + 1) : ((int64_t)(c + k - 1) * 2)) * F + f0; };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = w; k < n_part; k += 64) {   // eight loads in flight (zeros behind the last partial)
+      float4 t[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = __ldg(reinterpret_cast<const float4*>(part_ptr(k + 8 * i) + f0 + f));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+      for (int i = 0; i < 8; ++i) {
+        t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k + 8 * i < n_part) {
+          const float* p = part_ptr(k + 8 * i);
+          if (vec) {
+            if (f0 + lane * 4 < F) t[i] = __ldg(reinterpret_cast<const float4*>(p + lane * 4));
+          } else {
+            if (f0 + lane < F) t[i].x = __ldg(p + lane);
+            if (f0 + lane + 32 < F) t[i].y = __ldg(p + lane + 32);
+            if (f0 + lane + 64 < F) t[i].z = __ldg(p + lane + 64);
+            if (f0 + lane + 96 < F) t[i].w = __ldg(p + lane + 96);
           }
-          for (; k < n_part; k += 8) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(part_ptr(k) + f0 + f));
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-          }
-          *reinterpret_cast<float4*>(&red[w][f]) = acc;
-        }
-      } else {
-        for (int f = lane; f < fw; f += 32) {
-          float acc = 0.0f;
-          for (int k = w; k < n_part; k += 8) acc += __ldg(part_ptr(k) + f0 + f);
-          red[w][f] = acc;
         }
       }
-      __syncthreads();
-      for (int f = threadIdx.x; f < fw; f += 256) {
-        float acc = red[0][f];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) acc += red[i][f];
-        out[(int64_t)rp * ldo + f0 + f] = from_f32<T>(__fdiv_rn(acc, divisor));
+      for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+    }
+    // red[w][j]: column f0 + j of warp w's sum
+    if (vec) {
+      *reinterpret_cast<float4*>(&red[w][lane * 4]) = acc;
+    } else {
+      red[w][lane] = acc.x; red[w][lane + 32] = acc.y; red[w][lane + 64] = acc.z; red[w][lane + 96] = acc.w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 128 && f0 + (int)threadIdx.x < F) {
+      float sum = red[0][threadIdx.x];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) sum += red[i][threadIdx.x];
+      out[(int64_t)rp * ldo + f0 + threadIdx.x] = from_f32<T>(__fdiv_rn(sum, divisor));
+    }
+    __syncthreads();
+  }
+  const int h = blockIdx.x * kFixHubsPerBlock + w;
+  if (h < n_small) {
+    const int4 rec = hub_tbl[1 + h];
+    const int c = rec.x, rp = rec.y, ps = rec.z, pe = rec.w;
+    const int n_part = (pe - 1) / kEPW - c + 2;  // slot 1 of chunk c-1, then slot 0 of chunks c .. c_last
+    const float divisor = mean ? (float)(pe - ps) : 1.0f;
+    const float* p0 = partial + ((int64_t)(c - 1) * 2 + 1) * F;   // partial k >= 1 lies at p0 + (2k - 1) * F
+    if (vec) {
+      for (int f = lane * 4; f < F; f += 128) {
+        float4 t[kFixWarpParts];
+#pragma unroll
+        for (int k = 0; k < kFixWarpParts; ++k)
+          t[k] = k < n_part ? __ldg(reinterpret_cast<const float4*>(p0 + (k == 0 ? 0 : (int64_t)(2 * k - 1) * F) + f))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = t[0];
+#pragma unroll
+        for (int k = 1; k < kFixWarpParts; ++k) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+        float r[4] = {__fdiv_rn(acc.x, divisor), __fdiv_rn(acc.y, divisor), __fdiv_rn(acc.z, divisor), __fdiv_rn(acc.w, divisor)};
+        T* dst = out + (int64_t)rp * ldo + f;
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+        else *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
       }
-      __syncthreads();
+    } else {
+      for (int f = lane; f < F; f += 32) {
+        float acc = __ldg(p0 + f);
+        for (int k = 1; k < n_part; ++k) acc += __ldg(p0 + (int64_t)(2 * k - 1) * F + f);
+        out[(int64_t)rp * ldo + f] = from_f32<T>(__fdiv_rn(acc, divisor));
+      }
     }
   }
 }
@@ -648,10 +669,10 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
     LLP_LAUNCH_OK();
   }
   if (E > 0) {   // hub rows: add the partials; rows without edges: zeros (the main kernel writes neither)
-    const int hub_blocks = (int)ceil_div(num_hubs, kFixHubsPerBlock);
+    const int hub_blocks = (int)ceil_div(num_hubs, kFixHubsPerBlock);   // >= ceil(n_small / 8); big hubs stride over them
     const unsigned fix_blocks = (unsigned)(hub_blocks + ceil_div(N, kFixZeroRows));
-    spmm_fixup_kernel<T><<<fix_blocks, 256, 0, stream>>>(rowptr, first_row, hub_list, num_hubs, hub_blocks, (int)N, (int)F, mean,
-                                                        out, ldo, partial);
+    spmm_fixup_kernel<T><<<fix_blocks, 256, 0, stream>>>(rowptr, reinterpret_cast<const int4*>(hub_list), hub_blocks, (int)N, (int)F,
+                                                        mean, out, ldo, partial);
     LLP_LAUNCH_OK();
   } else {
     LLP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(T), 0, (size_t)F * sizeof(T), (size_t)N, stream));
@@ -691,11 +712,13 @@ extern "C" int llp_spmm_plan(const int32_t* rowptr, int64_t N, int64_t E, int32_
   spmm_plan_kernel<<<(unsigned)ceil_div(n_chunks + 1, 256), 256, 0, stream>>>(rowptr, N, n_chunks, chunk_first_row);
   LLP_LAUNCH_OK();
   spmm_desc_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(
-      rowptr, chunk_first_row, N, n_chunks, reinterpret_cast<int4*>(chunk_first_row + spmm_desc_offset_ints(n_chunks)));
+      rowptr, chunk_first_row, N, n_chunks, reinterpret_cast<int4*>(chunk_first_row + spmm_desc_offset_ints(n_chunks)),
+      reinterpret_cast<int4*>(hub_list));
   LLP_LAUNCH_OK();
   LLP_CUDA(cudaMemsetAsync(num_hubs, 0, sizeof(int32_t), stream));
   if (n_chunks > 1) {
-    spmm_hub_list_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(rowptr, chunk_first_row, n_chunks, hub_list, num_hubs);
+    spmm_hub_list_kernel<<<(unsigned)ceil_div(n_chunks, 256), 256, 0, stream>>>(rowptr, chunk_first_row, n_chunks,
+                                                                                reinterpret_cast<int4*>(hub_list), num_hubs);
     LLP_LAUNCH_OK();
   }
   return 0;
@@ -710,7 +733,7 @@ extern "C" int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, co
                         void* out, int64_t ldo, void* workspace, const int32_t* hub_list, int64_t num_hubs, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0 && F > 0 && ldx >= F && ldo >= F);
-  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (num_hubs == 0 || hub_list));
+  LLP_CHECK_ARG((E == 0 || (col && x && workspace)) && (N == 0 || out) && num_hubs >= 0 && (E == 0 || hub_list));
   LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && F < (1 << 24) && ldx * 4 < (int64_t)UINT32_MAX);
   if (int rc = check_device()) return rc;
   if (N == 0) return 0;

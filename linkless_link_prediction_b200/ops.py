@@ -268,12 +268,15 @@ def _build_csr(val: torch.Tensor, key: torch.Tensor, num_rows: int, want_inv: bo
     N.check(lib.llp_csr_build(val.data_ptr(), key.data_ptr(), E, num_rows, rowptr.data_ptr(), col.data_ptr(),
                               perm.data_ptr(), N.ptr(inv), ws.data_ptr(), nbytes, N.stream_ptr()), "llp_csr_build")
     plan = torch.empty(lib.llp_spmm_plan_ints(E), dtype=torch.int32, device=dev)   # torch allocations are 512-byte aligned
-    hub_list = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    hub_tbl = torch.empty((n_chunks + 1, 4), dtype=torch.int32, device=dev)   # header + one record per split row
     n_hubs = torch.zeros(1, dtype=torch.int32, device=dev)
-    N.check(lib.llp_spmm_plan(rowptr.data_ptr(), num_rows, E, plan.data_ptr(), hub_list.data_ptr(), n_hubs.data_ptr(),
+    N.check(lib.llp_spmm_plan(rowptr.data_ptr(), num_rows, E, plan.data_ptr(), hub_tbl.data_ptr(), n_hubs.data_ptr(),
                               N.stream_ptr()), "llp_spmm_plan")
-    n_hubs = int(n_hubs.item())  # the one host sync per graph, at build time
-    return rowptr, col, perm, inv, plan, (hub_list[:max(n_hubs, 1)].clone(), n_hubs)
+    n_small, n_big = (int(v) for v in hub_tbl[0, :2].tolist())  # the one host sync per graph, at build time
+    # compact copy: header, small records, big records (the kernel indexes big hub j at header[2] - j)
+    compact = torch.cat([hub_tbl[:1 + n_small], hub_tbl[n_chunks + 1 - n_big:]]) if n_big else hub_tbl[:1 + n_small].clone()
+    compact[0, 2] = n_small + n_big
+    return rowptr, col, perm, inv, plan, (compact, n_small + n_big)
 
 
 def _spmm_launch(csr, num_rows: int, num_edges: int, x: torch.Tensor, src_scale, mean: bool, transpose: bool) -> torch.Tensor:
