@@ -99,6 +99,35 @@ int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t
              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Node-partitioned encoder over peer memory (the reference is single-GPU, its aggregation call
+ * sites are models.py:113,118).  One process per GPU: every rank exports its activation block (llp_ipc_export), maps the
+ * peers' blocks (llp_ipc_open) and aggregates its own rows with llp_spmm_peer, whose gathers of remote rows are plain
+ * loads over NVLink / NVSwitch - no staged all-gather.  llp_peer_barrier orders "blocks in place" / "blocks read".
+ * ------------------------------------------------------------------------------------- */
+/* IPC handle (64 bytes) of the device allocation that contains `ptr`, and ptr's offset inside it. */
+int llp_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+/* Map a peer's allocation; *ptr_out corresponds to the exporter's `ptr`, *base_out is what llp_ipc_close takes. */
+int llp_ipc_open(const void* handle64, int64_t offset, void** ptr_out, void** base_out);
+int llp_ipc_close(void* base);
+/* Barrier of `world` ranks on `stream` (CUDA-graph capturable): flags[r] = rank r's zero-initialised uint64[world + 2]
+ * flag array as mapped into this process (HOST array of pointers).  Bounded wait (~2 s): on a timeout slot world + 1 of
+ * this rank's array becomes non-zero and the kernel returns. */
+int llp_peer_barrier(void* const* flags, int rank, int world, void* stream);
+/* dst[i, :] = row (src[i] & ((1 << shift) - 1)) of rank (src[i] >> shift)'s block, i < n_rows (row_bytes % 16 == 0,
+ * <= 4096): every remote row a rank's local messages reference, fetched once over NVLink into a local staging matrix
+ * that an ordinary llp_spmm then reads.  peer_x = DEVICE table of block base pointers. */
+int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, int shift, int64_t n_rows, int64_t row_bytes,
+                         void* dst, void* stream);
+/* llp_spmm with the source rows in peer-mapped blocks: peer_x = DEVICE array of `world` base pointers (rank r's
+ * [peer_nloc, ldx] block), col[e] = (owner rank << peer_shift) | row inside the owner's block, src_scale (optional)
+ * indexed by owner * peer_nloc + row.  Row widths of 256 or 512 bytes; LLP_E_SHAPE otherwise (use llp_spmm on an
+ * all-gathered matrix then). */
+int llp_spmm_peer(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
+                  int64_t num_rows, int64_t num_edges, const void* const* peer_x, int world, int peer_shift,
+                  int64_t peer_nloc, int64_t ldx, int64_t feat, const float* src_scale, int mean, void* out, int64_t ldo,
+                  void* workspace, const int32_t* hub_list, int64_t num_hubs, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Dense layers.  Replaces cuBLAS SGEMM behind F.linear (sageconv_updated.py:71,76; PyG
  * SAGEConv lin_l/lin_r; models.py:48,143,146) plus the relu/dropout/bias ATen kernels
  * (models.py:116-117,144-145).

@@ -76,6 +76,13 @@ PROTOTYPES = {
     "llp_spmm_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_spmm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                          c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "llp_ipc_export": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_int64)]),
+    "llp_ipc_open": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "llp_ipc_close": (c_int, [c_void_p]),
+    "llp_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "llp_peer_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "llp_spmm_peer": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int64, c_int64,
+                              c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),
     "llp_gemm_tn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "llp_gemm_tn": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,

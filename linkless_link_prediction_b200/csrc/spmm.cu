@@ -405,11 +405,16 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     if constexpr (kScale) sc = __shfl_sync(0xffffffffu, mys, o + (k_));       \
     add_row_pinned<T, VE, NV, kScale>(acc, v[k_], sc);                        \
   }
-template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks>
+// kPeer (node-partitioned encoder): the source rows live in the peer-mapped buffers of W ranks (`x` is
+// then a device table of W base pointers) and a column index is (owner rank << peer_shift) | row inside the owner's
+// block.  Each lane turns ITS entry of an index batch into a full 64-bit row address once per batch (one cached table
+// load); the gathers of remote rows are ordinary 128-bit loads that travel over NVLink, issued next to the local ones.
+template <typename T, int VE, int NV, int U, bool kScale, int kMinBlocks, bool kPeer = false>
 __global__ void __launch_bounds__(kSpmmThreads, kMinBlocks)
 spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int4* __restrict__ desc,
                    int n_chunks, const T* __restrict__ x, int ldx, int F, const float* __restrict__ src_scale, int mean,
-                   T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int n_rows, int n_edges) {
+                   T* __restrict__ out, int64_t ldo, float* __restrict__ partial, int n_rows, int n_edges,
+                   int peer_shift = 0, int peer_nloc = 0) {
   static_assert(U == 2 || U == 4 || U == 8, "load groups of 2, 4 or 8 (a group must not straddle a 32-wide index batch)");
   const int lane = threadIdx.x & 31;
   const int c = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
@@ -433,18 +438,36 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     return (i < n_edges) ? __ldg(col + i) : 0;
   };
   int my = fetch_idx(e & ~31), my_next = fetch_idx((e & ~31) + 32);
+  // kPeer: byte address of row `idx` for THIS lane's columns; scale index = the row's global (rank-major) number
+  auto peer_addr = [&](int idx) -> uint64_t {
+    const uint64_t base = (uint64_t)__ldg(reinterpret_cast<const unsigned long long*>(x) + (idx >> peer_shift));
+    return base + (uint64_t)(uint32_t)(idx & ((1 << peer_shift) - 1)) * ld_bytes;
+  };
+  auto scale_index = [&](int idx) -> int {
+    if constexpr (kPeer) return (idx >> peer_shift) * peer_nloc + (idx & ((1 << peer_shift) - 1));
+    else return idx;
+  };
+  uint64_t myaddr = 0;
+  if constexpr (kPeer) myaddr = peer_addr(my);
   // the scale of the CURRENT batch is requested when the batch becomes current (its indices are in registers by then)
   // and first read behind the batch's first gathers; requesting it for the NEXT batch would wait on that batch's indices
   float mys = 1.0f;
-  if constexpr (kScale) mys = __ldg(src_scale + my);
+  if constexpr (kScale) mys = __ldg(src_scale + scale_index(my));
   const int ee = cr.ee;
   while (e < ee) {
     const int o = e & 31;
     uint4 v[U][NV];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const int src = __shfl_sync(0xffffffffu, my, o + k);
-      const char* row = xlane + (uint64_t)((uint32_t)src) * ld_bytes;
+      const char* row;
+      if constexpr (kPeer) {
+        const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)myaddr, o + k);
+        const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(myaddr >> 32), o + k);
+        row = reinterpret_cast<const char*>(((uint64_t)hi << 32 | lo) + (uint64_t)(lane * VE * (int)sizeof(T)));
+      } else {
+        const int src = __shfl_sync(0xffffffffu, my, o + k);
+        row = xlane + (uint64_t)((uint32_t)src) * ld_bytes;
+      }
 #pragma unroll
       for (int j = 0; j < NV; ++j) v[k][j] = load_vec<T, VE>(reinterpret_cast<const T*>(row) + j * 32 * VE);
     }
@@ -482,7 +505,8 @@ spmm_stream_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     e += U;
     if ((e & 31) == 0) {   // next index batch (already in registers), prefetch the one after
       my = my_next;
-      if constexpr (kScale) mys = __ldg(src_scale + my);
+      if constexpr (kPeer) myaddr = peer_addr(my);
+      if constexpr (kScale) mys = __ldg(src_scale + scale_index(my));
       my_next = fetch_idx(e + 32);
     }
   }
@@ -680,6 +704,41 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const int32_t*
   return 0;
 }
 
+// Peer variant: only the streaming kernel's full-width single-vector rows (the caller falls back to a staged all-gather
+// for anything else).
+template <typename T, bool kScale>
+static int spmm_peer_launch(const int32_t* rowptr, const int32_t* col, const int32_t* first_row, int64_t N, int64_t E,
+                            const void* const* peer_x, int peer_shift, int64_t peer_nloc, int64_t ldx, int64_t F,
+                            const float* src_scale, int mean, void* out_, int64_t ldo, void* ws, const int32_t* hub_list,
+                            int num_hubs, cudaStream_t stream) {
+  T* out = reinterpret_cast<T*>(out_);
+  float* partial = reinterpret_cast<float*>(ws);
+  const int n_chunks = (int)llp_spmm_num_chunks(E);
+  const int4* desc = reinterpret_cast<const int4*>(first_row + spmm_desc_offset_ints(n_chunks));
+  constexpr int VE = Vec16<T>::n;
+  const unsigned blocks = (unsigned)ceil_div((int64_t)n_chunks * 32, kSpmmThreads);
+  const T* table = reinterpret_cast<const T*>(peer_x);
+  if (E > 0) {
+    if (F == 32 * VE)
+      spmm_stream_kernel<T, VE, 1, 4, kScale, 8, true><<<blocks, kSpmmThreads, 0, stream>>>(
+          rowptr, col, desc, n_chunks, table, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, (int)N, (int)E, peer_shift, (int)peer_nloc);
+    else if (F == 32 * (VE / 2))
+      spmm_stream_kernel<T, VE / 2, 1, 8, kScale, 8, true><<<blocks, kSpmmThreads, 0, stream>>>(
+          rowptr, col, desc, n_chunks, table, (int)ldx, (int)F, src_scale, mean, out, ldo, partial, (int)N, (int)E, peer_shift, (int)peer_nloc);
+    else
+      return LLP_E_SHAPE;
+    LLP_LAUNCH_OK();
+    const int hub_blocks = (int)ceil_div(num_hubs, kFixHubsPerBlock);
+    const unsigned fix_blocks = (unsigned)(hub_blocks + ceil_div(N, kFixZeroRows));
+    spmm_fixup_kernel<T><<<fix_blocks, 256, 0, stream>>>(rowptr, reinterpret_cast<const int4*>(hub_list), hub_blocks, (int)N, (int)F,
+                                                        mean, out, ldo, partial);
+    LLP_LAUNCH_OK();
+  } else {
+    LLP_CUDA(cudaMemset2DAsync(out, (size_t)ldo * sizeof(T), 0, (size_t)F * sizeof(T), (size_t)N, stream));
+  }
+  return 0;
+}
+
 }  // namespace llp
 
 using namespace llp;
@@ -744,5 +803,33 @@ extern "C" int llp_spmm(int dtype, const int32_t* rowptr, const int32_t* col, co
   if (dtype == LLP_F32) { LLP_SPMM(float); }
   if (dtype == LLP_BF16) { LLP_SPMM(__nv_bfloat16); }
 #undef LLP_SPMM
+  return LLP_E_BADARG;
+}
+
+// llp_spmm over peer-mapped source blocks (node-partitioned encoder): `peer_x` is a DEVICE array of `world` base
+// pointers (rank r's [peer_nloc, ldx] block as mapped into this process, llp_ipc_open), `col` holds
+// (owner rank << peer_shift) | local row, `src_scale` (optional) is indexed by owner * peer_nloc + local row.
+// Supported widths: feat * sizeof(elt) in {256, 512} bytes (one 8- or 16-byte vector per lane); LLP_E_SHAPE otherwise.
+extern "C" int llp_spmm_peer(int dtype, const int32_t* rowptr, const int32_t* col, const int32_t* chunk_first_row,
+                             int64_t N, int64_t E, const void* const* peer_x, int world, int peer_shift, int64_t peer_nloc,
+                             int64_t ldx, int64_t F, const float* src_scale, int mean, void* out, int64_t ldo,
+                             void* workspace, const int32_t* hub_list, int64_t num_hubs, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(rowptr && chunk_first_row && N >= 0 && E >= 0 && F > 0 && ldx >= F && ldo >= F && peer_x && world >= 1);
+  LLP_CHECK_ARG(peer_shift >= 0 && peer_shift < 31 && peer_nloc > 0 && peer_nloc <= ((int64_t)1 << peer_shift) &&
+                ((int64_t)world << peer_shift) <= (int64_t)INT32_MAX);
+  LLP_CHECK_ARG((E == 0 || (col && workspace && hub_list)) && (N == 0 || out) && num_hubs >= 0);
+  LLP_CHECK_ARG(E < (int64_t)INT32_MAX - kEPW && N < (int64_t)INT32_MAX && ldx * 4 < (int64_t)UINT32_MAX);
+  if (int rc = check_device()) return rc;
+  if (N == 0) return 0;
+  const int64_t elt = dtype == LLP_F32 ? 4 : 2;
+  if ((ldx * elt) % 16 != 0 || (ldo * elt) % 16 != 0 || !aligned(out, 16)) return LLP_E_ALIGN;
+#define LLP_SPMM_PEER(T)                                                                                                \
+  return src_scale != nullptr                                                                                           \
+             ? spmm_peer_launch<T, true>(rowptr, col, chunk_first_row, N, E, peer_x, peer_shift, peer_nloc, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)  \
+             : spmm_peer_launch<T, false>(rowptr, col, chunk_first_row, N, E, peer_x, peer_shift, peer_nloc, ldx, F, src_scale, mean, out, ldo, workspace, hub_list, (int)num_hubs, stream)
+  if (dtype == LLP_F32) { LLP_SPMM_PEER(float); }
+  if (dtype == LLP_BF16) { LLP_SPMM_PEER(__nv_bfloat16); }
+#undef LLP_SPMM_PEER
   return LLP_E_BADARG;
 }

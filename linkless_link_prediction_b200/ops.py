@@ -369,9 +369,18 @@ class PartitionedGraph(Graph):
     rank in CSR order and there is no cross-rank reduction: results equal the single-GPU ``Graph``'s bit for bit, except
     that rows longer than one 64-edge chunk regroup their fp32 partial sums (the chunk grid follows the local edge array).
     Everything row-wise around it (lin_l/lin_r GEMMs, relu/dropout, weight gradients over the local rows) runs
-    unchanged on ``n_loc`` rows; weight gradients are partial sums that the optimiser's all-reduce completes."""
+    unchanged on ``n_loc`` rows; weight gradients are partial sums that the optimiser's all-reduce completes.
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int, rank: int, world: int, group=None):
+    ``peer=True`` (= ``"stage"``): no all-gather.  Every rank keeps its block in a buffer that all other ranks have mapped
+    through CUDA IPC and pulls exactly the remote rows its local messages reference — each one ONCE, from a list built
+    with the graph — straight out of the owners' memory over NVLink / NVSwitch (``llp_peer_gather_rows``) into staging
+    rows behind its own block, then aggregates locally; two device-side barriers (``llp_peer_barrier``) bracket the
+    pull, all of it capturable in the step's CUDA graph.  ``peer="load"``: the SpMM kernel itself loads remote rows per
+    edge (``llp_spmm_peer``; rows of 256 or 512 bytes) — more NVLink bytes on graphs whose rows are referenced several
+    times per rank, kept for comparison.  Same per-row summation order as the all-gather path: bit-identical results."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, rank: int, world: int, group=None, peer: bool = False,
+                 peer_row_bytes: int = 512):
         N.require_gpu()
         if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_index.dtype != torch.int64 or not edge_index.is_cuda:
             raise RuntimeError("edge_index must be a CUDA LongTensor of shape [2, E] (no CPU fallback)")
@@ -385,6 +394,146 @@ class PartitionedGraph(Graph):
         self.num_edges, self.t_num_edges = int(f_src.numel()), int(t_dst.numel())
         self.rowptr, self.col, self.perm, _, self.plan, self.hubs = _build_csr(f_src, f_dst, self.n_loc, False)
         self.t_rowptr, self.t_col, self.t_perm, _, self.t_plan, self.t_hubs = _build_csr(t_dst, t_src, self.n_loc, False)
+        self.peer = None
+        if peer and self.world > 1:
+            self._init_peer(int(peer_row_bytes), "load" if peer == "load" else "stage")
+
+    # ---- peer-memory mode: remote rows are loaded by the SpMM kernel itself over NVLink (llp_spmm_peer) --------------
+    def _init_peer(self, row_bytes: int, how: str) -> None:
+        """One peer-visible activation buffer per rank + one flag array for the barrier, exported through CUDA IPC and
+        mapped by every other rank.  ``how == "stage"``: the buffer is ``[n_loc + n_ref, row_bytes]`` — this rank's block
+        followed by a staging area for the ``n_ref`` DISTINCT remote rows its local messages reference (listed once here,
+        per direction); the column indices are re-coded into that local matrix.  ``how == "load"``: ``[n_loc, row_bytes]``
+        and column indices re-coded as (owner << shift) | row for ``llp_spmm_peer``."""
+        import ctypes
+        import torch.distributed as dist
+        lib = N.require_gpu()
+        dev = self.rowptr.device
+        W, n_loc = self.world, self.n_loc
+        shift = max(1, (n_loc - 1).bit_length())
+        if (W << shift) >= 2 ** 31:
+            raise RuntimeError("peer mode: world << ceil_log2(n_loc) must fit an int32 column index")
+        recode = lambda c: (((c.long() // n_loc) << shift) | (c.long() % n_loc)).to(torch.int32).contiguous()
+
+        def stage_plan(col, scale):
+            """distinct remote sources (sorted), the column indices into [own block | staged rows], the scale in that order"""
+            c = col.long()
+            own = (c >= self.lo) & (c < self.hi)
+            ref = torch.unique(c[~own])                                    # sorted global ids of the referenced remote rows
+            local = torch.where(own, c - self.lo, n_loc + torch.searchsorted(ref, c))
+            sc = None if scale is None else torch.cat([scale[self.lo:self.hi], scale[ref]]).contiguous()
+            return recode(ref), local.to(torch.int32).contiguous(), sc
+
+        stage = None
+        n_ref = 0
+        if how == "stage":
+            f_ref, f_col, _ = stage_plan(self.col, None)
+            t_ref, t_col, t_scale = stage_plan(self.t_col, self.inv_deg)
+            stage = dict(f_ref=f_ref, f_col=f_col, t_ref=t_ref, t_col=t_col, t_scale=t_scale)
+            n_ref = max(int(f_ref.numel()), int(t_ref.numel()))
+        buf = torch.zeros((n_loc + n_ref) * row_bytes + 256, dtype=torch.uint8, device=dev)   # rows are 16-byte aligned
+        flags = torch.zeros(W + 2, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+
+        def export(t):
+            h, off = ctypes.create_string_buffer(64), ctypes.c_int64(0)
+            N.check(lib.llp_ipc_export(t.data_ptr(), h, ctypes.byref(off)), "llp_ipc_export")
+            return bytes(h.raw), int(off.value)
+
+        mine = (export(buf), export(flags))
+        everyone = [None] * W
+        dist.all_gather_object(everyone, mine, group=self.group)
+        bases, buf_ptrs, flag_ptrs = [], [], []
+        for r in range(W):
+            if r == self.rank:
+                buf_ptrs.append(buf.data_ptr()); flag_ptrs.append(flags.data_ptr())
+                continue
+            for (handle, off), dst in ((everyone[r][0], buf_ptrs), (everyone[r][1], flag_ptrs)):
+                ptr, base = ctypes.c_void_p(), ctypes.c_void_p()
+                N.check(lib.llp_ipc_open(handle, off, ctypes.byref(ptr), ctypes.byref(base)), "llp_ipc_open")
+                bases.append(base.value); dst.append(ptr.value)
+        dist.barrier(group=self.group)   # nobody tears its buffers down before everyone has mapped them
+        self.peer = dict(how=how, shift=shift, row_bytes=row_bytes, buf=buf, flags=flags, bases=bases,
+                         table=torch.tensor(buf_ptrs, dtype=torch.int64, device=dev),
+                         flag_ptrs=(ctypes.c_void_p * W)(*flag_ptrs), stage=stage,
+                         col=recode(self.col) if how == "load" else None, t_col=recode(self.t_col) if how == "load" else None)
+
+    def close_peer(self) -> None:
+        """Unmap the peers' buffers (call on every rank before the process group goes away)."""
+        if self.peer is not None:
+            lib = N.require_gpu()
+            torch.cuda.synchronize(self.rowptr.device)
+            for base in self.peer["bases"]:
+                lib.llp_ipc_close(base)
+            self.peer = None
+
+    def _peer_barrier(self) -> None:
+        N.check(N.require_gpu().llp_peer_barrier(self.peer["flag_ptrs"], self.rank, self.world, N.stream_ptr()), "llp_peer_barrier")
+
+    def peer_barrier_timed_out(self) -> bool:
+        """True when a barrier of this rank ever gave up waiting (~2 s) for a peer (host read: synchronises)."""
+        return self.peer is not None and bool(int(self.peer["flags"][self.world + 1].item()))
+
+    def _peer_ok(self, x: torch.Tensor) -> bool:
+        if self.peer is None:
+            return False
+        rb = x.size(1) * x.element_size()
+        if self.peer["how"] == "stage":
+            return rb % 16 == 0 and rb <= self.peer["row_bytes"]
+        return rb in (256, 512) and rb <= self.peer["row_bytes"]
+
+    def _spmm_staged(self, x: torch.Tensor, transpose: bool) -> torch.Tensor:
+        """copy this rank's rows into its exported block -> barrier (every block in place) -> pull each referenced remote
+        row ONCE over NVLink into the staging rows behind the block (``llp_peer_gather_rows``) -> barrier (every rank has
+        finished reading: blocks may be overwritten) -> ordinary local SpMM over [own block | staged rows]."""
+        lib = N.require_gpu()
+        pr, st, F = self.peer, self.peer["stage"], x.size(1)
+        if x.size(0) != self.n_loc:
+            raise RuntimeError(f"expected this rank's {self.n_loc} rows, got {x.size(0)}")
+        ref, col, scale = (st["t_ref"], st["t_col"], st["t_scale"]) if transpose else (st["f_ref"], st["f_col"], None)
+        n_ref, rb = int(ref.numel()), F * x.element_size()
+        mat = pr["buf"][:(self.n_loc + n_ref) * rb].view(x.dtype).view(self.n_loc + n_ref, F)
+        mat[:self.n_loc].copy_(x)
+        self._peer_barrier()
+        N.check(lib.llp_peer_gather_rows(pr["table"].data_ptr(), ref.data_ptr(), pr["shift"], n_ref, rb,
+                                         mat[self.n_loc:].data_ptr() if n_ref else None, N.stream_ptr()), "llp_peer_gather_rows")
+        self._peer_barrier()
+        rowptr, plan, hubs = (self.t_rowptr, self.t_plan, self.t_hubs) if transpose else (self.rowptr, self.plan, self.hubs)
+        E = self.t_num_edges if transpose else self.num_edges
+        return _spmm_launch((rowptr, col, plan, hubs), self.n_loc, E, mat, scale, not transpose, transpose)
+
+    def _spmm_peer(self, x: torch.Tensor, transpose: bool) -> torch.Tensor:
+        """copy this rank's rows into its exported block -> barrier (every block in place) -> SpMM whose gathers of
+        remote rows are loads over NVLink -> barrier (every rank has finished reading: the block may be overwritten)."""
+        lib = N.require_gpu()
+        pr, F = self.peer, x.size(1)
+        if x.size(0) != self.n_loc:
+            raise RuntimeError(f"expected this rank's {self.n_loc} rows, got {x.size(0)}")
+        block = pr["buf"][:self.n_loc * F * x.element_size()].view(x.dtype).view(self.n_loc, F)
+        block.copy_(x)
+        self._peer_barrier()
+        rowptr, col, plan, hubs = (self.t_rowptr, pr["t_col"], self.t_plan, self.t_hubs) if transpose else \
+            (self.rowptr, pr["col"], self.plan, self.hubs)
+        E = self.t_num_edges if transpose else self.num_edges
+        out = empty_mat(self.n_loc, F, x.dtype, x.device)
+        ws = _ws(lib.llp_spmm_workspace_bytes(E, F), x.device)
+        op, ldo = N.mat(out)
+        prof = SPMM_PROFILE
+        if prof is not None:
+            ext = torch.cuda.is_current_stream_capturing()
+            ev0 = torch.cuda.Event(enable_timing=True, external=ext)
+            ev1 = torch.cuda.Event(enable_timing=True, external=ext)
+            ev0.record()
+        N.check(lib.llp_spmm_peer(N.dtype_id(x.dtype), rowptr.data_ptr(), col.data_ptr(), plan.data_ptr(), self.n_loc, E,
+                                  pr["table"].data_ptr(), self.world, pr["shift"], self.n_loc, F, F,
+                                  N.ptr(self.inv_deg) if transpose else None, 0 if transpose else 1, op, ldo, ws.data_ptr(),
+                                  hubs[0].data_ptr(), hubs[1], N.stream_ptr()), "llp_spmm_peer")
+        if prof is not None:
+            ev1.record()
+            s_elt = x.element_size()
+            prof.append((ev0, ev1, E * F * s_elt + self.n_loc * F * s_elt + 4 * E + 4 * (self.n_loc + 1)))
+        self._peer_barrier()
+        return out
 
     @property
     def rows_out(self) -> int:
@@ -419,6 +568,9 @@ class PartitionedGraph(Graph):
         return buf[:, :F]
 
     def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+        if self._peer_ok(x):
+            xc = x if x.is_contiguous() else x.contiguous()
+            return self._spmm_staged(xc, transpose) if self.peer["how"] == "stage" else self._spmm_peer(xc, transpose)
         full = self.gather_rows(x)
         if not transpose:
             return _spmm_launch((self.rowptr, self.col, self.plan, self.hubs), self.n_loc, self.num_edges, full, None, True,

@@ -39,3 +39,14 @@ def test_node_partitioned_encoder_equals_replicated(cuda):
     out = _run_two_ranks("np_parity.py", port=29618)
     assert out["ok"] and out["fp32"]["eval_identical"] and out["bf16"]["eval_identical"]
     assert out["bf16"]["embeddings_bit_identical"]
+
+
+@pytest.mark.parametrize("flag", ["--peer", "--peer-load"])
+def test_node_partitioned_encoder_peer_memory_spmm(cuda, flag):
+    """The same parity job with ``PartitionedGraph(peer=...)``: buffers mapped through CUDA IPC, ``llp_peer_barrier``
+    around the NVLink traffic; ``--peer`` pulls every referenced remote row once (``llp_peer_gather_rows``) and
+    aggregates locally, ``--peer-load`` lets the SpMM kernel load remote rows per edge (``llp_spmm_peer``).  Both are
+    bit-identical to the all-gather SpMM of the same partition."""
+    out = _run_two_ranks("np_parity.py", flag, port=29619 if flag == "--peer" else 29620)
+    assert out["ok"] and out["fp32"]["peer"] and out["fp32"]["peer_spmm_bit_identical"] and out["bf16"]["peer_spmm_bit_identical"]
+    assert not out["fp32"]["barrier_timed_out"] and not out["bf16"]["barrier_timed_out"]

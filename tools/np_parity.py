@@ -33,9 +33,15 @@ def build(dev, f, h, layers, p, seed=0):
     return model, pred
 
 
+PEER = ("load" if "--peer-load" in sys.argv else "stage") if ("--peer" in sys.argv or "--peer-load" in sys.argv) else False
+# --peer: referenced remote rows pulled once over NVLink (llp_peer_gather_rows); --peer-load: per-edge remote loads (llp_spmm_peer)
+
+
 def parity(rank, world, dev, mode):
     ops.set_compute_dtype(mode)
     n, f, h = 1001, 40, 64                       # odd node count: the last block is padded
+    if PEER:
+        f, h = 128, 128                          # rows of 256 / 512 bytes in both modes: every aggregation takes the peer path
     ei = undirected_graph(n, 6000, 3, True).to(dev)
     g = torch.Generator().manual_seed(5)
     x = torch.randn(n, f, generator=g).to(dev)
@@ -49,9 +55,15 @@ def parity(rank, world, dev, mode):
     # ---- node-partitioned ----
     mp, pp = build(dev, f, h, 3, 0.0)
     op = L.FusedAdam(list(mp.parameters()) + list(pp.parameters()), lr=0.01)
-    pg = ops.PartitionedGraph(ei, n, rank, world)
+    pg = ops.PartitionedGraph(ei, n, rank, world, peer=PEER)
     dp = shims.Data(x=pg.local_rows(x), adj_t=pg)
-    out = {"mode": str(mode), "n_loc": pg.n_loc, "local_messages": [pg.num_edges, pg.t_num_edges]}
+    out = {"mode": str(mode), "n_loc": pg.n_loc, "local_messages": [pg.num_edges, pg.t_num_edges], "peer": PEER}
+    if PEER:   # the peer SpMM against the all-gather SpMM of the same partition: same rows, same order -> same bits
+        pg_ag = ops.PartitionedGraph(ei, n, rank, world)
+        xl = pg.local_rows(torch.randn(n, h, generator=g).to(dev)).to(ops.compute_dtype())
+        assert pg._peer_ok(xl)
+        out["peer_spmm_bit_identical"] = bool(torch.equal(pg.spmm(xl), pg_ag.spmm(xl)) and
+                                              torch.equal(pg.spmm(xl, transpose=True), pg_ag.spmm(xl, transpose=True)))
     # forward: bit-identical embeddings
     with torch.no_grad():
         m1.eval(); mp.eval()
@@ -93,6 +105,14 @@ def parity(rank, world, dev, mode):
     out["hits_auc_replicated"] = res_1
     out["hits_auc_partitioned"] = res_p
     out["eval_identical"] = res_1 == res_p and h_full.size(0) == n
+    if PEER:
+        # fp32 embeddings of ANY partition differ from the replicated ones in the last bit of rows behind hub rows (the
+        # chunk grid regroups their partial sums), which can move a Hits@K count by one: the exact reference for the
+        # peer path is the all-gather path of the SAME partition; against the replicated encoder the metrics must be close
+        res_ag, _ = teacher.test_transductive(mp, pp, shims.Data(x=dp.x, adj_t=pg_ag), split, L.Evaluator(), 512, "sage", "cora", args)
+        close = all(abs(a - b) <= 0.01 for k in res_1 for a, b in zip(res_1[k], res_p[k]))
+        out["eval_identical_to_allgather_partition"] = res_ag == res_p
+        out["eval_identical"] = bool(res_ag == res_p and close and h_full.size(0) == n)
     tol = 1e-4 if mode == torch.float32 else 3e-2
     # rows longer than one 64-edge chunk are split into partial sums along the chunk grid of the (local vs global) edge
     # array, so hub rows (and, layers later, their neighbourhoods) may differ in the last fp32 bit.  Parameters are compared
@@ -100,6 +120,11 @@ def parity(rank, world, dev, mode):
     emb_ok = out["embeddings_max_abs_diff"] <= (1e-5 if mode == torch.float32 else 2e-2)
     out["ok"] = bool(emb_ok and out["eval_identical"] and gdiff < tol and (pdiff < 1e-4 or mode != torch.float32)
                      and all(abs(a - b) <= (1e-5 if mode == torch.float32 else 2e-2) * abs(a) for a, b in zip(losses_1, losses_p)))
+    if PEER:
+        out["barrier_timed_out"] = pg.peer_barrier_timed_out()
+        out["ok"] = bool(out["ok"] and out["peer_spmm_bit_identical"] and not out["barrier_timed_out"])
+        del op, mp, pp, dp
+        pg.close_peer()
     return out
 
 
@@ -138,9 +163,11 @@ def timing(rank, world, dev, steps=10, warm=4):
         return float(t)
 
     ms_rep = bench_one(shims.Data(x=x, adj_t=ei), B, 1.0, False)   # every rank: the whole job alone (no collectives)
-    pg = ops.PartitionedGraph(ei, n, rank, world)
+    pg = ops.PartitionedGraph(ei, n, rank, world, peer=PEER)
     ms_part = bench_one(shims.Data(x=pg.local_rows(x), adj_t=pg), B // world, 1.0, True)
-    return {"workload": "collab-shaped teacher step, global batch 65,536 positive edges (strong scaling)", "world": world,
+    timed_out = pg.peer_barrier_timed_out()
+    pg.close_peer()
+    return {"peer": PEER, "barrier_timed_out": timed_out, "workload": "collab-shaped teacher step, global batch 65,536 positive edges (strong scaling)", "world": world,
             "ms_per_step_replicated_1gpu": ms_rep, "ms_per_step_node_partitioned": ms_part,
             "speedup": ms_rep / ms_part, "pos_edges_per_sec_partitioned": B / ms_part * 1e3,
             "allgather_bytes_per_rank_per_step": int((world - 1) * pg.n_loc * 2 * (128 + 256 * 5))}
@@ -152,18 +179,24 @@ def comm_microbench(rank, world, dev, iters=10):
     data_cpu, _ = synthetic_dataset("collab", seed=0)
     n = data_cpu.x.size(0)
     ei = data_cpu.adj_t.to(dev)
-    pg = ops.PartitionedGraph(ei, n, rank, world)
+    pg = ops.PartitionedGraph(ei, n, rank, world, peer=PEER)
     g1 = ops.Graph(ei, n)
-    out = {}
+    out = {"peer": PEER}
 
-    def t(name, fn, nbytes=None):
+    def t(name, fn, nbytes=None, graph=False):
         for _ in range(3):
             fn()
         torch.cuda.synchronize(); dist.barrier()
+        run = lambda: [fn() for _ in range(iters)]
+        if graph:   # device time without host launch gaps: the iterations replayed as one CUDA graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            run = g.replay
+            run(); torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(iters):
-            fn()
+        run()
         e1.record()
         torch.cuda.synchronize(); dist.barrier()
         v = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
@@ -178,8 +211,30 @@ def comm_microbench(rank, world, dev, iters=10):
         recv = (world - 1) * pg.n_loc * F * 2
         t(f"all_gather rows F={F} (received bytes/rank)", lambda: pg.gather_rows(xl), recv)
         t(f"local-row spmm fwd F={F} (gathered input given)", lambda: ops._spmm_launch((pg.rowptr, pg.col, pg.plan, pg.hubs), pg.n_loc, pg.num_edges, xf, None, True, False))
-        t(f"partitioned spmm fwd F={F} (gather + local rows)", lambda: pg.spmm(xl))
-        t(f"partitioned spmm transpose F={F}", lambda: pg.spmm(xl, transpose=True))
+        remote = (world - 1) / world * pg.num_edges * F * 2   # bytes the peer SpMM pulls over NVLink (uniform sources)
+        t(f"partitioned spmm fwd F={F} ({PEER or 'all-gather'} + local rows)", lambda: pg.spmm(xl), remote if PEER == 'load' else None)
+        t(f"partitioned spmm transpose F={F}", lambda: pg.spmm(xl, transpose=True), remote if PEER == 'load' else None)
+        if PEER == "stage":
+            st, pr, lib = pg.peer["stage"], pg.peer, L._native.load()
+            n_ref = int(st["f_ref"].numel())
+            stage_dst = pr["buf"][pg.n_loc * F * 2:]
+            t(f"peer row pull alone F={F} ({n_ref} distinct remote rows of {(world - 1) * pg.n_loc}), graph replay",
+              lambda: lib.llp_peer_gather_rows(pr["table"].data_ptr(), st["f_ref"].data_ptr(), pr["shift"], n_ref, F * 2,
+                                               stage_dst.data_ptr(), L._native.stream_ptr()), n_ref * F * 2, graph=True)
+            t(f"partitioned spmm fwd F={F} (staged pull + local spmm), graph replay", lambda: pg.spmm(xl), n_ref * F * 2, graph=True)
+            t("peer barrier alone, graph replay", lambda: pg._peer_barrier(), graph=True)
+        if PEER == "load":
+            t(f"partitioned spmm fwd F={F} (peer loads), graph replay", lambda: pg.spmm(xl), remote, graph=True)
+            pr = pg.peer
+            lib = L._native.load()
+            outb = ops.empty_mat(pg.n_loc, F, xl.dtype, dev)
+            wsb = torch.empty(lib.llp_spmm_workspace_bytes(pg.num_edges, F), dtype=torch.uint8, device=dev)
+            kern = lambda: lib.llp_spmm_peer(1, pg.rowptr.data_ptr(), pr["col"].data_ptr(), pg.plan.data_ptr(), pg.n_loc, pg.num_edges,
+                                             pr["table"].data_ptr(), world, pr["shift"], pg.n_loc, F, F, None, 1, outb.data_ptr(),
+                                             outb.stride(0), wsb.data_ptr(), pg.hubs[0].data_ptr(), pg.hubs[1],
+                                             L._native.stream_ptr())
+            t(f"peer spmm kernels alone F={F} (no copy, no barriers), graph replay", kern, remote, graph=True)
+            t("peer barrier alone, graph replay", lambda: pg._peer_barrier(), graph=True)
         xg = torch.randn(n, F, device=dev).bfloat16()
         t(f"replicated spmm fwd F={F}", lambda: g1.spmm(xg))
     gf = torch.randn(pg.num_nodes_padded, 256, device=dev).bfloat16()
@@ -187,6 +242,8 @@ def comm_microbench(rank, world, dev, iters=10):
     t("reduce_scatter embedding gradient [N,256] bf16 (sent bytes/rank)", lambda: dist.reduce_scatter_tensor(go, gf), (world - 1) * pg.n_loc * 512)
     flat = torch.randn(400_000, device=dev)
     t("all_reduce flat fp32 gradient bucket (1.6 MB)", lambda: dist.all_reduce(flat))
+    out["barrier_timed_out"] = pg.peer_barrier_timed_out()
+    pg.close_peer()
     return out
 
 
