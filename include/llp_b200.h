@@ -113,11 +113,12 @@ int llp_ipc_close(void* base);
  * flag array as mapped into this process (HOST array of pointers).  Bounded wait (~2 s): on a timeout slot world + 1 of
  * this rank's array becomes non-zero and the kernel returns. */
 int llp_peer_barrier(void* const* flags, int rank, int world, void* stream);
-/* dst[i, :] = row (src[i] & ((1 << shift) - 1)) of rank (src[i] >> shift)'s block, i < n_rows (row_bytes % 16 == 0,
- * <= 4096): every remote row a rank's local messages reference, fetched once over NVLink into a local staging matrix
- * that an ordinary llp_spmm then reads.  peer_x = DEVICE table of block base pointers. */
-int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, int shift, int64_t n_rows, int64_t row_bytes,
-                         void* dst, void* stream);
+/* dst[dst_rows ? dst_rows[i] : i, :] = row (src[i] & ((1 << shift) - 1)) of rank (src[i] >> shift)'s block, i < n_rows
+ * (row_bytes % 16 == 0, <= 4096): every remote row a rank's local messages reference, fetched once over NVLink into a
+ * local staging matrix that an ordinary llp_spmm then reads; with dst_rows, the embedding rows an edge batch scores,
+ * dropped into their places of an otherwise untouched [N, feat] matrix.  peer_x = DEVICE table of block base pointers. */
+int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, const int32_t* dst_rows /* or NULL */, int shift,
+                         int64_t n_rows, int64_t row_bytes, void* dst, void* stream);
 /* llp_spmm with the source rows in peer-mapped blocks: peer_x = DEVICE array of `world` base pointers (rank r's
  * [peer_nloc, ldx] block), col[e] = (owner rank << peer_shift) | row inside the owner's block, src_scale (optional)
  * indexed by owner * peer_nloc + row.  Row widths of 256 or 512 bytes; LLP_E_SHAPE otherwise (use llp_spmm on an

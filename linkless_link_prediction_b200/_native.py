@@ -80,7 +80,7 @@ PROTOTYPES = {
     "llp_ipc_open": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "llp_ipc_close": (c_int, [c_void_p]),
     "llp_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p]),
-    "llp_peer_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "llp_peer_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_spmm_peer": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int64, c_int64,
                               c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),

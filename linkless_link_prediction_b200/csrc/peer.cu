@@ -53,7 +53,8 @@ __global__ void peer_barrier_kernel(PeerFlagPtrs peers, int rank, int world, lon
 // locally.  A row is covered by row_bytes / 16 lanes (16-byte vectors); every lane keeps kPeerRowsInFlight rows in flight.
 constexpr int kPeerRowsInFlight = 8;
 __global__ void __launch_bounds__(256)
-peer_gather_rows_kernel(const unsigned long long* __restrict__ table, const int32_t* __restrict__ src, int shift, int64_t n_rows,
+peer_gather_rows_kernel(const unsigned long long* __restrict__ table, const int32_t* __restrict__ src,
+                        const int32_t* __restrict__ dst_rows /* or null: row i goes to dst row i */, int shift, int64_t n_rows,
                         int row_vecs /* 16-byte vectors per row */, uint4* __restrict__ dst) {
   const int rows_per_pass = 256 / row_vecs;                  // rows one block covers with one load per thread
   const int sub = threadIdx.x / row_vecs, v = threadIdx.x % row_vecs;
@@ -73,7 +74,7 @@ peer_gather_rows_kernel(const unsigned long long* __restrict__ table, const int3
 #pragma unroll
     for (int k = 0; k < kPeerRowsInFlight; ++k) {
       const int64_t i = i0 + k * stride;
-      if (i < n_rows) dst[i * row_vecs + v] = t[k];
+      if (i < n_rows) dst[(dst_rows != nullptr ? (int64_t)__ldg(dst_rows + i) : i) * row_vecs + v] = t[k];
     }
   }
 }
@@ -143,10 +144,11 @@ extern "C" int llp_peer_barrier(void* const* flags, int rank, int world, void* s
   return 0;
 }
 
-// dst[i, :] = row (src[i] & mask) of rank (src[i] >> shift)'s block, i < n_rows; row_bytes a multiple of 16 up to 4096;
-// peer_x = DEVICE table of the blocks' base pointers as mapped into this process.
-extern "C" int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, int shift, int64_t n_rows, int64_t row_bytes,
-                                    void* dst, void* stream_) {
+// dst[dst_rows ? dst_rows[i] : i, :] = row (src[i] & mask) of rank (src[i] >> shift)'s block, i < n_rows; row_bytes a
+// multiple of 16 up to 4096; peer_x = DEVICE table of the blocks' base pointers as mapped into this process.  With
+// dst_rows several i may name the same destination row as long as they name the same source row.
+extern "C" int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, const int32_t* dst_rows, int shift,
+                                    int64_t n_rows, int64_t row_bytes, void* dst, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LLP_CHECK_ARG(peer_x && n_rows >= 0 && shift >= 0 && shift < 31 && row_bytes > 0 && row_bytes % 16 == 0 && row_bytes <= 4096);
   if (int rc = check_device()) return rc;
@@ -156,7 +158,7 @@ extern "C" int llp_peer_gather_rows(const void* const* peer_x, const int32_t* sr
   const int rows_per_pass = 256 / row_vecs;
   const int64_t want = ceil_div(n_rows, (int64_t)rows_per_pass * kPeerRowsInFlight);
   const unsigned blocks = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
-  peer_gather_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(peer_x), src, shift, n_rows,
+  peer_gather_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(peer_x), src, dst_rows, shift, n_rows,
                                                       row_vecs, reinterpret_cast<uint4*>(dst));
   LLP_LAUNCH_OK();
   return 0;

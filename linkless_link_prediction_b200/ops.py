@@ -474,6 +474,23 @@ class PartitionedGraph(Graph):
         """True when a barrier of this rank ever gave up waiting (~2 s) for a peer (host read: synchronises)."""
         return self.peer is not None and bool(int(self.peer["flags"][self.world + 1].item()))
 
+    def pull_rows(self, x_loc: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+        """``[N_padded, F]`` matrix in which exactly the rows ``rows`` (global node ids, duplicates allowed) hold the
+        owners' rows of ``x_loc``, pulled over NVLink; all other rows are uninitialised."""
+        lib = N.require_gpu()
+        pr, F = self.peer, x_loc.size(1)
+        rb = F * x_loc.element_size()
+        ids = rows.reshape(-1)
+        src = (((ids // self.n_loc) << pr["shift"]) | (ids % self.n_loc)).to(torch.int32)
+        dst_rows = ids.to(torch.int32)
+        pr["buf"][:self.n_loc * rb].view(x_loc.dtype).view(self.n_loc, F).copy_(x_loc)
+        full = torch.empty((self.num_nodes_padded, F), dtype=x_loc.dtype, device=x_loc.device)
+        self._peer_barrier()
+        N.check(lib.llp_peer_gather_rows(pr["table"].data_ptr(), src.data_ptr(), dst_rows.data_ptr(), pr["shift"], int(ids.numel()),
+                                         rb, full.data_ptr(), N.stream_ptr()), "llp_peer_gather_rows")
+        self._peer_barrier()
+        return full
+
     def _peer_ok(self, x: torch.Tensor) -> bool:
         if self.peer is None:
             return False
@@ -495,7 +512,7 @@ class PartitionedGraph(Graph):
         mat = pr["buf"][:(self.n_loc + n_ref) * rb].view(x.dtype).view(self.n_loc + n_ref, F)
         mat[:self.n_loc].copy_(x)
         self._peer_barrier()
-        N.check(lib.llp_peer_gather_rows(pr["table"].data_ptr(), ref.data_ptr(), pr["shift"], n_ref, rb,
+        N.check(lib.llp_peer_gather_rows(pr["table"].data_ptr(), ref.data_ptr(), None, pr["shift"], n_ref, rb,
                                          mat[self.n_loc:].data_ptr() if n_ref else None, N.stream_ptr()), "llp_peer_gather_rows")
         self._peer_barrier()
         rowptr, plan, hubs = (self.t_rowptr, self.t_plan, self.t_hubs) if transpose else (self.rowptr, self.plan, self.hubs)
@@ -580,12 +597,16 @@ class PartitionedGraph(Graph):
 
 
 class GatherRowsFn(torch.autograd.Function):
-    """Embedding rows of all ranks for the edge scorer: forward = all-gather of the local blocks, backward = the
-    reduce-scatter (sum) of the per-rank gradients of the gathered matrix back onto the owning rank's rows."""
+    """Embedding rows of all ranks for the edge scorer: forward = all-gather of the local blocks — or, with a peer-memory
+    graph and the node ids ``rows`` the scorer is going to index, a pull of just those rows over NVLink into their places
+    of an otherwise untouched ``[N_padded, F]`` matrix (a rank scores B/W edges: 2B/W rows instead of N) —, backward =
+    the reduce-scatter (sum) of the per-rank gradients of the gathered matrix back onto the owning rank's rows."""
 
     @staticmethod
-    def forward(ctx, x_loc, graph):
+    def forward(ctx, x_loc, graph, rows=None):
         ctx.graph = graph
+        if rows is not None and graph.peer is not None and graph._peer_ok(x_loc):
+            return graph.pull_rows(x_loc, rows)
         return graph.gather_rows(x_loc)
 
     @staticmethod
@@ -595,14 +616,15 @@ class GatherRowsFn(torch.autograd.Function):
         g = g_full if g_full.is_contiguous() else g_full.contiguous()
         out = torch.empty((graph.n_loc, g.size(1)), dtype=g.dtype, device=g.device)
         dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=graph.group)
-        return out, None
+        return out, None, None
 
 
-def gather_encoder_output(h: torch.Tensor, graph) -> torch.Tensor:
+def gather_encoder_output(h: torch.Tensor, graph, rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Full embedding matrix the scorers index: identity for a replicated ``Graph``, autograd-aware all-gather for a
-    ``PartitionedGraph`` (rows beyond the real node count are padding)."""
+    ``PartitionedGraph`` (rows beyond the real node count are padding).  ``rows`` (optional): the node ids that are going
+    to be read — a peer-memory graph then fetches only those (every other row of the result is undefined)."""
     if isinstance(graph, PartitionedGraph):
-        return GatherRowsFn.apply(h, graph)
+        return GatherRowsFn.apply(h, graph, rows)
     return h
 
 

@@ -71,7 +71,7 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     if encoder_name == 'mlp':
         h = model(data.x)
     else:
-        h = ops.gather_encoder_output(model(data.x, graph), graph)
+        h = ops.gather_encoder_output(model(data.x, graph), graph, rows=train_edges)   # peer-memory graphs fetch only these rows
     out = predictor.score(h, u, v, plan=plan).reshape(-1)
     loss = ops.bce_loss(out, edge.size(1))
     if loss_weight != 1.0:

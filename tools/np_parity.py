@@ -219,7 +219,7 @@ def comm_microbench(rank, world, dev, iters=10):
             n_ref = int(st["f_ref"].numel())
             stage_dst = pr["buf"][pg.n_loc * F * 2:]
             t(f"peer row pull alone F={F} ({n_ref} distinct remote rows of {(world - 1) * pg.n_loc}), graph replay",
-              lambda: lib.llp_peer_gather_rows(pr["table"].data_ptr(), st["f_ref"].data_ptr(), pr["shift"], n_ref, F * 2,
+              lambda: lib.llp_peer_gather_rows(pr["table"].data_ptr(), st["f_ref"].data_ptr(), None, pr["shift"], n_ref, F * 2,
                                                stage_dst.data_ptr(), L._native.stream_ptr()), n_ref * F * 2, graph=True)
             t(f"partitioned spmm fwd F={F} (staged pull + local spmm), graph replay", lambda: pg.spmm(xl), n_ref * F * 2, graph=True)
             t("peer barrier alone, graph replay", lambda: pg._peer_barrier(), graph=True)
