@@ -60,7 +60,7 @@ STUDENT = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per SpMM launch (mean of one step's five launches) from the committed
 # `ncu --set full` capture of this same command (tools/ncu_summary.py).  Only meaningful for the collab bf16 workload.
-SPMM_TRAFFIC_SOURCE = "profiles/r01_spmm_ncu_full_summary.json"
+SPMM_TRAFFIC_SOURCE = "profiles/r02_spmm_ncu_full_summary.json"
 
 
 def spmm_traffic(workload, precision):
@@ -68,7 +68,7 @@ def spmm_traffic(workload, precision):
     if workload != "collab" or precision != "bf16" or not os.path.exists(path):
         return None
     try:
-        t = [l["traffic_bytes"] for l in json.load(open(path))["launches"] if "spmm_kernel" in l["kernel"] and "traffic_bytes" in l]
+        t = [l["traffic_bytes"] for l in json.load(open(path))["launches"] if ("spmm_kernel" in l["kernel"] or "spmm_stream_kernel" in l["kernel"]) and "traffic_bytes" in l]
         return sum(t) / len(t) if t else None
     except (OSError, ValueError, KeyError):
         return None
@@ -417,7 +417,7 @@ def make_teacher(hz, precision, data_cpu, split):
     h2d = host_batches[0].numel() * host_batches[0].element_size()
     keep = (model, predictor, optimizer, data)
     return dict(step=step, resident=resident, e2e=e2e, evaluate=evaluate, batch=batch, h2d=h2d, keep=keep, modules=(model, predictor),
-                kernel="spmm_kernel (+fix-up), SAGE mean aggregation fwd + transpose-bwd", bound="hbm")
+                kernel="spmm_stream_kernel + spmm_fixup_kernel, SAGE mean aggregation fwd + transpose-bwd", bound="hbm")
 
 
 def make_student(hz, precision, data_cpu, split):
