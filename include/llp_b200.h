@@ -119,6 +119,15 @@ int llp_peer_barrier(void* const* flags, int rank, int world, void* stream);
  * dropped into their places of an otherwise untouched [N, feat] matrix.  peer_x = DEVICE table of block base pointers. */
 int llp_peer_gather_rows(const void* const* peer_x, const int32_t* src, const int32_t* dst_rows /* or NULL */, int shift,
                          int64_t n_rows, int64_t row_bytes, void* dst, void* stream);
+/* Sparse return of the embedding gradient (transpose of the pull by node id): every rank publishes {count, ids...} of the
+ * nodes its edge shard scored and its gradient rows for them inside an exported [N_padded, ld] matrix; the owner of a node
+ * block marks which of its rows each rank touched (llp_peer_mark_rows; `mark` = zeroed uint8[world * n_loc]) and pulls +
+ * adds the marked rows in rank order with fp32 accumulation (llp_peer_reduce_rows; rows nobody marked become zero).
+ * Replaces a dense reduce-scatter of all N rows (the reference is single-GPU: autograd's index_put_ of models.py:140). */
+int llp_peer_mark_rows(const void* const* ids_table /* DEVICE [world] */, int world, int64_t lo, int64_t n_loc, int64_t max_ids,
+                       void* mark, void* stream);
+int llp_peer_reduce_rows(int dtype, const void* const* g_table /* DEVICE [world] */, int world, const void* mark, int64_t lo,
+                         int64_t n_loc, int64_t feat, int64_t ld, void* out, int64_t ldo, void* stream);
 /* llp_spmm with the source rows in peer-mapped blocks: peer_x = DEVICE array of `world` base pointers (rank r's
  * [peer_nloc, ldx] block), col[e] = (owner rank << peer_shift) | row inside the owner's block, src_scale (optional)
  * indexed by owner * peer_nloc + row.  Row widths of 256 or 512 bytes; LLP_E_SHAPE otherwise (use llp_spmm on an

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "llp_ipc_close": (c_int, [c_void_p]),
     "llp_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "llp_peer_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "llp_peer_mark_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "llp_peer_reduce_rows": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "llp_spmm_peer": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int64, c_int64,
                               c_int64, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "llp_gemm_nt": (c_int, [ctypes.POINTER(GemmNtArgs), c_void_p]),

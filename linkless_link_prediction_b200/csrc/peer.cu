@@ -79,6 +79,59 @@ peer_gather_rows_kernel(const unsigned long long* __restrict__ table, const int3
   }
 }
 
+// ---- sparse return of the embedding gradient (the transpose of the pull by node id) -------------------------------------
+// Every rank q has published (a) the node ids its edge shard scored, as {count, ids...} in an exported int32 buffer, and
+// (b) its gradient rows for exactly those nodes, in their places of an exported [N_padded, F] matrix.  The OWNER of a
+// node block then (1) marks, per source rank, which of its rows that rank touched and (2) pulls and adds the marked rows
+// in rank order 0..W-1 (fp32 accumulation, fixed order: deterministic) — 2B/W rows per rank over NVLink instead of a dense
+// reduce-scatter of all N rows.
+__global__ void peer_mark_rows_kernel(const unsigned long long* __restrict__ ids_table, int64_t lo, int64_t n_loc, int64_t max_ids,
+                                      uint8_t* __restrict__ mark) {
+  const int q = blockIdx.y;
+  const int32_t* ids = reinterpret_cast<const int32_t*>(__ldg(ids_table + q));
+  const int64_t count = min((int64_t)ids[0], max_ids);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = ids[1 + i];
+    if (id >= lo && id < lo + n_loc) mark[(int64_t)q * n_loc + (id - lo)] = 1;
+  }
+}
+
+// one warp per owned row; lane l covers the 16-byte vectors l, l + 32, ... of the row
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_reduce_rows_kernel(const unsigned long long* __restrict__ g_table, int world, const uint8_t* __restrict__ mark, int64_t lo,
+                        int64_t n_loc, int F, int64_t ld, T* __restrict__ out, int64_t ldo) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (n >= n_loc) return;
+  for (int c0 = lane * VE; c0 < F; c0 += 32 * VE) {
+    float acc[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) acc[i] = 0.0f;
+    for (int q = 0; q < world; ++q) {
+      if (!mark[(int64_t)q * n_loc + n]) continue;   // warp-uniform
+      const T* row = reinterpret_cast<const T*>(__ldg(g_table + q)) + (lo + n) * ld + c0;
+      uint4 v;
+      asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(row));
+      if constexpr (sizeof(T) == 4) {
+        acc[0] += __uint_as_float(v.x); acc[1] += __uint_as_float(v.y); acc[2] += __uint_as_float(v.z); acc[3] += __uint_as_float(v.w);
+      } else {
+        acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xffff0000u);
+        acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xffff0000u);
+        acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xffff0000u);
+        acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xffff0000u);
+      }
+    }
+    T* dst = out + n * ldo + c0;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+}
+
 }  // namespace llp
 
 using namespace llp;
@@ -160,6 +213,45 @@ extern "C" int llp_peer_gather_rows(const void* const* peer_x, const int32_t* sr
   const unsigned blocks = (unsigned)(want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8);
   peer_gather_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(peer_x), src, dst_rows, shift, n_rows,
                                                       row_vecs, reinterpret_cast<uint4*>(dst));
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+// mark[q * n_loc + (id - lo)] = 1 for every id that rank q published and that lies in [lo, lo + n_loc); ids_table = DEVICE
+// array of `world` pointers to the ranks' int32 id buffers {count, id_0, id_1, ...} (peer-mapped).  `mark` must be zeroed
+// by the caller.
+extern "C" int llp_peer_mark_rows(const void* const* ids_table, int world, int64_t lo, int64_t n_loc, int64_t max_ids,
+                                  void* mark, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(ids_table && mark && world >= 1 && world <= kPeerMaxRanks && lo >= 0 && n_loc > 0 && max_ids >= 0);
+  if (int rc = check_device()) return rc;
+  if (max_ids == 0) return 0;
+  const int64_t bx = ceil_div(max_ids, 256);
+  dim3 grid((unsigned)(bx < 256 ? bx : 256), (unsigned)world);
+  peer_mark_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(ids_table), lo, n_loc, max_ids,
+                                                  reinterpret_cast<uint8_t*>(mark));
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
+// out[n, :] = sum over q = 0..world-1 with mark[q * n_loc + n] of row (lo + n) of rank q's [N_padded, ld] matrix
+// (g_table = DEVICE array of peer-mapped base pointers), fp32 accumulation in rank order; rows nobody marked become zero.
+extern "C" int llp_peer_reduce_rows(int dtype, const void* const* g_table, int world, const void* mark, int64_t lo, int64_t n_loc,
+                                    int64_t feat, int64_t ld, void* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LLP_CHECK_ARG(g_table && mark && out && world >= 1 && world <= kPeerMaxRanks && lo >= 0 && n_loc > 0 && feat > 0 && ld >= feat && ldo >= feat);
+  if (int rc = check_device()) return rc;
+  const int64_t elt = dtype == LLP_F32 ? 4 : 2;
+  if ((feat * elt) % 16 != 0 || (ld * elt) % 16 != 0 || (ldo * elt) % 16 != 0 || !aligned(out, 16)) return LLP_E_ALIGN;
+  const unsigned blocks = (unsigned)ceil_div(n_loc * 32, 256);
+  if (dtype == LLP_F32)
+    peer_reduce_rows_kernel<float><<<blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(g_table), world,
+        reinterpret_cast<const uint8_t*>(mark), lo, n_loc, (int)feat, ld, reinterpret_cast<float*>(out), ldo);
+  else if (dtype == LLP_BF16)
+    peer_reduce_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(g_table), world,
+        reinterpret_cast<const uint8_t*>(mark), lo, n_loc, (int)feat, ld, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  else
+    return LLP_E_BADARG;
   LLP_LAUNCH_OK();
   return 0;
 }

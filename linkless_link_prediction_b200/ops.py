@@ -399,7 +399,7 @@ class PartitionedGraph(Graph):
             self._init_peer(int(peer_row_bytes), "load" if peer == "load" else "stage")
 
     # ---- peer-memory mode: remote rows are loaded by the SpMM kernel itself over NVLink (llp_spmm_peer) --------------
-    def _init_peer(self, row_bytes: int, how: str) -> None:
+    def _init_peer(self, row_bytes: int, how: str, max_ids: int = 1 << 20) -> None:
         """One peer-visible activation buffer per rank + one flag array for the barrier, exported through CUDA IPC and
         mapped by every other rank.  ``how == "stage"``: the buffer is ``[n_loc + n_ref, row_bytes]`` — this rank's block
         followed by a staging area for the ``n_ref`` DISTINCT remote rows its local messages reference (listed once here,
@@ -433,6 +433,10 @@ class PartitionedGraph(Graph):
             n_ref = max(int(f_ref.numel()), int(t_ref.numel()))
         buf = torch.zeros((n_loc + n_ref) * row_bytes + 256, dtype=torch.uint8, device=dev)   # rows are 16-byte aligned
         flags = torch.zeros(W + 2, dtype=torch.int64, device=dev)
+        # sparse return of the embedding gradient: this rank's gradient rows in their places of an [N_padded, row_bytes]
+        # matrix + the node ids it scored, both readable by the owners of those nodes
+        gbuf = torch.zeros(self.num_nodes_padded * row_bytes + 256, dtype=torch.uint8, device=dev)
+        idsbuf = torch.zeros(1 + max_ids, dtype=torch.int32, device=dev)
         torch.cuda.synchronize(dev)
 
         def export(t):
@@ -440,22 +444,25 @@ class PartitionedGraph(Graph):
             N.check(lib.llp_ipc_export(t.data_ptr(), h, ctypes.byref(off)), "llp_ipc_export")
             return bytes(h.raw), int(off.value)
 
-        mine = (export(buf), export(flags))
+        mine_t = (buf, flags, gbuf, idsbuf)
         everyone = [None] * W
-        dist.all_gather_object(everyone, mine, group=self.group)
-        bases, buf_ptrs, flag_ptrs = [], [], []
+        dist.all_gather_object(everyone, tuple(export(t) for t in mine_t), group=self.group)
+        bases, ptrs = [], [[] for _ in mine_t]
         for r in range(W):
-            if r == self.rank:
-                buf_ptrs.append(buf.data_ptr()); flag_ptrs.append(flags.data_ptr())
-                continue
-            for (handle, off), dst in ((everyone[r][0], buf_ptrs), (everyone[r][1], flag_ptrs)):
+            for k, t in enumerate(mine_t):
+                if r == self.rank:
+                    ptrs[k].append(t.data_ptr())
+                    continue
+                handle, off = everyone[r][k]
                 ptr, base = ctypes.c_void_p(), ctypes.c_void_p()
                 N.check(lib.llp_ipc_open(handle, off, ctypes.byref(ptr), ctypes.byref(base)), "llp_ipc_open")
-                bases.append(base.value); dst.append(ptr.value)
+                bases.append(base.value); ptrs[k].append(ptr.value)
         dist.barrier(group=self.group)   # nobody tears its buffers down before everyone has mapped them
-        self.peer = dict(how=how, shift=shift, row_bytes=row_bytes, buf=buf, flags=flags, bases=bases,
-                         table=torch.tensor(buf_ptrs, dtype=torch.int64, device=dev),
-                         flag_ptrs=(ctypes.c_void_p * W)(*flag_ptrs), stage=stage,
+        table = lambda k: torch.tensor(ptrs[k], dtype=torch.int64, device=dev)
+        self.peer = dict(how=how, shift=shift, row_bytes=row_bytes, buf=buf, flags=flags, gbuf=gbuf, idsbuf=idsbuf, bases=bases,
+                         table=table(0), g_table=table(2), ids_table=table(3), max_ids=max_ids,
+                         mark=torch.zeros(W * n_loc, dtype=torch.uint8, device=dev),
+                         flag_ptrs=(ctypes.c_void_p * W)(*ptrs[1]), stage=stage,
                          col=recode(self.col) if how == "load" else None, t_col=recode(self.t_col) if how == "load" else None)
 
     def close_peer(self) -> None:
@@ -474,13 +481,12 @@ class PartitionedGraph(Graph):
         """True when a barrier of this rank ever gave up waiting (~2 s) for a peer (host read: synchronises)."""
         return self.peer is not None and bool(int(self.peer["flags"][self.world + 1].item()))
 
-    def pull_rows(self, x_loc: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
-        """``[N_padded, F]`` matrix in which exactly the rows ``rows`` (global node ids, duplicates allowed) hold the
+    def pull_rows(self, x_loc: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """``[N_padded, F]`` matrix in which exactly the rows ``ids`` (global node ids, int64, duplicates allowed) hold the
         owners' rows of ``x_loc``, pulled over NVLink; all other rows are uninitialised."""
         lib = N.require_gpu()
         pr, F = self.peer, x_loc.size(1)
         rb = F * x_loc.element_size()
-        ids = rows.reshape(-1)
         src = (((ids // self.n_loc) << pr["shift"]) | (ids % self.n_loc)).to(torch.int32)
         dst_rows = ids.to(torch.int32)
         pr["buf"][:self.n_loc * rb].view(x_loc.dtype).view(self.n_loc, F).copy_(x_loc)
@@ -490,6 +496,29 @@ class PartitionedGraph(Graph):
                                          rb, full.data_ptr(), N.stream_ptr()), "llp_peer_gather_rows")
         self._peer_barrier()
         return full
+
+    def return_rows_grad(self, g_full: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """Transpose of ``pull_rows``: ``g_full`` ``[N_padded, F]`` is non-zero only in the rows ``ids``; every rank publishes
+        those rows and ids, and the OWNER of each node block pulls and adds the rows the ranks touched in it (rank order,
+        fp32 accumulation).  Returns this rank's ``[n_loc, F]`` gradient block — what a dense reduce-scatter of all N rows
+        would return, up to the summation order."""
+        lib = N.require_gpu()
+        pr, F = self.peer, g_full.size(1)
+        rb, cnt = F * g_full.element_size(), int(ids.numel())
+        G = pr["gbuf"][:self.num_nodes_padded * rb].view(g_full.dtype).view(self.num_nodes_padded, F)
+        G.index_copy_(0, ids, g_full.index_select(0, ids))       # duplicates carry identical rows
+        pr["idsbuf"][:1].fill_(cnt)
+        pr["idsbuf"][1:1 + cnt].copy_(ids)
+        self._peer_barrier()                                      # every rank's rows and ids are published
+        pr["mark"].zero_()
+        N.check(lib.llp_peer_mark_rows(pr["ids_table"].data_ptr(), self.world, self.lo, self.n_loc, pr["max_ids"],
+                                       pr["mark"].data_ptr(), N.stream_ptr()), "llp_peer_mark_rows")
+        out = empty_mat(self.n_loc, F, g_full.dtype, g_full.device)
+        op, ldo = N.mat(out)
+        N.check(lib.llp_peer_reduce_rows(N.dtype_id(g_full.dtype), pr["g_table"].data_ptr(), self.world, pr["mark"].data_ptr(),
+                                         self.lo, self.n_loc, F, F, op, ldo, N.stream_ptr()), "llp_peer_reduce_rows")
+        self._peer_barrier()                                      # every owner has read: the buffers may be overwritten
+        return out
 
     def _peer_ok(self, x: torch.Tensor) -> bool:
         if self.peer is None:
@@ -604,9 +633,10 @@ class GatherRowsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_loc, graph, rows=None):
-        ctx.graph = graph
-        if rows is not None and graph.peer is not None and graph._peer_ok(x_loc):
-            return graph.pull_rows(x_loc, rows)
+        ctx.graph, ctx.ids = graph, None
+        if rows is not None and graph.peer is not None and graph._peer_ok(x_loc) and rows.numel() <= graph.peer["max_ids"]:
+            ctx.ids = rows.reshape(-1).contiguous()
+            return graph.pull_rows(x_loc, ctx.ids)
         return graph.gather_rows(x_loc)
 
     @staticmethod
@@ -614,6 +644,8 @@ class GatherRowsFn(torch.autograd.Function):
         import torch.distributed as dist
         graph = ctx.graph
         g = g_full if g_full.is_contiguous() else g_full.contiguous()
+        if ctx.ids is not None:
+            return graph.return_rows_grad(g, ctx.ids), None, None
         out = torch.empty((graph.n_loc, g.size(1)), dtype=g.dtype, device=g.device)
         dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=graph.group)
         return out, None, None
