@@ -64,6 +64,15 @@ def parity(rank, world, dev, mode):
         assert pg._peer_ok(xl)
         out["peer_spmm_bit_identical"] = bool(torch.equal(pg.spmm(xl), pg_ag.spmm(xl)) and
                                               torch.equal(pg.spmm(xl, transpose=True), pg_ag.spmm(xl, transpose=True)))
+        # sparse gradient return against the dense reduce-scatter of the same [N_padded, F] matrix (rows outside `ids` zero)
+        gi = torch.Generator().manual_seed(11 + rank)
+        ids = torch.randint(0, n, (700,), generator=gi).to(dev)
+        gfull = torch.zeros(pg.num_nodes_padded, h, device=dev, dtype=ops.compute_dtype())
+        gfull[ids] = torch.randn(700, h, generator=gi).to(dev).to(gfull.dtype)      # duplicates: last write wins, one row per id
+        sparse = pg.return_rows_grad(gfull, ids).float()
+        dense = torch.empty(pg.n_loc, h, device=dev, dtype=torch.float32)
+        dist.reduce_scatter_tensor(dense, gfull.float().contiguous())
+        out["sparse_grad_return_max_rel_diff"] = float((sparse - dense).abs().max() / dense.abs().max())
     # forward: bit-identical embeddings
     with torch.no_grad():
         m1.eval(); mp.eval()
@@ -122,7 +131,13 @@ def parity(rank, world, dev, mode):
                      and all(abs(a - b) <= (1e-5 if mode == torch.float32 else 2e-2) * abs(a) for a, b in zip(losses_1, losses_p)))
     if PEER:
         out["barrier_timed_out"] = pg.peer_barrier_timed_out()
-        out["ok"] = bool(out["ok"] and out["peer_spmm_bit_identical"] and not out["barrier_timed_out"])
+        # fp32: the owner-side sum runs in rank order, NCCL's in ring order; Adam's first steps turn last-bit differences of
+        # near-zero gradient entries into parameter differences of a few 1e-4 (losses still agree to 1e-7): the parameter
+        # bound of this path is 1e-3, the sparse return itself is checked against the dense reduce-scatter directly
+        grad_ok = out["sparse_grad_return_max_rel_diff"] <= (1e-6 if mode == torch.float32 else 1e-2)
+        base_ok = bool(emb_ok and out["eval_identical"] and gdiff < tol and (pdiff < 1e-3 or mode != torch.float32)
+                       and all(abs(a - b) <= (1e-5 if mode == torch.float32 else 2e-2) * abs(a) for a, b in zip(losses_1, losses_p)))
+        out["ok"] = bool(base_ok and grad_ok and out["peer_spmm_bit_identical"] and not out["barrier_timed_out"])
         del op, mp, pp, dp
         pg.close_peer()
     return out
