@@ -12,7 +12,8 @@ edges consumed per second over all ranks with inputs resident in HBM; ``e2e`` = 
 the step's edge batch coming from pinned host memory and the loss read back every step.  One eval pass (encoder forward
 + 4 scoring sets + Hits@{10,50,100}) is timed separately and reported under ``eval``.  The default bf16 line also carries
 an ``"fp32"`` object: the same measurement in the fp32-parity mode (3xTF32 tensor-core GEMMs), run inside the same
-invocation.
+invocation, and (N = 1) a ``"student"`` object: the LLP_D + LLP_R + True_label student step of the same graph
+(``collab-student`` below; tensor roofline of its dense layers).
 
 Other workloads (``--workload``): ``powerlaw-10m`` (configs[4], ``--scale``), ``coauthor-physics`` (configs[2] teacher),
 ``cora`` (configs[0] on the GPU) and the LLP student steps ``cora-student`` (configs[1]: MLP student, LLP_D = LLP_R =
@@ -84,6 +85,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debugging only)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement the default bf16 run appends")
+    ap.add_argument("--no-student", action="store_true", help="skip the LLP student step the default single-GPU run appends")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (ops.OVERLAP_WGRAD = False)")
@@ -652,6 +654,19 @@ def main():
         fp32_res = measure(hz, "fp32", data_cpu, split, max(args.steps // 2, 5), args.warmup)
         ops.set_compute_dtype(torch.bfloat16)
 
+    student_res = None
+    if args.precision == "bf16" and not args.no_student and args.workload == "collab" and world == 1:
+        # the distillation half of the path (LLP_D + LLP_R + True_label, main.py:147-236) on the SAME graph: the collab student
+        # of scripts/LLP_transductive.sh (1024-wide MLP, K = 36 contexts, --minibatch), same invocation
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        args.workload = "collab-student"
+        try:
+            student_res = measure(hz, "bf16", data_cpu, split, max(args.steps // 4, 5), args.warmup)
+        finally:
+            args.workload = "collab"
+        ops.set_compute_dtype(torch.bfloat16)
+
     if world > 1:
         import gc
         gc.collect()
@@ -676,6 +691,11 @@ def main():
                             "promotion (csrc/gemm_tf32.cu)", ratio_to_bf16_step=fp32_res["ms_per_step"] / main_res["ms_per_step"])
         if "eval" in fp32_res:
             line["fp32"]["eval"] = fp32_res["eval"]
+    if student_res is not None:
+        line["student"] = {k: student_res[k] for k in ("value", "ms_per_step", "host_enqueue_ms_per_step", "e2e", "roofline", "gpu_launches")
+                           if k in student_res}
+        line["student"].update(unit="edges/s", steps=max(args.steps // 4, 5), workload="collab-student: LLP student train step "
+                               "(" + STUDENT["collab-student"]["cfg"] + ")", config=student_res.get("extra"))
     if tuning:
         line["llp_tuning"] = tuning
     if world == 1 and not args.no_cpu_baseline:
