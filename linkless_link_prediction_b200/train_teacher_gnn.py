@@ -67,6 +67,8 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
     # node-partitioned encoder (ops.PartitionedGraph): data.x holds this rank's rows; the scorer indexes
     # the all-gathered embedding matrix and its gradient is reduce-scattered back to the owning ranks
     n_rows = graph.num_nodes_padded if isinstance(graph, ops.PartitionedGraph) else data.x.size(0)
+    if isinstance(graph, ops.PartitionedGraph):
+        graph.begin_step()
     plan = ops.EdgePlan(u, v, n_rows, side_stream=True) if torch.is_grad_enabled() else None
     if encoder_name == 'mlp':
         h = model(data.x)
@@ -81,6 +83,26 @@ def train_step(model, predictor, data, edge, neg_edge, optimizer, encoder_name='
         plan.wait()  # no-op when the backward consumed it; otherwise re-join the side stream
     optimizer_tail(model, predictor, optimizer)
     return loss.detach()
+
+
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def _capture(graph):
+    """``torch.cuda.graph(graph)`` with the cyclic garbage collector paused: a collection that runs in the middle of a
+    capture can finalise unrelated CUDA objects of earlier work (events, streams, graphs of a previous run), and a
+    destructor that calls a capture-unsafe API invalidates the capture (seen after a failed test had left its frames
+    behind).  torch.cuda.graph collects once on entry; nothing new needs collecting until the capture has ended."""
+    was_enabled = gc.isenabled()
+    try:
+        with torch.cuda.graph(graph):
+            gc.disable()
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 USE_CUDA_GRAPH = True   # replay whole training steps as one CUDA graph once their shapes have been seen twice
@@ -124,7 +146,7 @@ class CapturedStep:
             if self.profile_what in (True, "gemm"):
                 ops.GEMM_PROFILE = self.gemm_events = []
         try:
-            with torch.cuda.graph(self.graph):
+            with _capture(self.graph):
                 self.loss = self.fn(*self.static)
         finally:
             ops.SPMM_PROFILE, ops.GEMM_PROFILE = saved_profile
@@ -382,7 +404,7 @@ class _CapturedEval:
             return self._pass()
         if self.graph is None:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with _capture(self.graph):
                 self.out = self._pass()
         self.graph.replay()
         return self.out

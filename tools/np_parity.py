@@ -232,9 +232,9 @@ def comm_microbench(rank, world, dev, iters=10):
         if PEER == "stage":
             st, pr, lib = pg.peer["stage"], pg.peer, L._native.load()
             n_ref = int(st["f_ref"].numel())
-            stage_dst = pr["buf"][pg.n_loc * F * 2:]
+            stage_dst = pr["buf"][pg.n_loc * F * 2:pr["block_bytes"]]
             t(f"peer row pull alone F={F} ({n_ref} distinct remote rows of {(world - 1) * pg.n_loc}), graph replay",
-              lambda: lib.llp_peer_gather_rows(pr["table"].data_ptr(), st["f_ref"].data_ptr(), None, pr["shift"], n_ref, F * 2,
+              lambda: lib.llp_peer_gather_rows(pr["tables"][0].data_ptr(), st["f_ref"].data_ptr(), None, pr["shift"], n_ref, F * 2,
                                                stage_dst.data_ptr(), L._native.stream_ptr()), n_ref * F * 2, graph=True)
             t(f"partitioned spmm fwd F={F} (staged pull + local spmm), graph replay", lambda: pg.spmm(xl), n_ref * F * 2, graph=True)
             t("peer barrier alone, graph replay", lambda: pg._peer_barrier(), graph=True)
@@ -245,7 +245,7 @@ def comm_microbench(rank, world, dev, iters=10):
             outb = ops.empty_mat(pg.n_loc, F, xl.dtype, dev)
             wsb = torch.empty(lib.llp_spmm_workspace_bytes(pg.num_edges, F), dtype=torch.uint8, device=dev)
             kern = lambda: lib.llp_spmm_peer(1, pg.rowptr.data_ptr(), pr["col"].data_ptr(), pg.plan.data_ptr(), pg.n_loc, pg.num_edges,
-                                             pr["table"].data_ptr(), world, pr["shift"], pg.n_loc, F, F, None, 1, outb.data_ptr(),
+                                             pr["tables"][0].data_ptr(), world, pr["shift"], pg.n_loc, F, F, None, 1, outb.data_ptr(),
                                              outb.stride(0), wsb.data_ptr(), pg.hubs[0].data_ptr(), pg.hubs[1],
                                              L._native.stream_ptr())
             t(f"peer spmm kernels alone F={F} (no copy, no barriers), graph replay", kern, remote, graph=True)
