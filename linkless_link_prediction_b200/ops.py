@@ -360,6 +360,21 @@ def partition_messages(edge_index: torch.Tensor, num_nodes: int, rank: int, worl
     return n_loc, lo, hi, into, out_of, inv_deg
 
 
+def stage_columns(col: torch.Tensor, lo: int, hi: int, scale: Optional[torch.Tensor] = None):
+    """Bookkeeping of the staged peer pull (pure torch; exercised on the CPU by tests/test_dist_gloo.py): ``col`` holds
+    GLOBAL source ids of a rank's local messages, ``[lo, hi)`` is the rank's own node block.  Returns ``(ref, local,
+    scale')``: the sorted distinct REMOTE ids the messages reference (each is pulled once), the column indices re-coded
+    into the local matrix ``[own block | staged rows]`` (own id g -> g - lo, remote id -> n_loc + its position in
+    ``ref``), and ``scale`` (indexed by global id) gathered into that order."""
+    c = col.long()
+    n_loc = hi - lo
+    own = (c >= lo) & (c < hi)
+    ref = torch.unique(c[~own])
+    local = torch.where(own, c - lo, n_loc + torch.searchsorted(ref, c))
+    sc = None if scale is None else torch.cat([scale[lo:hi], scale[ref]]).contiguous()
+    return ref, local.to(torch.int32).contiguous(), sc
+
+
 class PartitionedGraph(Graph):
     """Node-partitioned message graph: rank r of W owns the contiguous node block
     ``[r*n_loc, (r+1)*n_loc)`` with ``n_loc = ceil(N / W)`` (the last block is padded with isolated nodes), i.e. the rows
@@ -416,13 +431,8 @@ class PartitionedGraph(Graph):
         recode = lambda c: (((c.long() // n_loc) << shift) | (c.long() % n_loc)).to(torch.int32).contiguous()
 
         def stage_plan(col, scale):
-            """distinct remote sources (sorted), the column indices into [own block | staged rows], the scale in that order"""
-            c = col.long()
-            own = (c >= self.lo) & (c < self.hi)
-            ref = torch.unique(c[~own])                                    # sorted global ids of the referenced remote rows
-            local = torch.where(own, c - self.lo, n_loc + torch.searchsorted(ref, c))
-            sc = None if scale is None else torch.cat([scale[self.lo:self.hi], scale[ref]]).contiguous()
-            return recode(ref), local.to(torch.int32).contiguous(), sc
+            ref, local, sc = stage_columns(col, self.lo, self.hi, scale)
+            return recode(ref), local, sc
 
         stage = None
         n_ref = 0

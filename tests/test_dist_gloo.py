@@ -88,6 +88,34 @@ def _worker(rank, world, port, ret):
         # every message is owned exactly once per direction
         cnt = torch.tensor([f_src.numel(), t_src.numel()]); dist.all_reduce(cnt)
         assert cnt.tolist() == [ei_p.size(1), ei_p.size(1)]
+        # ---- peer-memory variant (ops.stage_columns): each referenced remote row is staged ONCE behind the own block
+        # and the re-coded column indices aggregate from [own block | staged rows] exactly what the all-gathered matrix
+        # gives (the GPU path pulls the staged rows over NVLink; here they are read out of the gathered matrix) ----
+        from linkless_link_prediction_b200.ops import stage_columns
+        for (col_g, scale, mean, ref_out) in ((col, None, True, agg_loc), (col_t, inv_deg, False, gt_loc)):
+            ref, local, sc = stage_columns(col_g, lo, hi, scale)
+            assert torch.equal(ref, torch.unique(ref)) and bool(((ref < lo) | (ref >= hi)).all())      # sorted, distinct, remote
+            assert int(local.max()) < n_loc + ref.numel() and int(local.min()) >= 0
+            mat = torch.cat([x_full[lo:hi], x_full[ref]])                                          # [own block | staged rows]
+            assert torch.equal(mat[local.long()], x_full[col_g.long()])                            # same row behind every edge
+            rp_s = rp if mean else rp_t
+            out = O.spmm_csr(rp_s, local.long(), mat, mean=mean, src_scale=sc)
+            assert torch.equal(out, ref_out)
+        # ---- sparse return of the embedding gradient: owners add, in rank order, the rows each rank touched in their
+        # block == dense reduce-scatter (sum) of the [N_padded, F] matrices ----
+        gi = torch.Generator().manual_seed(20 + rank)
+        ids = torch.randint(0, n_nodes, (37,), generator=gi)
+        g_full = torch.zeros(n_loc * world, feat)
+        g_full[torch.unique(ids)] = torch.randn(torch.unique(ids).numel(), feat, generator=gi)
+        published = [None] * world
+        dist.all_gather_object(published, (ids, g_full))
+        mine = torch.zeros(n_loc, feat)
+        for q in range(world):                                   # rank order, marked rows only
+            q_ids, q_g = published[q]
+            marked = torch.unique(q_ids[(q_ids >= lo) & (q_ids < hi)])
+            mine[marked - lo] += q_g[marked]
+        total = g_full.clone(); dist.all_reduce(total)
+        assert torch.equal(mine, total[lo:hi])
         # ---- training step: W ranks on shards of a 2B batch == 1 rank on the whole batch ----
         torch.manual_seed(0)
         n, f, H, B = 120, 16, 16, 101  # odd batch -> ragged shards
