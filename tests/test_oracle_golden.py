@@ -90,6 +90,38 @@ def test_mean_aggregate_kat():
     torch.testing.assert_close(O.spmm_csr(rowptr, col, x, True), exp)
 
 
+def test_mean_aggregate_matches_scipy_and_networkx():
+    """Independent pins of the aggregation the third-party half of the path performs (PyG SAGEConv(aggr='mean') ->
+    torch_scatter.scatter(reduce='mean'), absent here): the row-normalised adjacency product computed by scipy.sparse
+    (multi-edges counted with their multiplicity, isolated nodes -> zero rows) and a per-node neighbour average over a
+    networkx MultiDiGraph.  Forward and the autograd transpose (A~^T g)."""
+    import networkx as nx
+    import scipy.sparse as sp
+    g = torch.Generator().manual_seed(7)
+    n, f, e = 60, 5, 400
+    ei = torch.randint(0, n - 6, (2, e), generator=g)          # multi-edges and self loops occur; the last 6 nodes are isolated
+    x = torch.randn(n, f, generator=g, dtype=torch.float64)
+    A = sp.coo_matrix((np.ones(e), (ei[1].numpy(), ei[0].numpy())), shape=(n, n)).tocsr()   # A[dst, src] = multiplicity
+    deg = np.asarray(A.sum(1)).ravel()
+    An = sp.diags(1.0 / np.maximum(deg, 1.0)) @ A
+    ours = O.mean_aggregate(x, ei, n)
+    np.testing.assert_allclose(ours.numpy(), An @ x.numpy(), rtol=1e-12, atol=1e-12)
+    assert torch.equal(ours[n - 6:], torch.zeros(6, f, dtype=torch.float64))
+    G = nx.MultiDiGraph(); G.add_nodes_from(range(n)); G.add_edges_from(zip(ei[0].tolist(), ei[1].tolist()))
+    for v in (0, 3, 17, n - 1):
+        preds = [u for u, _ in G.in_edges(v)]                 # with multiplicity
+        want = x[preds].mean(0) if preds else torch.zeros(f, dtype=torch.float64)
+        torch.testing.assert_close(ours[v], want, rtol=1e-12, atol=1e-12)
+    # the transpose autograd applies: d/dx sum(w * mean_aggregate(x)) = A~^T w
+    xg = x.clone().requires_grad_(True)
+    w = torch.randn(n, f, generator=g, dtype=torch.float64)
+    (O.mean_aggregate(xg, ei, n) * w).sum().backward()
+    np.testing.assert_allclose(xg.grad.numpy(), An.T @ w.numpy(), rtol=1e-12, atol=1e-12)
+    # and the CSR form the CUDA kernels are compared against
+    rp, col, _ = O.csr_build(ei, n, "dst")
+    np.testing.assert_allclose(O.spmm_csr(rp, col, x, mean=True).numpy(), An @ x.numpy(), rtol=1e-12, atol=1e-12)
+
+
 def test_sageconv_isolated_node_bias_quirk():
     # SURVEY Q2: SAGEConv keeps b_l on isolated nodes, SAGEConv_updated aggregates it away
     torch.manual_seed(0)
