@@ -95,6 +95,23 @@ def parity(rank, world, dev, mode):
         # flat_grad after the step: partitioned holds the all-reduced SUM over ranks (the 1/W is folded into Adam)
         gdiff = max(gdiff, float((op.flat_grad / world - o1.flat_grad).abs().max() / o1.flat_grad.abs().max()))
     pdiff = float((op.flat_param - o1.flat_param).abs().max() / o1.flat_param.abs().max())
+    # the same step replayed as ONE CUDA graph (collectives / peer pulls / barriers captured in it) against further eager
+    # steps of the replicated model: two eager steps, the capture, then replays on fresh batches.  After nine Adam steps
+    # the two parameter sets have drifted by round-off, so the bound on the loss is 1e-4 (fp32) / 3e-2 (bf16)
+    cap = teacher.CapturedTrainStep(mp, pp, dp, op, loss_weight=weight, eager_steps=2)
+    cap_1, cap_p = [], []
+    for step in range(6):
+        gi2 = torch.Generator().manual_seed(100 + step)
+        pos_s = ei[:, torch.randperm(ei.size(1), generator=gi2)[:B].to(dev)]
+        neg_s = torch.randint(0, n, (2, B), generator=gi2).to(dev)
+        l1 = teacher.train_step(m1, p1, d1, pos_s, neg_s, o1)
+        lp = cap(pos_s[:, lo:hi].contiguous(), neg_s[:, lo:hi].contiguous())
+        t = lp.clone()
+        dist.all_reduce(t)
+        cap_1.append(float(l1)); cap_p.append(float(t) / world)
+    cap.graph = None
+    out["captured_steps_loss_replicated"], out["captured_steps_loss_partitioned"] = cap_1, cap_p
+    out["captured_ok"] = all(abs(a - b) <= (1e-4 if mode == torch.float32 else 3e-2) * abs(a) for a, b in zip(cap_1, cap_p))
     out.update(loss_replicated=losses_1, loss_partitioned=losses_p, max_rel_grad_diff=gdiff, max_rel_param_diff=pdiff)
     # sharded evaluation through the public test function
     g2 = torch.Generator().manual_seed(9)
@@ -135,7 +152,7 @@ def parity(rank, world, dev, mode):
         # near-zero gradient entries into parameter differences of a few 1e-4 (losses still agree to 1e-7): the parameter
         # bound of this path is 1e-3, the sparse return itself is checked against the dense reduce-scatter directly
         grad_ok = out["sparse_grad_return_max_rel_diff"] <= (1e-6 if mode == torch.float32 else 1e-2)
-        base_ok = bool(emb_ok and out["eval_identical"] and gdiff < tol and (pdiff < 1e-3 or mode != torch.float32)
+        base_ok = bool(emb_ok and out["eval_identical"] and out["captured_ok"] and gdiff < tol and (pdiff < 1e-3 or mode != torch.float32)
                        and all(abs(a - b) <= (1e-5 if mode == torch.float32 else 2e-2) * abs(a) for a, b in zip(losses_1, losses_p)))
         out["ok"] = bool(base_ok and grad_ok and out["peer_spmm_bit_identical"] and not out["barrier_timed_out"])
         del op, mp, pp, dp
