@@ -360,6 +360,16 @@ def partition_messages(edge_index: torch.Tensor, num_nodes: int, rank: int, worl
     return n_loc, lo, hi, into, out_of, inv_deg
 
 
+_LIVE_PEER_GRAPHS = weakref.WeakSet()   # PartitionedGraph objects with mapped peer buffers (closed by close_all_peers)
+
+
+def close_all_peers() -> None:
+    """Unmap every peer buffer still mapped by this process (``train_teacher_gnn.finish_distributed`` calls this before
+    the process group is destroyed; collective: every rank must call it)."""
+    for g in list(_LIVE_PEER_GRAPHS):
+        g.close_peer()
+
+
 def stage_columns(col: torch.Tensor, lo: int, hi: int, scale: Optional[torch.Tensor] = None):
     """Bookkeeping of the staged peer pull (pure torch; exercised on the CPU by tests/test_dist_gloo.py): ``col`` holds
     GLOBAL source ids of a rank's local messages, ``[lo, hi)`` is the rank's own node block.  Returns ``(ref, local,
@@ -473,6 +483,7 @@ class PartitionedGraph(Graph):
         peer_block = [everyone[r][-1] for r in range(W)]   # the staging area differs per rank, so do the block sizes
         tables = [torch.tensor([ptrs[0][r] + s * peer_block[r] for r in range(W)], dtype=torch.int64, device=dev) for s in (0, 1)]
         self._slot, self._need_pre, self._was_capturing = 0, True, False
+        _LIVE_PEER_GRAPHS.add(self)
         self.peer = dict(how=how, shift=shift, row_bytes=row_bytes, buf=buf, block_bytes=block_bytes, flags=flags, gbuf=gbuf,
                          idsbuf=idsbuf, bases=bases, tables=tables, g_table=table(2), ids_table=table(3), max_ids=max_ids,
                          mark=torch.zeros(W * n_loc, dtype=torch.uint8, device=dev),
@@ -487,6 +498,7 @@ class PartitionedGraph(Graph):
             for base in self.peer["bases"]:
                 lib.llp_ipc_close(base)
             self.peer = None
+            _LIVE_PEER_GRAPHS.discard(self)
 
     def begin_step(self) -> None:
         """Call at the start of every function that is captured into (or replayed as) its own CUDA graph: the first peer

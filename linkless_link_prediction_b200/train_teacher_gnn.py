@@ -520,6 +520,8 @@ def finish_distributed() -> None:
     if dist.is_available() and dist.is_initialized():
         gc.collect()
         torch.cuda.synchronize()
+        dist.barrier()               # nobody unmaps a buffer a peer may still be reading
+        ops.close_all_peers()        # CUDA-IPC mappings of node-partitioned graphs (ops.PartitionedGraph(peer=True))
         dist.barrier()
         dist.destroy_process_group()
 
