@@ -215,10 +215,11 @@ int llp_gate(int dtype, const void* g, int64_t ldg, const void* gate, int64_t ld
 /* z[m,:] = h[u[m],:] * h[v[m],:] */
 int llp_edge_hadamard(int dtype, const void* h, int64_t ldh, int64_t feat, const int64_t* u, const int64_t* v,
                       int64_t num_edges, void* z, int64_t ldz, void* stream);
-/* Incidence plan of an edge batch: the 2*num_edges (node, edge) incidences stably sorted by node.
+/* Incidence plan of an edge batch: the 2*num_edges (node, edge) incidences stably sorted by node (own counting sort:
+ * per-node counts -> exclusive scan -> scatter -> rows put back into incidence order; no library sort).
  * rowptr[n] = first sorted position of node n (int32[num_nodes+1]); meta[2p], meta[2p+1] = (edge m, OTHER endpoint of m)
  * of sorted position p (int32[4*num_edges]).  Depends only on u and v: callers run it early / on a side stream. */
-size_t llp_edge_plan_workspace_bytes(int64_t num_edges);
+size_t llp_edge_plan_workspace_bytes(int64_t num_edges, int64_t num_nodes);
 int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t num_edges, int64_t num_nodes, int32_t* rowptr, int32_t* meta,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* Backward of the gather: gh[n,:] = sum_{u[m]==n} dz[m,:]*h[v[m],:] + sum_{v[m]==n} dz[m,:]*h[u[m],:] for EVERY node row

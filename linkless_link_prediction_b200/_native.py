@@ -102,7 +102,7 @@ PROTOTYPES = {
                          c_void_p]),
     "llp_edge_hadamard": (c_int, [c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                   c_void_p]),
-    "llp_edge_plan_workspace_bytes": (c_size_t, [c_int64]),
+    "llp_edge_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "llp_edge_plan": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "llp_edge_hadamard_bwd_workspace_bytes": (c_size_t, [c_int64]),
     "llp_edge_hadamard_bwd": (c_int, [c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p,

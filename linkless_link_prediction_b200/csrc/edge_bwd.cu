@@ -3,15 +3,15 @@
 //
 //     gh[n,:] = sum_{m: u[m]==n} dz[m,:]*h[v[m],:]  +  sum_{m: v[m]==n} dz[m,:]*h[u[m],:]
 //
-// as a gather-REDUCE instead of a scatter.  `llp_edge_plan` stably radix-sorts the 2M (node, edge) incidences of the
-// batch by node (it depends only on u and v, so the host runs it on a side stream while the encoder works); the backward
+// as a gather-REDUCE instead of a scatter.  `llp_edge_plan` stably sorts the 2M (node, edge) incidences of the batch by
+// node with its own counting sort (keys are node ids: count per node -> exclusive scan = the row pointers -> scatter ->
+// every row put back into incidence order; it depends only on u and v, so the host runs it on a side stream while the
+// encoder works); the backward
 // kernel then walks node rows in order, adds each row's incidences in sorted order and writes the row once in the
 // activation dtype (rows without incidences are written as zeros).  No atomics, no fp32 staging buffer, no separate
 // zero-fill / cast passes; the result is bit-reproducible.  Rows with more than kHubThreshold incidences (hub nodes of
 // a power-law graph) are deferred to a block-per-row kernel (8 warps take every 8th incidence, fixed order combine) so
 // that no single warp serialises on a long row.
-#include <cub/cub.cuh>
-
 #include "common.cuh"
 
 namespace llp {
@@ -21,30 +21,172 @@ constexpr int kHubThreshold = 48;
 constexpr int kHubWarpsMax = 32;  // warps of a hub block (fewer when F is wide: [warps][F] floats of shared memory)
 constexpr int kRowsPerWarp = 16;
 
-__global__ void incidence_keys_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M,
-                                      int32_t* __restrict__ key, int32_t* __restrict__ idx) {
+// ---- incidence plan: stable counting sort of the 2M incidences (i < M: endpoint u[i] of edge i; i >= M: endpoint v[i - M])
+//      by node.  Row r of the plan lists its incidences in increasing i, exactly the order of a stable sort by key.
+constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+constexpr int kSmallRow = 16;       // rows up to this length are ordered by one thread, longer ones by whole blocks
+constexpr int kBigThreads = 256, kBigTile = 4096;   // kBigTile: rows one block orders alone (16 KB of shared memory)
+
+__device__ __forceinline__ int incidence_node(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t i) {
+  return (int)(i < M ? __ldg(u + i) : __ldg(v + (i - M)));
+}
+
+// cnt[node] += 1 per incidence; the value the atomic returns is the incidence's arrival slot inside its row
+__global__ void incidence_count_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M,
+                                       int32_t* __restrict__ cnt, int32_t* __restrict__ slot) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < 2 * M) {
-    key[i] = (int32_t)(i < M ? u[i] : v[i - M]);
-    idx[i] = (int32_t)i;
+  if (i < 2 * M) slot[i] = atomicAdd(cnt + incidence_node(u, v, M, i), 1);
+}
+
+// In-place exclusive scan of x[0..n) in three launches: tiles of kScanTile (thread-local prefix + block scan), the tile
+// totals (one block walks them with a carry), and the add-back.
+__global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(int32_t* __restrict__ x, int64_t n, int32_t* __restrict__ tile_sum) {
+  __shared__ int32_t warp_sum[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int32_t v[kScanItems];
+  int32_t t = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    v[k] = base + k < n ? x[base + k] : 0;
+    t += v[k];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) warp_sum[w] = inc;
+  __syncthreads();
+  int32_t before = inc - t;
+  for (int q = 0; q < w; ++q) before += warp_sum[q];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) x[base + k] = before;
+    before += v[k];
+  }
+  if (threadIdx.x == kScanThreads - 1) tile_sum[blockIdx.x] = before;
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(int32_t* __restrict__ tile_sum, int64_t tiles) {
+  __shared__ int32_t warp_sum[32];
+  __shared__ int32_t carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t t0 = 0; t0 < tiles; t0 += 1024) {
+    const int64_t i = t0 + threadIdx.x;
+    const int32_t t = i < tiles ? tile_sum[i] : 0;
+    int32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sum[w] = inc;
+    __syncthreads();
+    int32_t before = carry_s + inc - t;
+    for (int q = 0; q < w; ++q) before += warp_sum[q];
+    if (i < tiles) tile_sum[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + t;
+    __syncthreads();
   }
 }
 
-// From the sorted incidences: rowptr[r] = first sorted position whose node is >= r, and per sorted position the pair
-// meta[p] = (edge m, the OTHER endpoint of that edge), so that the backward kernel has no index chains to chase.
-__global__ void incidence_finish_kernel(const int32_t* __restrict__ sorted_key, const int32_t* __restrict__ sorted_idx,
-                                        const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t N,
-                                        int32_t* __restrict__ rowptr, int2* __restrict__ meta) {
-  const int64_t E = 2 * M;
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int32_t* __restrict__ x, int64_t n, const int32_t* __restrict__ tile_sum) {
+  const int32_t add = tile_sum[blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (base + k < n) x[base + k] += add;
+}
+
+// ids[rowptr[node] + slot] = i: every row now holds its incidences, in arrival (arbitrary) order
+__global__ void incidence_scatter_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M,
+                                         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slot,
+                                         int32_t* __restrict__ ids) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i > E) return;
-  const int64_t prev = i == 0 ? -1 : (int64_t)sorted_key[i - 1];
-  const int64_t cur = i == E ? N : (int64_t)sorted_key[i];
-  for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = (int32_t)i;
-  if (i < E) {
-    const int e = sorted_idx[i];
-    const int64_t m = e < M ? e : e - M;
-    meta[i] = make_int2((int)m, (int)(e < M ? v[m] : u[m]));
+  if (i < 2 * M) ids[rowptr[incidence_node(u, v, M, i)] + slot[i]] = (int32_t)i;
+}
+
+// meta[p] = (edge m, the OTHER endpoint of that edge) of incidence e, so that the backward kernel has no index chains
+__device__ __forceinline__ int2 incidence_meta(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int e) {
+  const int64_t m = e < M ? e : e - M;
+  return make_int2((int)m, (int)(e < M ? __ldg(v + m) : __ldg(u + m)));
+}
+
+// Put every row back into increasing incidence order (ids are distinct: the rank of an id is the number of smaller ids
+// in its row) and write the plan.  One thread per short row; long rows are only listed for the block kernel below.
+__global__ void incidence_order_rows_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t N,
+                                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ids,
+                                            int2* __restrict__ meta, int32_t* __restrict__ big_count, int32_t* __restrict__ big_list,
+                                            int32_t* __restrict__ huge_list) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const int s = rowptr[r], n = rowptr[r + 1] - s;
+  if (n == 0) return;
+  if (n > kSmallRow) {
+    if (n <= kBigTile) big_list[atomicAdd(big_count, 1)] = (int32_t)r;   // slot order does not matter
+    else huge_list[atomicAdd(big_count + 1, 1)] = (int32_t)r;
+    return;
+  }
+  int e[kSmallRow];
+#pragma unroll
+  for (int a = 0; a < kSmallRow; ++a) e[a] = a < n ? ids[s + a] : INT32_MAX;
+#pragma unroll
+  for (int a = 0; a < kSmallRow; ++a) {
+    if (a < n) {
+      int rank = 0;
+#pragma unroll
+      for (int b = 0; b < kSmallRow; ++b) rank += e[b] < e[a] ? 1 : 0;
+      meta[s + rank] = incidence_meta(u, v, M, e[a]);
+    }
+  }
+}
+
+// Long rows.  A row of up to kBigTile incidences is ordered by ONE block (the row sits in shared memory, every thread ranks
+// its ids against it); the few rows beyond that (at most 2M / kBigTile of them: a node that owns a large share of the
+// whole batch) are ranked slice by slice by all blocks together, the row streamed through shared memory in tiles.
+__global__ void __launch_bounds__(kBigThreads) incidence_order_big_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v,
+                                                                          int64_t M, const int32_t* __restrict__ rowptr,
+                                                                          const int32_t* __restrict__ ids, int2* __restrict__ meta,
+                                                                          const int32_t* __restrict__ big_count,
+                                                                          const int32_t* __restrict__ big_list,
+                                                                          const int32_t* __restrict__ huge_list) {
+  __shared__ int32_t tile[kBigTile];
+  const int n_big = big_count[0], n_huge = big_count[1];
+  for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
+    const int64_t r = big_list[b];
+    const int s = rowptr[r], n = rowptr[r + 1] - s;
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += kBigThreads) tile[q] = ids[s + q];
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += kBigThreads) {
+      const int ea = tile[a];
+      int rank = 0;
+      for (int q = 0; q < n; ++q) rank += tile[q] < ea ? 1 : 0;
+      meta[s + rank] = incidence_meta(u, v, M, ea);
+    }
+  }
+  for (int b = 0; b < n_huge; ++b) {
+    const int64_t r = huge_list[b];
+    const int s = rowptr[r], n = rowptr[r + 1] - s;
+    const int slices = (n + kBigThreads - 1) / kBigThreads;
+    for (int sl = blockIdx.x; sl < slices; sl += gridDim.x) {
+      const int a = sl * kBigThreads + threadIdx.x;
+      const int ea = a < n ? ids[s + a] : INT32_MAX;
+      int rank = 0;
+      for (int t0 = 0; t0 < n; t0 += kBigTile) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < kBigTile; q += kBigThreads) tile[q] = t0 + q < n ? ids[s + t0 + q] : INT32_MAX;
+        __syncthreads();
+        const int lim = n - t0 < kBigTile ? n - t0 : kBigTile;
+        for (int q = 0; q < lim; ++q) rank += tile[q] < ea ? 1 : 0;
+      }
+      if (a < n) meta[s + rank] = incidence_meta(u, v, M, ea);
+    }
   }
 }
 
@@ -227,34 +369,24 @@ __global__ void __launch_bounds__(256) hadamard_bwd_rows_scalar_kernel(const Row
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t sort_temp_bytes(int64_t E) {
-  size_t temp = 0;
-  cub::DoubleBuffer<int32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp, k, v, (int)E, 0, 32);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    temp = ((size_t)16 << 20) + (size_t)E / 64;
-  }
-  return temp;
-}
-
 struct Workspace {
-  int32_t *key_a, *key_b, *idx_a, *idx_b;
-  void* cub_temp;
-  size_t cub_bytes, total;
+  int32_t *slot, *ids, *tile_sum, *big_count, *big_list, *huge_list;
+  int64_t tiles;
+  size_t total;
 };
 
-static Workspace carve(char* base, int64_t M) {
+static Workspace carve(char* base, int64_t M, int64_t N) {
   const int64_t E = 2 * M;
   Workspace w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
-  w.key_a = (int32_t*)take((size_t)E * 4 + 4);
-  w.key_b = (int32_t*)take((size_t)E * 4 + 4);
-  w.idx_a = (int32_t*)take((size_t)E * 4 + 4);
-  w.idx_b = (int32_t*)take((size_t)E * 4 + 4);
-  w.cub_bytes = sort_temp_bytes(E);
-  w.cub_temp = take(w.cub_bytes);
+  w.tiles = ceil_div(N + 1, (int64_t)kScanTile);
+  w.slot = (int32_t*)take((size_t)E * 4 + 4);
+  w.ids = (int32_t*)take((size_t)E * 4 + 4);
+  w.tile_sum = (int32_t*)take((size_t)w.tiles * 4 + 4);
+  w.big_count = (int32_t*)take(8);                                        // {rows one block orders, rows all blocks order}
+  w.big_list = (int32_t*)take((size_t)(E / (kSmallRow + 1) + 1) * 4);
+  w.huge_list = (int32_t*)take((size_t)(E / (kBigTile + 1) + 1) * 4);
   w.total = off + 256;
   return w;
 }
@@ -288,7 +420,9 @@ static int run(const void* h, int64_t ldh, int64_t F, int64_t M, const void* dz,
 
 using namespace llp;
 
-extern "C" size_t llp_edge_plan_workspace_bytes(int64_t M) { return M < 0 ? 256 : eb::carve(nullptr, M).total; }
+extern "C" size_t llp_edge_plan_workspace_bytes(int64_t M, int64_t N) {
+  return (M < 0 || N < 0) ? 256 : eb::carve(nullptr, M, N).total;
+}
 
 extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int64_t N, int32_t* rowptr, int32_t* meta,
                              void* workspace, size_t workspace_bytes, void* stream_) {
@@ -296,21 +430,31 @@ extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int6
   LLP_CHECK_ARG(M >= 0 && N >= 0 && rowptr && workspace && (M == 0 || (u && v && meta)));
   LLP_CHECK_ARG(2 * M < (int64_t)INT32_MAX && N < (int64_t)INT32_MAX);
   if (int rc = check_device()) return rc;
-  if (workspace_bytes < llp_edge_plan_workspace_bytes(M)) return LLP_E_WORKSPACE;
+  if (workspace_bytes < llp_edge_plan_workspace_bytes(M, N)) return LLP_E_WORKSPACE;
   const int64_t E = 2 * M;
-  eb::Workspace w = eb::carve(reinterpret_cast<char*>(workspace), M);
-  cub::DoubleBuffer<int32_t> k(w.key_a, w.key_b), x(w.idx_a, w.idx_b);
-  if (E > 0) {
-    eb::incidence_keys_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, stream>>>(u, v, M, w.key_a, w.idx_a);
+  eb::Workspace w = eb::carve(reinterpret_cast<char*>(workspace), M, N);
+  int2* meta2 = reinterpret_cast<int2*>(meta);
+  LLP_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
+  if (E == 0) return 0;
+  LLP_CUDA(cudaMemsetAsync(w.big_count, 0, 2 * sizeof(int32_t), stream));
+  const unsigned e_blocks = (unsigned)ceil_div(E, 256);
+  eb::incidence_count_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot);
+  LLP_LAUNCH_OK();
+  eb::scan_tiles_kernel<<<(unsigned)w.tiles, eb::kScanThreads, 0, stream>>>(rowptr, N + 1, w.tile_sum);
+  LLP_LAUNCH_OK();
+  if (w.tiles > 1) {
+    eb::scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tiles);
     LLP_LAUNCH_OK();
-    int end_bit = 1;
-    while (end_bit < 31 && ((int64_t)1 << end_bit) < N) ++end_bit;
-    size_t temp = w.cub_bytes;
-    LLP_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, temp, k, x, (int)E, 0, end_bit, stream));
-    count_launch(3);
+    eb::scan_add_kernel<<<(unsigned)w.tiles, eb::kScanThreads, 0, stream>>>(rowptr, N + 1, w.tile_sum);
+    LLP_LAUNCH_OK();
   }
-  eb::incidence_finish_kernel<<<(unsigned)ceil_div(E + 1, 256), 256, 0, stream>>>(
-      k.Current(), x.Current(), u, v, M, N, rowptr, reinterpret_cast<int2*>(meta));
+  eb::incidence_scatter_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot, w.ids);
+  LLP_LAUNCH_OK();
+  eb::incidence_order_rows_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(u, v, M, N, rowptr, w.ids, meta2, w.big_count,
+                                                                                 w.big_list, w.huge_list);
+  LLP_LAUNCH_OK();
+  eb::incidence_order_big_kernel<<<kNumSMs * 2, eb::kBigThreads, 0, stream>>>(u, v, M, rowptr, w.ids, meta2, w.big_count, w.big_list,
+                                                                              w.huge_list);
   LLP_LAUNCH_OK();
   return 0;
 }

@@ -22,7 +22,8 @@ constexpr int kTileM = 128;
 constexpr int kBK = 64;                 // bf16 elements per K block = one 128-byte swizzle row
 constexpr int kGatherWarps = 8;         // split over the K blocks of a tile
 constexpr int kEpiWarps = 8;
-constexpr int kCtrlWarps = 1;            // warp 0: W1 loader, TMEM allocator and MMA issuer
+constexpr int kCtrlWarps = 4;            // warpgroup 0: warp 0 = W1 loader, TMEM allocator and MMA issuer; warps 1..3 only give
+                                         // their registers away (setmaxnreg works on whole warpgroups)
 constexpr int kThreads = 32 * (kCtrlWarps + kGatherWarps + kEpiWarps);
 constexpr int kAccStages = 2;
 #ifndef LLP_EM_GROUP_ROWS
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // Register budget (640 threads x 96): warpgroup 0 keeps 24 per thread, the two producer warpgroups take 128 (two load
+  // groups of 16 rows x 2 operands in flight per lane = 64 registers of 128-bit loads), the epilogue warpgroups stay at 96.
+  if (warp < kCtrlWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  else if (warp < kCtrlWarps + kGatherWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
   if (warp == 0) {
     // ===================== W1: all K blocks, once; then the MMA issue loop =====================
     if ((int64_t)blockIdx.x < m_tiles && elect_one_sync()) {
@@ -140,6 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
       p.dbg[blockIdx.x * 4 + 1] = w_full_ns;
       p.dbg[blockIdx.x * 4 + 2] = w_acc_ns;
     }
+  } else if (warp < kCtrlWarps) {
+    // idle warps of warpgroup 0
   } else if (warp < kCtrlWarps + kGatherWarps) {
     // ===================== gather producers: z = h[u] * h[v] straight into the swizzled A stages =====================
     // The 8 warps are split over the K blocks of the tile (8 / num_kb warps per K block, each owning a slice of the
@@ -152,45 +159,65 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
     const int kb_mine = gw % num_kb, part = gw / num_kb;
     const int rows_mine = kTileM / wpk;                  // 16, 32 or 64 rows per warp
     const int sub = lane >> 3, j = lane & 7;
+    // The producer is latency-bound (ncu: its warps wait on the row loads and on the endpoint indices in front of them),
+    // so a warp keeps TWO load groups in flight (group g + 1 is issued before group g is multiplied and stored) and
+    // fetches the endpoints of its rows of the NEXT tile while it works on the current one.
+    constexpr int kIt = kGroupRows / 4;                  // 128-bit loads per operand, lane and group
+    constexpr int kMaxGroups = 64 / kGroupRows;          // rows_mine <= 64
+    const int n_groups = rows_mine / kGroupRows;
+    const __nv_bfloat16* hk = p.h + kb_mine * kBK + j * 8;
+    int cu[2], cv[2], nu[2] = {0, 0}, nv[2] = {0, 0};    // endpoints of row (batch * 32 + lane) of my slice: current / next tile
+    auto load_idx = [&](int64_t mt, int (&U)[2], int (&V)[2]) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int64_t m_l = mt * kTileM + part * rows_mine + b * 32 + lane;
+        const bool ok = b * 32 + lane < rows_mine && m_l < p.M;
+        U[b] = ok ? (int)__ldg(p.u + m_l) : 0;
+        V[b] = ok ? (int)__ldg(p.v + m_l) : 0;
+      }
+    };
+    if ((int64_t)blockIdx.x < m_tiles) load_idx(blockIdx.x, cu, cv);
     int64_t slot = kb_mine;                              // ring position of my K block: stage = slot % stages
     for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, slot += num_kb) {
       const int stage = (int)(slot % p.stages);
-      mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)(((slot / p.stages) & 1) ^ 1));
       uint8_t* sa = smem_a + (size_t)stage * kABytes;
-      for (int r0 = 0; r0 < rows_mine; r0 += 32) {       // batches of up to 32 rows
-        const int batch = rows_mine - r0 < 32 ? rows_mine - r0 : 32;
-        const int row_l = part * rows_mine + r0 + lane;  // the row whose endpoints this lane fetches
-        const int64_t m_l = mt * kTileM + row_l;
-        int uu = 0, vv = 0;
-        if (lane < batch && m_l < p.M) { uu = (int)__ldg(p.u + m_l); vv = (int)__ldg(p.v + m_l); }
+      uint4 a[2][kIt], b[2][kIt];
+      auto issue = [&](int g, int bu, int bv, uint4 (&A)[kIt], uint4 (&B)[kIt]) {   // bu, bv: endpoints of the group's batch
 #pragma unroll
-        for (int g0 = 0; g0 < 32; g0 += kGroupRows) {
-          if (g0 >= batch) break;
-          constexpr int kIt = kGroupRows / 4;
-          uint4 a[kIt], b[kIt];
-#pragma unroll
-          for (int it = 0; it < kIt; ++it) {
-            const int rl = g0 + it * 4 + sub;            // row inside the batch
-            const int ur = __shfl_sync(0xffffffffu, uu, rl), vr = __shfl_sync(0xffffffffu, vv, rl);
-            a[it] = ldg_v4(p.h + (int64_t)ur * p.ldh + kb_mine * kBK + j * 8);
-            b[it] = ldg_v4(p.h + (int64_t)vr * p.ldh + kb_mine * kBK + j * 8);
-          }
-#pragma unroll
-          for (int it = 0; it < kIt; ++it) {
-            const int row = part * rows_mine + r0 + g0 + it * 4 + sub;   // row inside the tile
-            const int64_t m = mt * kTileM + row;
-            uint4 z;
-            z.x = mul_bf16x2(a[it].x, b[it].x); z.y = mul_bf16x2(a[it].y, b[it].y);
-            z.z = mul_bf16x2(a[it].z, b[it].z); z.w = mul_bf16x2(a[it].w, b[it].w);
-            if (m >= p.M) z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(sa + row * 128 + ((j ^ (row & 7)) << 4)) = z;   // SWIZZLE_128B, K-major
-            if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb_mine * kBK + j * 8, z);
-          }
+        for (int it = 0; it < kIt; ++it) {
+          const int rl = (g * kGroupRows) % 32 + it * 4 + sub;      // row inside its batch of 32
+          const int ur = __shfl_sync(0xffffffffu, bu, rl);
+          const int vr = __shfl_sync(0xffffffffu, bv, rl);
+          A[it] = ldg_v4(hk + (int64_t)ur * p.ldh);
+          B[it] = ldg_v4(hk + (int64_t)vr * p.ldh);
         }
+      };
+      auto consume = [&](int g, const uint4 (&A)[kIt], const uint4 (&B)[kIt]) {
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int row = part * rows_mine + g * kGroupRows + it * 4 + sub;   // row inside the tile
+          const int64_t m = mt * kTileM + row;
+          uint4 z;
+          z.x = mul_bf16x2(A[it].x, B[it].x); z.y = mul_bf16x2(A[it].y, B[it].y);
+          z.z = mul_bf16x2(A[it].z, B[it].z); z.w = mul_bf16x2(A[it].w, B[it].w);
+          if (m >= p.M) z = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sa + row * 128 + ((j ^ (row & 7)) << 4)) = z;   // SWIZZLE_128B, K-major
+          if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb_mine * kBK + j * 8, z);
+        }
+      };
+      issue(0, cu[0], cv[0], a[0], b[0]);
+      if (mt + gridDim.x < m_tiles) load_idx(mt + gridDim.x, nu, nv);
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g) {
+        if (g + 1 < kMaxGroups && g + 1 < n_groups)
+          issue(g + 1, cu[((g + 1) * kGroupRows) / 32], cv[((g + 1) * kGroupRows) / 32], a[(g + 1) & 1], b[(g + 1) & 1]);
+        if (g == 0) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)(((slot / p.stages) & 1) ^ 1));   // first store below
+        if (g < n_groups) consume(g, a[g & 1], b[g & 1]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+      cu[0] = nu[0]; cu[1] = nu[1]; cv[0] = nv[0]; cv[1] = nv[1];
     }
   } else {
     // ===================== epilogue: bias + relu + dropout -> y, row . w2 -> sigmoid =====================

@@ -1032,7 +1032,7 @@ class EdgePlan:
         dev = u.device
         self.rowptr = torch.empty(self.num_nodes + 1, dtype=torch.int32, device=dev)
         self.meta = torch.empty(max(4 * self.num_edges, 2), dtype=torch.int32, device=dev)
-        nbytes = lib.llp_edge_plan_workspace_bytes(self.num_edges)
+        nbytes = lib.llp_edge_plan_workspace_bytes(self.num_edges, self.num_nodes)
         self._ws = _ws(nbytes, dev)   # kept alive until the plan dies (the side stream may still be using it)
         self._event = None
 

@@ -98,6 +98,38 @@ def spmm_csr(rowptr: Tensor, col: Tensor, x: Tensor, mean: bool, src_scale: Opti
 # --------------------------------------------------------------------------------------
 # O2/O3: SAGE convolutions
 # --------------------------------------------------------------------------------------
+def edge_incidence_plan(u: Tensor, v: Tensor, num_nodes: int) -> Tuple[Tensor, Tensor]:
+    """Incidences of an edge batch grouped by node — what autograd's ``index_put_(accumulate=True)`` walks for the
+    backward of the two gathers ``h[u] * h[v]`` in front of ``LinkPredictor`` (``train_teacher_gnn.py:58``,
+    ``main.py:186,214``, ``models.py:140``), restated as a stable sort so that the summation order is fixed.
+
+    Incidence ``i < M`` is endpoint ``u[i]`` of edge ``i``; incidence ``i >= M`` is endpoint ``v[i-M]`` of edge
+    ``i-M``.  Returns ``(rowptr int32 [N+1], meta int32 [2M,2])``: row ``n`` lists, in increasing ``i``, the pairs
+    ``(edge, other endpoint of that edge)`` of the incidences whose node is ``n``.
+    """
+    u, v = u.reshape(-1).long(), v.reshape(-1).long()
+    M = u.numel()
+    key = torch.cat([u, v])
+    order = torch.sort(key, stable=True).indices
+    rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(key, minlength=num_nodes), 0)
+    edge = torch.where(order < M, order, order - M)
+    other = torch.where(order < M, v[edge], u[edge]) if M else edge
+    return rowptr.to(torch.int32), torch.stack([edge, other], 1).to(torch.int32)
+
+
+def hadamard_backward(h: Tensor, u: Tensor, v: Tensor, dz: Tensor) -> Tensor:
+    """``gh[n] = sum_{u[m]==n} dz[m]*h[v[m]] + sum_{v[m]==n} dz[m]*h[u[m]]`` added in the order of
+    ``edge_incidence_plan`` (fp32, one fused multiply-add per incidence and element is NOT assumed: plain mul + add)."""
+    rowptr, meta = edge_incidence_plan(u, v, h.size(0))
+    gh = torch.zeros_like(h, dtype=torch.float32)
+    for n in range(h.size(0)):
+        for p in range(int(rowptr[n]), int(rowptr[n + 1])):
+            m, o = int(meta[p, 0]), int(meta[p, 1])
+            gh[n] += dz[m].float() * h[o].float()
+    return gh
+
+
 class SAGEConv(nn.Module):
     """PyG 2.2.0 ``SAGEConv(aggr='mean', root_weight=True, bias=True)`` [3P]:
     ``lin_l(mean_{s->d} x[s]) + lin_r(x)``; ``lin_l`` has the bias, ``lin_r`` none.

@@ -347,6 +347,41 @@ def test_edge_hadamard_and_backward(cuda, dtype, n, f, m):
         torch.testing.assert_close(hd.grad.float().cpu(), ho.grad, **(dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=0.25)))
 
 
+@pytest.mark.parametrize("n,m,hubs", [(100, 1000, ()), (7, 0, ()), (1, 5, ()), (5000, 3, ()), (3000, 20000, (17, 300, 5000)),
+                                      (235868, 131072, (40, 700)), (2200000, 4096, (2000,)), (9, 40000, ())])
+def test_edge_plan_bit_exact(cuda, n, m, hubs):
+    """llp_edge_plan (own counting sort) against the oracle's stable sort: row pointers and (edge, other endpoint) pairs
+    index for index — empty batch, one node, rows of every length class (one thread / whole blocks / many slices),
+    more scan tiles than one block handles at once."""
+    g = torch.Generator().manual_seed(5)
+    u, v = torch.randint(0, n, (m,), generator=g), torch.randint(0, n, (m,), generator=g)
+    pos = 0
+    for k, cnt in enumerate(hubs):   # node k + 1 gets `cnt` extra incidences, spread over both endpoint arrays
+        (u if k % 2 == 0 else v)[pos:pos + cnt] = min(k + 1, n - 1)
+        pos += cnt
+    plan = ops.EdgePlan(u.to(cuda), v.to(cuda), n)
+    rowptr, meta = O.edge_incidence_plan(u, v, n)
+    assert torch.equal(plan.rowptr.cpu(), rowptr)
+    assert torch.equal(plan.meta.cpu()[: 4 * m].view(-1, 2), meta)
+
+
+def test_edge_hadamard_backward_bit_exact_fp32(cuda):
+    """fp32 gather-reduce in plan order: the CUDA kernel adds fma(dz, h, acc) incidence by incidence, so it equals a
+    float64-free restatement with the same order up to the fma's single rounding; against the oracle at 1e-6."""
+    g = torch.Generator().manual_seed(6)
+    n, f, m = 300, 64, 4000
+    h = torch.randn(n, f, generator=g)
+    u, v = torch.randint(0, n, (m,), generator=g), torch.randint(0, n, (m,), generator=g)
+    u[:900] = 3   # a hub row (block kernel)
+    dz = torch.randn(m, f, generator=g)
+    plan = ops.EdgePlan(u.to(cuda), v.to(cuda), n)
+    gh = ops.hadamard_bwd(h.to(cuda), plan, dz.to(cuda))
+    want = O.hadamard_backward(h, u, v, dz)
+    torch.testing.assert_close(gh.cpu(), want, rtol=1e-5, atol=1e-4)
+    gh2 = ops.hadamard_bwd(h.to(cuda), ops.EdgePlan(u.to(cuda), v.to(cuda), n), dz.to(cuda))
+    assert torch.equal(gh, gh2)   # bit-reproducible: no atomics on the data path
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_score_head_forward_backward(cuda, dtype):
     g = torch.Generator().manual_seed(3)

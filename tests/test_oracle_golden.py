@@ -122,6 +122,27 @@ def test_mean_aggregate_matches_scipy_and_networkx():
     np.testing.assert_allclose(O.spmm_csr(rp, col, x, mean=True).numpy(), An @ x.numpy(), rtol=1e-12, atol=1e-12)
 
 
+def test_edge_incidence_plan_kat_and_autograd():
+    """The incidence plan (backward of the gathers h[u] * h[v], train_teacher_gnn.py:58 / models.py:140): a hand-checked
+    case, and its gather-reduce against what torch autograd (index_put_ with accumulation) produces for the same op."""
+    u, v = torch.tensor([2, 0, 2, 3]), torch.tensor([0, 2, 2, 0])
+    rowptr, meta = O.edge_incidence_plan(u, v, 5)
+    assert rowptr.tolist() == [0, 3, 3, 7, 8, 8]
+    # node 0: incidences 1 (u[1]), 4 (v[0]), 7 (v[3]); node 2: 0, 2, 5 (v[1]), 6 (v[2]); node 3: 3
+    assert meta.tolist() == [[1, 2], [0, 2], [3, 3], [0, 0], [2, 2], [1, 0], [2, 2], [3, 0]]
+    g = torch.Generator().manual_seed(11)
+    n, f, m = 40, 6, 300
+    h = torch.randn(n, f, generator=g, dtype=torch.float64).requires_grad_(True)
+    uu, vv = torch.randint(0, n - 4, (m,), generator=g), torch.randint(0, n - 4, (m,), generator=g)
+    dz = torch.randn(m, f, generator=g, dtype=torch.float64)
+    (h[uu] * h[vv]).backward(dz)
+    torch.testing.assert_close(O.hadamard_backward(h.detach(), uu, vv, dz).double(), h.grad, rtol=1e-6, atol=1e-6)
+    rp, mt = O.edge_incidence_plan(uu, vv, n)
+    assert int(rp[-1]) == 2 * m and torch.equal(rp[n - 4:], torch.full((5,), 2 * m, dtype=torch.int32))
+    e0, e1 = O.edge_incidence_plan(torch.zeros(0, dtype=torch.long), torch.zeros(0, dtype=torch.long), 3)
+    assert e0.tolist() == [0, 0, 0, 0] and e1.shape == (0, 2)
+
+
 def test_sageconv_isolated_node_bias_quirk():
     # SURVEY Q2: SAGEConv keeps b_l on isolated nodes, SAGEConv_updated aggregates it away
     torch.manual_seed(0)
