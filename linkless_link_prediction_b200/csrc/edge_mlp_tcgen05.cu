@@ -4,10 +4,10 @@
 //     y[m,:]  = dropout(relu(z[m,:] W1^T + b1))             (first predictor layer, models.py:143-145)
 //     prob[m] = sigmoid(y[m,:] . w2 + b2)                   (1-output last layer + sigmoid, models.py:146,150)
 //
-// in ONE kernel: the gather-Hadamard is the A-operand PRODUCER of the first predictor GEMM.  Four
-// producer warps gather the two embedding rows of every edge of a 128-edge tile with 128-bit loads, multiply them and
-// write the bf16 products straight into the 128B-swizzled K-major shared-memory stage the tensor core reads (and, for
-// training, also to `z`, which the weight gradient needs); W1 (<= 128 KB) is loaded into shared memory once per CTA by
+// in ONE kernel: the gather-Hadamard is the A-operand PRODUCER of the first predictor GEMM.  Eight
+// producer warps gather the two embedding rows of every edge of a 128-edge tile with 128-bit loads (whole rows per
+// load instruction), multiply them and write the bf16 products straight into the 128B-swizzled K-major shared-memory
+// stages the tensor core reads (and, for training, also to `z`, which the weight gradient needs); W1 (<= 128 KB) is loaded into shared memory once per CTA by
 // TMA; one elected lane issues tcgen05.mma into a double-buffered TMEM accumulator; eight epilogue warps apply
 // bias + relu + Philox dropout, store `y` (training) and reduce the row against w2 for the sigmoid score.  With z and y
 // switched off (evaluation) a scored edge costs two row gathers and four bytes of output.
@@ -20,17 +20,12 @@ using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kBK = 64;                 // bf16 elements per K block = one 128-byte swizzle row
-constexpr int kGatherWarps = 8;         // split over the K blocks of a tile
+constexpr int kGatherWarps = 8;         // 16 rows of every tile each
 constexpr int kEpiWarps = 8;
 constexpr int kCtrlWarps = 4;            // warpgroup 0: warp 0 = W1 loader, TMEM allocator and MMA issuer; warps 1..3 only give
                                          // their registers away (setmaxnreg works on whole warpgroups)
 constexpr int kThreads = 32 * (kCtrlWarps + kGatherWarps + kEpiWarps);
 constexpr int kAccStages = 2;
-#ifndef LLP_EM_GROUP_ROWS
-#define LLP_EM_GROUP_ROWS 16
-#endif
-constexpr int kGroupRows = LLP_EM_GROUP_ROWS;   // rows per load group of a producer warp: 2 x (rows / 4) 128-bit loads in flight
-                                                // per lane (32 was measured too: 68 us vs 64 us for the M = 131072 issue loop)
 constexpr int kABytes = kTileM * 128;   // one A stage: 128 rows x 128 B
 constexpr int kSmemMax = 226 * 1024;
 
@@ -77,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), kGatherWarps / num_kb); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), kGatherWarps); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), kEpiWarps); }
     mbar_init(smem_u32(w_full), 1);
     fence_barrier_init();
@@ -154,40 +149,39 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
     // soon as the tensor core has consumed it, while later K blocks of the current tile are still being multiplied.
     // 8 lanes cover one 128-byte K slice of a row (a full L2 line), 4 rows per instruction, 16 row loads in flight
     // per lane batch (8 x (h[u], h[v])).
+    // Every producer warp owns 16 rows of each tile and fetches WHOLE embedding rows: K / 8 lanes cover one row (K = 256:
+    // one 512-byte row per load instruction, like the SpMM's gathers; the first version gave each warp a 128-byte
+    // K slice of 64 rows, i.e. four separate requests per row at four different times), so a lane's 8 columns belong to
+    // K block (lane % (K/8)) / 8 and its product goes to that K block's stage.  All 8 warps arrive on every stage.
+    // The producer is latency-bound (ncu: its warps wait on the row loads and on the endpoint indices in front of them):
+    // a warp keeps TWO load groups (4 instructions x 2 operands each) in flight and fetches the endpoints of its rows of
+    // the NEXT tile while it works on the current one.
     const int gw = warp - kCtrlWarps;
-    const int wpk = kGatherWarps / num_kb;               // warps per K block (num_kb in {1, 2, 4})
-    const int kb_mine = gw % num_kb, part = gw / num_kb;
-    const int rows_mine = kTileM / wpk;                  // 16, 32 or 64 rows per warp
-    const int sub = lane >> 3, j = lane & 7;
-    // The producer is latency-bound (ncu: its warps wait on the row loads and on the endpoint indices in front of them),
-    // so a warp keeps TWO load groups in flight (group g + 1 is issued before group g is multiplied and stored) and
-    // fetches the endpoints of its rows of the NEXT tile while it works on the current one.
-    constexpr int kIt = kGroupRows / 4;                  // 128-bit loads per operand, lane and group
-    constexpr int kMaxGroups = 64 / kGroupRows;          // rows_mine <= 64
-    const int n_groups = rows_mine / kGroupRows;
-    const __nv_bfloat16* hk = p.h + kb_mine * kBK + j * 8;
-    int cu[2], cv[2], nu[2] = {0, 0}, nv[2] = {0, 0};    // endpoints of row (batch * 32 + lane) of my slice: current / next tile
-    auto load_idx = [&](int64_t mt, int (&U)[2], int (&V)[2]) {
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int64_t m_l = mt * kTileM + part * rows_mine + b * 32 + lane;
-        const bool ok = b * 32 + lane < rows_mine && m_l < p.M;
-        U[b] = ok ? (int)__ldg(p.u + m_l) : 0;
-        V[b] = ok ? (int)__ldg(p.v + m_l) : 0;
-      }
+    const int lpr = num_kb * 8;                          // lanes per row
+    const int rpi = 32 / lpr;                            // rows per load instruction: 1, 2 or 4 (num_kb in {4, 2, 1})
+    const int sub = lane / lpr, jj = lane % lpr;
+    const int kb_l = jj >> 3, j = jj & 7;                // K block / 16-byte chunk inside its 128-byte stage row
+    constexpr int kRowsW = kTileM / kGatherWarps;        // 16 rows per warp and tile
+    constexpr int kIt = 4;                               // load instructions per operand and group
+    constexpr int kMaxGroups = 4;
+    const int n_groups = num_kb;                         // kRowsW = n_groups * kIt * rpi
+    const __nv_bfloat16* hk = p.h + jj * 8;
+    // endpoints of my 16 rows: lanes 0..15 hold u of row (lane), lanes 16..31 hold v of row (lane - 16)
+    auto load_idx = [&](int64_t mt) -> int {
+      const int64_t m_l = mt * kTileM + gw * kRowsW + (lane & 15);
+      return m_l < p.M ? (int)__ldg((lane < 16 ? p.u : p.v) + m_l) : 0;
     };
-    if ((int64_t)blockIdx.x < m_tiles) load_idx(blockIdx.x, cu, cv);
-    int64_t slot = kb_mine;                              // ring position of my K block: stage = slot % stages
-    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, slot += num_kb) {
-      const int stage = (int)(slot % p.stages);
-      uint8_t* sa = smem_a + (size_t)stage * kABytes;
+    int ci = (int64_t)blockIdx.x < m_tiles ? load_idx(blockIdx.x) : 0, ni = 0;
+    int64_t slot0 = 0;                                   // ring position of K block 0 of the current tile
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, slot0 += num_kb) {
+      const int64_t my_slot = slot0 + kb_l;
+      uint8_t* sa = smem_a + (size_t)(my_slot % p.stages) * kABytes;
       uint4 a[2][kIt], b[2][kIt];
-      auto issue = [&](int g, int bu, int bv, uint4 (&A)[kIt], uint4 (&B)[kIt]) {   // bu, bv: endpoints of the group's batch
+      auto issue = [&](int g, uint4 (&A)[kIt], uint4 (&B)[kIt]) {
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
-          const int rl = (g * kGroupRows) % 32 + it * 4 + sub;      // row inside its batch of 32
-          const int ur = __shfl_sync(0xffffffffu, bu, rl);
-          const int vr = __shfl_sync(0xffffffffu, bv, rl);
+          const int rl = (g * kIt + it) * rpi + sub;     // row inside my 16
+          const int ur = __shfl_sync(0xffffffffu, ci, rl), vr = __shfl_sync(0xffffffffu, ci, 16 + rl);
           A[it] = ldg_v4(hk + (int64_t)ur * p.ldh);
           B[it] = ldg_v4(hk + (int64_t)vr * p.ldh);
         }
@@ -195,29 +189,33 @@ __global__ void __launch_bounds__(kThreads, 1) edge_mlp_kernel(const __grid_cons
       auto consume = [&](int g, const uint4 (&A)[kIt], const uint4 (&B)[kIt]) {
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
-          const int row = part * rows_mine + g * kGroupRows + it * 4 + sub;   // row inside the tile
+          const int row = gw * kRowsW + (g * kIt + it) * rpi + sub;   // row inside the tile
           const int64_t m = mt * kTileM + row;
           uint4 z;
           z.x = mul_bf16x2(A[it].x, B[it].x); z.y = mul_bf16x2(A[it].y, B[it].y);
           z.z = mul_bf16x2(A[it].z, B[it].z); z.w = mul_bf16x2(A[it].w, B[it].w);
           if (m >= p.M) z = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(sa + row * 128 + ((j ^ (row & 7)) << 4)) = z;   // SWIZZLE_128B, K-major
-          if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + kb_mine * kBK + j * 8, z);
+          if (p.z != nullptr && m < p.M) stg_v4(p.z + m * p.ldz + jj * 8, z);
         }
       };
-      issue(0, cu[0], cv[0], a[0], b[0]);
-      if (mt + gridDim.x < m_tiles) load_idx(mt + gridDim.x, nu, nv);
+      issue(0, a[0], b[0]);
+      if (mt + gridDim.x < m_tiles) ni = load_idx(mt + gridDim.x);
 #pragma unroll
       for (int g = 0; g < kMaxGroups; ++g) {
-        if (g + 1 < kMaxGroups && g + 1 < n_groups)
-          issue(g + 1, cu[((g + 1) * kGroupRows) / 32], cv[((g + 1) * kGroupRows) / 32], a[(g + 1) & 1], b[(g + 1) & 1]);
-        if (g == 0) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)(((slot / p.stages) & 1) ^ 1));   // first store below
+        if (g + 1 < kMaxGroups && g + 1 < n_groups) issue(g + 1, a[(g + 1) & 1], b[(g + 1) & 1]);
+        if (g == 0) {   // first store below: every stage of this tile must have been consumed
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int64_t sl = slot0 + kb;
+            mbar_wait(smem_u32(&empty_bar[sl % p.stages]), (uint32_t)(((sl / p.stages) & 1) ^ 1));
+          }
+        }
         if (g < n_groups) consume(g, a[g & 1], b[g & 1]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-      cu[0] = nu[0]; cu[1] = nu[1]; cv[0] = nv[0]; cv[1] = nv[1];
+      if (lane < num_kb) mbar_arrive(smem_u32(&full_bar[(slot0 + lane) % p.stages]));
+      ci = ni;
     }
   } else {
     // ===================== epilogue: bias + relu + dropout -> y, row . w2 -> sigmoid =====================
