@@ -315,6 +315,16 @@ int llp_auc_pairs(const float* pos, int64_t n_pos, const float* neg, int64_t n_n
  * ------------------------------------------------------------------------------------- */
 int llp_py_random_sample(uint32_t* host_mt_state /*[625] in/out*/, uint64_t n, int64_t k, int64_t* host_out /*[k]*/);
 
+/* Device half of PyG 2.2.0 negative_sampling(method='dense') (train_teacher_gnn.py:50-51; main.py:81-82,206-207): of the k
+ * candidate ids (the host's random.sample), keep — in order — those that are not in taken_sorted (the sorted linearised
+ * ids row*(N-1)+col' of the existing non-self-loop edges; what indexing PyG's N*N-N mask answers), write the first max_out
+ * to kept[max_out] and, de-linearised (r = id/(N-1), c = id%(N-1), c += r <= c), to edges[2,max_out] (optional);
+ * *count = how many were kept in total (device int32; may exceed max_out). */
+size_t llp_negative_filter_workspace_bytes(int64_t k);
+int llp_negative_filter(const int64_t* cand, int64_t k, const int64_t* taken_sorted, int64_t n_taken, int64_t num_nodes,
+                        int64_t max_out, int64_t* kept, int64_t* edges, int32_t* count, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Context sampling.  Replaces torch_cluster.random_walk(coalesced=False) uniform kernel
  * (main.py:37,43,45).  rand is the [B,L] fp32 torch.rand tensor; out is [B,L+1] int64.

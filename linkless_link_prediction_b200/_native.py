@@ -126,6 +126,9 @@ PROTOTYPES = {
     "llp_auc_workspace_bytes": (c_size_t, [c_int64]),
     "llp_auc_pairs": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "llp_py_random_sample": (c_int, [c_void_p, c_uint64, c_int64, c_void_p]),
+    "llp_negative_filter_workspace_bytes": (c_size_t, [c_int64]),
+    "llp_negative_filter": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
     "llp_random_walk": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "llp_rng_advance": (c_int, [c_void_p, c_void_p]),
     "llp_clip_adam_workspace_bytes": (c_size_t, [c_int]),

@@ -231,6 +231,10 @@ long long* debug_buffer();   // lazily allocated device scratch of 4096 int64 fo
 
 int check_device();  // 0 if the current device is sm_100, LLP_E_DEVICE otherwise (cached)
 
+// In-place exclusive scan of n int32 (edge_bwd.cu); tile_sum: scan_i32_tiles(n) int32 of scratch
+int64_t scan_i32_tiles(int64_t n);
+int exclusive_scan_i32(int32_t* x, int64_t n, int32_t* tile_sum, cudaStream_t stream);
+
 // Deterministic reduction helpers implemented in loss.cu
 int sum_f32(const float* in, int64_t n, float scale, float* out, void* workspace, cudaStream_t stream);
 

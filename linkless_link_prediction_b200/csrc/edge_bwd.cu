@@ -418,6 +418,24 @@ static int run(const void* h, int64_t ldh, int64_t F, int64_t M, const void* dz,
 }  // namespace eb
 }  // namespace llp
 
+namespace llp {
+// In-place exclusive scan of n int32 on the device (three small launches); tile_sum: scan_i32_tiles(n) int32 of scratch.
+int64_t scan_i32_tiles(int64_t n) { return ceil_div(n, (int64_t)eb::kScanTile); }
+int exclusive_scan_i32(int32_t* x, int64_t n, int32_t* tile_sum, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  const int64_t tiles = scan_i32_tiles(n);
+  eb::scan_tiles_kernel<<<(unsigned)tiles, eb::kScanThreads, 0, stream>>>(x, n, tile_sum);
+  LLP_LAUNCH_OK();
+  if (tiles > 1) {
+    eb::scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(tile_sum, tiles);
+    LLP_LAUNCH_OK();
+    eb::scan_add_kernel<<<(unsigned)tiles, eb::kScanThreads, 0, stream>>>(x, n, tile_sum);
+    LLP_LAUNCH_OK();
+  }
+  return 0;
+}
+}  // namespace llp
+
 using namespace llp;
 
 extern "C" size_t llp_edge_plan_workspace_bytes(int64_t M, int64_t N) {
@@ -440,14 +458,7 @@ extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int6
   const unsigned e_blocks = (unsigned)ceil_div(E, 256);
   eb::incidence_count_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot);
   LLP_LAUNCH_OK();
-  eb::scan_tiles_kernel<<<(unsigned)w.tiles, eb::kScanThreads, 0, stream>>>(rowptr, N + 1, w.tile_sum);
-  LLP_LAUNCH_OK();
-  if (w.tiles > 1) {
-    eb::scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tiles);
-    LLP_LAUNCH_OK();
-    eb::scan_add_kernel<<<(unsigned)w.tiles, eb::kScanThreads, 0, stream>>>(rowptr, N + 1, w.tile_sum);
-    LLP_LAUNCH_OK();
-  }
+  if (int rc = exclusive_scan_i32(rowptr, N + 1, w.tile_sum, stream)) return rc;
   eb::incidence_scatter_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot, w.ids);
   LLP_LAUNCH_OK();
   eb::incidence_order_rows_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(u, v, M, N, rowptr, w.ids, meta2, w.big_count,

@@ -8,6 +8,7 @@
 // in C++.  No CUDA here: the function runs on any host (tests/test_host_logic.py pins it against `random.sample`).
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <vector>
 
@@ -18,31 +19,33 @@ namespace {
 constexpr int kN = 624, kM = 397;
 
 struct MT {
-  uint32_t* s;   // 624 state words
-  uint32_t* pos; // index (0..624)
-  uint32_t next() {
-    static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
-    if (*pos >= (uint32_t)kN) {
-      int kk;
-      uint32_t y;
-      for (kk = 0; kk < kN - kM; kk++) {
-        y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
-        s[kk] = s[kk + kM] ^ (y >> 1) ^ mag01[y & 0x1u];
-      }
-      for (; kk < kN - 1; kk++) {
-        y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
-        s[kk] = s[kk + (kM - kN)] ^ (y >> 1) ^ mag01[y & 0x1u];
-      }
-      y = (s[kN - 1] & 0x80000000u) | (s[0] & 0x7fffffffu);
-      s[kN - 1] = s[kM - 1] ^ (y >> 1) ^ mag01[y & 0x1u];
-      *pos = 0;
+  uint32_t s[kN];  // private copy of the 624 state words (the caller's block is written back once, at the end)
+  uint32_t pos;    // index (0..624)
+  void twist() {
+    int kk;
+    uint32_t y;
+    for (kk = 0; kk < kN - kM; kk++) {
+      y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
+      s[kk] = s[kk + kM] ^ (y >> 1) ^ ((y & 0x1u) ? 0x9908b0dfu : 0u);
     }
-    uint32_t y = s[(*pos)++];
+    for (; kk < kN - 1; kk++) {
+      y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
+      s[kk] = s[kk + (kM - kN)] ^ (y >> 1) ^ ((y & 0x1u) ? 0x9908b0dfu : 0u);
+    }
+    y = (s[kN - 1] & 0x80000000u) | (s[0] & 0x7fffffffu);
+    s[kN - 1] = s[kM - 1] ^ (y >> 1) ^ ((y & 0x1u) ? 0x9908b0dfu : 0u);
+    pos = 0;
+  }
+  static uint32_t temper(uint32_t y) {
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= (y >> 18);
     return y;
+  }
+  uint32_t next() {
+    if (pos >= (uint32_t)kN) twist();
+    return temper(s[pos++]);
   }
   // _random.Random.getrandbits(k), 1 <= k <= 64: words are filled little-endian, the LAST word keeps its top bits
   uint64_t getrandbits(int k) {
@@ -65,8 +68,10 @@ struct MT {
 
 extern "C" int llp_py_random_sample(uint32_t* mt_state, uint64_t n, int64_t k, int64_t* out) {
   if (mt_state == nullptr || out == nullptr || k < 0 || n == 0 || (uint64_t)k > n || n >= (1ull << 63)) return LLP_E_BADARG;
-  MT mt{mt_state, mt_state + kN};
-  if (*mt.pos > (uint32_t)kN) return LLP_E_BADARG;
+  if (mt_state[kN] > (uint32_t)kN) return LLP_E_BADARG;
+  MT mt;
+  memcpy(mt.s, mt_state, sizeof(mt.s));
+  mt.pos = mt_state[kN];
   // setsize = 21; if k > 5: setsize += 4 ** _ceil(_log(k * 3, 4))    (math.log(x, 4) == log(x) / log(4) in C doubles)
   double setsize = 21.0;
   if (k > 5) setsize += pow(4.0, ceil(log((double)(k * 3)) / log(4.0)));
@@ -79,25 +84,63 @@ extern "C" int llp_py_random_sample(uint32_t* mt_state, uint64_t n, int64_t k, i
       pool[j] = pool[n - (uint64_t)i - 1];   // move non-selected item into vacancy
     }
   } else {
-    // `selected` set: open addressing over a power-of-two table (load <= 1/4), empty slot = ~0 (never a valid index)
+    // `selected` set: open addressing over a power-of-two table (load <= 1/2), empty slot = all ones (never a valid
+    // index).  32-bit slots when the population allows it: the table of a 72k-candidate draw is 1 MB instead of 4 MB
+    // (it is filled at random, so its size against the host's cache is what a draw costs).
     size_t cap = 16;
-    while (cap < (size_t)k * 4) cap <<= 1;
-    std::vector<uint64_t> table(cap, ~0ull);
+    int shift = 60;   // 64 - log2(cap): the multiplicative hash keeps its HIGH bits
+    while (cap < (size_t)k * 2) { cap <<= 1; --shift; }
     const size_t mask = cap - 1;
-    auto insert = [&](uint64_t v) -> bool {   // false if v was already selected
-      size_t h = (size_t)((v * 0x9E3779B97F4A7C15ull) >> 17) & mask;
-      while (table[h] != ~0ull) {
-        if (table[h] == v) return false;
-        h = (h + 1) & mask;
+    auto run = [&](auto empty) {
+      using Slot = decltype(empty);
+      std::vector<Slot> table(cap, empty);
+      auto insert = [&](uint64_t v) -> bool {   // false if v was already selected
+        size_t h = (size_t)((v * 0x9E3779B97F4A7C15ull) >> shift) & mask;
+        const Slot key = (Slot)v;
+        while (table[h] != empty) {
+          if (table[h] == key) return false;
+          h = (h + 1) & mask;
+        }
+        table[h] = key;
+        return true;
+      };
+      int bits = 0;
+      for (uint64_t t = n; t != 0; t >>= 1) ++bits;   // n.bit_length(), hoisted out of randbelow
+      // random.sample = "walk the stream of randbelow(n) values, keep first occurrences, stop at k".  The values do not
+      // depend on the set, so they are drawn a batch ahead and their table slots prefetched (the table is hit at random:
+      // a cache miss per draw otherwise); a batch never holds more values than outputs still missing, so the generator
+      // stops exactly where CPython's loop stops.
+      constexpr int kBatch = 32;
+      uint64_t cand[kBatch];
+      int64_t done = 0;
+      while (done < k) {
+        const int nb = (int)(k - done < kBatch ? k - done : kBatch);
+        if (bits <= 32) {
+          // _randbelow's rejection loop without a data-dependent branch (45 % of the draws are rejected when n sits just
+          // above a power of two: a mispredicted branch per draw otherwise)
+          const int sh = 32 - bits;
+          int c = 0;
+          while (c < nb) {
+            const uint64_t j = (uint64_t)(mt.next() >> sh);
+            cand[c] = j;
+            c += j < n ? 1 : 0;
+          }
+        } else {
+          for (int q = 0; q < nb; ++q) {
+            uint64_t j;
+            do { j = mt.getrandbits(bits); } while (j >= n);
+            cand[q] = j;
+          }
+        }
+        for (int q = 0; q < nb; ++q) __builtin_prefetch(&table[(size_t)((cand[q] * 0x9E3779B97F4A7C15ull) >> shift) & mask], 1, 1);
+        for (int q = 0; q < nb; ++q)
+          if (insert(cand[q])) out[done++] = (int64_t)cand[q];
       }
-      table[h] = v;
-      return true;
     };
-    for (int64_t i = 0; i < k; ++i) {
-      uint64_t j = mt.randbelow(n);
-      while (!insert(j)) j = mt.randbelow(n);
-      out[i] = (int64_t)j;
-    }
+    if (n < 0xffffffffull) run((uint32_t)0xffffffffu);
+    else run(~0ull);
   }
+  memcpy(mt_state, mt.s, sizeof(mt.s));
+  mt_state[kN] = mt.pos;
   return 0;
 }

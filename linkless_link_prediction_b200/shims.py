@@ -54,21 +54,20 @@ class Data:
         return self.x.size(1)
 
 
-def py_random_sample(population: int, k: int) -> torch.Tensor:
+def py_random_sample(population: int, k: int, pin: bool = False) -> torch.Tensor:
     """``torch.tensor(random.sample(range(population), k))`` — same values, same advance of Python's global ``random``
     state — through the C++ restatement of CPython's algorithm in ``libllp_b200.so`` (``llp_py_random_sample``; host code,
-    works without a GPU).  The Python loop costs ~0.4 us per draw: 4-30 ms per training step at 10^4-10^5 candidates."""
-    import ctypes
-
-    import numpy as np
+    works without a GPU).  The Python loop costs ~0.4 us per draw: 4-30 ms per training step at 10^4-10^5 candidates.
+    ``pin``: return page-locked memory (for an asynchronous copy to the device)."""
+    import array
 
     from . import _native as N
     version, internal, gauss = random.getstate()
-    state = np.array(internal, dtype=np.uint32)
-    out = torch.empty(k, dtype=torch.int64)
-    N.check(N.load().llp_py_random_sample(state.ctypes.data_as(ctypes.c_void_p), int(population), int(k), out.data_ptr()),
+    state = array.array("I", internal)   # 624 MT19937 words + the position; array <-> tuple is ~10x cheaper than via numpy
+    out = torch.empty(k, dtype=torch.int64, pin_memory=bool(pin))
+    N.check(N.load().llp_py_random_sample(state.buffer_info()[0], int(population), int(k), out.data_ptr()),
             "llp_py_random_sample")
-    random.setstate((version, tuple(int(v) for v in state), gauss))
+    random.setstate((version, tuple(state), gauss))
     return out
 
 
@@ -97,6 +96,62 @@ def _sorted_edge_ids(edge_index: torch.Tensor, idx: torch.Tensor, num_nodes: int
     return srt
 
 
+def _dense_ids_cached(edge_index: torch.Tensor, num_nodes: int):
+    """(sorted linearised ids of the non-self-loop edges, their count) of a graph the training loop passes every step:
+    computed once per (edge_index tensor, version) — the per-step call then launches nothing for the graph side."""
+    import weakref
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), "dense")
+    hit = _EDGE_ID_CACHE.get(key)
+    if hit is not None and hit[0]() is edge_index:
+        return hit[1]
+    while len(_EDGE_ID_CACHE) >= 8:
+        _EDGE_ID_CACHE.pop(next(iter(_EDGE_ID_CACHE)))
+    row, col = edge_index[0], edge_index[1]
+    keep = row != col
+    row, col = row[keep], col[keep].clone()
+    col[row < col] -= 1
+    srt = torch.sort(row * (num_nodes - 1) + col).values
+    torch.cuda.current_stream(edge_index.device).synchronize()   # the side stream reads it from the next call on
+    val = (srt, int(srt.numel()))
+    _EDGE_ID_CACHE[key] = (weakref.ref(edge_index), val)
+    return val
+
+
+_COUNT_PINNED: Dict[int, torch.Tensor] = {}
+
+
+def _dense_round_on_side_stream(population: int, sample_size: int, taken: torch.Tensor, num_nodes: int, num_neg: int, dev):
+    """One round of upstream's dense loop: ``rnd = sample(population, k); rnd = rnd[mask[rnd]]`` cut to ``num_neg`` and
+    de-linearised, on a side stream.  Returns ``(edges [2, num_neg], kept ids [num_neg], kept count)``; ``edges`` is valid
+    on the CURRENT stream when the call returns and complete only if ``count >= num_neg``."""
+    from . import _native as N
+    lib = N.require_gpu()
+    cur, side = torch.cuda.current_stream(dev), ops._side_stream(dev, "neg")
+    rnd_host = py_random_sample(population, sample_size, pin=True)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    cnt_host = _COUNT_PINNED.get(idx)
+    if cnt_host is None:
+        cnt_host = _COUNT_PINNED[idx] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    with torch.cuda.stream(side):
+        rnd = rnd_host.to(dev, non_blocking=True)
+        edges = torch.empty((2, num_neg), dtype=torch.int64, device=dev)
+        kept = torch.empty(num_neg, dtype=torch.int64, device=dev)
+        cnt = torch.empty(1, dtype=torch.int32, device=dev)
+        nbytes = lib.llp_negative_filter_workspace_bytes(sample_size)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        N.check(lib.llp_negative_filter(rnd.data_ptr(), sample_size, taken.data_ptr(), taken.numel(), num_nodes, num_neg,
+                                        kept.data_ptr(), edges.data_ptr(), cnt.data_ptr(), ws.data_ptr(), nbytes,
+                                        side.cuda_stream), "llp_negative_filter")
+        cnt_host.copy_(cnt, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    done.synchronize()            # waits for the side stream only: the previous training step keeps running
+    cur.wait_event(done)
+    edges.record_stream(cur)
+    kept.record_stream(cur)
+    return edges, kept, int(cnt_host[0])
+
+
 def _not_in_sorted(values: torch.Tensor, sorted_ids: torch.Tensor) -> torch.Tensor:
     """``~isin(values, sorted_ids)`` by binary search — what indexing PyG's N*N - N boolean mask answers, without the mask."""
     if sorted_ids.numel() == 0:
@@ -122,35 +177,50 @@ def negative_sampling(edge_index: torch.Tensor, num_nodes: Optional[int] = None,
             raise NotImplementedError("bipartite negative sampling is never used by the reference")
         num_nodes = int(num_nodes[0])
     dev = edge_index.device
-    row, col = edge_index[0].clone(), edge_index[1].clone()
-    # edge_index_to_vector
-    if force_undirected:
-        keep = row < col
-        row, col = row[keep], col[keep]
-        offset = torch.arange(1, num_nodes, device=dev).cumsum(0)[row]
-        idx = row * num_nodes + col - offset
-        population = (num_nodes * (num_nodes + 1)) // 2 - num_nodes
-    else:
-        keep = row != col
-        row, col = row[keep], col[keep]
-        col[row < col] -= 1
-        idx = row * (num_nodes - 1) + col
+    fast = method == "dense" and not force_undirected and dev.type == "cuda" and num_nodes >= 2
+    cached = _dense_ids_cached(edge_index, num_nodes) if fast else None
+    if cached is not None:
+        taken, n_existing = cached
         population = num_nodes * num_nodes - num_nodes
-    if idx.numel() >= population:
+    else:
+        row, col = edge_index[0].clone(), edge_index[1].clone()
+        # edge_index_to_vector
+        if force_undirected:
+            keep = row < col
+            row, col = row[keep], col[keep]
+            offset = torch.arange(1, num_nodes, device=dev).cumsum(0)[row]
+            idx = row * num_nodes + col - offset
+            population = (num_nodes * (num_nodes + 1)) // 2 - num_nodes
+        else:
+            keep = row != col
+            row, col = row[keep], col[keep]
+            col[row < col] -= 1
+            idx = row * (num_nodes - 1) + col
+            population = num_nodes * num_nodes - num_nodes
+        n_existing = idx.numel()
+        taken = _sorted_edge_ids(edge_index, idx, num_nodes, force_undirected) if method == "dense" else None
+    if n_existing >= population:
         return edge_index.new_empty((2, 0))
     if num_neg_samples is None:
         num_neg_samples = edge_index.size(1)
     if force_undirected:
         num_neg_samples = num_neg_samples // 2
-    prob = 1.0 - idx.numel() / population
+    prob = 1.0 - n_existing / population
     sample_size = int(1.1 * num_neg_samples / prob)
     neg_idx = None
     if method == "dense":
         # PyG builds a boolean mask over the whole N*N - N population (1.2 GB per step at the Coauthor-Physics size) and
         # indexes it with the candidates; membership in the SORTED edge ids answers the same question (same candidates
         # kept, same order), on the device, without the mask
-        taken = _sorted_edge_ids(edge_index, idx, num_nodes, force_undirected)
-        for _ in range(3):
+        first_round = 0
+        if fast and population > sample_size and num_neg_samples > 0:
+            # round 1 without a device-wide sync: candidates -> pinned memory -> side stream -> one fused filter /
+            # compaction / de-linearisation call; the host only waits for that call's kept count
+            edges, kept, count = _dense_round_on_side_stream(population, sample_size, taken, num_nodes, num_neg_samples, dev)
+            if count >= num_neg_samples:
+                return edges
+            neg_idx, first_round = kept[:count], 1   # (rare) continue with upstream's rounds 2 and 3
+        for _ in range(first_round, 3):
             rnd = _sample_ids(population, sample_size, dev)
             keep = _not_in_sorted(rnd, taken)
             if neg_idx is not None:   # upstream: mask[neg_idx] = False after an incomplete round

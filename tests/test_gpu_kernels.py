@@ -403,6 +403,53 @@ def test_score_head_forward_backward(cuda, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
+# dense negative sampling (train_teacher_gnn.py:50-51; main.py:81-82,206-207)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,e,want", [(60, 300, 150), (2708, 10556, 8976), (30, 400, 5), (30, 400, 40), (12, 100, 30), (500, 0, 64)])
+def test_negative_sampling_dense_bit_exact(cuda, n, e, want):
+    """shims.negative_sampling(method='dense') on the device (host random.sample -> side stream -> fused filter /
+    compaction / de-linearisation; rounds 2 and 3 on the slow path) against the oracle's mask formulation: the same
+    negatives index for index and the same advance of Python's random state, over seeds that do and do not need a
+    second round (tiny requests on a half-full graph)."""
+    import random
+
+    from linkless_link_prediction_b200 import shims
+    g = torch.Generator().manual_seed(3)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    eid = ei.to(cuda)
+    for seed in range(12):
+        random.seed(seed); ref = O.negative_sampling_dense(ei, n, want); s_ref = random.getstate()
+        random.seed(seed); got = shims.negative_sampling(eid, num_nodes=n, num_neg_samples=want, method="dense"); s_got = random.getstate()
+        assert torch.equal(got.cpu(), ref), (n, e, want, seed)
+        assert s_got == s_ref
+
+
+def test_negative_filter_counts_beyond_capacity(cuda):
+    """llp_negative_filter reports every kept candidate in `count` while writing only the first max_out."""
+    lib = N.require_gpu()
+    n = 50
+    taken = torch.arange(0, n * (n - 1), 3, device=cuda)
+    cand = torch.randperm(n * (n - 1), generator=torch.Generator().manual_seed(1))[:900].to(cuda)
+    keep = ~torch.isin(cand, taken)
+    want = cand[keep]
+    for cap in (0, 10, int(want.numel()), 2000):
+        kept = torch.full((max(cap, 1),), -1, dtype=torch.int64, device=cuda)
+        edges = torch.full((2, max(cap, 1)), -1, dtype=torch.int64, device=cuda)
+        cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+        nb = lib.llp_negative_filter_workspace_bytes(cand.numel())
+        ws = torch.empty(nb, dtype=torch.uint8, device=cuda)
+        N.check(lib.llp_negative_filter(cand.data_ptr(), cand.numel(), taken.data_ptr(), taken.numel(), n, cap, kept.data_ptr(),
+                                        edges.data_ptr(), cnt.data_ptr(), ws.data_ptr(), nb, N.stream_ptr()), "llp_negative_filter")
+        assert int(cnt.item()) == want.numel()
+        m = min(cap, want.numel())
+        assert torch.equal(kept[:m], want[:m])
+        r = want[:m] // (n - 1); c = want[:m] % (n - 1); c = c + (r <= c).long()
+        if cap:
+            assert torch.equal(edges.view(2, -1)[0, :m] if cap == 0 else edges.reshape(-1)[:m], r)
+            assert torch.equal(edges.reshape(-1)[cap:cap + m], c)
+
+
+# ------------------------------------------------------------------------------------------------
 # losses
 # ------------------------------------------------------------------------------------------------
 def test_bce_value_and_grad(cuda):
