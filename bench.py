@@ -398,19 +398,26 @@ def make_teacher(hz, precision, data_cpu, split):
     step = teacher.CapturedTrainStep(model, predictor, data, optimizer, eager_steps=min(2, max(args.warmup - 1, 1)),
                                      profile_spmm=True if (args.profile_dense or precision == "fp32") else "spmm")
 
+    row, col = data.adj_t
+    edge_index = torch.stack([col, row], dim=0)
+
+    def negatives(edge):
+        if ds in ("cora", "coauthor-physics"):   # train_teacher_gnn.py:49-51: PyG dense negative sampling (host random.sample + device filter)
+            return shims.negative_sampling(edge_index, num_nodes=n_nodes, num_neg_samples=edge.size(1), method="dense")
+        # collab branch, train_teacher_gnn.py:52-54 (also the 10M-node graph: upstream's N*N - N mask does not exist there)
+        return torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)
+
     def resident():
         perm = torch.randint(0, pos_dev.size(0), (batch,), device=dev)
         edge = pos_dev[perm].t()
-        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)  # collab branch, train_teacher_gnn.py:53
-        return step(edge, neg)
+        return step(edge, negatives(edge))
 
     host_batches = [split["train"]["edge"][torch.randint(0, pos_dev.size(0), (batch,))].t().contiguous().pin_memory()
                     for _ in range(8)]
 
     def e2e(i):
         edge = host_batches[i % len(host_batches)].to(dev, non_blocking=True)
-        neg = torch.randint(0, n_nodes, edge.size(), dtype=torch.long, device=dev)
-        return step(edge, neg).item()  # 4-byte D2H + sync every step, like the reference's loss.item() (:70)
+        return step(edge, negatives(edge)).item()  # 4-byte D2H + sync every step, like the reference's loss.item() (:70)
 
     def evaluate():
         ev_args = type("A", (), {"minibatch": False, "compute_auc": False})()
