@@ -55,21 +55,30 @@ def neighbor_samplers(row, col, sample, x, step, ps_method, ns_rate, hops):
     return pos_batch.to(batch.device), neg_batch.to(batch.device)
 
 
-def _kd_losses(predictor, teacher_predictor, h, t_h, samples, args, weight=1.0):
-    """``weight * (LLP_D * llp_d + LLP_R * llp_r)`` for the anchors in ``samples[:,0]`` against the contexts
-    ``samples[:,1:]`` (main.py:183-203), plus the two unweighted values.  ``predictor(h[a].repeat(K), h[ctx])`` becomes
-    one fused edge-scoring call over the (anchor, context) pairs and the two losses one pass over the score rows."""
-    K = samples.size(1) - 1
-    if samples.size(0) == 0:   # empty anchor shard (fewer anchors than ranks): contributes nothing
-        zero = torch.zeros((), dtype=torch.float32, device=h.device)
-        return zero, zero, zero
-    anchor = samples[:, :1].expand(-1, K).contiguous()
-    ctx = samples[:, 1:].contiguous()
-    s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
+def _score_kd_and_edges(predictor, h, anchor, ctx, src, dst):
+    """Student scores of the (anchor, context) pairs AND of the train edges in ONE scorer call over the concatenated pair
+    list: ``h`` then receives a single gradient from the scorer's backward (two calls make autograd add two full-size
+    ``[rows, H]`` gradients) and the predictor's layers run once over all pairs.  Returns ``(s_r [B_n, K] or None,
+    out [2B] or None)`` — the same values ``predictor(h[a].repeat(K), h[ctx])`` (main.py:184-186) and
+    ``predictor(h[src], h[dst])`` (:212-214) give row for row."""
+    n_kd = 0 if anchor is None else anchor.numel()
+    n_e = 0 if src is None else src.numel()
+    if n_kd == 0 and n_e == 0:
+        return None, None
+    if n_kd == 0:
+        return None, predictor.score(h, src.contiguous(), dst.contiguous()).reshape(-1)
+    if n_e == 0:
+        return predictor.score(h, anchor, ctx).reshape(anchor.shape), None
+    u = torch.cat((anchor.reshape(-1), src))
+    v = torch.cat((ctx.reshape(-1), dst))
+    s_r, out = torch.split(predictor.score(h, u, v).reshape(-1), (n_kd, n_e))
+    return s_r.reshape(anchor.shape), out
+
+
+def _teacher_kd_scores(teacher_predictor, t_h, anchor, ctx):
     with torch.no_grad():
         # the teacher predictor is never put in eval() by the reference (SURVEY.md Q4): dropout stays active
-        t_r = teacher_predictor.score(t_h, anchor, ctx).reshape(samples.size(0), K)
-    return ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * weight, args.LLP_R * weight)
+        return teacher_predictor.score(t_h, anchor, ctx).reshape(anchor.shape)
 
 
 def student_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge, samples=None, node_perm=None,
@@ -82,17 +91,28 @@ def student_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, e
     optimizer.zero_grad()
     ops.advance_rng(x.device)
     h = model(x)
+    train_edges = torch.cat((edge, neg_edge), dim=-1)
+    anchor = ctx = None
+    if samples is not None and samples.size(0) > 0:
+        K = samples.size(1) - 1
+        anchor = samples[:, :1].expand(-1, K).contiguous()
+        ctx = samples[:, 1:].contiguous()
+    have_edges = train_edges.size(1) > 0
+    # predictor(h[a].repeat(K), h[ctx]) (main.py:183-186) and predictor(h[src], h[dst]) (:212-214): one fused call
+    s_r, out = _score_kd_and_edges(predictor, h, anchor, ctx, train_edges[0] if have_edges else None,
+                                   train_edges[1] if have_edges else None)
     kd_total = None
     if samples is not None:
-        kd_total, _, _ = _kd_losses(predictor, teacher_predictor, h, t_h, samples, args, kd_weight)
-    train_edges = torch.cat((edge, neg_edge), dim=-1)
-    if train_edges.size(1) > 0:
-        out = predictor.score(h, train_edges[0].contiguous(), train_edges[1].contiguous()).reshape(-1)
+        if s_r is not None:
+            t_r = _teacher_kd_scores(teacher_predictor, t_h, anchor, ctx)
+            kd_total, _, _ = ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * kd_weight, args.LLP_R * kd_weight)
+        else:   # empty anchor shard (fewer anchors than ranks): contributes nothing
+            kd_total = torch.zeros((), dtype=torch.float32, device=h.device)
+    if out is not None:
         label_loss = ops.bce_loss(out, edge.size(1))
         if edge_share != 1.0:
             label_loss = label_loss * edge_share
     else:   # empty shard: zero loss that still reaches backward / the gradient all-reduce through h
-        out = None
         label_loss = h.float().sum() * 0.0
     loss = args.True_label * label_loss
     if args.KD_RM:  # baselines, weight 0 by default; the reference evaluates them regardless
@@ -209,21 +229,21 @@ def student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimize
     h = model(x[this_target])  # rows of the touched nodes only
     n_s = samples.numel()
     K = samples.size(1) - 1
+    anchor = ctx = src_pos = dst_pos = None
     if samples.size(0) > 0:
         local = torch.arange(n_s, device=dev).reshape(samples.shape)   # positions inside h of every sample
         anchor = local[:, :1].expand(-1, K).contiguous()
         ctx = local[:, 1:].contiguous()
-        s_r = predictor.score(h, anchor, ctx).reshape(samples.size(0), K)
-        with torch.no_grad():
-            t_r = teacher_predictor.score(t_h, samples[:, :1].expand(-1, K).contiguous(),
-                                          samples[:, 1:].contiguous()).reshape(samples.size(0), K)
-        kd_total, _, _ = ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * kd_weight, args.LLP_R * kd_weight)
-    else:
-        kd_total = h.float().sum() * 0.0
     if src.numel() > 0:
         src_pos = torch.arange(n_s, n_s + src.numel(), device=dev)
         dst_pos = src_pos + src.numel()
-        out = predictor.score(h, src_pos, dst_pos).reshape(-1)
+    s_r, out = _score_kd_and_edges(predictor, h, anchor, ctx, src_pos, dst_pos)   # one scorer call: one gradient into h
+    if s_r is not None:
+        t_r = _teacher_kd_scores(teacher_predictor, t_h, samples[:, :1].expand(-1, K).contiguous(), samples[:, 1:].contiguous())
+        kd_total, _, _ = ops.kd_losses(s_r, t_r, 1, args.margin, args.LLP_D * kd_weight, args.LLP_R * kd_weight)
+    else:
+        kd_total = h.float().sum() * 0.0
+    if out is not None:
         label_loss = ops.bce_loss(out, edge.size(1))
         if edge_share != 1.0:
             label_loss = label_loss * edge_share
