@@ -667,6 +667,173 @@ static int launch_pair(const Maps& maps, const TcParams& p, int num_kb, cudaStre
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// NT on TALL tiles: 256 output rows per weight pass.  The streaming kernel above re-reads the whole [N, K] weight matrix
+// from L2 for every 128-row tile — at K = 512 that is 256 KB of W per 128 KB of activations, and the kernels' L2 -> SM
+// traffic (not HBM) is what bounds them (~9.4 TB/s measured).  Here one weight k-block in shared memory feeds TWO 128-row
+// MMAs (rows [m0, m0+128) -> TMEM columns [0, 256), rows [m0+128, m0+256) -> columns [256, 512)): a third less L2 -> SM
+// traffic, no second CTA involved.  The price: the two accumulators take all 512 TMEM columns, so the epilogue of a tile
+// does not overlap the MMAs of the next one (the TMA ring keeps filling meanwhile) — and that price is too high on B200:
+// 100 us against the streaming kernel's 76 us at M = 235,868, K = 512 (tools/kbench.py tall).  Opt-in only.  Every CTA owns a contiguous range of
+// 128-row units (12 or 13 of the 1,843 at the collab size: max/mean = 1.04 instead of 7 / 6.23 whole tall tiles); an odd
+// unit at the end of the range is a half tile.  Same MMA order per output element as the streaming kernel: bit-identical.
+constexpr int kTallStages = 3;
+constexpr int kTallStageBytes = 2 * BLOCK_M * 128 + 256 * 128;   // A rows 0..127 | A rows 128..255 | W k-block
+constexpr int kTallSmemBytes = kTallStages * kTallStageBytes + 1024 + 256;
+
+template <typename TO>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_nt_tall_kernel(const __grid_constant__ Maps maps, const TcParams p) {
+  constexpr int BLOCK_N = 256;
+  constexpr int kABytes = BLOCK_M * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTallStages * kTallStageBytes);
+  uint64_t* full_bar = bars;                       // [kTallStages]
+  uint64_t* empty_bar = bars + kTallStages;        // [kTallStages]
+  uint64_t* tmem_full = bars + 2 * kTallStages;    // [1]
+  uint64_t* tmem_empty = tmem_full + 1;            // [1]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb1 = (int)((p.K1 + BLOCK_K - 1) / BLOCK_K), kb2 = (int)((p.K2 + BLOCK_K - 1) / BLOCK_K);
+  const int num_kb = kb1 + kb2;
+  // my contiguous range of 128-row units
+  const int64_t units = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int64_t base = units / gridDim.x, rem = units % gridDim.x;
+  const int64_t u_begin = blockIdx.x * base + ((int64_t)blockIdx.x < rem ? blockIdx.x : rem);
+  const int u_count = (int)(base + ((int64_t)blockIdx.x < rem ? 1 : 0));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a1);
+    tma_prefetch_desc(&maps.b1);
+    if (kb2 > 0) { tma_prefetch_desc(&maps.a2); tma_prefetch_desc(&maps.b2); }
+    for (int s = 0; s < kTallStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    mbar_init(smem_u32(tmem_full), 1);
+    mbar_init(smem_u32(tmem_empty), kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < u_count; t += 2) {
+      const bool tall = t + 1 < u_count;
+      const int m0 = (int)((u_begin + t) * BLOCK_M);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(bar, (uint32_t)((tall ? 2 : 1) * kABytes + BLOCK_N * 128));
+          const uint32_t sa = smem_u32(smem + stage * kTallStageBytes);
+          const bool second = kb >= kb1;
+          const int k0 = (second ? kb - kb1 : kb) * BLOCK_K;
+          const CUtensorMap* ma = second ? &maps.a2 : &maps.a1;
+          tma_load_2d(sa, ma, k0, m0, bar);
+          if (tall) tma_load_2d(sa + kABytes, ma, k0, m0 + BLOCK_M, bar);
+          tma_load_2d(sa + 2 * kABytes, second ? &maps.b2 : &maps.b1, k0, 0, bar);
+        }
+        __syncwarp();
+        if (++stage == kTallStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, false);
+    constexpr uint32_t kHi = desc_hi_sw128(1024);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem), 16);
+    int stage = 0; uint32_t phase = 0, acc_phase = 0;
+    for (int t = 0; t < u_count; t += 2) {
+      const bool tall = t + 1 < u_count;
+      mbar_wait(smem_u32(tmem_empty), acc_phase ^ 1);
+      tcgen05_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a0 = a_lo0 + (uint32_t)stage * (kTallStageBytes >> 4);
+          const uint32_t a1 = a0 + (kABytes >> 4), b = a0 + (2 * kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_base, desc_from(a0 + k * 2, kHi), desc_from(b + k * 2, kHi), idesc, (uint32_t)((kb | k) != 0));
+          if (tall) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(tmem_base + BLOCK_N, desc_from(a1 + k * 2, kHi), desc_from(b + k * 2, kHi), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));
+        }
+        __syncwarp();
+        if (++stage == kTallStages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) umma_commit(smem_u32(tmem_full));
+      __syncwarp();
+      acc_phase ^= 1;
+    }
+  } else {
+    // ===================== epilogue =====================
+    TcParams pe = p;
+    if (pe.ep.dropout_p > 0.0f) resolve_rng(pe.ep);
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kColsPerWarp = BLOCK_N / 2;
+    uint32_t acc_phase = 0;
+    for (int t = 0; t < u_count; t += 2) {
+      const int halves = t + 1 < u_count ? 2 : 1;
+      mbar_wait(smem_u32(tmem_full), acc_phase);
+      tcgen05_fence_after();
+      for (int rh = 0; rh < halves; ++rh) {
+        const int64_t m = (u_begin + t + rh) * BLOCK_M + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(rh * BLOCK_N);
+        uint4 rnd128 = make_uint4(0, 0, 0, 0);
+        uint32_t rnd_group = 0xffffffffu;
+#pragma unroll 1
+        for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
+          if (c0 >= p.N) break;
+          if (pe.ep.dropout_p == 0.5f && (uint32_t)(c0 >> 7) != rnd_group) {
+            rnd_group = (uint32_t)(c0 >> 7);
+            rnd128 = philox4x32_10(pe.ep.seed, (uint64_t)m, pe.ep.offset + (uint64_t)rnd_group);
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          if (m < p.M) epilogue_chunk<TO>(r, m, c0, pe, rnd128, pe.ep.seed, pe.ep.offset);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tmem_empty));
+      acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename TO>
+static int launch_tall(const Maps& maps, const TcParams& p, cudaStream_t stream) {
+  auto kern = gemm_nt_tall_kernel<TO>;
+  static PerDeviceOnce configured;  // cudaFuncSetAttribute is per device
+  if (configured.need()) {
+    LLP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTallSmemBytes));
+    configured.done();
+  }
+  const int64_t units = ceil_div(p.M, BLOCK_M);
+  const unsigned grid = (unsigned)(units < kNumSMs ? units : kNumSMs);
+  kern<<<grid, kThreads, kTallSmemBytes, stream>>>(maps, p);
+  LLP_LAUNCH_OK();
+  return 0;
+}
+
 template <int BLOCK_N, bool kTN, typename TO>
 static int launch(const Maps& maps, const TcParams& p, cudaStream_t stream) {
   using Cfg = Config<BLOCK_N>;
@@ -708,6 +875,11 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
   // is left is a ~5 us stage round trip across the pair with only 96 KB of A stages per CTA beside the resident weights.
   const bool pair = g_tuning[20] == 2 && !res_bn && a.M >= (int64_t)BLOCK_M * kNumSMs * 2 && a.N > 128 && a.N <= 256 &&
                     num_kb * kPairHalfBytes <= kResBBudget;
+  // tall tiles (two 128-row MMAs per weight k-block; opt-in, llp_set_tuning(20, 3)): bit-identical and a third less
+  // L2 -> SM traffic, but SLOWER on B200 (100 us vs 76 us at M = 235,868, K = 512): both accumulators fill the TMEM, so the
+  // 3.5 us epilogue of every 128 x 256 half tile is no longer hidden behind the next tile's MMAs.  Measured negative result.
+  const bool tall = !pair && !res_bn && g_tuning[20] == 3 && a.M >= (int64_t)BLOCK_M * kNumSMs * 2 && a.N > 128 && a.N <= 256;
+  if (tall) bn = 256;
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   if (int rc = make_map(&maps.a1, a.A1, a.M, a.K1, a.lda1, BLOCK_K, BLOCK_M)) return rc;
@@ -733,6 +905,11 @@ int gemm_nt_tcgen05(const llp_gemm_nt_args& a, cudaStream_t stream) {
                  (ok32(a.addend, a.ldadd) ? kVec32Addend : 0) | (ok32(a.gate, a.ldgate) ? kVec32Gate : 0) |
                  (ok32(a.D, a.ldd) ? kVec32Out : 0);
     if (g_tuning[19]) p.ep_flags &= ~(kVec32Addend | kVec32Gate | kVec32Out);  // experiment: 128-bit epilogue accesses
+  }
+  if (tall) {
+    if (a.out_dtype == LLP_BF16) return launch_tall<__nv_bfloat16>(maps, p, stream);
+    if (a.out_dtype == LLP_F32) return launch_tall<float>(maps, p, stream);
+    return LLP_E_BADARG;
   }
   if (pair) {
     if (a.out_dtype == LLP_BF16) return launch_pair<__nv_bfloat16>(maps, p, num_kb, stream);

@@ -151,6 +151,28 @@ def main():
                 t = fl / us / 1e6
                 print(f"gemm_tn fp32 [{bname}] M={M} {N1}x{N2} {us:9.1f} us  {t:7.1f} fp32-TFLOP/s "
                       f"({100 * 3 * t / tf_peak:5.1f}% of the TF32 tensor peak counting 3 MMAs)", flush=True)
+    if "tall" in which:   # tall-tile NT kernel (opt-in, llp_set_tuning(20, 3)) against the streaming kernel (the default)
+        lib = N.load()
+        H = 256
+        for M, K1, K2, kw, tag in ((n, 256, 256, dict(relu=True, dropout_p=0.5, seed=1), "L2 fwd relu+drop"),
+                                   (n, 256, 256, dict(), "L3 fwd / dgrad"), (n + 77, 256, 256, dict(relu=True), "odd M"),
+                                   (n, 320, 0, dict(), "single operand K=320"), (n, 256, 256, dict(gate=True), "dgrad with gate")):
+            A1 = torch.randn(M, K1, device=dev).bfloat16(); B1 = torch.randn(H, K1, device=dev).bfloat16()
+            A2 = torch.randn(M, K2, device=dev).bfloat16() if K2 else None
+            B2 = torch.randn(H, K2, device=dev).bfloat16() if K2 else None
+            bias = torch.randn(H, device=dev)
+            kw = dict(kw)
+            if kw.pop("gate", False):
+                kw.update(gate=torch.randn(M, H, device=dev).bfloat16(), gate_scale=2.0)
+            outs = {}
+            for vtag, knob in (("tall", 3), ("streaming", 0)):
+                lib.llp_set_tuning(20, knob)
+                outs[vtag] = ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw)
+                report(f"gemm_nt [{vtag}] M={M} K={K1}+{K2} {tag}",
+                       timeit(lambda: ops.gemm_nt(A1, B1, A2, B2, bias=bias, **kw)), nbytes=M * (K1 + K2) * 2 + M * H * 2,
+                       flops=2 * M * H * (K1 + K2))
+            lib.llp_set_tuning(20, 0)
+            print(f"   bit-identical: {bool(torch.equal(outs['tall'], outs['streaming']))}", flush=True)
     if "gemmexp" in which:
         import ctypes
         lib = N.load()
