@@ -198,6 +198,37 @@ def test_py_random_sample_is_bit_exact_with_cpython():
     assert a == b
 
 
+def test_speculative_candidate_draw_keeps_cpython_stream():
+    """shims._candidates_pinned starts the NEXT step's random.sample on a worker thread; the result is only used (and
+    Python's state only advanced) when the next request is identical and nobody touched `random` in between."""
+    import random
+
+    import torch
+
+    from linkless_link_prediction_b200 import shims
+    for seed in (1, 2):
+        random.seed(seed)
+        got = []
+        for i in range(6):
+            got.append(shims._candidates_pinned(7330556, 2000 if i != 4 else 2500, pin=False).clone())
+            if i == 2:
+                random.random()          # another user of the generator: the speculation must be dropped
+        s_got = random.getstate()
+        random.seed(seed)
+        ref = []
+        for i in range(6):
+            ref.append(torch.tensor(random.sample(range(7330556), 2000 if i != 4 else 2500)))
+            if i == 2:
+                random.random()
+        assert all(torch.equal(a, b) for a, b in zip(got, ref))
+        assert s_got == random.getstate()
+    random.seed(9); shims._candidates_pinned(10 ** 6, 300, pin=False)
+    random.seed(9)                       # re-seeding between two calls: the pending draw belongs to the old stream
+    a = shims._candidates_pinned(10 ** 6, 300, pin=False)
+    random.seed(9)
+    assert torch.equal(a, torch.tensor(random.sample(range(10 ** 6), 300)))
+
+
 def test_negative_sampling_dense_equals_mask_formulation():
     """The sorted-id membership test that replaced PyG's N*N - N boolean mask keeps exactly the candidates the mask keeps
     (same order), including the second round after an incomplete first one."""
