@@ -214,29 +214,60 @@ def train(model, predictor, t_h, teacher_predictor, data, split_edge, optimizer,
     return total_loss.item() / total_examples
 
 
+ENCODE_EVERY_NODE_ONCE = True   # feature-minibatch loop: see encode_every_node_once
+
+
+def encode_every_node_once(model, num_nodes: int, rows_touched: int) -> bool:
+    """Feature-minibatch step (main.py:93-101): may the encoder run once over all ``num_nodes`` rows instead of over the
+    ``rows_touched`` gathered rows (duplicates included)?  Only when that is less work AND gives the same embeddings row for
+    row: the student MLP is row-wise and deterministic when it has no norm layer and its dropout is inactive (every
+    ``--minibatch`` configuration of the reference's scripts sets ``--dropout=0.0``, scripts/LLP_transductive.sh:5-8)."""
+    if not ENCODE_EVERY_NODE_ONCE or rows_touched < num_nodes:
+        return False
+    if getattr(model, "norm_type", "none") != "none":
+        return False
+    drop = getattr(model, "dropout", None)
+    p = float(getattr(drop, "p", drop if isinstance(drop, (int, float)) else 1.0))
+    return (not model.training) or p == 0.0
+
+
 def student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimizer, args, edge, neg_edge, samples,
                            kd_weight=1.0, edge_share=1.0):
     """One step of the feature-minibatch student loop (main.py:75-139) on explicit device tensors: only the rows the step
     touches — ``[samples.flatten(), src, dst]`` (:93-101) — go through the encoder; the scorers index that compact
-    embedding matrix by position.  ``x`` stays resident in HBM (the reference keeps it on the host and copies the rows
+    embedding matrix by position (or, when the touched rows with their duplicates outnumber the nodes and the encoder is
+    deterministic, every node goes through it once and the scorers index by node id: ``encode_every_node_once``).  ``x`` stays resident in HBM (the reference keeps it on the host and copies the rows
     every step, :95-96), so the row gather is a device gather.  Capturable (``StudentCapturedStep``)."""
     optimizer.zero_grad()
     dev = x.device
     ops.advance_rng(dev)
     train_edges = torch.cat((edge, neg_edge), dim=-1)
     src, dst = train_edges[0], train_edges[1]
-    this_target = torch.cat((samples.reshape(-1), src, dst), 0)
-    h = model(x[this_target])  # rows of the touched nodes only
     n_s = samples.numel()
     K = samples.size(1) - 1
     anchor = ctx = src_pos = dst_pos = None
-    if samples.size(0) > 0:
-        local = torch.arange(n_s, device=dev).reshape(samples.shape)   # positions inside h of every sample
-        anchor = local[:, :1].expand(-1, K).contiguous()
-        ctx = local[:, 1:].contiguous()
-    if src.numel() > 0:
-        src_pos = torch.arange(n_s, n_s + src.numel(), device=dev)
-        dst_pos = src_pos + src.numel()
+    if encode_every_node_once(model, x.size(0), n_s + 2 * src.numel()):
+        # The step touches at least as many rows (duplicates included: every anchor K + 1 times, hub contexts over and
+        # over) as the graph has nodes, and the encoder is deterministic and row-wise (no dropout, no norm): encoding
+        # every node ONCE and indexing the scorers by node id gives, row for row, the embeddings the reference's
+        # `model(x[this_target])` (main.py:95-101) produces, and the same parameter gradients (the duplicates' upstream
+        # gradients are summed before the weight gradient instead of inside it).  collab: 616k rows -> 236k.
+        h = model(x)
+        if samples.size(0) > 0:
+            anchor = samples[:, :1].expand(-1, K).contiguous()
+            ctx = samples[:, 1:].contiguous()
+        if src.numel() > 0:
+            src_pos, dst_pos = src.contiguous(), dst.contiguous()
+    else:
+        this_target = torch.cat((samples.reshape(-1), src, dst), 0)
+        h = model(x[this_target])  # rows of the touched nodes only
+        if samples.size(0) > 0:
+            local = torch.arange(n_s, device=dev).reshape(samples.shape)   # positions inside h of every sample
+            anchor = local[:, :1].expand(-1, K).contiguous()
+            ctx = local[:, 1:].contiguous()
+        if src.numel() > 0:
+            src_pos = torch.arange(n_s, n_s + src.numel(), device=dev)
+            dst_pos = src_pos + src.numel()
     s_r, out = _score_kd_and_edges(predictor, h, anchor, ctx, src_pos, dst_pos)   # one scorer call: one gradient into h
     if s_r is not None:
         t_r = _teacher_kd_scores(teacher_predictor, t_h, samples[:, :1].expand(-1, K).contiguous(), samples[:, 1:].contiguous())

@@ -267,6 +267,48 @@ def test_student_minibatch_equals_fullbatch_losses(cuda):
         shims.draw_rand_on_host(False)
 
 
+def test_minibatch_every_node_once_equals_gathered_rows(cuda):
+    """student_minibatch_step encodes every node ONCE when the step touches >= N rows and the encoder is deterministic
+    (main.encode_every_node_once) instead of the gathered rows with their duplicates (main.py:93-101): same epoch loss and
+    the same parameters after the epoch as the gathered-row path; with dropout the rule must not apply."""
+    ops.set_compute_dtype(torch.float32)
+    try:
+        n, f, H = 300, 24, 32
+        ei = O.synthetic_undirected_graph(n, 900, seed=5)
+        split = {"train": {"edge": ei.t().contiguous()}}
+        data = shims.Data(x=torch.randn(n, f), adj_t=ei).to(cuda)
+        t_h = torch.randn(n, H).to(cuda)
+        args = type("A", (), dict(transductive="transductive", node_batch_size=40, link_batch_size=300, LLP_R=1.0,
+                                  LLP_D=1.0, True_label=1.0, KD_RM=0.0, KD_LM=0.0, margin=0.1, rw_step=2, ps_method="nb",
+                                  ns_rate=2, hops=2, datasets="cora"))()   # 8 node batches >= the link batches of the epoch
+        res = []
+        for once in (True, False):
+            student.ENCODE_EVERY_NODE_ONCE = once
+            seed_all(3)
+            model = L.MLP(3, f, H, H, 0.0).to(cuda)
+            pred = L.LinkPredictor("mlp", H, H, 1, 3, 0.0).to(cuda)
+            t_pred = L.LinkPredictor("mlp", H, H, 1, 2, 0.0).to(cuda)
+            opt = L.FusedAdam(list(model.parameters()) + list(pred.parameters()), lr=0.01)
+            assert student.encode_every_node_once(model, n, 10 * n) == once
+            shims.draw_rand_on_host(True)
+            seed_all(4)
+            loss = student.train_minibatch(model, pred, t_h, t_pred, data, split, opt, args, cuda)
+            shims.draw_rand_on_host(False)
+            res.append((loss, [q.detach().clone() for q in list(model.parameters()) + list(pred.parameters())]))
+        assert res[0][0] == pytest.approx(res[1][0], rel=1e-5)
+        for a, b in zip(res[0][1], res[1][1]):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5)
+        student.ENCODE_EVERY_NODE_ONCE = True
+        drop = L.MLP(3, f, H, H, 0.5).to(cuda).train()
+        assert not student.encode_every_node_once(drop, n, 10 * n)      # active dropout: one mask per occurrence upstream
+        assert student.encode_every_node_once(drop.eval(), n, 10 * n)
+        assert not student.encode_every_node_once(L.MLP(3, f, H, H, 0.0), n, n - 1)   # fewer rows than nodes: gather
+    finally:
+        student.ENCODE_EVERY_NODE_ONCE = True
+        ops.set_compute_dtype(torch.bfloat16)
+        shims.draw_rand_on_host(False)
+
+
 def test_training_with_dropout_learns(cuda):
     """Dropout path (fused Philox epilogue + gate backward): the loss must go down on a learnable toy problem."""
     seed_all(0)
