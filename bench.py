@@ -13,7 +13,10 @@ the step's edge batch coming from pinned host memory and the loss read back ever
 + 4 scoring sets + Hits@{10,50,100}) is timed separately and reported under ``eval``.  The default bf16 line also carries
 an ``"fp32"`` object: the same measurement in the fp32-parity mode (3xTF32 tensor-core GEMMs), run inside the same
 invocation, and (N = 1) a ``"student"`` object: the LLP_D + LLP_R + True_label student step of the same graph
-(``collab-student`` below; tensor roofline of its dense layers).
+(``collab-student`` below; tensor roofline of its dense layers), and an ``"invariant_hoisted"`` object: the teacher step
+with the library's default ``ops.CACHE_INPUT_AGGREGATION`` (the aggregate of the constant input features is computed once
+per graph, not once per step).  ``value`` / ``e2e`` / ``fp32`` / ``eval`` are measured with that switched OFF: every step
+runs all of its aggregations.
 
 Other workloads (``--workload``): ``powerlaw-10m`` (configs[4], ``--scale``), ``coauthor-physics`` (configs[2] teacher),
 ``cora`` (configs[0] on the GPU) and the LLP student steps ``cora-student`` (configs[1]: MLP student, LLP_D = LLP_R =
@@ -86,6 +89,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement the default bf16 run appends")
     ap.add_argument("--no-student", action="store_true", help="skip the LLP student step the default single-GPU run appends")
+    ap.add_argument("--no-hoisted", action="store_true", help="skip the extra measurement with the loop-invariant layer-1 "
+                    "aggregation kept across steps (ops.CACHE_INPUT_AGGREGATION) the default single-GPU run appends")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="weight gradients on the main stream (ops.OVERLAP_WGRAD = False)")
@@ -582,15 +587,18 @@ def measure(hz, precision, data_cpu, split, steps, warmup):
         n_scored = sum(split[k][j].size(0) for k in ("valid", "test") for j in ("edge", "edge_neg"))
         for _ in range(3):   # eager pass, graph capture, first replay
             w["evaluate"]()
-        hz.barrier()
-        e0.record()
-        results = w["evaluate"]()
-        e1.record()
-        hz.barrier()
-        ms_eval = hz.max_over_ranks(e0.elapsed_time(e1))
+        times = []
+        for _ in range(5):   # five timed passes, the median is reported (a single replay is at the mercy of one hiccup)
+            hz.barrier()
+            e0.record()
+            results = w["evaluate"]()
+            e1.record()
+            hz.barrier()
+            times.append(hz.max_over_ranks(e0.elapsed_time(e1)))
+        ms_eval = sorted(times)[len(times) // 2]
         for m in w["modules"]:
             m.train()
-        out["eval"] = {"scored_edges_per_sec": n_scored * 1e3 / ms_eval, "ms": ms_eval, "scored_edges": n_scored,
+        out["eval"] = {"scored_edges_per_sec": n_scored * 1e3 / ms_eval, "ms": ms_eval, "ms_of_5_passes": times, "scored_edges": n_scored,
                        "hits": {k: v for k, v in results.items()}}
     # release the captured graph (it holds the in-graph gradient all-reduce) and everything it pinned
     step.graph = None
@@ -652,6 +660,12 @@ def main():
     config.update(nodes=data_cpu.x.size(0), messages=data_cpu.adj_t.size(1), feat=data_cpu.x.size(1),
                   batch_pos_edges_per_gpu=min(BATCH, split["train"]["edge"].size(0)))
 
+    # The aggregate of the constant input features (layer 1) does not change from step to step; the library keeps it on the
+    # graph by default (ops.Graph.spmm_input).  The headline numbers below are measured WITHOUT that: every step runs
+    # every aggregation, as the reference's step does; the variant with it is reported separately (`invariant_hoisted`).
+    ops.CACHE_INPUT_AGGREGATION = False
+    config["input_aggregation"] = ("recomputed in every step (ops.CACHE_INPUT_AGGREGATION switched off for value / e2e / fp32 / "
+                                   "eval; the library default keeps this loop-invariant tensor: key invariant_hoisted)")
     main_res = measure(hz, args.precision, data_cpu, split, args.steps, args.warmup)
     fp32_res = None
     if args.precision == "bf16" and not args.no_fp32 and args.workload == "collab":
@@ -673,6 +687,16 @@ def main():
         finally:
             args.workload = "collab"
         ops.set_compute_dtype(torch.bfloat16)
+
+    hoisted_res = None
+    if args.precision == "bf16" and not args.no_hoisted and args.workload == "collab" and world == 1:
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        ops.CACHE_INPUT_AGGREGATION = True
+        try:
+            hoisted_res = measure(hz, "bf16", data_cpu, split, args.steps, args.warmup)
+        finally:
+            ops.CACHE_INPUT_AGGREGATION = False
 
     if world > 1:
         import gc
@@ -703,6 +727,13 @@ def main():
                            if k in student_res}
         line["student"].update(unit="edges/s", steps=max(args.steps // 4, 5), workload="collab-student: LLP student train step "
                                "(" + STUDENT["collab-student"]["cfg"] + ")", config=student_res.get("extra"))
+    if hoisted_res is not None:
+        line["invariant_hoisted"] = {k: hoisted_res[k] for k in ("value", "ms_per_step", "e2e", "roofline", "gpu_launches", "eval")
+                                     if k in hoisted_res}
+        line["invariant_hoisted"].update(unit="edges/s", steps=args.steps, what="the same teacher step with the library default "
+                                         "ops.CACHE_INPUT_AGGREGATION = True: the mean aggregation of the constant input features "
+                                         "(layer 1, models.py:113 with x = data.x) is computed once per graph and reused by every "
+                                         "step and evaluation pass; results are bit-identical")
     if tuning:
         line["llp_tuning"] = tuning
     if world == 1 and not args.no_cpu_baseline:

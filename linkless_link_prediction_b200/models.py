@@ -105,10 +105,10 @@ class SAGE(nn.Module):
             fused = self.norm_type == "none" and not conv.normalize
             if fused:   # relu + dropout inside the layer's GEMM epilogue, their backward mask in the next layer's
                 x = conv(x, graph, _relu=not last, _dropout=0.0 if last else self.dropout,
-                         _in_gate=_gate_scale(p) if deferred else 0.0, _defer_gate=not last)
+                         _in_gate=_gate_scale(p) if deferred else 0.0, _defer_gate=not last, _input_layer=l == 0)
                 deferred = not last
             else:       # a norm layer (models.py:113-116) or L2 normalisation (sageconv_updated.py:78-79) sits between the
-                x = conv(x, graph, _in_gate=_gate_scale(p) if deferred else 0.0)   # layer and relu: those go through torch
+                x = conv(x, graph, _in_gate=_gate_scale(p) if deferred else 0.0, _input_layer=l == 0)   # layer and relu: those go through torch
                 deferred = False
                 if not last:
                     if self.norm_type != "none":

@@ -308,6 +308,10 @@ def _spmm_launch(csr, num_rows: int, num_edges: int, x: torch.Tensor, src_scale,
     return out
 
 
+# The aggregation of the constant input features (layer 1 of SAGE over PyG SAGEConv) is loop-invariant: see Graph.spmm_input
+CACHE_INPUT_AGGREGATION = True
+
+
 class Graph:
     """Device CSR of the message graph ``edge_index[0] -> edge_index[1]`` and of its transpose.
     Stands in for PyG's per-call gather/scatter bookkeeping (models.py:113 -> SAGEConv.propagate)."""
@@ -330,6 +334,21 @@ class Graph:
     def rows_out(self) -> int:
         """Rows the encoder produces on this rank (all nodes here; the local block of a PartitionedGraph)."""
         return self.num_nodes
+
+    def spmm_input(self, x: torch.Tensor) -> torch.Tensor:
+        """``spmm(x)`` of CONSTANT input features (the first SAGEConv layer aggregates ``data.x``, which no training step
+        changes and which has no gradient: models.py:113 with x = data.x): computed once per (feature tensor, version,
+        compute dtype) and kept on the graph — every later step and evaluation pass reuses the same tensor, bit for bit what
+        recomputing it gives.  Off with ``CACHE_INPUT_AGGREGATION = False``; never populated during a stream capture."""
+        if not CACHE_INPUT_AGGREGATION or type(self) is not Graph or x.requires_grad:
+            return self.spmm(x)
+        hit = getattr(self, "_input_agg", None)
+        if hit is not None and hit[0]() is x and hit[1] == (x._version, x.dtype, x.data_ptr()):
+            return hit[2]
+        out = self.spmm(x)
+        if not torch.cuda.is_current_stream_capturing():
+            self._input_agg = (weakref.ref(x), (x._version, x.dtype, x.data_ptr()), out)
+        return out
 
     def spmm(self, x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
         """forward: ``out[d] = mean_{s->d} x[s]``; transpose: ``out[s] = sum_{s->d} x[d] / deg_in(d)``."""
@@ -931,8 +950,10 @@ class SageConvFn(torch.autograd.Function):
     [agg | x] with the relu/dropout of SAGE.forward fused into the epilogue (models.py:110-119)."""
 
     @staticmethod
-    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
-        agg = graph.spmm(x)
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False, input_layer=False):
+        # ``input_layer``: x is the constant feature matrix (set by models.SAGE for its first layer): its aggregate is
+        # loop-invariant and kept on the graph (Graph.spmm_input)
+        agg = graph.spmm_input(x) if (input_layer and not ctx.needs_input_grad[0] and hasattr(graph, "spmm_input")) else graph.spmm(x)
         y = gemm_nt(agg, _weights(Wl), x, _weights(Wr), bias=bl, relu=relu, dropout_p=p, seed=seed, offset=offset,
                     rng_state=rng_state(x.device) if p > 0 else None)
         ctx.save_for_backward(x, agg, Wl, Wr, y if ((relu or p > 0) and not defer_gate) else None)
@@ -959,14 +980,15 @@ class SageConvFn(torch.autograd.Function):
             t = ctx.graph.spmm(g, transpose=True)
             gx = gemm_nt(t, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
         branch.join()
-        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
+        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None, None
 
 
 class SageConvUpdatedFn(torch.autograd.Function):
     """SAGEConv_updated (sageconv_updated.py:65-81): y = epi(mean_{s->d}(W_l x[s] + b_l) + W_r x)."""
 
     @staticmethod
-    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False):
+    def forward(ctx, x, Wl, bl, Wr, graph, relu, p, seed, offset, in_gate=0.0, defer_gate=False, input_layer=False):
+        # (transform-then-aggregate: what is aggregated depends on W_l, so nothing here is loop-invariant)
         S = stacked_weights(Wl, Wr) if x.size(1) >= STACK_MIN_IN_FEATURES else None
         if S is not None:
             # wide inputs (Coauthor-Physics: 8415 features): [t | r] = x [W_l ; W_r]^T in ONE tensor-core GEMM (x is read
@@ -1003,7 +1025,7 @@ class SageConvUpdatedFn(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = gemm_nt(gt, _weights_t(Wl), g, _weights_t(Wr), gate=x if in_gate > 0 else None, gate_scale=in_gate)
-        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None
+        return gx, gWl, gbl, gWr, None, None, None, None, None, None, None, None
 
 
 _SIDE_STREAMS: Dict[Tuple[int, str], "torch.cuda.Stream"] = {}

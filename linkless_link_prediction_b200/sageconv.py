@@ -33,9 +33,10 @@ class _SageBase(nn.Module):
         self.lin_r.reset_parameters()
 
     def forward(self, x, edge_index, size=None, *, _relu: bool = False, _dropout: float = 0.0, _in_gate: float = 0.0,
-                _defer_gate: bool = False):
+                _defer_gate: bool = False, _input_layer: bool = False):
         """``_relu`` / ``_dropout`` are set by ``models.SAGE`` to fuse its relu + dropout into this layer's epilogue;
-        ``_in_gate`` / ``_defer_gate`` move the relu/dropout backward mask into the consumer's GEMM epilogue (ops.py)."""
+        ``_in_gate`` / ``_defer_gate`` move the relu/dropout backward mask into the consumer's GEMM epilogue (ops.py);
+        ``_input_layer`` says that ``x`` is the constant feature matrix (its aggregate is loop-invariant, ops.Graph.spmm_input)."""
         if isinstance(x, (tuple, list)):
             x = x[0]
         graph = edge_index if isinstance(edge_index, ops.Graph) else ops.graph_of(edge_index, x.size(0))
@@ -46,7 +47,7 @@ class _SageBase(nn.Module):
             # sageconv_updated.py:78-79 (and PyG SAGEConv): L2-normalise the layer output; relu / dropout asked for by the
             # caller then run after the normalisation through torch (never enabled by the reference drivers)
             out = type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, False, 0.0, 0, 0,
-                                       float(_in_gate), False)
+                                       float(_in_gate), False, bool(_input_layer))
             out = torch.nn.functional.normalize(out.float(), p=2.0, dim=-1)
             if _relu:
                 out = torch.relu(out)
@@ -54,7 +55,7 @@ class _SageBase(nn.Module):
                 out = torch.nn.functional.dropout(out, p=float(_dropout), training=self.training)
             return out.to(ops.compute_dtype()).contiguous()
         return type(self)._fn.apply(x, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight, graph, bool(_relu), p, seed,
-                                    offset, float(_in_gate), bool(_defer_gate))
+                                    offset, float(_in_gate), bool(_defer_gate), bool(_input_layer))
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"

@@ -309,6 +309,47 @@ def test_minibatch_every_node_once_equals_gathered_rows(cuda):
         shims.draw_rand_on_host(False)
 
 
+def test_input_aggregation_cache_is_bit_identical_and_invalidated(cuda):
+    """ops.Graph.spmm_input keeps the aggregate of the constant input features on the graph (layer 1 of SAGE over PyG
+    SAGEConv): training steps with and without it give bit-identical embeddings, losses and parameters; an in-place change
+    of the features (version counter) or another feature tensor recomputes it; hidden layers never use it."""
+    data, split = L.data.synthetic_dataset("cora", seed=0, scale=0.5)
+    data = data.to(cuda)
+    pos = split["train"]["edge"].to(cuda)[:1500].t().contiguous()
+    neg = torch.randint(0, data.x.size(0), pos.size(), device=cuda)
+    outs = []
+    for cached in (True, False):
+        ops.CACHE_INPUT_AGGREGATION = cached
+        seed_all(1)
+        model = L.SAGE("cora", data.x.size(1), 64, 64, 3, 0.5).to(cuda)
+        pred = L.LinkPredictor("mlp", 64, 64, 1, 2, 0.5).to(cuda)
+        opt = L.FusedAdam(list(model.parameters()) + list(pred.parameters()), lr=0.01)
+        model.train(); pred.train()
+        ops.seed_dropout(5)
+        graph = ops.graph_of(data.adj_t, data.x.size(0))
+        graph.__dict__.pop("_input_agg", None)
+        losses = [float(teacher.train_step(model, pred, data, pos, neg, opt)) for _ in range(3)]
+        assert (getattr(graph, "_input_agg", None) is not None) == cached
+        model.eval()
+        with torch.no_grad():
+            h = model(data.x, data.adj_t)
+        outs.append((losses, h.clone(), [q.detach().clone() for q in model.parameters()]))
+    ops.CACHE_INPUT_AGGREGATION = True
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))
+    # invalidation
+    g = ops.graph_of(data.adj_t, data.x.size(0))
+    xc = ops.to_compute(data.x.clone())
+    a1 = g.spmm_input(xc)
+    assert g.spmm_input(xc) is a1
+    xc.mul_(2.0)                                   # in-place change: version counter moves
+    a2 = g.spmm_input(xc)
+    assert a2 is not a1 and torch.equal(a2, g.spmm(xc))
+    other = ops.to_compute(torch.randn_like(data.x))
+    assert torch.equal(g.spmm_input(other), g.spmm(other))
+
+
 def test_training_with_dropout_learns(cuda):
     """Dropout path (fused Philox epilogue + gate backward): the loss must go down on a learnable toy problem."""
     seed_all(0)
