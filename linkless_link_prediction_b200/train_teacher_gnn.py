@@ -194,6 +194,9 @@ class CapturedTrainStep(CapturedStep):
                 keep.append(ops.graph_of(adj, data.x.size(0)))
             elif adj is not None:
                 keep.append(adj)
+            # the loop-invariant aggregate of the input features the capture read (ops.Graph.spmm_input): the graph object
+            # keeps one such tensor and replaces it when another feature matrix comes by
+            keep.append(getattr(keep[-1], "_input_agg", None) if len(keep) > 1 else None)
             return keep
 
         super().__init__(fn, (model, predictor), eager_steps, profile_spmm, pin)
