@@ -409,6 +409,13 @@ class _CapturedEval:
             self.graph = torch.cuda.CUDAGraph()
             with _capture(self.graph):
                 self.out = self._pass()
+            # strong references to the cached buffers whose pointers the capture baked in (as CapturedTrainStep.pin):
+            # converted features, CSR / plan, and the loop-invariant input aggregate kept on the graph
+            data, encoder_name = self.refs[2], self.cfg[1]
+            self._pinned = [ops.to_compute(data.x, cache=True)] if data.x.is_cuda else []
+            if encoder_name != 'mlp':
+                g = data.adj_t if isinstance(data.adj_t, ops.Graph) else ops.graph_of(data.adj_t, data.x.size(0))
+                self._pinned += [g, getattr(g, "_input_agg", None)]
         self.graph.replay()
         return self.out
 
