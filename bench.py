@@ -487,12 +487,17 @@ def make_student(hz, precision, data_cpu, split):
         return sample_and_step(host_batches[i % len(host_batches)].to(dev, non_blocking=True)).item()
 
     h2d = host_batches[0].numel() * host_batches[0].element_size()
+    touched = int(a.node_batch_size) * (1 + int(a.rw_step * a.hops * (1 + a.ns_rate))) + 4 * batch   # samples + src + dst rows
     keep = (model, predictor, t_pred, t_h, optimizer, data)
     return dict(step=step, resident=resident, e2e=e2e, evaluate=None, batch=batch, h2d=h2d, keep=keep, modules=(model, predictor),
                 kernel="dense layers (MLP encoder + predictor GEMMs, forward / input-gradient / weight-gradient)", bound="tensor",
                 extra={"anchors_per_step": int(a.node_batch_size), "contexts_per_anchor": int(a.rw_step * a.hops * (1 + a.ns_rate)),
                        "loss_weights": {"True_label": a.True_label, "LLP_D": a.LLP_D, "LLP_R": a.LLP_R},
-                       "student": f"MLP {cfg['L']} x {cfg['H']}", "loop": "train_minibatch" if cfg["minibatch"] else "train"})
+                       "student": f"MLP {cfg['L']} x {cfg['H']}", "loop": "train_minibatch" if cfg["minibatch"] else "train",
+                       "encoder_rows": (("every node once (%d rows): the step touches %d rows, duplicates included, and the encoder is "
+                                         "deterministic (dropout 0) — main.encode_every_node_once; the reference encodes the gathered "
+                                         "rows" % (n_nodes, touched)) if (cfg["minibatch"] and student.encode_every_node_once(model, n_nodes, touched))
+                                        else ("gathered rows of the step" if cfg["minibatch"] else "all nodes (full-batch loop)"))})
 
 
 def measure(hz, precision, data_cpu, split, steps, warmup):
