@@ -251,7 +251,7 @@ def student_minibatch_step(model, predictor, t_h, teacher_predictor, x, optimize
         # over) as the graph has nodes, and the encoder is deterministic and row-wise (no dropout, no norm): encoding
         # every node ONCE and indexing the scorers by node id gives, row for row, the embeddings the reference's
         # `model(x[this_target])` (main.py:95-101) produces, and the same parameter gradients (the duplicates' upstream
-        # gradients are summed before the weight gradient instead of inside it).  collab: 616k rows -> 236k.
+        # gradients are summed before the weight gradient instead of inside it).  collab: 747k rows -> 236k.
         h = model(x)
         if samples.size(0) > 0:
             anchor = samples[:, :1].expand(-1, K).contiguous()
