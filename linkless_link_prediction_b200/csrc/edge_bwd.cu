@@ -32,10 +32,14 @@ __device__ __forceinline__ int incidence_node(const int64_t* __restrict__ u, con
 }
 
 // cnt[node] += 1 per incidence; the value the atomic returns is the incidence's arrival slot inside its row
-__global__ void incidence_count_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M,
+// (an endpoint outside [0, N) is a caller error — the reference's fancy index would raise —; it is skipped here and in
+// the scatter so that it can never write outside the plan)
+__global__ void incidence_count_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t N,
                                        int32_t* __restrict__ cnt, int32_t* __restrict__ slot) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < 2 * M) slot[i] = atomicAdd(cnt + incidence_node(u, v, M, i), 1);
+  if (i >= 2 * M) return;
+  const int node = incidence_node(u, v, M, i);
+  slot[i] = ((unsigned)node < (unsigned)N) ? atomicAdd(cnt + node, 1) : -1;
 }
 
 // In-place exclusive scan of x[0..n) in three launches: tiles of kScanTile (thread-local prefix + block scan), the tile
@@ -108,7 +112,7 @@ __global__ void incidence_scatter_kernel(const int64_t* __restrict__ u, const in
                                          const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slot,
                                          int32_t* __restrict__ ids) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < 2 * M) ids[rowptr[incidence_node(u, v, M, i)] + slot[i]] = (int32_t)i;
+  if (i < 2 * M && slot[i] >= 0) ids[rowptr[incidence_node(u, v, M, i)] + slot[i]] = (int32_t)i;
 }
 
 // meta[p] = (edge m, the OTHER endpoint of that edge) of incidence e, so that the backward kernel has no index chains
@@ -456,7 +460,7 @@ extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int6
   if (E == 0) return 0;
   LLP_CUDA(cudaMemsetAsync(w.big_count, 0, 2 * sizeof(int32_t), stream));
   const unsigned e_blocks = (unsigned)ceil_div(E, 256);
-  eb::incidence_count_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot);
+  eb::incidence_count_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, N, rowptr, w.slot);
   LLP_LAUNCH_OK();
   if (int rc = exclusive_scan_i32(rowptr, N + 1, w.tile_sum, stream)) return rc;
   eb::incidence_scatter_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot, w.ids);
