@@ -45,7 +45,8 @@ def _round_up(v: int, m: int) -> int:
 def empty_mat(rows: int, cols: int, dtype: torch.dtype, device) -> torch.Tensor:
     """[rows, cols] view of a row-padded buffer whose rows are 16-byte multiples (TMA / 128-bit loads)."""
     ld = _round_up(max(cols, 1), 16 // _ELT[dtype])
-    buf = torch.empty((max(rows, 1), ld), dtype=dtype, device=device)
+    # odd widths: the padding columns are read by kernels that run over the padded width (llp_spmm): keep them finite
+    buf = (torch.empty if ld == cols else torch.zeros)((max(rows, 1), ld), dtype=dtype, device=device)
     return buf[:rows, :cols]
 
 
