@@ -24,7 +24,8 @@ constexpr int kRowsPerWarp = 16;
 // ---- incidence plan: stable counting sort of the 2M incidences (i < M: endpoint u[i] of edge i; i >= M: endpoint v[i - M])
 //      by node.  Row r of the plan lists its incidences in increasing i, exactly the order of a stable sort by key.
 constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
-constexpr int kSmallRow = 16;       // rows up to this length are ordered by one thread, longer ones by whole blocks
+constexpr int kSmallRow = 16;       // rows up to this length are ordered by one thread,
+constexpr int kMidRow = 256;        // up to this one by a warp (anchors of a distillation batch: K + 1 incidences each), longer ones by blocks
 constexpr int kBigThreads = 256, kBigTile = 4096;   // kBigTile: rows one block orders alone (16 KB of shared memory)
 
 __device__ __forceinline__ int incidence_node(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t i) {
@@ -126,13 +127,14 @@ __device__ __forceinline__ int2 incidence_meta(const int64_t* __restrict__ u, co
 __global__ void incidence_order_rows_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v, int64_t M, int64_t N,
                                             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ ids,
                                             int2* __restrict__ meta, int32_t* __restrict__ big_count, int32_t* __restrict__ big_list,
-                                            int32_t* __restrict__ huge_list) {
+                                            int32_t* __restrict__ huge_list, int32_t* __restrict__ mid_list) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   const int s = rowptr[r], n = rowptr[r + 1] - s;
   if (n == 0) return;
   if (n > kSmallRow) {
-    if (n <= kBigTile) big_list[atomicAdd(big_count, 1)] = (int32_t)r;   // slot order does not matter
+    if (n <= kMidRow) mid_list[atomicAdd(big_count + 2, 1)] = (int32_t)r;       // slot order does not matter
+    else if (n <= kBigTile) big_list[atomicAdd(big_count, 1)] = (int32_t)r;
     else huge_list[atomicAdd(big_count + 1, 1)] = (int32_t)r;
     return;
   }
@@ -158,9 +160,29 @@ __global__ void __launch_bounds__(kBigThreads) incidence_order_big_kernel(const 
                                                                           const int32_t* __restrict__ ids, int2* __restrict__ meta,
                                                                           const int32_t* __restrict__ big_count,
                                                                           const int32_t* __restrict__ big_list,
-                                                                          const int32_t* __restrict__ huge_list) {
+                                                                          const int32_t* __restrict__ huge_list,
+                                                                          const int32_t* __restrict__ mid_list) {
   __shared__ int32_t tile[kBigTile];
-  const int n_big = big_count[0], n_huge = big_count[1];
+  const int n_big = big_count[0], n_huge = big_count[1], n_mid = big_count[2];
+  {  // rows of 17 .. kMidRow incidences: one WARP per row (a block per row spends its time on the row's dependent index
+     // loads: 5 us per row for the thousands of 21-incidence anchor rows of a student batch), 8 rows in flight per block
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* mine = tile + warp * kMidRow;
+    for (int b = blockIdx.x * (kBigThreads / 32) + warp; b < n_mid; b += gridDim.x * (kBigThreads / 32)) {
+      const int64_t r = mid_list[b];
+      const int s = rowptr[r], n = rowptr[r + 1] - s;
+      __syncwarp();
+      for (int q = lane; q < n; q += 32) mine[q] = ids[s + q];
+      __syncwarp();
+      for (int a = lane; a < n; a += 32) {
+        const int ea = mine[a];
+        int rank = 0;
+        for (int q = 0; q < n; ++q) rank += mine[q] < ea ? 1 : 0;
+        meta[s + rank] = incidence_meta(u, v, M, ea);
+      }
+    }
+  }
+  __syncthreads();
   for (int b = blockIdx.x; b < n_big; b += gridDim.x) {
     const int64_t r = big_list[b];
     const int s = rowptr[r], n = rowptr[r + 1] - s;
@@ -374,7 +396,7 @@ __global__ void __launch_bounds__(256) hadamard_bwd_rows_scalar_kernel(const Row
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Workspace {
-  int32_t *slot, *ids, *tile_sum, *big_count, *big_list, *huge_list;
+  int32_t *slot, *ids, *tile_sum, *big_count, *big_list, *huge_list, *mid_list;
   int64_t tiles;
   size_t total;
 };
@@ -388,8 +410,9 @@ static Workspace carve(char* base, int64_t M, int64_t N) {
   w.slot = (int32_t*)take((size_t)E * 4 + 4);
   w.ids = (int32_t*)take((size_t)E * 4 + 4);
   w.tile_sum = (int32_t*)take((size_t)w.tiles * 4 + 4);
-  w.big_count = (int32_t*)take(8);                                        // {rows one block orders, rows all blocks order}
-  w.big_list = (int32_t*)take((size_t)(E / (kSmallRow + 1) + 1) * 4);
+  w.big_count = (int32_t*)take(16);                                       // {rows one block orders, rows all blocks order, rows one warp orders}
+  w.mid_list = (int32_t*)take((size_t)(E / (kSmallRow + 1) + 1) * 4);
+  w.big_list = (int32_t*)take((size_t)(E / (kMidRow + 1) + 1) * 4);
   w.huge_list = (int32_t*)take((size_t)(E / (kBigTile + 1) + 1) * 4);
   w.total = off + 256;
   return w;
@@ -458,7 +481,7 @@ extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int6
   int2* meta2 = reinterpret_cast<int2*>(meta);
   LLP_CUDA(cudaMemsetAsync(rowptr, 0, (size_t)(N + 1) * sizeof(int32_t), stream));
   if (E == 0) return 0;
-  LLP_CUDA(cudaMemsetAsync(w.big_count, 0, 2 * sizeof(int32_t), stream));
+  LLP_CUDA(cudaMemsetAsync(w.big_count, 0, 4 * sizeof(int32_t), stream));
   const unsigned e_blocks = (unsigned)ceil_div(E, 256);
   eb::incidence_count_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, N, rowptr, w.slot);
   LLP_LAUNCH_OK();
@@ -466,10 +489,10 @@ extern "C" int llp_edge_plan(const int64_t* u, const int64_t* v, int64_t M, int6
   eb::incidence_scatter_kernel<<<e_blocks, 256, 0, stream>>>(u, v, M, rowptr, w.slot, w.ids);
   LLP_LAUNCH_OK();
   eb::incidence_order_rows_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(u, v, M, N, rowptr, w.ids, meta2, w.big_count,
-                                                                                 w.big_list, w.huge_list);
+                                                                                 w.big_list, w.huge_list, w.mid_list);
   LLP_LAUNCH_OK();
   eb::incidence_order_big_kernel<<<kNumSMs * 2, eb::kBigThreads, 0, stream>>>(u, v, M, rowptr, w.ids, meta2, w.big_count, w.big_list,
-                                                                              w.huge_list);
+                                                                              w.huge_list, w.mid_list);
   LLP_LAUNCH_OK();
   return 0;
 }
