@@ -152,7 +152,7 @@ __global__ void incidence_order_rows_kernel(const int64_t* __restrict__ u, const
   }
 }
 
-// Long rows.  A row of up to kBigTile incidences is ordered by ONE block (the row sits in shared memory, every thread ranks
+// Long rows.  Rows of up to kMidRow incidences take one warp each; a row of up to kBigTile incidences is ordered by ONE block (the row sits in shared memory, every thread ranks
 // its ids against it); the few rows beyond that (at most 2M / kBigTile of them: a node that owns a large share of the
 // whole batch) are ranked slice by slice by all blocks together, the row streamed through shared memory in tiles.
 __global__ void __launch_bounds__(kBigThreads) incidence_order_big_kernel(const int64_t* __restrict__ u, const int64_t* __restrict__ v,
